@@ -1,0 +1,256 @@
+"""CPU restatement of the region-grow driver -- TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+Follows /root/reference/test_region_grow.py:175-316 statement by statement (voxel-*set* semantics for the
+add/remove update, numpy median, numpy float32 arithmetic), parameterised by an RNG object so that it can
+either replay the reference's global ``numpy.random`` stream bit for bit (``NumpyLegacyRng``) or consume the
+counter-based Philox stream the CUDA engine uses (``PhiloxRng``).
+
+Parity: PINNED against the unmodified reference driver executed under import shims
+(oracle/make_golden.py -> tests/golden/driver_trace_*.npz; tests/test_oracle_driver.py).
+"""
+import numpy as np
+import scipy.special
+
+from . import philox
+
+
+# ----------------------------------------------------------------------------- RNG objects
+class NumpyLegacyRng:
+    """Replays the reference's draws: one global MT19937 stream (test_region_grow.py:21)."""
+
+    def __init__(self, seed=0, state=None):
+        self.rs = state if state is not None else np.random.RandomState(seed)
+
+    def begin_step(self, room, step):
+        pass
+
+    def sample(self, count, k, which):
+        # test_region_grow.py:237-240 / :249-252
+        if count >= k:
+            return np.asarray(self.rs.choice(count, k, replace=False))
+        return np.asarray(list(range(count)) + list(self.rs.choice(count, k - count, replace=True)))
+
+    def uniform(self, k, which):
+        return self.rs.random_sample(k)       # float64, compared with a float32 confidence (:266-267)
+
+
+class PhiloxRng:
+    """The engine's own stream: every draw is a pure function of (seed, room, step, stream, element)."""
+
+    def __init__(self, seed=0):
+        self.seed = int(seed)
+        self.room = 0
+        self.step = 0
+
+    def begin_step(self, room, step):
+        self.room, self.step = int(room), int(step)
+
+    def sample(self, count, k, which):
+        key_stream = philox.STREAM_INLIER_KEY if which == 'inlier' else philox.STREAM_NEIGHBOR_KEY
+        pad_stream = philox.STREAM_INLIER_PAD if which == 'inlier' else philox.STREAM_NEIGHBOR_PAD
+        if count >= k:
+            # k smallest (key, index) pairs, emitted in ascending index order
+            keys = philox.draw_u32(self.seed, self.room, self.step, key_stream, count)
+            chosen = np.lexsort((np.arange(count), keys))[:k]
+            return np.sort(chosen)
+        r = philox.draw_u32(self.seed, self.room, self.step, pad_stream, k - count).astype(np.uint64)
+        pad = (r * np.uint64(count)) >> np.uint64(32)          # multiply-high range reduction
+        return np.concatenate([np.arange(count), pad.astype(np.int64)])
+
+    def uniform(self, k, which):
+        stream = philox.STREAM_ADD_UNIFORM if which == 'add' else philox.STREAM_REMOVE_UNIFORM
+        return philox.u32_to_unit_float(philox.draw_u32(self.seed, self.room, self.step, stream, k))
+
+
+# ----------------------------------------------------------------------------- confidence
+def confidence(logits):
+    """test_region_grow.py:262-263: softmax over the two logits, column 1 (float32 in, float32 out)."""
+    return scipy.special.softmax(np.asarray(logits, np.float32), axis=-1)[:, 1]
+
+
+def voxelize(xyz, resolution):
+    """test_region_grow.py:175 -- float32 division by the python float, round-half-even, to int64."""
+    return np.round(np.asarray(xyz, np.float32) / resolution).astype(int)
+
+
+# ----------------------------------------------------------------------------- the state machine
+class RoomGrower:
+    """One room of test_region_grow.py:175-316.
+
+    ``forward_fn(inlier (1,Ni,F) f32, neighbor (1,Nj,F) f32) -> (add (1,Nj,2), remove (1,Ni,2))``.
+    """
+
+    def __init__(self, points, order, forward_fn, rng, resolution=0.1, num_inlier=512, num_neighbor=512,
+                 cluster_threshold=10, room_id=0, max_steps_per_region=None):
+        self.points = np.ascontiguousarray(points, dtype=np.float32)
+        self.order = np.asarray(order)
+        self.forward_fn = forward_fn
+        self.rng = rng
+        self.resolution = resolution
+        self.Ni, self.Nj = num_inlier, num_neighbor
+        self.cluster_threshold = cluster_threshold
+        self.room_id = room_id
+        self.max_steps_per_region = max_steps_per_region
+        n = len(self.points)
+        self.point_voxels = voxelize(self.points[:, :3], resolution)              # :175
+        self.cluster_label = np.zeros(n, dtype=int)                               # :176
+        self.cluster_id = 1                                                       # :177
+        self.visited = np.zeros(n, dtype=bool)                                    # :178
+        self.total_steps = 0
+        self.regions = []          # (seed, steps, size, reason, labelled)
+        self.trace = None          # optional list of per-step dicts
+
+    # -- region lifecycle ---------------------------------------------------------------------------
+    def begin_region(self, seed_id):
+        self.seed_id = int(seed_id)
+        self.currentMask = np.zeros(len(self.points), dtype=bool)                 # :198-199
+        self.currentMask[seed_id] = True
+        seed_voxel = self.point_voxels[seed_id]
+        self.minDims = seed_voxel.copy()                                          # :200-203
+        self.maxDims = seed_voxel.copy()
+        self.seqMinDims = self.minDims
+        self.seqMaxDims = self.maxDims
+        self.steps = 0
+        self.stuck = 0
+
+    def stop_growing(self, reason):                                               # :210-217
+        self.visited[self.currentMask] = True
+        size = int(np.sum(self.currentMask))
+        labelled = size > self.cluster_threshold
+        if labelled:
+            self.cluster_label[self.currentMask] = self.cluster_id
+            self.cluster_id += 1
+        self.regions.append((self.seed_id, self.steps, size, reason, labelled))
+
+    def prepare_step(self):
+        """:220-254.  Returns None after stopping with 'noneighbor', else the step's tiles."""
+        points, pv = self.points, self.point_voxels
+        currentPoints = points[self.currentMask, :].copy()
+        newMinDims = self.minDims.copy() - 1
+        newMaxDims = self.maxDims.copy() + 1
+        mask = np.logical_and(np.all(pv >= newMinDims, axis=1), np.all(pv <= newMaxDims, axis=1))
+        mask = np.logical_and(mask, np.logical_not(self.currentMask))
+        mask = np.logical_and(mask, np.logical_not(self.visited))
+        expandPoints = points[mask, :].copy()
+        if len(expandPoints) == 0:                                                # :233-235
+            self.stop_growing('noneighbor')
+            return None
+        self.rng.begin_step(self.room_id, self.total_steps)
+        subset_i = self.rng.sample(len(currentPoints), self.Ni, 'inlier')         # :237-240
+        center = np.median(currentPoints, axis=0)                                 # :241
+        expandPoints[:, :2] -= center[:2]                                         # :243-244
+        expandPoints[:, 6:] -= center[6:]
+        inlier = np.zeros((1, self.Ni, points.shape[1]), dtype=np.float32)
+        inlier[0, :, :] = currentPoints[subset_i, :]                              # :245-247
+        inlier[0, :, :2] -= center[:2]
+        inlier[0, :, 6:] -= center[6:]
+        subset_j = self.rng.sample(len(expandPoints), self.Nj, 'neighbor')        # :249-252
+        neighbor = np.zeros((1, self.Nj, points.shape[1]), dtype=np.float32)
+        neighbor[0, :, :] = expandPoints[subset_j, :]                             # :253
+        self._step = dict(center=center, inlier=inlier, neighbor=neighbor,
+                          inlier_idx=np.nonzero(self.currentMask)[0][subset_i],
+                          neighbor_idx=np.nonzero(mask)[0][subset_j],
+                          n_inlier=len(currentPoints), n_neighbor=len(expandPoints))
+        return self._step
+
+    def apply_step(self, add_logits, rmv_logits, add_mask=None, rmv_mask=None):
+        """:262-306.  Returns the stop reason or None if the region keeps growing.
+        ``add_mask`` / ``rmv_mask`` override the sampled masks (teacher forcing in parity tests); the uniforms
+        are drawn either way so the stream stays aligned."""
+        st = self._step
+        add_conf = confidence(add_logits)
+        rmv_conf = confidence(rmv_logits)
+        u_add = self.rng.uniform(len(add_conf), 'add')                            # :266
+        u_rmv = self.rng.uniform(len(rmv_conf), 'remove')                         # :267
+        st.update(add_conf=add_conf, rmv_conf=rmv_conf, u_add=u_add, u_rmv=u_rmv)
+        if add_mask is None:
+            add_mask = u_add < add_conf
+        if rmv_mask is None:
+            rmv_mask = u_rmv < rmv_conf
+        st.update(add_mask=np.asarray(add_mask, bool), rmv_mask=np.asarray(rmv_mask, bool))
+        center = st['center']
+        addPoints = st['neighbor'][0, :, :][st['add_mask']]                       # :270-273
+        addPoints[:, :2] += center[:2]
+        addVoxels = voxelize(addPoints[:, :3], self.resolution)
+        rmvPoints = st['inlier'][0, :, :][st['rmv_mask']]                         # :274-277
+        rmvPoints[:, :2] += center[:2]
+        rmvVoxels = voxelize(rmvPoints[:, :3], self.resolution)
+        in_add = _rows_in(self.point_voxels, addVoxels)                           # :282-287 (set membership)
+        in_rmv = _rows_in(self.point_voxels, rmvVoxels)
+        updated = bool(np.any(np.logical_and(~self.currentMask, in_add)))
+        self.currentMask = np.logical_and(np.logical_or(self.currentMask, in_add), ~in_rmv)
+        self.steps += 1                                                           # :288
+        self.total_steps += 1
+        if self.trace is not None:
+            self.trace.append(dict(st, seed=self.seed_id, size_after=int(self.currentMask.sum())))
+        if not updated:                                                           # :304-306
+            self.stop_growing('noexpand')
+            return 'noexpand'
+        if not self.currentMask.any():
+            # the reference would raise on min() of an empty array here; unreachable unless a re-rounded
+            # voxel collides -- treated as a stop so the oracle stays total
+            self.stop_growing('empty')
+            return 'empty'
+        self.minDims = self.point_voxels[self.currentMask, :].min(axis=0)         # :292-293
+        self.maxDims = self.point_voxels[self.currentMask, :].max(axis=0)
+        if not np.any(self.minDims < self.seqMinDims) and not np.any(self.maxDims > self.seqMaxDims):
+            if self.stuck >= 1:                                                   # :295-299
+                self.stop_growing('stuck')
+                return 'stuck'
+            self.stuck += 1
+        else:
+            self.stuck = 0                                                        # :300-301
+        self.seqMinDims = np.minimum(self.seqMinDims, self.minDims)               # :302-303
+        self.seqMaxDims = np.maximum(self.seqMaxDims, self.maxDims)
+        if self.max_steps_per_region is not None and self.steps >= self.max_steps_per_region:
+            self.stop_growing('maxsteps')      # engine safety cap; None (no cap) is the reference behaviour
+            return 'maxsteps'
+        return None
+
+    # -- whole room ---------------------------------------------------------------------------------
+    def grow_region(self, seed_id):
+        self.begin_region(seed_id)
+        while True:
+            st = self.prepare_step()
+            if st is None:
+                return 'noneighbor'
+            add, rmv = self.forward_fn(st['inlier'], st['neighbor'])
+            reason = self.apply_step(np.asarray(add)[0], np.asarray(rmv)[0])
+            if reason is not None:
+                return reason
+
+    def run(self):
+        for seed_id in np.arange(len(self.points))[self.order]:                   # :183-188
+            if self.visited[seed_id]:
+                continue
+            self.grow_region(seed_id)
+        return self.cluster_label
+
+    def fill(self):
+        return fill_unlabeled(self.points, self.cluster_label)
+
+
+def _rows_in(voxels, query):
+    """Row-wise membership of (N,3) int voxels in a set of (M,3) voxels (python ``tuple in set`` at :283-286)."""
+    if len(query) == 0:
+        return np.zeros(len(voxels), dtype=bool)
+    both = np.concatenate([voxels, query]).astype(np.int64)
+    lo = both.min(axis=0)
+    span = both.max(axis=0) - lo + 1
+    def key(v):
+        v = v.astype(np.int64) - lo
+        return (v[:, 0] * span[1] + v[:, 1]) * span[2] + v[:, 2]
+    return np.isin(key(voxels), key(query))
+
+
+def fill_unlabeled(points, cluster_label):
+    """test_region_grow.py:308-316: unlabeled points take the label of the nearest labelled point (13-D, fp32)."""
+    nonzero_idx = np.nonzero(cluster_label)[0]
+    filled = cluster_label.copy()
+    if len(nonzero_idx) == 0:
+        return filled           # the reference would raise in argmin([]); nothing to copy from
+    nonzero_points = points[nonzero_idx, :]
+    for i in np.nonzero(cluster_label == 0)[0]:
+        d = np.sum((nonzero_points - points[i]) ** 2, axis=1)
+        filled[i] = cluster_label[nonzero_idx[np.argmin(d)]]
+    return filled

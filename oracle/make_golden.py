@@ -1,0 +1,89 @@
+"""Generate the committed golden fixtures under tests/golden/ -- run in the BUILD container only
+(needs /root/reference).  TEST INFRASTRUCTURE (oracle/__init__.py).
+
+    python -m oracle.make_golden
+
+1. ``lrgnet_model5.npz``      - the 32 trainable tensors of /root/reference/models/lrgnet_model5.ckpt (the only
+                                LrgNet weight set the reference ships), read with learn_region_grow_b200/ckpt.py.
+2. ``driver_trace_<seed>.npz`` - the UNMODIFIED /root/reference/test_region_grow.py executed on one synthetic room
+                                (oracle/run_reference.py; forward = oracle/lrg_forward.py): the 13-D features and seed
+                                order it computed, a CRC of every tile it fed to / logits it got from Session.run, and
+                                its final (filled) cluster labels.  tests/test_oracle_driver.py replays these with
+                                oracle/lrg_driver.py.
+"""
+import contextlib
+import io
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+REF = '/root/reference'
+GOLD = os.path.join(REPO, 'tests', 'golden')
+sys.path.insert(0, REPO)
+
+from learn_region_grow_b200 import ckpt, rooms       # noqa: E402
+from oracle import run_reference                      # noqa: E402
+
+
+def golden_weights():
+    t = ckpt.load_checkpoint(os.path.join(REF, 'models', 'lrgnet_model5.ckpt'))
+    keep = {k: v for k, v in t.items() if k.startswith('lrg_') and 'Adam' not in k}
+    assert len(keep) == 32 and sum(v.size for v in keep.values()) == 791044
+    np.savez(os.path.join(GOLD, 'lrgnet_model5.npz'), **keep)
+    print('weights: %d tensors' % len(keep))
+
+
+def golden_trace(seed, n_raw, n_boxes):
+    room = rooms.generate_room(seed, n_raw=n_raw, n_boxes=n_boxes, dims=np.array([3.0, 2.5, 2.2]))
+    scratch = '/tmp/lrg_golden_%d' % seed
+    os.makedirs(os.path.join(scratch, 'data'), exist_ok=True)
+    os.makedirs(os.path.join(scratch, 'models'), exist_ok=True)
+    for ext in ('index', 'data-00000-of-00001'):
+        dst = os.path.join(scratch, 'models', 'lrgnet_model5.ckpt.' + ext)
+        if not os.path.exists(dst):
+            os.symlink(os.path.join(REF, 'models', 'lrgnet_model5.ckpt.' + ext), dst)
+    open(os.path.join(scratch, 'data', 's3dis_sampled.txt'), 'w').close()
+    head, tail = run_reference.shim_paths(REF)
+    sys.path[:0] = head
+    sys.path.extend(tail)
+    from learn_region_grow_b200 import io_util
+    cwd = os.getcwd()
+    os.chdir(scratch)
+    try:
+        io_util.saveToH5('data/s3dis_area5.h5', [room])
+        import learn_region_grow_util as shim_util
+        shim_util.TRACE = []
+        shim_util.FORWARD_DTYPE = np.float64
+        buf = io.StringIO()
+        t0 = time.time()
+        with contextlib.redirect_stdout(buf):
+            g = run_reference.run(os.path.join(REF, 'test_region_grow.py'), ['--area', '5'])
+        wall = time.time() - t0
+        trace = shim_util.TRACE
+        shim_util.TRACE = None
+        shim_util.FORWARD_DTYPE = np.float32
+    finally:
+        os.chdir(cwd)
+    log = buf.getvalue()
+    out = dict(room=room, points=g['points'].astype(np.float32), order=np.asarray(g['order']),
+               curvatures=np.asarray(g['curvatures']), cluster_label=np.asarray(g['cluster_label']),
+               inlier_crc=np.array([t['inlier_crc'] for t in trace], dtype=np.uint32),
+               neighbor_crc=np.array([t['neighbor_crc'] for t in trace], dtype=np.uint32),
+               add_crc=np.array([t['add_crc'] for t in trace], dtype=np.uint32),
+               remove_crc=np.array([t['remove_crc'] for t in trace], dtype=np.uint32),
+               log=np.array(log), reference_wall_s=np.array(wall),
+               buckets=np.array([g['comp_time_analysis'][k] for k in ('feature', 'net', 'neighbor', 'inlier')]))
+    np.savez_compressed(os.path.join(GOLD, 'driver_trace_%d.npz' % seed), **out)
+    print('trace %d: N_raw %d N_eq %d steps %d wall %.1fs' % (seed, len(room), len(out['points']), len(trace), wall))
+    print(log[-400:])
+
+
+if __name__ == '__main__':
+    os.makedirs(GOLD, exist_ok=True)
+    golden_weights()
+    golden_trace(1000, 2500, 4)
+    golden_trace(1001, 6000, 8)

@@ -1,0 +1,39 @@
+"""Pins oracle/lrg_driver.py against the UNMODIFIED reference driver (tests/golden/driver_trace_*.npz were produced by
+running /root/reference/test_region_grow.py under import shims, oracle/make_golden.py)."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import lrg_driver, lrg_forward
+from conftest import GOLDEN
+
+
+def _crc(a):
+    return zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xFFFFFFFF
+
+
+@pytest.mark.parametrize('seed', [1000, 1001])
+def test_driver_replays_reference_trace(seed, golden_weights):
+    g = np.load(os.path.join(GOLDEN, 'driver_trace_%d.npz' % seed))
+    calls = []
+
+    def fwd(inlier, neighbor):
+        calls.append((_crc(inlier), _crc(neighbor)))
+        add, rmv = lrg_forward.forward(golden_weights, inlier, neighbor, dtype=np.float64)
+        return add.astype(np.float32), rmv.astype(np.float32)
+
+    grower = lrg_driver.RoomGrower(g['points'], g['order'], fwd, lrg_driver.NumpyLegacyRng(0), resolution=0.1)
+    grower.run()
+    assert len(calls) == len(g['inlier_crc'])
+    assert [c[0] for c in calls] == [int(x) for x in g['inlier_crc']]        # every tile fed to Session.run, bit for bit
+    assert [c[1] for c in calls] == [int(x) for x in g['neighbor_crc']]
+    np.testing.assert_array_equal(grower.fill(), g['cluster_label'])          # final labels after the NN fill
+    # region lines printed by the reference (room R target T CLS: step S n/m points ...) agree with the oracle's record
+    lines = [l for l in str(g['log']).split('\n') if l.startswith('room ')]
+    labelled = [r for r in grower.regions if r[4]]
+    assert len(lines) == len(labelled)
+    for line, (seed_id, steps, size, reason, _) in zip(lines, labelled):
+        tok = line.split()
+        assert int(tok[6]) == steps and int(tok[7].split('/')[0]) == size and tok[-1] == reason
