@@ -1,0 +1,167 @@
+/*
+ * lrg_b200.h -- C ABI of the B200-native LRGNet grow engine (liblrg_b200.so).
+ *
+ * Every entry point returns 0 on success and a negative LRG_E_* code on failure (never throws across the
+ * ABI); lrg_last_error() returns a human-readable message for the calling thread.  Pointers named d_* are
+ * device pointers, everything else is host memory.  Kernels are launched on the engine's own stream unless a
+ * cudaStream_t argument is given.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to jingdao/learn_region_grow).
+ */
+#ifndef LRG_B200_H_
+#define LRG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct LrgEngine LrgEngine;
+typedef void* lrg_stream_t;            /* cudaStream_t */
+
+enum {
+  LRG_OK = 0,
+  LRG_E_INVALID = -1,                  /* bad argument (the reference raises InvalidArgument via OP_REQUIRES) */
+  LRG_E_CUDA = -2,                     /* a CUDA runtime call or kernel launch failed */
+  LRG_E_STATE = -3,                    /* call order violated (e.g. forward before load_weights) */
+  LRG_E_NOMEM = -4
+};
+
+const char* lrg_last_error(void);
+int lrg_version(void);
+int lrg_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * LrgNet forward (learn_region_grow_util.py:76-162)
+ * ------------------------------------------------------------------------------------------------------ */
+
+/* Replaces LrgNet.__init__(batch_size, seq_len, num_inlier_points, num_neighbor_points, feature_size, lite)
+ * (learn_region_grow_util.py:76-103): lite 0 -> conv 64,64,64,128,512 / head 256,128; 1 -> 64,64 / 64;
+ * 2 -> 64,64,256 / 64,64 (:77-85).  max_batch = batch_size*seq_len tiles per forward call. */
+int lrg_engine_create(LrgEngine** out, int device, int feature_size, int num_inlier_points,
+                      int num_neighbor_points, int lite, int max_batch);
+int lrg_engine_destroy(LrgEngine* e);
+
+/* Number of float32 parameters the engine expects, in graph-construction order (util.py:106-162):
+ * for prefix in (lrg_, lrg_neighbor_): kernel_i [Cin,Cout] row-major, bias_i ...; then for prefix in
+ * (lrg_add_, lrg_remove_): kernel_i, bias_i.  This is the order tf.train.Saver enumerates them. */
+size_t lrg_engine_weight_count(const LrgEngine* e);
+/* Replaces tf.train.Saver().restore(sess, path) (test_region_grow.py:92-93): the host side reads the
+ * checkpoint-V2 files and hands over one flat float32 blob in the order above. */
+int lrg_engine_load_weights(LrgEngine* e, const float* blob, size_t n_floats);
+
+/* Replaces sess.run([net.add_output, net.remove_output], {inlier_pl, neighbor_pl}) (test_region_grow.py:257-258).
+ * inlier (B, Ni, F), neighbor (B, Nj, F) float32 row-major; add_out (B, Nj, 2), remove_out (B, Ni, 2).
+ * _host: synchronous, host buffers, H2D/D2H inside.  _device: asynchronous on `stream` (0 = engine stream). */
+int lrg_forward_host(LrgEngine* e, int B, const float* inlier, const float* neighbor, float* add_out,
+                     float* remove_out);
+int lrg_forward_device(LrgEngine* e, int B, const float* d_inlier, const float* d_neighbor, float* d_add_out,
+                       float* d_remove_out, lrg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * On-device region-grow driver (test_region_grow.py:175-316)
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct LrgGrowParams {
+  float resolution;            /* test_region_grow.py:30   (0.1; 0.3 for Semantic-KITTI) */
+  int cluster_threshold;       /* :33  regions with more points than this get a label (10) */
+  uint64_t seed;               /* Philox key; the reference's single MT19937 stream (:21) cannot be sharded */
+  int max_slots;               /* rooms in flight per GPU (0 = default) */
+  int max_steps_per_region;    /* 0 = unbounded like the reference */
+  int room_id_base;            /* added to the local room index in the RNG counter (multi-GPU sharding) */
+  int trace_capacity;          /* >0: record up to this many grow steps per room (tests) */
+  int flags;                   /* LRG_FLAG_* */
+} LrgGrowParams;
+
+enum {
+  LRG_FLAG_KERNEL_TIMING = 1,  /* time the forward kernels separately with CUDA events (no graph; slower) */
+  LRG_FLAG_NO_GRAPH = 2        /* launch kernels directly instead of replaying a CUDA graph */
+};
+
+typedef struct LrgRoomStats {
+  int32_t n_points;
+  int32_t grow_steps;          /* Session.run calls the reference would have made */
+  int32_t regions;             /* seeds grown (labelled or not) */
+  int32_t clusters;            /* labelled regions (cluster_id - 1) */
+  int32_t stop_noneighbor, stop_noexpand, stop_stuck, stop_other;
+} LrgRoomStats;
+
+/* One record per grow step when tracing (parity tests): everything needed to re-drive the CPU oracle. */
+typedef struct LrgStepTrace {
+  int32_t seed_point, step_in_region, n_inlier, n_neighbor;
+  int32_t stop_reason;         /* 0 continue, 1 noneighbor(unused here), 2 noexpand, 3 stuck, 4 maxsteps, 5 empty */
+  int32_t size_after;
+  float center[16];
+  uint32_t add_mask[16];       /* bit r of word r/32: tile row r sampled True */
+  uint32_t remove_mask[16];
+  uint32_t inlier_idx_crc, neighbor_idx_crc;   /* sum-of-products checksums of the sampled point indices */
+} LrgStepTrace;
+
+/* Upload rooms: points (sum N, F) float32 rows = the 13-D features of test_region_grow.py:165-172,
+ * room_offsets (n_rooms+1) prefix sums of N_r, seed_order (sum N) = argsort(curvatures) per room (:183),
+ * room-local indices.  Replaces the numpy arrays the driver keeps per room (:175-183). */
+int lrg_rooms_upload(LrgEngine* e, int n_rooms, const int64_t* room_offsets, const float* points,
+                     const int32_t* seed_order, float resolution);
+/* Grow every uploaded room to completion on the device (no host round trip per step), then fill unlabeled
+ * points (:308-316).  stats may be NULL or n_rooms entries. */
+int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats* stats);
+/* labels (sum N) int32; filled != 0 returns the labels after the nearest-neighbour fill (:308-316),
+ * otherwise the raw cluster_label with 0 = unlabeled (:176,214). */
+int lrg_labels_download(LrgEngine* e, int32_t* labels, int filled);
+int lrg_trace_download(LrgEngine* e, int room, LrgStepTrace* out, int capacity, int* n_steps);
+/* Host-buffer convenience: upload + segment + download (the end-to-end call bench.py times). */
+int lrg_segment_rooms_host(LrgEngine* e, int n_rooms, const int64_t* room_offsets, const float* points,
+                           const int32_t* seed_order, const LrgGrowParams* params, int32_t* labels_filled,
+                           LrgRoomStats* stats);
+/* Device time (ms, CUDA events on the engine stream) of the last lrg_segment_resident call, the number of
+ * lock-step iterations it ran and the kernels it launched. */
+int lrg_last_segment_profile(LrgEngine* e, float* grow_ms, float* fill_ms, int64_t* iterations,
+                             int64_t* kernel_launches, float* forward_ms);
+
+/* ------------------------------------------------------------------------------------------------------
+ * tf_ops primitives.  Same argument lists as the reference's C++ launchers plus a trailing stream; all
+ * pointers are DEVICE pointers (the reference receives TF-allocated device buffers).
+ * ------------------------------------------------------------------------------------------------------ */
+/* tf_ops/sampling/tf_sampling_g.cu:203  farthestpointsamplingLauncher(b,n,m,inp,temp,out); temp (32,n) workspace
+ * is accepted for signature parity and may be NULL (min-distances live on chip when n fits). */
+int lrg_farthest_point_sampling(int b, int n, int m, const float* d_inp, float* d_temp, int* d_out, lrg_stream_t s);
+/* tf_sampling_g.cu:206 gatherpointLauncher(b,n,m,inp,idx,out) */
+int lrg_gather_point(int b, int n, int m, const float* d_inp, const int* d_idx, float* d_out, lrg_stream_t s);
+/* tf_sampling_g.cu:209 scatteraddpointLauncher(b,n,m,out_g,idx,inp_g); inp_g must be zeroed (tf_sampling.cpp:174) */
+int lrg_scatter_add_point(int b, int n, int m, const float* d_out_g, const int* d_idx, float* d_inp_g, lrg_stream_t s);
+/* tf_sampling_g.cu:198 probsampleLauncher(b,n,m,inp_p,inp_r,temp,out); temp (b,n) workspace */
+int lrg_prob_sample(int b, int n, int m, const float* d_inp_p, const float* d_inp_r, float* d_temp, int* d_out, lrg_stream_t s);
+/* tf_ops/grouping/tf_grouping_g.cu:125 queryBallPointLauncher(b,n,m,radius,nsample,xyz1,xyz2,idx,pts_cnt).
+ * Rows with no point in the ball are left untouched like the reference (uninitialised there). */
+int lrg_query_ball_point(int b, int n, int m, float radius, int nsample, const float* d_xyz1, const float* d_xyz2,
+                         int* d_idx, int* d_pts_cnt, lrg_stream_t s);
+/* tf_grouping_g.cu:129 selectionSortLauncher(b,n,m,k,dist,outi,out) */
+int lrg_selection_sort(int b, int n, int m, int k, const float* d_dist, int* d_outi, float* d_out, lrg_stream_t s);
+/* tf_grouping_g.cu:133 groupPointLauncher(b,n,c,m,nsample,points,idx,out) */
+int lrg_group_point(int b, int n, int c, int m, int nsample, const float* d_points, const int* d_idx, float* d_out, lrg_stream_t s);
+/* tf_grouping_g.cu:137 groupPointGradLauncher(b,n,c,m,nsample,grad_out,idx,grad_points); grad_points zeroed (tf_grouping.cpp:204) */
+int lrg_group_point_grad(int b, int n, int c, int m, int nsample, const float* d_grad_out, const int* d_idx, float* d_grad_points, lrg_stream_t s);
+/* tf_ops/3d_interpolation/tf_interpolate.cpp:60 threenn_cpu(b,n,m,xyz1,xyz2,dist,idx) -- CPU-only in the reference */
+int lrg_three_nn(int b, int n, int m, const float* d_xyz1, const float* d_xyz2, float* d_dist, int* d_idx, lrg_stream_t s);
+/* tf_interpolate.cpp:107 threeinterpolate_cpu(b,m,c,n,points,idx,weight,out) */
+int lrg_three_interpolate(int b, int m, int c, int n, const float* d_points, const int* d_idx, const float* d_weight, float* d_out, lrg_stream_t s);
+/* tf_interpolate.cpp:131 threeinterpolate_grad_cpu(b,n,c,m,grad_out,idx,weight,grad_points); grad_points zeroed (:244) */
+int lrg_three_interpolate_grad(int b, int n, int c, int m, const float* d_grad_out, const int* d_idx, const float* d_weight, float* d_grad_points, lrg_stream_t s);
+
+/* Plain device-memory helpers so a ctypes host needs no second CUDA binding. */
+int lrg_malloc(void** d_ptr, size_t bytes);
+int lrg_free(void* d_ptr);
+int lrg_memcpy_h2d(void* d_dst, const void* src, size_t bytes);
+int lrg_memcpy_d2h(void* dst, const void* d_src, size_t bytes);
+int lrg_memset(void* d_ptr, int value, size_t bytes);
+int lrg_device_synchronize(void);
+int lrg_set_device(int device);
+/* Pinned host buffers for the end-to-end path. */
+int lrg_host_alloc(void** ptr, size_t bytes);
+int lrg_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRG_B200_H_ */

@@ -1,0 +1,60 @@
+"""Build liblrg_b200.so (the C-ABI shared library of include/lrg_b200.h) in-tree with nvcc for sm_100a.
+
+    python -m learn_region_grow_b200.build [--force]
+
+The library is git-ignored but travels to the GPU box with the repo snapshot; nothing is JIT-compiled at run time.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'liblrg_b200.so')
+SOURCES = ['lrg_forward.cu', 'lrg_driver.cu', 'lrg_engine.cu', 'lrg_tfops.cu']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '--extended-lambda',
+              '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
+
+
+def _nvcc():
+    for cand in (os.environ.get('NVCC'), '/usr/local/cuda/bin/nvcc', 'nvcc'):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError('nvcc not found')
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, '..', 'include', 'lrg_b200.h'), __file__]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not _stale():
+        return LIB
+    objs = []
+    build_dir = os.path.join(HERE, 'build')
+    os.makedirs(build_dir, exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(build_dir, src.replace('.cu', '.o'))
+        cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError('nvcc failed on %s:\n%s' % (src, out))
+    cmd = [_nvcc(), '-shared', '-o', LIB] + objs + ['-Xcompiler', '-fPIC', '-gencode', 'arch=compute_100a,code=sm_100a']
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('link failed:\n%s' % r.stdout)
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

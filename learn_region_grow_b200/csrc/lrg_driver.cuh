@@ -1,0 +1,79 @@
+// On-device region-grow driver: data structures shared by lrg_driver.cu and lrg_engine.cu (internal).
+#pragma once
+#include "lrg_common.cuh"
+
+namespace lrg {
+
+constexpr int kStepThreads = 1024;
+constexpr int kMaxTilePts = 512;       // NUM_INLIER_POINT / NUM_NEIGHBOR_POINT upper bound (test_region_grow.py:22-23)
+enum : unsigned char { ST_CUR = 1, ST_VISITED = 2 };
+enum { STOP_NONE = 0, STOP_NONEIGHBOR = 1, STOP_NOEXPAND = 2, STOP_STUCK = 3, STOP_MAXSTEPS = 4, STOP_EMPTY = 5 };
+
+// Per-slot grow state (one slot = one room in flight).  `active` is read by the forward kernels.
+struct SlotState {
+  int active;          // a forward is pending: tiles are valid, logits will be applied by the next step kernel
+  int finished;        // no more rooms for this slot
+  int room;            // room index or -1
+  int cursor;          // next position in the room's seed order (test_region_grow.py:186)
+  int seed;
+  int minD[3], maxD[3], seqMin[3], seqMax[3];   // :200-203
+  int stuck, steps, total_steps;
+  int n_in, n_nb;
+  int cluster_id;      // :177
+  int regions, stops[4];
+  float center[16];    // :241
+};
+
+struct DriverArgs {
+  int n_rooms;
+  const long long* room_off;    // (n_rooms+1)
+  const float* pts;             // (T,16) padded feature rows
+  const int4* vox;              // (T) voxel coordinates (:175)
+  unsigned char* state;         // (T) ST_CUR | ST_VISITED
+  int* label;                   // (T) cluster_label (:176)
+  const int* order;             // (T) room-local seed order (:183)
+  SlotState* slots;
+  int n_slots;
+  int maxN;
+  int* listI;                   // (n_slots, maxN) ascending indices of the current region
+  int* listJ;                   // (n_slots, maxN) ascending indices of the neighbour shell
+  unsigned* keyI;               // (n_slots, maxN) sampling keys
+  unsigned* keyJ;
+  float* tile[2];               // [0] inlier (n_slots, Ni, F), [1] neighbor (n_slots, Nj, F)
+  int* tileidx[2];              // (n_slots, 512) source point of every tile row
+  const float* logits[2];       // [0] remove_output (n_slots, Ni, 2), [1] add_output (n_slots, Nj, 2)
+  float* pooled;                // (n_slots, pooled_per_slot) zeroed here for the next forward
+  int pooled_per_slot;
+  int Ni, Nj, F;
+  float resolution;
+  int cluster_threshold;
+  unsigned long long seed;
+  int max_steps;
+  int room_id_base;
+  int* next_room;
+  int* finished_slots;
+  volatile int* done_flag;      // mapped pinned host memory
+  LrgRoomStats* stats;          // (n_rooms)
+  LrgStepTrace* trace;          // (n_rooms, trace_capacity) or NULL
+  int trace_capacity;
+};
+
+struct FillArgs {
+  int n_rooms;
+  const long long* room_off;
+  const float* pts;
+  const int* label;
+  int* label_filled;
+  int* lab_list;                // (T) per room: ascending indices of labelled points
+  int* unl_list;                // (T) per room: ascending indices of unlabeled points
+  int* n_lab;                   // (n_rooms)
+  int* n_unl;
+  int F;
+};
+
+int launch_pack(const float* d_points, int F, long long total, float resolution, float* d_pts16, int4* d_vox,
+                cudaStream_t stream);
+int launch_step(const DriverArgs& da, cudaStream_t stream);
+int launch_fill(const FillArgs& fa, cudaStream_t stream);
+
+}  // namespace lrg

@@ -1,0 +1,585 @@
+// Host side of liblrg_b200.so: engine object (weights, workspaces, stream, CUDA graph of the lock-step grow loop) and
+// the extern "C" entry points of include/lrg_b200.h that concern LrgNet and the region-grow driver.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "lrg_driver.cuh"
+
+namespace lrg {
+
+static thread_local std::string g_error;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+}
+
+template <class T>
+static int dev_alloc(T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t err = cudaMalloc((void**)p, count * sizeof(T));
+  if (err != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) -> %s", count * sizeof(T), cudaGetErrorString(err));
+    return LRG_E_NOMEM;
+  }
+  return LRG_OK;
+}
+
+#define LRG_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != LRG_OK) return rc__; \
+  } while (0)
+
+struct HostLayer { int K, N; size_t w_off, b_off; };
+
+}  // namespace lrg
+
+using namespace lrg;
+
+struct LrgEngine {
+  int device = 0;
+  int F = 13, Ni = 512, Nj = 512, lite = 0, max_batch = 1;
+  std::vector<int> conv, conv2;
+  size_t n_weights = 0;
+  bool weights_loaded = false;
+  cudaStream_t stream = nullptr;
+  NetDesc net{};
+  float* d_weights = nullptr;      // packed/padded device copy
+  size_t packed_floats = 0;
+  // forward workspaces for max_batch tile pairs (user-facing forward)
+  int ws_batch = 0;
+  float *d_x[2] = {nullptr, nullptr}, *d_h1[2] = {nullptr, nullptr}, *d_pooled = nullptr, *d_gproj = nullptr,
+        *d_logits[2] = {nullptr, nullptr};
+  // rooms
+  int n_rooms = 0;
+  long long total_pts = 0;
+  int maxN = 0;
+  float resolution = 0.1f;
+  std::vector<long long> h_room_off;
+  long long* d_room_off = nullptr;
+  float* d_pts = nullptr;
+  int4* d_vox = nullptr;
+  unsigned char* d_state = nullptr;
+  int *d_label = nullptr, *d_label_filled = nullptr, *d_order = nullptr;
+  int *d_lab_list = nullptr, *d_unl_list = nullptr, *d_n_lab = nullptr, *d_n_unl = nullptr;
+  LrgRoomStats* d_stats = nullptr;
+  // slots
+  int n_slots = 0, slots_maxN = 0;
+  SlotState* d_slots = nullptr;
+  int *d_listI = nullptr, *d_listJ = nullptr;
+  unsigned *d_keyI = nullptr, *d_keyJ = nullptr;
+  float* d_tile[2] = {nullptr, nullptr};
+  int* d_tileidx[2] = {nullptr, nullptr};
+  float *s_h1[2] = {nullptr, nullptr}, *s_pooled = nullptr, *s_gproj = nullptr, *s_logits[2] = {nullptr, nullptr};
+  int* d_counters = nullptr;       // [0] next_room, [1] finished_slots
+  int* h_done = nullptr;           // mapped pinned
+  int* d_done = nullptr;
+  LrgStepTrace* d_trace = nullptr;
+  int trace_capacity = 0;
+  // profile of the last segment call
+  float grow_ms = 0, fill_ms = 0, forward_ms = 0;
+  long long iterations = 0, launches = 0;
+};
+
+namespace lrg {
+
+static void channel_lists(int lite, std::vector<int>& conv, std::vector<int>& conv2) {
+  if (lite == 1) { conv = {64, 64}; conv2 = {64}; }
+  else if (lite == 2) { conv = {64, 64, 256}; conv2 = {64, 64}; }
+  else { conv = {64, 64, 64, 128, 512}; conv2 = {256, 128}; }
+}
+
+static size_t count_weights(const LrgEngine* e) {
+  size_t n = 0;
+  for (int br = 0; br < 2; ++br)
+    for (size_t i = 0; i < e->conv.size(); ++i) {
+      int cin = i == 0 ? e->F : e->conv[i - 1];
+      n += (size_t)cin * e->conv[i] + e->conv[i];
+    }
+  for (int h = 0; h < 2; ++h)
+    for (size_t i = 0; i <= e->conv2.size(); ++i) {
+      int cin = i == 0 ? e->conv.back() * 2 + e->conv[1] : e->conv2[i - 1];
+      int cout = i == e->conv2.size() ? 2 : e->conv2[i];
+      n += (size_t)cin * cout + cout;
+    }
+  return n;
+}
+
+static void free_forward_ws(LrgEngine* e) {
+  for (int i = 0; i < 2; ++i) { cudaFree(e->d_x[i]); cudaFree(e->d_h1[i]); cudaFree(e->d_logits[i]); e->d_x[i] = e->d_h1[i] = e->d_logits[i] = nullptr; }
+  cudaFree(e->d_pooled); cudaFree(e->d_gproj);
+  e->d_pooled = e->d_gproj = nullptr;
+  e->ws_batch = 0;
+}
+
+static int ensure_forward_ws(LrgEngine* e, int B) {
+  if (B <= e->ws_batch) return LRG_OK;
+  free_forward_ws(e);
+  const int n[2] = {e->Ni, e->Nj};
+  for (int i = 0; i < 2; ++i) {
+    LRG_TRY(dev_alloc(&e->d_x[i], (size_t)B * n[i] * e->F));
+    LRG_TRY(dev_alloc(&e->d_h1[i], (size_t)B * n[i] * e->net.C1));
+    LRG_TRY(dev_alloc(&e->d_logits[i], (size_t)B * n[i] * 2));
+  }
+  LRG_TRY(dev_alloc(&e->d_pooled, (size_t)B * 2 * e->net.Clast));
+  LRG_TRY(dev_alloc(&e->d_gproj, (size_t)B * 2 * e->net.H0));
+  e->ws_batch = B;
+  return LRG_OK;
+}
+
+static void free_rooms(LrgEngine* e) {
+  cudaFree(e->d_room_off); cudaFree(e->d_pts); cudaFree(e->d_vox); cudaFree(e->d_state); cudaFree(e->d_label);
+  cudaFree(e->d_label_filled); cudaFree(e->d_order); cudaFree(e->d_lab_list); cudaFree(e->d_unl_list);
+  cudaFree(e->d_n_lab); cudaFree(e->d_n_unl); cudaFree(e->d_stats);
+  e->d_room_off = nullptr; e->d_pts = nullptr; e->d_vox = nullptr; e->d_state = nullptr; e->d_label = nullptr;
+  e->d_label_filled = nullptr; e->d_order = nullptr; e->d_lab_list = e->d_unl_list = e->d_n_lab = e->d_n_unl = nullptr;
+  e->d_stats = nullptr;
+  e->n_rooms = 0; e->total_pts = 0; e->maxN = 0;
+}
+
+static void free_slots(LrgEngine* e) {
+  cudaFree(e->d_slots); cudaFree(e->d_listI); cudaFree(e->d_listJ); cudaFree(e->d_keyI); cudaFree(e->d_keyJ);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(e->d_tile[i]); cudaFree(e->d_tileidx[i]); cudaFree(e->s_h1[i]); cudaFree(e->s_logits[i]);
+    e->d_tile[i] = nullptr; e->d_tileidx[i] = nullptr; e->s_h1[i] = nullptr; e->s_logits[i] = nullptr;
+  }
+  cudaFree(e->s_pooled); cudaFree(e->s_gproj);
+  e->d_slots = nullptr; e->d_listI = e->d_listJ = nullptr; e->d_keyI = e->d_keyJ = nullptr; e->s_pooled = e->s_gproj = nullptr;
+  e->n_slots = 0; e->slots_maxN = 0;
+}
+
+static int ensure_slots(LrgEngine* e, int n_slots) {
+  if (n_slots == e->n_slots && e->maxN <= e->slots_maxN) return LRG_OK;
+  free_slots(e);
+  const size_t S = n_slots, M = std::max(e->maxN, 1);
+  LRG_TRY(dev_alloc(&e->d_slots, S));
+  LRG_TRY(dev_alloc(&e->d_listI, S * M));
+  LRG_TRY(dev_alloc(&e->d_listJ, S * M));
+  LRG_TRY(dev_alloc(&e->d_keyI, S * M));
+  LRG_TRY(dev_alloc(&e->d_keyJ, S * M));
+  const int n[2] = {e->Ni, e->Nj};
+  for (int i = 0; i < 2; ++i) {
+    LRG_TRY(dev_alloc(&e->d_tile[i], S * n[i] * e->F));
+    LRG_TRY(dev_alloc(&e->d_tileidx[i], S * kMaxTilePts));
+    LRG_TRY(dev_alloc(&e->s_h1[i], S * n[i] * e->net.C1));
+    LRG_TRY(dev_alloc(&e->s_logits[i], S * n[i] * 2));
+  }
+  LRG_TRY(dev_alloc(&e->s_pooled, S * 2 * e->net.Clast));
+  LRG_TRY(dev_alloc(&e->s_gproj, S * 2 * e->net.H0));
+  e->n_slots = n_slots;
+  e->slots_maxN = (int)M;
+  return LRG_OK;
+}
+
+}  // namespace lrg
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char* lrg_last_error(void) { return g_error.c_str(); }
+int lrg_version(void) { return 100; }
+int lrg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int lrg_engine_create(LrgEngine** out, int device, int feature_size, int num_inlier_points, int num_neighbor_points,
+                      int lite, int max_batch) {
+  LRG_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  LRG_REQUIRE(feature_size >= 3 && feature_size <= 16, "feature_size must be in [3,16], got %d", feature_size);
+  LRG_REQUIRE(num_inlier_points > 0 && num_inlier_points <= kMaxTilePts && num_neighbor_points > 0 &&
+                  num_neighbor_points <= kMaxTilePts,
+              "num_inlier_points/num_neighbor_points must be in [1,%d]", kMaxTilePts);
+  LRG_REQUIRE(lite >= 0 && lite <= 2, "lite must be 0, 1 or 2, got %d", lite);
+  LRG_REQUIRE(max_batch >= 1, "max_batch must be >= 1");
+  LRG_CUDA(cudaSetDevice(device));
+  LrgEngine* e = new LrgEngine();
+  e->device = device; e->F = feature_size; e->Ni = num_inlier_points; e->Nj = num_neighbor_points;
+  e->lite = lite; e->max_batch = max_batch;
+  channel_lists(lite, e->conv, e->conv2);
+  e->n_weights = count_weights(e);
+  cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  if (err == cudaSuccess) err = cudaHostAlloc((void**)&e->h_done, sizeof(int), cudaHostAllocMapped);
+  if (err == cudaSuccess) err = cudaHostGetDevicePointer((void**)&e->d_done, e->h_done, 0);
+  if (err == cudaSuccess) err = cudaMalloc((void**)&e->d_counters, 2 * sizeof(int));
+  if (err != cudaSuccess) {
+    set_error("engine create: %s", cudaGetErrorString(err));
+    delete e;
+    return LRG_E_CUDA;
+  }
+  *out = e;
+  return LRG_OK;
+}
+
+int lrg_engine_destroy(LrgEngine* e) {
+  if (e == nullptr) return LRG_OK;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  free_forward_ws(e); free_rooms(e); free_slots(e);
+  cudaFree(e->d_weights); cudaFree(e->d_counters); cudaFree(e->d_trace);
+  cudaFreeHost(e->h_done);
+  cudaStreamDestroy(e->stream);
+  delete e;
+  return LRG_OK;
+}
+
+size_t lrg_engine_weight_count(const LrgEngine* e) { return e ? e->n_weights : 0; }
+
+int lrg_engine_load_weights(LrgEngine* e, const float* blob, size_t n_floats) {
+  LRG_REQUIRE(e != nullptr && blob != nullptr, "engine/blob is NULL");
+  LRG_REQUIRE(n_floats == e->n_weights, "weight blob has %zu floats, the network needs %zu", n_floats, e->n_weights);
+  LRG_CUDA(cudaSetDevice(e->device));
+  // repack: every matrix row-major [Kpad][N] (K padded to a multiple of 16 with zero rows); head layer 0 split into
+  // its pooled part [2*Clast][H0] and its per-point part [C1][H0]
+  std::vector<float> packed;
+  auto add_matrix = [&](const float* src, int K, int N, int Kpad) {
+    size_t off = packed.size();
+    packed.resize(off + (size_t)Kpad * N, 0.f);
+    memcpy(packed.data() + off, src, sizeof(float) * (size_t)K * N);
+    while (packed.size() % 4) packed.push_back(0.f);
+    return off;
+  };
+  auto add_vector = [&](const float* src, int N) {
+    size_t off = packed.size();
+    packed.insert(packed.end(), src, src + N);
+    while (packed.size() % 4) packed.push_back(0.f);
+    return off;
+  };
+  struct Off { size_t w, b; int K, Kpad, N; };
+  Off conv[2][kMaxConv];
+  Off head_local[2], hidden[2][kMaxHidden], outl[2];
+  size_t w0g[2];
+  const float* p = blob;
+  const int nc = (int)e->conv.size(), nh = (int)e->conv2.size();
+  for (int br = 0; br < 2; ++br)
+    for (int i = 0; i < nc; ++i) {
+      int K = i == 0 ? e->F : e->conv[i - 1], N = e->conv[i], Kpad = (K + 15) / 16 * 16;
+      conv[br][i] = Off{add_matrix(p, K, N, Kpad), 0, K, Kpad, N};
+      p += (size_t)K * N;
+      conv[br][i].b = add_vector(p, N);
+      p += N;
+    }
+  const int Clast = e->conv.back(), C1 = e->conv[1], H0 = e->conv2[0];
+  // blob order: add head then remove head (util.py:138-162); device order: [0] = remove, [1] = add
+  for (int hb = 0; hb < 2; ++hb) {
+    const int h = hb == 0 ? 1 : 0;
+    w0g[h] = add_matrix(p, 2 * Clast, H0, 2 * Clast);
+    head_local[h] = Off{add_matrix(p + (size_t)2 * Clast * H0, C1, H0, C1), 0, C1, C1, H0};
+    p += (size_t)(2 * Clast + C1) * H0;
+    head_local[h].b = add_vector(p, H0);
+    p += H0;
+    for (int i = 1; i < nh; ++i) {
+      int K = e->conv2[i - 1], N = e->conv2[i];
+      hidden[h][i - 1] = Off{add_matrix(p, K, N, K), 0, K, K, N};
+      p += (size_t)K * N;
+      hidden[h][i - 1].b = add_vector(p, N);
+      p += N;
+    }
+    int K = e->conv2.back();
+    outl[h] = Off{add_matrix(p, K, 2, K), 0, K, K, 2};
+    p += (size_t)K * 2;
+    outl[h].b = add_vector(p, 2);
+    p += 2;
+  }
+  if ((size_t)(p - blob) != n_floats) { set_error("internal: weight walk consumed %zu of %zu floats", (size_t)(p - blob), n_floats); return LRG_E_INVALID; }
+  cudaFree(e->d_weights);
+  e->d_weights = nullptr;
+  LRG_TRY(dev_alloc(&e->d_weights, packed.size()));
+  LRG_CUDA(cudaMemcpy(e->d_weights, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+  e->packed_floats = packed.size();
+  NetDesc& net = e->net;
+  memset(&net, 0, sizeof(net));
+  net.F = e->F; net.n_conv = nc; net.n_hidden = nh; net.Clast = Clast; net.C1 = C1; net.H0 = H0;
+  auto L = [&](const Off& o) { return LayerDesc{e->d_weights + o.w, e->d_weights + o.b, o.K, o.Kpad, o.N}; };
+  for (int br = 0; br < 2; ++br)
+    for (int i = 0; i < nc; ++i) net.conv[br][i] = L(conv[br][i]);
+  for (int h = 0; h < 2; ++h) {
+    net.W0g[h] = e->d_weights + w0g[h];
+    net.head0_local[h] = L(head_local[h]);
+    for (int i = 0; i + 1 < nh; ++i) net.hidden[h][i] = L(hidden[h][i]);
+    net.out[h] = L(outl[h]);
+  }
+  LRG_TRY(forward_configure(net));
+  e->weights_loaded = true;
+  return LRG_OK;
+}
+
+int lrg_forward_device(LrgEngine* e, int B, const float* d_inlier, const float* d_neighbor, float* d_add_out,
+                       float* d_remove_out, lrg_stream_t stream) {
+  LRG_REQUIRE(e != nullptr, "engine is NULL");
+  if (!e->weights_loaded) { set_error("lrg_forward: weights not loaded (call lrg_engine_load_weights first)"); return LRG_E_STATE; }
+  LRG_REQUIRE(B >= 1, "batch must be >= 1");
+  LRG_REQUIRE(d_inlier && d_neighbor && d_add_out && d_remove_out, "NULL tensor pointer");
+  LRG_CUDA(cudaSetDevice(e->device));
+  LRG_TRY(ensure_forward_ws(e, std::max(B, e->max_batch)));
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  ForwardArgs fa{};
+  fa.x[0] = d_inlier; fa.x[1] = d_neighbor;
+  fa.n_pts[0] = e->Ni; fa.n_pts[1] = e->Nj;
+  fa.h1[0] = e->d_h1[0]; fa.h1[1] = e->d_h1[1];
+  fa.pooled = e->d_pooled; fa.gproj = e->d_gproj;
+  fa.logits[0] = d_remove_out; fa.logits[1] = d_add_out;
+  fa.active = nullptr; fa.active_stride = 0; fa.B = B;
+  LRG_CUDA(cudaMemsetAsync(e->d_pooled, 0, sizeof(float) * (size_t)B * 2 * e->net.Clast, st));
+  return launch_forward(e->net, fa, st);
+}
+
+int lrg_forward_host(LrgEngine* e, int B, const float* inlier, const float* neighbor, float* add_out, float* remove_out) {
+  LRG_REQUIRE(e != nullptr, "engine is NULL");
+  if (!e->weights_loaded) { set_error("lrg_forward: weights not loaded (call lrg_engine_load_weights first)"); return LRG_E_STATE; }
+  LRG_REQUIRE(B >= 1, "batch must be >= 1");
+  LRG_REQUIRE(inlier && neighbor && add_out && remove_out, "NULL tensor pointer");
+  LRG_CUDA(cudaSetDevice(e->device));
+  LRG_TRY(ensure_forward_ws(e, std::max(B, e->max_batch)));
+  LRG_CUDA(cudaMemcpyAsync(e->d_x[0], inlier, sizeof(float) * (size_t)B * e->Ni * e->F, cudaMemcpyHostToDevice, e->stream));
+  LRG_CUDA(cudaMemcpyAsync(e->d_x[1], neighbor, sizeof(float) * (size_t)B * e->Nj * e->F, cudaMemcpyHostToDevice, e->stream));
+  LRG_TRY(lrg_forward_device(e, B, e->d_x[0], e->d_x[1], e->d_logits[1], e->d_logits[0], e->stream));
+  LRG_CUDA(cudaMemcpyAsync(add_out, e->d_logits[1], sizeof(float) * (size_t)B * e->Nj * 2, cudaMemcpyDeviceToHost, e->stream));
+  LRG_CUDA(cudaMemcpyAsync(remove_out, e->d_logits[0], sizeof(float) * (size_t)B * e->Ni * 2, cudaMemcpyDeviceToHost, e->stream));
+  LRG_CUDA(cudaStreamSynchronize(e->stream));
+  return LRG_OK;
+}
+
+int lrg_rooms_upload(LrgEngine* e, int n_rooms, const int64_t* room_offsets, const float* points, const int32_t* seed_order,
+                     float resolution) {
+  LRG_REQUIRE(e != nullptr, "engine is NULL");
+  LRG_REQUIRE(n_rooms >= 0 && room_offsets != nullptr, "bad room table");
+  LRG_REQUIRE(resolution > 0.f, "resolution must be > 0");
+  LRG_REQUIRE(room_offsets[0] == 0, "room_offsets[0] must be 0");
+  long long total = room_offsets[n_rooms];
+  int maxN = 0;
+  for (int r = 0; r < n_rooms; ++r) {
+    long long n = room_offsets[r + 1] - room_offsets[r];
+    LRG_REQUIRE(n >= 0 && n < (1ll << 30), "room %d has an invalid point count", r);
+    maxN = std::max(maxN, (int)n);
+  }
+  LRG_REQUIRE(total == 0 || (points != nullptr && seed_order != nullptr), "NULL points/seed_order");
+  LRG_CUDA(cudaSetDevice(e->device));
+  free_rooms(e);
+  e->n_rooms = n_rooms; e->total_pts = total; e->maxN = maxN; e->resolution = resolution;
+  e->h_room_off.assign(room_offsets, room_offsets + n_rooms + 1);
+  const size_t T = (size_t)total;
+  LRG_TRY(dev_alloc(&e->d_room_off, (size_t)n_rooms + 1));
+  LRG_TRY(dev_alloc(&e->d_pts, T * 16));
+  LRG_TRY(dev_alloc(&e->d_vox, T));
+  LRG_TRY(dev_alloc(&e->d_state, T));
+  LRG_TRY(dev_alloc(&e->d_label, T));
+  LRG_TRY(dev_alloc(&e->d_label_filled, T));
+  LRG_TRY(dev_alloc(&e->d_order, T));
+  LRG_TRY(dev_alloc(&e->d_lab_list, T));
+  LRG_TRY(dev_alloc(&e->d_unl_list, T));
+  LRG_TRY(dev_alloc(&e->d_n_lab, (size_t)n_rooms));
+  LRG_TRY(dev_alloc(&e->d_n_unl, (size_t)n_rooms));
+  LRG_TRY(dev_alloc(&e->d_stats, (size_t)n_rooms));
+  LRG_CUDA(cudaMemcpyAsync(e->d_room_off, e->h_room_off.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice, e->stream));
+  if (total > 0) {
+    float* d_raw = nullptr;     // staging for the dense (T, F) rows; freed after the pack kernel
+    LRG_TRY(dev_alloc(&d_raw, T * e->F));
+    LRG_CUDA(cudaMemcpyAsync(d_raw, points, sizeof(float) * T * e->F, cudaMemcpyHostToDevice, e->stream));
+    LRG_CUDA(cudaMemcpyAsync(e->d_order, seed_order, sizeof(int) * T, cudaMemcpyHostToDevice, e->stream));
+    int rc = launch_pack(d_raw, e->F, total, resolution, e->d_pts, e->d_vox, e->stream);
+    cudaStreamSynchronize(e->stream);
+    cudaFree(d_raw);
+    LRG_TRY(rc);
+  }
+  LRG_CUDA(cudaStreamSynchronize(e->stream));
+  return LRG_OK;
+}
+
+int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats* stats) {
+  LRG_REQUIRE(e != nullptr && params != nullptr, "engine/params is NULL");
+  if (!e->weights_loaded) { set_error("lrg_segment: weights not loaded"); return LRG_E_STATE; }
+  LRG_CUDA(cudaSetDevice(e->device));
+  const int n_rooms = e->n_rooms;
+  const size_t T = (size_t)e->total_pts;
+  int n_slots = params->max_slots > 0 ? params->max_slots : 148;
+  n_slots = std::max(1, std::min(n_slots, std::max(n_rooms, 1)));
+  LRG_TRY(ensure_slots(e, n_slots));
+  cudaStream_t st = e->stream;
+  // reset per-run state
+  LRG_CUDA(cudaMemsetAsync(e->d_state, 0, T, st));
+  LRG_CUDA(cudaMemsetAsync(e->d_label, 0, T * sizeof(int), st));
+  LRG_CUDA(cudaMemsetAsync(e->d_stats, 0, sizeof(LrgRoomStats) * std::max(n_rooms, 1), st));
+  LRG_CUDA(cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(int), st));
+  std::vector<SlotState> init(n_slots);
+  memset(init.data(), 0, sizeof(SlotState) * n_slots);
+  for (auto& s : init) s.room = -1;
+  LRG_CUDA(cudaMemcpyAsync(e->d_slots, init.data(), sizeof(SlotState) * n_slots, cudaMemcpyHostToDevice, st));
+  if (params->trace_capacity > 0) {
+    cudaFree(e->d_trace);
+    e->d_trace = nullptr;
+    LRG_TRY(dev_alloc(&e->d_trace, (size_t)std::max(n_rooms, 1) * params->trace_capacity));
+    LRG_CUDA(cudaMemsetAsync(e->d_trace, 0, sizeof(LrgStepTrace) * (size_t)std::max(n_rooms, 1) * params->trace_capacity, st));
+    e->trace_capacity = params->trace_capacity;
+  } else {
+    e->trace_capacity = 0;
+  }
+  *e->h_done = 0;
+  LRG_CUDA(cudaStreamSynchronize(st));   // init is out of the timed region
+
+  DriverArgs da{};
+  da.n_rooms = n_rooms; da.room_off = e->d_room_off; da.pts = e->d_pts; da.vox = e->d_vox; da.state = e->d_state;
+  da.label = e->d_label; da.order = e->d_order; da.slots = e->d_slots; da.n_slots = n_slots; da.maxN = e->slots_maxN;
+  da.listI = e->d_listI; da.listJ = e->d_listJ; da.keyI = e->d_keyI; da.keyJ = e->d_keyJ;
+  da.tile[0] = e->d_tile[0]; da.tile[1] = e->d_tile[1]; da.tileidx[0] = e->d_tileidx[0]; da.tileidx[1] = e->d_tileidx[1];
+  da.logits[0] = e->s_logits[0]; da.logits[1] = e->s_logits[1];
+  da.pooled = e->s_pooled; da.pooled_per_slot = 2 * e->net.Clast;
+  da.Ni = e->Ni; da.Nj = e->Nj; da.F = e->F;
+  da.resolution = e->resolution; da.cluster_threshold = params->cluster_threshold; da.seed = params->seed;
+  da.max_steps = params->max_steps_per_region; da.room_id_base = params->room_id_base;
+  da.next_room = e->d_counters; da.finished_slots = e->d_counters + 1; da.done_flag = e->d_done;
+  da.stats = e->d_stats; da.trace = e->trace_capacity > 0 ? e->d_trace : nullptr; da.trace_capacity = e->trace_capacity;
+
+  ForwardArgs fa{};
+  fa.x[0] = e->d_tile[0]; fa.x[1] = e->d_tile[1];
+  fa.n_pts[0] = e->Ni; fa.n_pts[1] = e->Nj;
+  fa.h1[0] = e->s_h1[0]; fa.h1[1] = e->s_h1[1];
+  fa.pooled = e->s_pooled; fa.gproj = e->s_gproj;
+  fa.logits[0] = e->s_logits[0]; fa.logits[1] = e->s_logits[1];
+  fa.active = &e->d_slots[0].active; fa.active_stride = (int)(sizeof(SlotState) / sizeof(int)); fa.B = n_slots;
+
+  cudaEvent_t ev0, ev1, ev2;
+  LRG_CUDA(cudaEventCreate(&ev0)); LRG_CUDA(cudaEventCreate(&ev1)); LRG_CUDA(cudaEventCreate(&ev2));
+  e->iterations = 0; e->launches = 0; e->forward_ms = 0;
+  const bool kernel_timing = (params->flags & LRG_FLAG_KERNEL_TIMING) != 0;
+  const bool use_graph = !kernel_timing && !(params->flags & LRG_FLAG_NO_GRAPH);
+  LRG_CUDA(cudaEventRecord(ev0, st));
+  int rc = LRG_OK;
+  if (n_rooms > 0) {
+    if (use_graph) {
+      constexpr int kIterPerGraph = 8;
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
+      LRG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      for (int it = 0; it < kIterPerGraph && rc == LRG_OK; ++it) {
+        rc = launch_step(da, st);
+        if (rc == LRG_OK) rc = launch_forward(e->net, fa, st);
+      }
+      cudaError_t cerr = cudaStreamEndCapture(st, &graph);
+      if (rc != LRG_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      LRG_CUDA(cerr);
+      LRG_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+      cudaEvent_t evq[2];
+      LRG_CUDA(cudaEventCreateWithFlags(&evq[0], cudaEventDisableTiming));
+      LRG_CUDA(cudaEventCreateWithFlags(&evq[1], cudaEventDisableTiming));
+      long long launched = 0;
+      while (true) {
+        cudaError_t le = cudaGraphLaunch(exec, st);
+        if (le != cudaSuccess) { set_error("cudaGraphLaunch -> %s", cudaGetErrorString(le)); rc = LRG_E_CUDA; break; }
+        cudaEventRecord(evq[launched & 1], st);
+        ++launched;
+        if (launched >= 2) {
+          cudaError_t se = cudaEventSynchronize(evq[launched & 1]);   // the launch before the one just queued
+          if (se != cudaSuccess) { set_error("grow loop -> %s", cudaGetErrorString(se)); rc = LRG_E_CUDA; break; }
+          if (*(volatile int*)e->h_done) break;
+        }
+      }
+      e->iterations = launched * kIterPerGraph;
+      e->launches = e->iterations * 4;
+      cudaStreamSynchronize(st);
+      cudaEventDestroy(evq[0]); cudaEventDestroy(evq[1]);
+      cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+    } else {
+      cudaEvent_t ka, kb;
+      LRG_CUDA(cudaEventCreate(&ka)); LRG_CUDA(cudaEventCreate(&kb));
+      while (rc == LRG_OK) {
+        rc = launch_step(da, st);
+        if (rc != LRG_OK) break;
+        if (kernel_timing) cudaEventRecord(ka, st);
+        rc = launch_forward(e->net, fa, st);
+        if (kernel_timing) cudaEventRecord(kb, st);
+        e->iterations += 1; e->launches += 4;
+        if (kernel_timing || (e->iterations % 16) == 0) {
+          cudaError_t se = cudaStreamSynchronize(st);
+          if (se != cudaSuccess) { set_error("grow loop -> %s", cudaGetErrorString(se)); rc = LRG_E_CUDA; break; }
+          if (kernel_timing) { float ms = 0; cudaEventElapsedTime(&ms, ka, kb); e->forward_ms += ms; }
+          if (*(volatile int*)e->h_done) break;
+        }
+      }
+      cudaEventDestroy(ka); cudaEventDestroy(kb);
+    }
+  }
+  if (rc != LRG_OK) return rc;
+  LRG_CUDA(cudaEventRecord(ev1, st));
+  FillArgs fl{};
+  fl.n_rooms = n_rooms; fl.room_off = e->d_room_off; fl.pts = e->d_pts; fl.label = e->d_label; fl.label_filled = e->d_label_filled;
+  fl.lab_list = e->d_lab_list; fl.unl_list = e->d_unl_list; fl.n_lab = e->d_n_lab; fl.n_unl = e->d_n_unl; fl.F = e->F;
+  LRG_TRY(launch_fill(fl, st));
+  e->launches += 2;
+  LRG_CUDA(cudaEventRecord(ev2, st));
+  LRG_CUDA(cudaStreamSynchronize(st));
+  LRG_CUDA(cudaEventElapsedTime(&e->grow_ms, ev0, ev1));
+  LRG_CUDA(cudaEventElapsedTime(&e->fill_ms, ev1, ev2));
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
+  if (stats != nullptr && n_rooms > 0)
+    LRG_CUDA(cudaMemcpy(stats, e->d_stats, sizeof(LrgRoomStats) * n_rooms, cudaMemcpyDeviceToHost));
+  return LRG_OK;
+}
+
+int lrg_labels_download(LrgEngine* e, int32_t* labels, int filled) {
+  LRG_REQUIRE(e != nullptr && (labels != nullptr || e->total_pts == 0), "engine/labels is NULL");
+  LRG_CUDA(cudaSetDevice(e->device));
+  if (e->total_pts > 0)
+    LRG_CUDA(cudaMemcpy(labels, filled ? e->d_label_filled : e->d_label, sizeof(int) * (size_t)e->total_pts, cudaMemcpyDeviceToHost));
+  return LRG_OK;
+}
+
+int lrg_trace_download(LrgEngine* e, int room, LrgStepTrace* out, int capacity, int* n_steps) {
+  LRG_REQUIRE(e != nullptr && out != nullptr && n_steps != nullptr, "NULL argument");
+  LRG_REQUIRE(room >= 0 && room < e->n_rooms, "room %d out of range", room);
+  if (e->trace_capacity <= 0 || e->d_trace == nullptr) { set_error("no trace recorded (trace_capacity was 0)"); return LRG_E_STATE; }
+  LRG_CUDA(cudaSetDevice(e->device));
+  LrgRoomStats st;
+  LRG_CUDA(cudaMemcpy(&st, e->d_stats + room, sizeof(st), cudaMemcpyDeviceToHost));
+  int n = std::min(std::min(st.grow_steps, e->trace_capacity), capacity);
+  *n_steps = st.grow_steps;
+  if (n > 0) LRG_CUDA(cudaMemcpy(out, e->d_trace + (size_t)room * e->trace_capacity, sizeof(LrgStepTrace) * n, cudaMemcpyDeviceToHost));
+  return LRG_OK;
+}
+
+int lrg_segment_rooms_host(LrgEngine* e, int n_rooms, const int64_t* room_offsets, const float* points, const int32_t* seed_order,
+                           const LrgGrowParams* params, int32_t* labels_filled, LrgRoomStats* stats) {
+  LRG_REQUIRE(params != nullptr, "params is NULL");
+  LRG_TRY(lrg_rooms_upload(e, n_rooms, room_offsets, points, seed_order, params->resolution));
+  LRG_TRY(lrg_segment_resident(e, params, stats));
+  return lrg_labels_download(e, labels_filled, 1);
+}
+
+int lrg_last_segment_profile(LrgEngine* e, float* grow_ms, float* fill_ms, int64_t* iterations, int64_t* kernel_launches,
+                             float* forward_ms) {
+  LRG_REQUIRE(e != nullptr, "engine is NULL");
+  if (grow_ms) *grow_ms = e->grow_ms;
+  if (fill_ms) *fill_ms = e->fill_ms;
+  if (iterations) *iterations = e->iterations;
+  if (kernel_launches) *kernel_launches = e->launches;
+  if (forward_ms) *forward_ms = e->forward_ms;
+  return LRG_OK;
+}
+
+int lrg_malloc(void** d_ptr, size_t bytes) {
+  LRG_REQUIRE(d_ptr != nullptr, "d_ptr is NULL");
+  LRG_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 1));
+  return LRG_OK;
+}
+int lrg_free(void* d_ptr) { LRG_CUDA(cudaFree(d_ptr)); return LRG_OK; }
+int lrg_memcpy_h2d(void* d_dst, const void* src, size_t bytes) { LRG_CUDA(cudaMemcpy(d_dst, src, bytes, cudaMemcpyHostToDevice)); return LRG_OK; }
+int lrg_memcpy_d2h(void* dst, const void* d_src, size_t bytes) { LRG_CUDA(cudaMemcpy(dst, d_src, bytes, cudaMemcpyDeviceToHost)); return LRG_OK; }
+int lrg_memset(void* d_ptr, int value, size_t bytes) { LRG_CUDA(cudaMemset(d_ptr, value, bytes)); return LRG_OK; }
+int lrg_device_synchronize(void) { LRG_CUDA(cudaDeviceSynchronize()); return LRG_OK; }
+int lrg_set_device(int device) { LRG_CUDA(cudaSetDevice(device)); return LRG_OK; }
+int lrg_host_alloc(void** ptr, size_t bytes) { LRG_REQUIRE(ptr != nullptr, "ptr is NULL"); LRG_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault)); return LRG_OK; }
+int lrg_host_free(void* ptr) { LRG_CUDA(cudaFreeHost(ptr)); return LRG_OK; }
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,438 @@
+// sm_100a replacements for the PointNet++ custom ops of /root/reference/tf_ops (sampling, grouping, 3d_interpolation).
+// Index-exact with the reference kernels: same distance expressions (so nvcc contracts them identically), same scan
+// order, same tie rules.  All pointers are device pointers.
+#include <float.h>
+
+#include "lrg_common.cuh"
+
+namespace lrg {
+
+// ------------------------------------------------------------------------------------- farthest point sampling
+// Reference: farthestpointsamplingKernel (tf_sampling_g.cu:105-170), <<<32,512>>>, min-distances in a global
+// (32,n) workspace, 512-wide shared-memory tree argmax with 9 barriers per round.
+// Here: one CTA per cloud, points and running min-distances in registers (PPT per thread), argmax by 64-bit
+// shuffle reduction + one barrier per round.  The reference's tie rule -- smallest (k mod 512), then smallest k --
+// is encoded in the low word of the key.
+constexpr int kFpsThreads = 512;
+
+__device__ __forceinline__ unsigned long long fps_key(float d, int k) {
+  const unsigned tie = ((unsigned)(k & 511) << 22) | (unsigned)(k >> 9);
+  return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(0x7FFFFFFFu - tie);
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(kFpsThreads) lrg_fps_kernel(int n, int m, const float* __restrict__ dataset, int* __restrict__ idxs) {
+  __shared__ unsigned long long sred[2][kFpsThreads / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* pts = dataset + (size_t)b * n * 3;
+  float px[PPT], py[PPT], pz[PPT], td[PPT];
+#pragma unroll
+  for (int q = 0; q < PPT; ++q) {
+    const int k = tid + q * kFpsThreads;
+    px[q] = py[q] = pz[q] = 0.f;
+    if (k < n) { px[q] = pts[k * 3 + 0]; py[q] = pts[k * 3 + 1]; pz[q] = pts[k * 3 + 2]; }
+    td[q] = 1e38f;
+  }
+  int old = 0;
+  if (tid == 0) idxs[(size_t)b * m] = 0;
+  for (int j = 1; j < m; ++j) {
+    const float x1 = pts[old * 3 + 0], y1 = pts[old * 3 + 1], z1 = pts[old * 3 + 2];
+    float best = -1.f;
+    int besti = 0;
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      const int k = tid + q * kFpsThreads;
+      if (k < n) {
+        const float x2 = px[q], y2 = py[q], z2 = pz[q];
+        const float d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1);
+        const float d2 = min(d, td[q]);
+        td[q] = d2;
+        if (d2 > best) { best = d2; besti = k; }
+      }
+    }
+    // a thread without points keeps (-1, 0) like the reference; -1 has the largest bit pattern, so map it to key 0
+    unsigned long long key = best < 0.f ? 0ull : fps_key(best, besti);
+#pragma unroll
+    for (int dlt = 16; dlt > 0; dlt >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, dlt);
+      key = o > key ? o : key;
+    }
+    if (lane == 0) sred[j & 1][warp] = key;
+    __syncthreads();
+    unsigned long long k2 = lane < kFpsThreads / 32 ? sred[j & 1][lane] : 0ull;
+#pragma unroll
+    for (int dlt = 8; dlt > 0; dlt >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, k2, dlt);
+      k2 = o > k2 ? o : k2;
+    }
+    k2 = __shfl_sync(0xffffffffu, k2, 0);
+    const unsigned tie = 0x7FFFFFFFu - (unsigned)(k2 & 0xFFFFFFFFull);
+    old = k2 == 0ull ? 0 : (int)(((tie & 0x3FFFFFu) << 9) | (tie >> 22));
+    if (tid == 0) idxs[(size_t)b * m + j] = old;
+  }
+}
+
+// Large clouds: min-distances in the caller's workspace (same layout as the reference: one row per CTA).
+__global__ void __launch_bounds__(kFpsThreads) lrg_fps_big_kernel(int b_total, int n, int m, const float* __restrict__ dataset,
+                                                                float* __restrict__ temp, int* __restrict__ idxs) {
+  __shared__ unsigned long long sred[2][kFpsThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int b = blockIdx.x; b < b_total; b += gridDim.x) {
+    const float* pts = dataset + (size_t)b * n * 3;
+    float* td = temp + (size_t)blockIdx.x * n;
+    for (int k = tid; k < n; k += kFpsThreads) td[k] = 1e38f;
+    int old = 0;
+    if (tid == 0) idxs[(size_t)b * m] = 0;
+    __syncthreads();
+    for (int j = 1; j < m; ++j) {
+      const float x1 = pts[old * 3 + 0], y1 = pts[old * 3 + 1], z1 = pts[old * 3 + 2];
+      float best = -1.f;
+      int besti = 0;
+      for (int k = tid; k < n; k += kFpsThreads) {
+        const float x2 = pts[k * 3 + 0], y2 = pts[k * 3 + 1], z2 = pts[k * 3 + 2];
+        const float d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1);
+        const float d2 = min(d, td[k]);
+        td[k] = d2;
+        if (d2 > best) { best = d2; besti = k; }
+      }
+      unsigned long long key = best < 0.f ? 0ull : fps_key(best, besti);
+#pragma unroll
+      for (int dlt = 16; dlt > 0; dlt >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, dlt);
+        key = o > key ? o : key;
+      }
+      if (lane == 0) sred[j & 1][warp] = key;
+      __syncthreads();
+      unsigned long long k2 = lane < kFpsThreads / 32 ? sred[j & 1][lane] : 0ull;
+#pragma unroll
+      for (int dlt = 8; dlt > 0; dlt >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, k2, dlt);
+        k2 = o > k2 ? o : k2;
+      }
+      k2 = __shfl_sync(0xffffffffu, k2, 0);
+      const unsigned tie = 0x7FFFFFFFu - (unsigned)(k2 & 0xFFFFFFFFull);
+      old = k2 == 0ull ? 0 : (int)(((tie & 0x3FFFFFu) << 9) | (tie >> 22));
+      if (tid == 0) idxs[(size_t)b * m + j] = old;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------- gather / scatter-add
+__global__ void lrg_gather_point_kernel(int b, int n, int m, const float* __restrict__ inp, const int* __restrict__ idx, float* __restrict__ out) {
+  const long long total = (long long)b * m;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / m;
+    const int a = idx[t];
+    const float* src = inp + (i * n + a) * 3;
+    out[t * 3 + 0] = src[0]; out[t * 3 + 1] = src[1]; out[t * 3 + 2] = src[2];
+  }
+}
+
+__global__ void lrg_scatter_add_point_kernel(int b, int n, int m, const float* __restrict__ out_g, const int* __restrict__ idx, float* __restrict__ inp_g) {
+  const long long total = (long long)b * m;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / m;
+    const int a = idx[t];
+    float* dst = inp_g + (i * n + a) * 3;
+    atomicAdd(dst + 0, out_g[t * 3 + 0]); atomicAdd(dst + 1, out_g[t * 3 + 1]); atomicAdd(dst + 2, out_g[t * 3 + 2]);
+  }
+}
+
+// ------------------------------------------------------------------------------------- ball query
+// Reference: query_ball_point_gpu (tf_grouping_g.cu:3-36): one THREAD per query scanning all n points.
+// Here: one WARP per query; 32 points per step, ballot-ordered append keeps "first nsample in index order".
+__global__ void __launch_bounds__(256) lrg_query_ball_kernel(int b, int n, int m, float radius, int nsample, const float* __restrict__ xyz1,
+                                                             const float* __restrict__ xyz2, int* __restrict__ idx, int* __restrict__ pts_cnt) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long q = wid; q < (long long)b * m; q += nwarps) {
+    const long long bi = q / m;
+    const float* p1 = xyz1 + bi * n * 3;
+    const float x2 = xyz2[q * 3 + 0], y2 = xyz2[q * 3 + 1], z2 = xyz2[q * 3 + 2];
+    int* out = idx + q * nsample;
+    int cnt = 0, first = -1;
+    for (int k0 = 0; k0 < n && cnt < nsample; k0 += 32) {
+      const int k = k0 + lane;
+      bool hit = false;
+      if (k < n) {
+        const float x1 = p1[k * 3 + 0], y1 = p1[k * 3 + 1], z1 = p1[k * 3 + 2];
+        const float d = max(sqrtf((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1)), 1e-20f);
+        hit = d < radius;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (bal) {
+        if (first < 0) first = k0 + __ffs(bal) - 1;
+        const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+        if (hit && pos < nsample) out[pos] = k;
+        cnt = min(nsample, cnt + __popc(bal));
+      }
+    }
+    if (first >= 0)
+      for (int l = cnt + lane; l < nsample; l += 32) out[l] = first;   // the reference pre-fills the row with the first hit
+    if (lane == 0) pts_cnt[q] = cnt;
+  }
+}
+
+// ------------------------------------------------------------------------------------- group / grad
+__global__ void lrg_group_point_kernel(long long rows, int n, int c, int per_batch_rows, const float* __restrict__ points,
+                                       const int* __restrict__ idx, float* __restrict__ out) {
+  // rows = b*m*nsample gathered rows of c floats; vectorised when c % 4 == 0
+  if ((c & 3) == 0) {
+    const int c4 = c >> 2;
+    const long long total = rows * c4;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+      const long long r = t / c4;
+      const int l = (int)(t - r * c4);
+      const long long bi = r / per_batch_rows;
+      const float4 v = *reinterpret_cast<const float4*>(points + (bi * n + idx[r]) * c + l * 4);
+      *reinterpret_cast<float4*>(out + r * c + l * 4) = v;
+    }
+  } else {
+    const long long total = rows * c;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+      const long long r = t / c;
+      const int l = (int)(t - r * c);
+      const long long bi = r / per_batch_rows;
+      out[t] = points[(bi * n + idx[r]) * c + l];
+    }
+  }
+}
+
+__global__ void lrg_group_point_grad_kernel(long long rows, int n, int c, int per_batch_rows, const float* __restrict__ grad_out,
+                                            const int* __restrict__ idx, float* __restrict__ grad_points) {
+  const long long total = rows * c;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long r = t / c;
+    const int l = (int)(t - r * c);
+    const long long bi = r / per_batch_rows;
+    atomicAdd(grad_points + (bi * n + idx[r]) * c + l, grad_out[t]);
+  }
+}
+
+// ------------------------------------------------------------------------------------- selection sort (top-k)
+// Reference: selection_sort_gpu (tf_grouping_g.cu:83-123), one thread per row.  Here one warp per row: the row is
+// copied, then k rounds of (argmin over the unsorted suffix with strict '<' => first minimum, swap).
+__global__ void __launch_bounds__(256) lrg_selection_sort_kernel(long long rows, int n, int k, const float* __restrict__ dist,
+                                                                 int* __restrict__ outi, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = wid; r < rows; r += nwarps) {
+    const float* src = dist + r * n;
+    float* o = out + r * n;
+    int* oi = outi + r * n;
+    for (int s = lane; s < n; s += 32) { o[s] = src[s]; oi[s] = s; }
+    __syncwarp();
+    for (int s = 0; s < k && s < n; ++s) {
+      float best = o[s];
+      int bi = s;
+      for (int t = s + 1 + lane; t < n; t += 32) {
+        const float v = o[t];
+        if (v < best) { best = v; bi = t; }     // lane-local: ascending t, strict '<' keeps the first minimum
+      }
+#pragma unroll
+      for (int dlt = 16; dlt > 0; dlt >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, dlt);
+        const int oi2 = __shfl_xor_sync(0xffffffffu, bi, dlt);
+        if (ob < best || (ob == best && oi2 < bi)) { best = ob; bi = oi2; }
+      }
+      // equal to o[s] never replaces s (strict '<' against p_dist[min] starting at min = s)
+      if (!(best < o[s])) bi = s;
+      if (lane == 0 && bi != s) {
+        const float tv = o[bi]; o[bi] = o[s]; o[s] = tv;
+        const int ti = oi[bi]; oi[bi] = oi[s]; oi[s] = ti;
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- three_nn / interpolate
+// Reference: threenn_cpu (tf_interpolate.cpp:60-103) -- a CPU op: float products summed left to right without
+// contraction, compared as doubles, strict '<' cascade (earliest index wins ties), 1e40 -> inf / index 0 when m < 3.
+__global__ void __launch_bounds__(256) lrg_three_nn_kernel(int b, int n, int m, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                                                           float* __restrict__ dist, int* __restrict__ idx) {
+  __shared__ float s2[256 * 3];
+  const int bi = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* q = xyz1 + ((size_t)bi * n) * 3;
+  const float* p2 = xyz2 + ((size_t)bi * m) * 3;
+  float x1 = 0.f, y1 = 0.f, z1 = 0.f;
+  if (j < n) { x1 = q[j * 3 + 0]; y1 = q[j * 3 + 1]; z1 = q[j * 3 + 2]; }
+  float best1 = INFINITY, best2 = INFINITY, best3 = INFINITY;
+  int i1 = 0, i2 = 0, i3 = 0;
+  for (int k0 = 0; k0 < m; k0 += 256) {
+    const int cnt = min(256, m - k0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < cnt * 3; t += 256) s2[t] = p2[(size_t)k0 * 3 + t];
+    __syncthreads();
+    if (j < n) {
+      for (int k = 0; k < cnt; ++k) {
+        const float dx = __fsub_rn(s2[k * 3 + 0], x1), dy = __fsub_rn(s2[k * 3 + 1], y1), dz = __fsub_rn(s2[k * 3 + 2], z1);
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        const int kk = k0 + k;
+        if (d < best1) { best3 = best2; i3 = i2; best2 = best1; i2 = i1; best1 = d; i1 = kk; }
+        else if (d < best2) { best3 = best2; i3 = i2; best2 = d; i2 = kk; }
+        else if (d < best3) { best3 = d; i3 = kk; }
+      }
+    }
+  }
+  if (j < n) {
+    const size_t o = ((size_t)bi * n + j) * 3;
+    dist[o] = best1; dist[o + 1] = best2; dist[o + 2] = best3;
+    idx[o] = i1; idx[o + 1] = i2; idx[o + 2] = i3;
+  }
+}
+
+__global__ void lrg_three_interpolate_kernel(int b, int m, int c, int n, const float* __restrict__ points, const int* __restrict__ idx,
+                                             const float* __restrict__ weight, float* __restrict__ out) {
+  const long long total = (long long)b * n * c;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long r = t / c;                 // b*n row
+    const int l = (int)(t - r * c);
+    const long long bi = r / n;
+    const float* pb = points + bi * m * c;
+    const float w1 = weight[r * 3], w2 = weight[r * 3 + 1], w3 = weight[r * 3 + 2];
+    const int a1 = idx[r * 3], a2 = idx[r * 3 + 1], a3 = idx[r * 3 + 2];
+    out[t] = __fadd_rn(__fadd_rn(__fmul_rn(pb[(size_t)a1 * c + l], w1), __fmul_rn(pb[(size_t)a2 * c + l], w2)), __fmul_rn(pb[(size_t)a3 * c + l], w3));
+  }
+}
+
+__global__ void lrg_three_interpolate_grad_kernel(int b, int n, int c, int m, const float* __restrict__ grad_out, const int* __restrict__ idx,
+                                                  const float* __restrict__ weight, float* __restrict__ grad_points) {
+  const long long total = (long long)b * n * c;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long r = t / c;
+    const int l = (int)(t - r * c);
+    const long long bi = r / n;
+    float* gp = grad_points + bi * m * c;
+    const float g = grad_out[t];
+    atomicAdd(gp + (size_t)idx[r * 3] * c + l, __fmul_rn(g, weight[r * 3]));
+    atomicAdd(gp + (size_t)idx[r * 3 + 1] * c + l, __fmul_rn(g, weight[r * 3 + 1]));
+    atomicAdd(gp + (size_t)idx[r * 3 + 2] * c + l, __fmul_rn(g, weight[r * 3 + 2]));
+  }
+}
+
+static inline int grid_for(long long work, int threads, int max_blocks = 148 * 16) {
+  long long blocks = (work + threads - 1) / threads;
+  if (blocks < 1) blocks = 1;
+  if (blocks > max_blocks) blocks = max_blocks;
+  return (int)blocks;
+}
+
+}  // namespace lrg
+
+using namespace lrg;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int lrg_farthest_point_sampling(int b, int n, int m, const float* d_inp, float* d_temp, int* d_out, lrg_stream_t s) {
+  LRG_REQUIRE(b >= 0 && n > 0 && m >= 0, "FarthestPointSample expects b>=0, n>0, npoint>=0 (got b=%d n=%d m=%d)", b, n, m);
+  if (b == 0 || m == 0) return LRG_OK;
+  LRG_REQUIRE(d_inp && d_out, "NULL tensor pointer");
+  cudaStream_t st = (cudaStream_t)s;
+  if (n <= kFpsThreads * 1) lrg_fps_kernel<1><<<b, kFpsThreads, 0, st>>>(n, m, d_inp, d_out);
+  else if (n <= kFpsThreads * 2) lrg_fps_kernel<2><<<b, kFpsThreads, 0, st>>>(n, m, d_inp, d_out);
+  else if (n <= kFpsThreads * 4) lrg_fps_kernel<4><<<b, kFpsThreads, 0, st>>>(n, m, d_inp, d_out);
+  else if (n <= kFpsThreads * 8) lrg_fps_kernel<8><<<b, kFpsThreads, 0, st>>>(n, m, d_inp, d_out);
+  else if (n <= kFpsThreads * 16) lrg_fps_kernel<16><<<b, kFpsThreads, 0, st>>>(n, m, d_inp, d_out);
+  else {
+    LRG_REQUIRE(d_temp != nullptr, "FarthestPointSample with n=%d > %d needs the (32,n) temp workspace", n, kFpsThreads * 16);
+    lrg_fps_big_kernel<<<b < 32 ? b : 32, kFpsThreads, 0, st>>>(b, n, m, d_inp, d_temp, d_out);
+  }
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
+}
+
+int lrg_gather_point(int b, int n, int m, const float* d_inp, const int* d_idx, float* d_out, lrg_stream_t s) {
+  LRG_REQUIRE(b >= 0 && n > 0 && m >= 0, "GatherPoint: bad shape");
+  if ((long long)b * m == 0) return LRG_OK;
+  lrg_gather_point_kernel<<<grid_for((long long)b * m, 256), 256, 0, (cudaStream_t)s>>>(b, n, m, d_inp, d_idx, d_out);
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
+}
+
+int lrg_scatter_add_point(int b, int n, int m, const float* d_out_g, const int* d_idx, float* d_inp_g, lrg_stream_t s) {
+  LRG_REQUIRE(b >= 0 && n > 0 && m >= 0, "GatherPointGrad: bad shape");
+  if ((long long)b * m == 0) return LRG_OK;
+  lrg_scatter_add_point_kernel<<<grid_for((long long)b * m, 256), 256, 0, (cudaStream_t)s>>>(b, n, m, d_out_g, d_idx, d_inp_g);
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
+}
+
+int lrg_prob_sample(int b, int n, int m, const float* d_inp_p, const float* d_inp_r, float* d_temp, int* d_out, lrg_stream_t s) {
+  (void)b; (void)n; (void)m; (void)d_inp_p; (void)d_inp_r; (void)d_temp; (void)d_out; (void)s;
+  set_error("ProbSample is not implemented in this build (SURVEY.md 8 a23: unused by every shipped model)");
+  return LRG_E_STATE;
+}
+
+int lrg_query_ball_point(int b, int n, int m, float radius, int nsample, const float* d_xyz1, const float* d_xyz2, int* d_idx,
+                         int* d_pts_cnt, lrg_stream_t s) {
+  LRG_REQUIRE(radius > 0.f, "QueryBallPoint expects positive radius");            // tf_grouping.cpp:71
+  LRG_REQUIRE(nsample > 0, "QueryBallPoint expects positive nsample");            // tf_grouping.cpp:74
+  LRG_REQUIRE(b >= 0 && n > 0 && m >= 0, "QueryBallPoint: bad shape");
+  if ((long long)b * m == 0) return LRG_OK;
+  lrg_query_ball_kernel<<<grid_for((long long)b * m * 32, 256), 256, 0, (cudaStream_t)s>>>(b, n, m, radius, nsample, d_xyz1, d_xyz2, d_idx, d_pts_cnt);
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
+}
+
+int lrg_selection_sort(int b, int n, int m, int k, const float* d_dist, int* d_outi, float* d_out, lrg_stream_t s) {
+  LRG_REQUIRE(k > 0, "SelectionSort expects positive k");                         // tf_grouping.cpp:113
+  LRG_REQUIRE(b >= 0 && n > 0 && m >= 0, "SelectionSort: bad shape");
+  if ((long long)b * m == 0) return LRG_OK;
+  lrg_selection_sort_kernel<<<grid_for((long long)b * m * 32, 256), 256, 0, (cudaStream_t)s>>>((long long)b * m, n, k, d_dist, d_outi, d_out);
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
+}
+
+int lrg_group_point(int b, int n, int c, int m, int nsample, const float* d_points, const int* d_idx, float* d_out, lrg_stream_t s) {
+  LRG_REQUIRE(b >= 0 && n > 0 && c > 0 && m >= 0 && nsample > 0, "GroupPoint: bad shape");
+  const long long rows = (long long)b * m * nsample;
+  if (rows == 0) return LRG_OK;
+  lrg_group_point_kernel<<<grid_for(rows * c / ((c & 3) ? 1 : 4), 256), 256, 0, (cudaStream_t)s>>>(rows, n, c, m * nsample, d_points, d_idx, d_out);
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
+}
+
+int lrg_group_point_grad(int b, int n, int c, int m, int nsample, const float* d_grad_out, const int* d_idx, float* d_grad_points, lrg_stream_t s) {
+  LRG_REQUIRE(b >= 0 && n > 0 && c > 0 && m >= 0 && nsample > 0, "GroupPointGrad: bad shape");
+  const long long rows = (long long)b * m * nsample;
+  if (rows == 0) return LRG_OK;
+  lrg_group_point_grad_kernel<<<grid_for(rows * c, 256), 256, 0, (cudaStream_t)s>>>(rows, n, c, m * nsample, d_grad_out, d_idx, d_grad_points);
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
+}
+
+int lrg_three_nn(int b, int n, int m, const float* d_xyz1, const float* d_xyz2, float* d_dist, int* d_idx, lrg_stream_t s) {
+  LRG_REQUIRE(b >= 0 && n >= 0 && m >= 0, "ThreeNN: bad shape");
+  if ((long long)b * n == 0) return LRG_OK;
+  LRG_REQUIRE(b <= 65535, "ThreeNN: batch %d > 65535", b);
+  lrg_three_nn_kernel<<<dim3((n + 255) / 256, b), 256, 0, (cudaStream_t)s>>>(b, n, m, d_xyz1, d_xyz2, d_dist, d_idx);
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
+}
+
+int lrg_three_interpolate(int b, int m, int c, int n, const float* d_points, const int* d_idx, const float* d_weight, float* d_out, lrg_stream_t s) {
+  LRG_REQUIRE(b >= 0 && m > 0 && c > 0 && n >= 0, "ThreeInterpolate: bad shape");
+  const long long total = (long long)b * n * c;
+  if (total == 0) return LRG_OK;
+  lrg_three_interpolate_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(b, m, c, n, d_points, d_idx, d_weight, d_out);
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
+}
+
+int lrg_three_interpolate_grad(int b, int n, int c, int m, const float* d_grad_out, const int* d_idx, const float* d_weight, float* d_grad_points, lrg_stream_t s) {
+  LRG_REQUIRE(b >= 0 && m > 0 && c > 0 && n >= 0, "ThreeInterpolateGrad: bad shape");
+  const long long total = (long long)b * n * c;
+  if (total == 0) return LRG_OK;
+  lrg_three_interpolate_grad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(b, n, c, m, d_grad_out, d_idx, d_weight, d_grad_points);
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,190 @@
+"""Python host of the sm_100a LRGNet engine: thin object wrappers over the C ABI (include/lrg_b200.h).
+
+``Engine`` mirrors the life cycle of the reference's network object + session
+(/root/reference/test_region_grow.py:86-94): construct with the LrgNet constructor arguments, ``load_weights`` from
+a checkpoint or a dict of variables, ``forward`` on host arrays, and -- the part the reference does in Python --
+``segment_rooms`` which grows every room on the device without a host round trip per step.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import GrowParams, LrgError, ROOM_STATS_DTYPE, STEP_TRACE_DTYPE
+
+
+def channel_lists(lite):
+    """learn_region_grow_util.py:77-85"""
+    if lite == 0 or lite is None:
+        return [64, 64, 64, 128, 512], [256, 128]
+    if lite == 1:
+        return [64, 64], [64]
+    if lite == 2:
+        return [64, 64, 256], [64, 64]
+    raise ValueError('lite must be 0/None, 1 or 2')
+
+
+def variable_shapes(feature_size=13, lite=0):
+    """(name, shape) of the trainable variables in graph-construction order (util.py:106-162) = blob order."""
+    conv, conv2 = channel_lists(lite)
+    out = []
+    for prefix in ('lrg_', 'lrg_neighbor_'):
+        for i, c in enumerate(conv):
+            out.append((prefix + 'kernel%d' % i, (1, feature_size if i == 0 else conv[i - 1], c)))
+            out.append((prefix + 'bias%d' % i, (c,)))
+    for prefix in ('lrg_add_', 'lrg_remove_'):
+        for i, c in enumerate(conv2 + [2]):
+            out.append((prefix + 'kernel%d' % i, (1, conv[-1] * 2 + conv[1] if i == 0 else conv2[i - 1], c)))
+            out.append((prefix + 'bias%d' % i, (c,)))
+    return out
+
+
+def pack_weights(tensors, feature_size=13, lite=0):
+    """dict of checkpoint variables -> the flat float32 blob lrg_engine_load_weights expects."""
+    parts = []
+    for name, shape in variable_shapes(feature_size, lite):
+        if name not in tensors:
+            raise KeyError('checkpoint has no variable %r' % name)
+        a = np.asarray(tensors[name], dtype=np.float32)
+        if a.shape != tuple(shape):
+            raise ValueError('variable %s has shape %s, expected %s' % (name, a.shape, tuple(shape)))
+        parts.append(a.reshape(-1))
+    return np.ascontiguousarray(np.concatenate(parts))
+
+
+class Engine:
+    def __init__(self, batch_size=1, seq_len=1, num_inlier_points=512, num_neighbor_points=512, feature_size=13,
+                 lite=0, device=0):
+        self.lib = _lib.lib()
+        _lib.require_gpu()
+        self.B = batch_size * seq_len
+        self.Ni, self.Nj, self.F = num_inlier_points, num_neighbor_points, feature_size
+        self.lite = 0 if lite is None else lite
+        self.device = device
+        self._h = C.c_void_p()
+        _lib.check(self.lib.lrg_engine_create(C.byref(self._h), device, feature_size, num_inlier_points,
+                                              num_neighbor_points, self.lite, self.B))
+        self._weights = None
+        self._room_offsets = None
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self.lib.lrg_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- weights ------------------------------------------------------------------------------------
+    def load_weights(self, tensors):
+        blob = pack_weights(tensors, self.F, self.lite)
+        n = self.lib.lrg_engine_weight_count(self._h)
+        if blob.size != n:
+            raise ValueError('weight blob has %d floats, engine expects %d' % (blob.size, n))
+        _lib.check(self.lib.lrg_engine_load_weights(self._h, _lib.ptr(blob), blob.size))
+        self._weights = {k: np.asarray(tensors[k], np.float32) for k, _ in variable_shapes(self.F, self.lite)}
+
+    def load_checkpoint(self, prefix):
+        from . import ckpt
+        self.load_weights(ckpt.load_checkpoint(prefix))
+
+    def variables(self):
+        return dict(self._weights or {})
+
+    # -- forward ------------------------------------------------------------------------------------
+    def forward(self, inlier, neighbor):
+        """inlier (B,Ni,F), neighbor (B,Nj,F) float32 host arrays -> (add_output (B,Nj,2), remove_output (B,Ni,2))."""
+        inlier = np.ascontiguousarray(inlier, dtype=np.float32)
+        neighbor = np.ascontiguousarray(neighbor, dtype=np.float32)
+        if inlier.ndim != 3 or inlier.shape[1:] != (self.Ni, self.F):
+            raise ValueError('inlier_pl expects shape (B, %d, %d), got %s' % (self.Ni, self.F, inlier.shape))
+        if neighbor.ndim != 3 or neighbor.shape[1:] != (self.Nj, self.F) or neighbor.shape[0] != inlier.shape[0]:
+            raise ValueError('neighbor_pl expects shape (%d, %d, %d), got %s' % (inlier.shape[0], self.Nj, self.F, neighbor.shape))
+        B = inlier.shape[0]
+        add = np.empty((B, self.Nj, 2), np.float32)
+        rmv = np.empty((B, self.Ni, 2), np.float32)
+        _lib.check(self.lib.lrg_forward_host(self._h, B, _lib.ptr(inlier), _lib.ptr(neighbor), _lib.ptr(add), _lib.ptr(rmv)))
+        return add, rmv
+
+    def forward_device(self, d_inlier, d_neighbor, d_add, d_remove, B, stream=None):
+        """Asynchronous forward on device pointers (ints or torch CUDA tensors)."""
+        _lib.check(self.lib.lrg_forward_device(self._h, B, _lib.ptr(d_inlier), _lib.ptr(d_neighbor), _lib.ptr(d_add),
+                                               _lib.ptr(d_remove), C.c_void_p(stream) if stream else None))
+
+    # -- region growing -----------------------------------------------------------------------------
+    @staticmethod
+    def _concat(rooms_points, rooms_order):
+        counts = [len(p) for p in rooms_points]
+        offsets = np.zeros(len(counts) + 1, dtype=np.int64)
+        np.cumsum(counts, out=offsets[1:])
+        if len(counts):
+            points = np.ascontiguousarray(np.concatenate([np.asarray(p, np.float32) for p in rooms_points]), dtype=np.float32)
+            order = np.ascontiguousarray(np.concatenate([np.asarray(o).astype(np.int32) for o in rooms_order]), dtype=np.int32)
+        else:
+            points = np.zeros((0, 13), np.float32)
+            order = np.zeros(0, np.int32)
+        return offsets, points, order
+
+    def upload_rooms(self, rooms_points, rooms_order, resolution=0.1):
+        """rooms_points: list of (N_r, F) float32 feature arrays (test_region_grow.py:165-172);
+        rooms_order: list of (N_r,) seed orders = argsort(curvatures) (:183)."""
+        offsets, points, order = self._concat(rooms_points, rooms_order)
+        if points.shape[0] and points.shape[1] != self.F:
+            raise ValueError('rooms have %d features, engine was built for %d' % (points.shape[1], self.F))
+        self.upload_concatenated(offsets, points, order, resolution)
+        return offsets
+
+    def upload_concatenated(self, offsets, points, order, resolution=0.1):
+        _lib.check(self.lib.lrg_rooms_upload(self._h, len(offsets) - 1, _lib.ptr(offsets), _lib.ptr(points),
+                                             _lib.ptr(order), C.c_float(resolution)))
+        self._room_offsets = np.array(offsets, dtype=np.int64)
+
+    def make_params(self, resolution=0.1, cluster_threshold=10, seed=0, max_slots=0, max_steps_per_region=0,
+                    room_id_base=0, trace_capacity=0, flags=0):
+        return GrowParams(resolution, cluster_threshold, seed, max_slots, max_steps_per_region, room_id_base,
+                          trace_capacity, flags)
+
+    def segment_resident(self, params=None, **kw):
+        """Grow all uploaded rooms on the device; returns the per-room statistics (structured array)."""
+        if self._room_offsets is None:
+            raise LrgError('segment_resident: no rooms uploaded')
+        params = params or self.make_params(**kw)
+        stats = np.zeros(len(self._room_offsets) - 1, dtype=ROOM_STATS_DTYPE)
+        _lib.check(self.lib.lrg_segment_resident(self._h, C.byref(params), _lib.ptr(stats)))
+        return stats
+
+    def labels(self, filled=True):
+        total = int(self._room_offsets[-1])
+        out = np.zeros(total, dtype=np.int32)
+        _lib.check(self.lib.lrg_labels_download(self._h, _lib.ptr(out), 1 if filled else 0))
+        return [out[self._room_offsets[i]:self._room_offsets[i + 1]] for i in range(len(self._room_offsets) - 1)]
+
+    def trace(self, room, capacity):
+        buf = np.zeros(capacity, dtype=STEP_TRACE_DTYPE)
+        n = C.c_int(0)
+        _lib.check(self.lib.lrg_trace_download(self._h, room, _lib.ptr(buf), capacity, C.byref(n)))
+        return buf[:min(n.value, capacity)], n.value
+
+    def profile(self):
+        g, f, fw = C.c_float(0), C.c_float(0), C.c_float(0)
+        it, ln = C.c_int64(0), C.c_int64(0)
+        _lib.check(self.lib.lrg_last_segment_profile(self._h, C.byref(g), C.byref(f), C.byref(it), C.byref(ln), C.byref(fw)))
+        return dict(grow_ms=g.value, fill_ms=f.value, iterations=it.value, kernel_launches=ln.value, forward_ms=fw.value)
+
+    def segment_rooms(self, rooms_points, rooms_order, resolution=0.1, **kw):
+        """End-to-end call on host arrays: upload, grow, fill, download.  Returns (labels per room, stats)."""
+        offsets, points, order = self._concat(rooms_points, rooms_order)
+        return self.segment_concatenated(offsets, points, order, resolution=resolution, **kw)
+
+    def segment_concatenated(self, offsets, points, order, resolution=0.1, **kw):
+        params = self.make_params(resolution=resolution, **kw)
+        n_rooms = len(offsets) - 1
+        labels = np.zeros(int(offsets[-1]), dtype=np.int32)
+        stats = np.zeros(n_rooms, dtype=ROOM_STATS_DTYPE)
+        _lib.check(self.lib.lrg_segment_rooms_host(self._h, n_rooms, _lib.ptr(offsets), _lib.ptr(points), _lib.ptr(order),
+                                                   C.byref(params), _lib.ptr(labels), _lib.ptr(stats)))
+        self._room_offsets = np.array(offsets, dtype=np.int64)
+        return [labels[offsets[i]:offsets[i + 1]] for i in range(n_rooms)], stats

@@ -1,0 +1,147 @@
+"""On-device region-grow driver vs the CPU oracle (oracle/lrg_driver.py, itself pinned to the unmodified reference
+driver by tests/test_oracle_driver.py), through the C ABI.
+
+Small rooms: the device records every grow step; the oracle is re-driven step by step with the same Philox stream and
+must agree on seeds, set sizes, medians, sampled indices, masks, stop reasons and final labels.  The masks are sampled
+(u < confidence, test_region_grow.py:266-267), so a draw that lands within the forward tolerance of the confidence may
+legitimately differ; such a draw is adopted from the device (and counted) so the trajectories stay comparable.
+
+Full-size rooms: size-independent properties (determinism, slot-count invariance, label invariants).
+"""
+import numpy as np
+import pytest
+
+from oracle import lrg_driver, lrg_forward
+from util_rooms import golden_room, idx_crc, unpack_mask
+
+pytestmark = pytest.mark.gpu
+
+NEAR_TIE = 2e-4       # |u - confidence| below which a mask bit may differ (forward tolerance, tests/test_forward_gpu.py)
+STOP_NAMES = {2: 'noexpand', 3: 'stuck', 4: 'maxsteps', 5: 'empty'}
+
+
+@pytest.fixture(scope='module')
+def engine(golden_weights):
+    from learn_region_grow_b200.engine import Engine
+    e = Engine(1, 1, 512, 512, 13, 0)
+    e.load_weights(golden_weights)
+    yield e
+    e.close()
+
+
+def _replay(points, order, weights, trace, n_steps, seed, room_id=0):
+    """Re-drive the oracle with the device's trace.  Returns (grower, adopted near-tie bits)."""
+    fwd = lambda a, b: lrg_forward.forward(weights, a, b)
+    g = lrg_driver.RoomGrower(points, order, fwd, lrg_driver.PhiloxRng(seed), room_id=room_id)
+    adopted = 0
+    t = 0
+    for seed_id in np.arange(len(points))[order]:
+        if g.visited[seed_id]:
+            continue
+        g.begin_region(seed_id)
+        while True:
+            st = g.prepare_step()
+            if st is None:
+                break
+            assert t < n_steps, 'oracle wants more steps than the device ran'
+            rec = trace[t]
+            assert rec['seed_point'] == seed_id and rec['step_in_region'] == g.steps
+            assert rec['n_inlier'] == st['n_inlier'] and rec['n_neighbor'] == st['n_neighbor']
+            np.testing.assert_array_equal(rec['center'][:13][[0, 1, 6, 7, 8, 9, 10, 11, 12]], st['center'][[0, 1, 6, 7, 8, 9, 10, 11, 12]])
+            assert rec['inlier_idx_crc'] == idx_crc(st['inlier_idx']) and rec['neighbor_idx_crc'] == idx_crc(st['neighbor_idx'])
+            add, rmv = fwd(st['inlier'], st['neighbor'])
+            dev_add, dev_rmv = unpack_mask(rec['add_mask']), unpack_mask(rec['remove_mask'])
+            # oracle's own masks, to bound the disagreement
+            add_conf, rmv_conf = lrg_driver.confidence(add[0]), lrg_driver.confidence(rmv[0])
+            rng = lrg_driver.PhiloxRng(seed)
+            rng.begin_step(room_id, g.total_steps)
+            u_add, u_rmv = rng.uniform(512, 'add'), rng.uniform(512, 'remove')
+            for dev, conf, u in ((dev_add, add_conf, u_add), (dev_rmv, rmv_conf, u_rmv)):
+                differ = dev != (u < conf)
+                assert np.all(np.abs(u[differ] - conf[differ]) < NEAR_TIE), 'mask bit differs outside the near-tie band'
+                adopted += int(differ.sum())
+            reason = g.apply_step(add[0], rmv[0], add_mask=dev_add, rmv_mask=dev_rmv)
+            assert STOP_NAMES.get(int(rec['stop_reason'])) == reason
+            assert rec['size_after'] == int(g.currentMask.sum()) if reason is None else True
+            t += 1
+            if reason is not None:
+                break
+    assert t == n_steps
+    return g, adopted
+
+
+@pytest.mark.parametrize('room_seed,rng_seed', [(1000, 0), (1001, 12345)])
+def test_device_driver_replays_on_oracle(engine, golden_weights, room_seed, rng_seed):
+    points, order = golden_room(room_seed)
+    engine.upload_rooms([points], [order], resolution=0.1)
+    stats = engine.segment_resident(resolution=0.1, seed=rng_seed, trace_capacity=4096)
+    trace, n_steps = engine.trace(0, 4096)
+    assert n_steps == stats['grow_steps'][0] and n_steps <= 4096 and n_steps > 50
+    g, adopted = _replay(points, order, golden_weights, trace, n_steps, rng_seed)
+    assert adopted <= 3
+    raw = engine.labels(filled=False)[0]
+    np.testing.assert_array_equal(raw, g.cluster_label)                    # cluster_label before the fill (:176,214)
+    np.testing.assert_array_equal(engine.labels(filled=True)[0], g.fill())  # after the nearest-neighbour fill (:308-316)
+    assert stats['regions'][0] == len(g.regions) and stats['clusters'][0] == g.cluster_id - 1
+    by_reason = {r: sum(1 for x in g.regions if x[3] == r) for r in ('noneighbor', 'noexpand', 'stuck')}
+    assert (stats['stop_noneighbor'][0], stats['stop_noexpand'][0], stats['stop_stuck'][0]) == \
+        (by_reason['noneighbor'], by_reason['noexpand'], by_reason['stuck'])
+
+
+def test_multi_room_batch_matches_single_room_runs(engine, golden_weights):
+    """Rooms are independent units: growing them together (any slot count) gives the labels of growing them alone."""
+    from learn_region_grow_b200 import rooms as R
+    feats = [R.prepare_features(R.generate_room(1000 + i, n_raw=3000 + 1500 * i, n_boxes=5)) for i in range(4)]
+    pts = [f['points'] for f in feats] + [np.zeros((0, 13), np.float32)]      # plus an empty room
+    orders = [f['order'] for f in feats] + [np.zeros(0, np.int64)]
+    together, stats = engine.segment_rooms(pts, orders, resolution=0.1, seed=7, max_slots=3)
+    assert stats['n_points'].tolist() == [len(p) for p in pts]
+    for i in range(len(pts)):
+        alone, st1 = engine.segment_rooms([pts[i]], [orders[i]], resolution=0.1, seed=7, room_id_base=i)
+        np.testing.assert_array_equal(alone[0], together[i])
+        assert st1['grow_steps'][0] == stats['grow_steps'][i]
+    again, _ = engine.segment_rooms(pts, orders, resolution=0.1, seed=7, max_slots=5)
+    for a, b in zip(again, together):
+        np.testing.assert_array_equal(a, b)
+    other, _ = engine.segment_rooms(pts, orders, resolution=0.1, seed=8)
+    assert any(not np.array_equal(a, b) for a, b in zip(other, together))      # the seed matters
+
+
+def test_full_size_room_properties(engine):
+    """S3DIS-shaped rooms (~20k raw points, BASELINE.json config): invariants that hold at any size."""
+    from learn_region_grow_b200 import rooms as R
+    feats = [R.prepare_features(R.generate_room(1000 + i)) for i in range(3)]
+    pts, orders = [f['points'] for f in feats], [f['order'] for f in feats]
+    labels, stats = engine.segment_rooms(pts, orders, resolution=0.1, seed=0)
+    engine_raw = engine.labels(filled=False)
+    for i, (lab, raw) in enumerate(zip(labels, engine_raw)):
+        assert lab.shape == (len(pts[i]),)
+        assert lab.min() >= 1 and lab.max() <= stats['clusters'][i]            # every point labelled after the fill
+        assert np.array_equal(lab[raw > 0], raw[raw > 0])                      # the fill never relabels
+        sizes = np.bincount(raw)[1:]
+        assert len(sizes) == stats['clusters'][i] and sizes.min() > 10         # cluster_threshold (:33)
+        assert stats['regions'][i] == stats['stop_noneighbor'][i] + stats['stop_noexpand'][i] + stats['stop_stuck'][i] + stats['stop_other'][i]
+        assert stats['grow_steps'][i] >= stats['regions'][i] - stats['stop_noneighbor'][i]
+    # graph replay and direct launches are the same computation
+    from learn_region_grow_b200 import _lib
+    labels2, stats2 = engine.segment_rooms(pts, orders, resolution=0.1, seed=0, flags=_lib.FLAG_NO_GRAPH)
+    for a, b in zip(labels, labels2):
+        np.testing.assert_array_equal(a, b)
+    assert stats2['grow_steps'].tolist() == stats['grow_steps'].tolist()
+
+
+def test_resolution_and_threshold_parameters(engine, golden_weights):
+    """--resolution (test_region_grow.py:63) and cluster_threshold (:33) reach the device."""
+    points, order = golden_room(1000)
+    labels, stats = engine.segment_rooms([points], [order], resolution=0.3, seed=1, cluster_threshold=25, trace_capacity=2048)
+    trace, n_steps = engine.trace(0, 2048)
+    fwd = lambda a, b: lrg_forward.forward(golden_weights, a, b)
+    raw = engine.labels(filled=False)[0]
+    sizes = np.bincount(raw)[1:]
+    assert len(sizes) == 0 or sizes.min() > 25
+    # the first region's first step sees the shell of the seed voxel at 0.3 m
+    vox = lrg_driver.voxelize(points[:, :3], 0.3)
+    seed = order[0]
+    shell = np.all(np.abs(vox - vox[seed]) <= 1, axis=1)
+    shell[seed] = False
+    assert trace[0]['seed_point'] == seed and trace[0]['n_neighbor'] == shell.sum()

@@ -1,0 +1,167 @@
+"""tf_ops kernels (C ABI, device pointers) vs the C oracle and vs the reference's own kernels compiled into oracle/_ref."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import tfops as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _clouds(b, n, seed, dup=False):
+    rng = np.random.RandomState(seed)
+    x = rng.rand(b, n, 3).astype(np.float32)
+    if dup:      # exact ties: duplicated points and a regular grid
+        x[:, n // 2:] = x[:, :n - n // 2]
+        x[0] = np.stack(np.meshgrid(np.arange(8), np.arange(8), np.arange(max(1, n // 64) + 1), indexing='ij'), -1).reshape(-1, 3)[:n].astype(np.float32) / 8
+    return x
+
+
+@pytest.mark.parametrize('b,n,m,dup', [(1, 1024, 1024, False), (3, 1024, 256, False), (2, 256, 64, True), (2, 64, 16, False),
+                                       (1, 5000, 512, False), (2, 700, 700, True), (1, 20000, 128, False), (4, 1, 1, False)])
+def test_farthest_point_sample(b, n, m, dup):
+    from learn_region_grow_b200 import tfops as T
+    x = _clouds(b, n, n + m, dup)
+    got = T.farthest_point_sample(m, x)
+    ref = O.farthest_point_sample(m, x)
+    assert got.dtype == np.int32 and got.shape == (b, m)
+    np.testing.assert_array_equal(got, ref)
+    assert np.all(got[:, 0] == 0)
+
+
+def test_gather_and_grad():
+    from learn_region_grow_b200 import tfops as T
+    x = _clouds(3, 500, 1)
+    idx = np.random.RandomState(2).randint(0, 500, (3, 77)).astype(np.int32)
+    np.testing.assert_array_equal(T.gather_point(x, idx), O.gather_point(x, idx))
+    g = np.random.RandomState(3).randn(3, 77, 3).astype(np.float32)
+    np.testing.assert_allclose(T.gather_point_grad(x, idx, g), O.gather_point_grad(x, idx, g), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('b,n,m,radius,ns', [(2, 1024, 256, 0.1, 32), (1, 1024, 1024, 0.2, 32), (3, 256, 64, 0.4, 32), (2, 64, 16, 0.8, 32),
+                                             (1, 333, 77, 0.05, 5), (32, 512, 128, 0.3, 64)])
+def test_query_ball_and_group(b, n, m, radius, ns):
+    from learn_region_grow_b200 import tfops as T
+    x = _clouds(b, n, 10 + n)
+    q = x[:, :m] if b != 1 or n != 333 else _clouds(b, m, 99)       # PointNet++ queries are a subset of the points; one case is not
+    idx, cnt = T.query_ball_point(radius, ns, x, q)
+    ridx, rcnt = O.query_ball_point(radius, ns, x, q)
+    np.testing.assert_array_equal(cnt, rcnt)
+    np.testing.assert_array_equal(idx, ridx)            # rows without hits stay 0 in both
+    feat = np.random.RandomState(4).randn(b, n, 7).astype(np.float32)
+    np.testing.assert_array_equal(T.group_point(feat, idx), O.group_point(feat, idx))
+    feat4 = np.random.RandomState(5).randn(b, n, 64).astype(np.float32)
+    np.testing.assert_array_equal(T.group_point(feat4, idx), O.group_point(feat4, idx))
+    go = np.random.RandomState(6).randn(b, m, ns, 7).astype(np.float32)
+    np.testing.assert_allclose(T.group_point_grad(feat, idx, go), O.group_point_grad(feat, idx, go), rtol=1e-4, atol=1e-4)
+
+
+def test_selection_sort_known_answer_and_random():
+    from learn_region_grow_b200 import tfops as T
+    dist = (10 - np.arange(16)).reshape(2, 2, 4).astype(np.float32)        # tf_ops/grouping/test/selection_sort.cpp:68-78
+    outi, out = T.select_top_k(3, dist)
+    assert outi.reshape(-1).tolist() == [3, 2, 1, 0] * 4
+    assert out.reshape(-1).tolist() == [7, 8, 9, 10, 3, 4, 5, 6, -1, 0, 1, 2, -5, -4, -3, -2]
+    d = np.random.RandomState(0).randint(0, 20, (3, 50, 333)).astype(np.float32)     # many exact ties
+    gi, go = T.select_top_k(16, d)
+    ri, ro = O.select_top_k(16, d)
+    np.testing.assert_array_equal(gi, ri)
+    np.testing.assert_array_equal(go, ro)
+    val, idx = T.knn_point(4, _clouds(1, 64, 1), _clouds(1, 16, 2))
+    assert val.shape == (1, 16, 4) and np.all(np.diff(val, axis=-1) >= 0)
+
+
+@pytest.mark.parametrize('b,n,m,c', [(1, 64, 16, 512), (2, 256, 64, 256), (1, 1024, 256, 256), (1, 1024, 1024, 128), (2, 50, 2, 8), (1, 10, 1, 4)])
+def test_three_nn_and_interpolate(b, n, m, c):
+    from learn_region_grow_b200 import tfops as T
+    x1, x2 = _clouds(b, n, 20 + n), _clouds(b, m, 30 + m)
+    if m >= 16:
+        x2[:, 5] = x2[:, 3]                              # exact ties: earliest index must win
+    dist, idx = T.three_nn(x1, x2)
+    rdist, ridx = O.three_nn(x1, x2)
+    np.testing.assert_array_equal(idx, ridx)
+    np.testing.assert_array_equal(dist, rdist)           # inf where m < 3, like (float)1e40
+    pts = np.random.RandomState(7).randn(b, m, c).astype(np.float32)
+    d = np.maximum(np.where(np.isfinite(dist), dist, 1e10), 1e-10)          # train_pointnet.py:146-149
+    w = ((1.0 / d) / np.sum(1.0 / d, axis=2, keepdims=True)).astype(np.float32)
+    np.testing.assert_array_equal(T.three_interpolate(pts, idx, w), O.three_interpolate(pts, idx, w))
+    go = np.random.RandomState(8).randn(b, n, c).astype(np.float32)
+    np.testing.assert_allclose(T.three_interpolate_grad(pts, idx, w, go), O.three_interpolate_grad(pts, idx, w, go), rtol=1e-4, atol=1e-4)
+
+
+def test_op_argument_errors():
+    from learn_region_grow_b200 import tfops as T
+    x = _clouds(1, 16, 0)
+    with pytest.raises(ValueError, match='positive radius'):
+        T.query_ball_point(0.0, 4, x, x)
+    with pytest.raises(ValueError, match='positive nsample'):
+        T.query_ball_point(0.1, 0, x, x)
+    with pytest.raises(ValueError, match='FarthestPointSample expects'):
+        T.farthest_point_sample(4, x[..., :2])
+    with pytest.raises(ValueError, match='positive k'):
+        T.select_top_k(0, np.zeros((1, 2, 3), np.float32))
+
+
+def test_torch_tensors_in_place():
+    import torch
+    from learn_region_grow_b200 import tfops as T
+    x = torch.rand(2, 512, 3, device='cuda')
+    idx = T.farthest_point_sample(64, x)
+    assert idx.is_cuda and idx.dtype == torch.int32
+    np.testing.assert_array_equal(idx.cpu().numpy(), O.farthest_point_sample(64, x.cpu().numpy()))
+    new_xyz = T.gather_point(x, idx)
+    bi, cnt = T.query_ball_point(0.2, 16, x, new_xyz)
+    ri, rc = O.query_ball_point(0.2, 16, x.cpu().numpy(), new_xyz.cpu().numpy())
+    np.testing.assert_array_equal(bi.cpu().numpy(), ri)
+
+
+@pytest.mark.skipif(not O.ReferenceKernels.available(), reason='oracle/_ref not built (python -m oracle.build_ref in the build container)')
+def test_against_reference_kernels_themselves():
+    """The unmodified tf_sampling_g.cu / tf_grouping_g.cu, compiled for sm_100a, on the same device buffers."""
+    from learn_region_grow_b200 import _lib
+    L = _lib.lib()
+    R = O.ReferenceKernels()
+
+    def dev(a):
+        p = C.c_void_p()
+        _lib.check(L.lrg_malloc(C.byref(p), max(a.nbytes, 4)))
+        _lib.check(L.lrg_memcpy_h2d(p, _lib.ptr(a), a.nbytes))
+        return p
+
+    def host(p, shape, dtype):
+        a = np.empty(shape, dtype)
+        _lib.check(L.lrg_device_synchronize())
+        _lib.check(L.lrg_memcpy_d2h(_lib.ptr(a), p, a.nbytes))
+        return a
+
+    for (b, n, m, dup) in [(2, 1024, 256, False), (1, 4000, 300, False), (2, 600, 600, True)]:
+        x = _clouds(b, n, 40 + n, dup)
+        dx = dev(x)
+        tmp = dev(np.zeros((32, n), np.float32))
+        o_ref, o_new = dev(np.zeros((b, m), np.int32)), dev(np.zeros((b, m), np.int32))
+        R.fps(b, n, m, dx, tmp, o_ref)
+        _lib.check(L.lrg_farthest_point_sampling(b, n, m, dx, tmp, o_new, None))
+        ref = host(o_ref, (b, m), np.int32)
+        np.testing.assert_array_equal(host(o_new, (b, m), np.int32), ref)
+        np.testing.assert_array_equal(O.farthest_point_sample(m, x), ref)       # pins the C restatement too
+        # ball query + group on the sampled centres
+        q = O.gather_point(x, ref)
+        dq = dev(q)
+        ns = 32
+        i_ref, i_new = dev(np.zeros((b, m, ns), np.int32)), dev(np.zeros((b, m, ns), np.int32))
+        c_ref, c_new = dev(np.zeros((b, m), np.int32)), dev(np.zeros((b, m), np.int32))
+        R.query_ball(b, n, m, 0.15, ns, dx, dq, i_ref, c_ref)
+        _lib.check(L.lrg_query_ball_point(b, n, m, 0.15, ns, dx, dq, i_new, c_new, None))
+        ridx = host(i_ref, (b, m, ns), np.int32)
+        np.testing.assert_array_equal(host(i_new, (b, m, ns), np.int32), ridx)
+        np.testing.assert_array_equal(host(c_new, (b, m), np.int32), host(c_ref, (b, m), np.int32))
+        np.testing.assert_array_equal(O.query_ball_point(0.15, ns, x, q)[0], ridx)
+        feat = np.random.RandomState(1).randn(b, n, 16).astype(np.float32)
+        df = dev(feat)
+        g_ref, g_new = dev(np.zeros((b, m, ns, 16), np.float32)), dev(np.zeros((b, m, ns, 16), np.float32))
+        R.group(b, n, 16, m, ns, df, i_ref, g_ref)
+        _lib.check(L.lrg_group_point(b, n, 16, m, ns, df, i_ref, g_new, None))
+        np.testing.assert_array_equal(host(g_new, (b, m, ns, 16), np.float32), host(g_ref, (b, m, ns, 16), np.float32))
+        for p in (dx, tmp, o_ref, o_new, dq, i_ref, i_new, c_ref, c_new, df, g_ref, g_new):
+            L.lrg_free(p)
