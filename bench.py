@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the LRGNet grow engine on synthetic S3DIS-shaped rooms (BASELINE.json metric: segmented points/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--rooms R] [--impl reference]
+
+One "step" = one full pass of the hot path over the workload: every room of the synthetic Area-5-shaped set
+(68 rooms, ~20k raw points each, seeds 1000+room) grown to completion and filled.  `value` is measured with the rooms'
+13-D features already resident in HBM (CUDA events on the engine stream, max over ranks); `e2e` is the same pass through
+the public host-buffer call (pinned host arrays in, labels out, copies inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+FLOPS_PER_STEP = 271712256                     # BASELINE.md section 4 (algorithmic, factored heads)
+BRANCH_FLOPS_PER_STEP = 2 * 2 * 512 * 82752    # both branches, 512 points, 82,752 MAC per point
+HEAD_FLOPS_PER_STEP = 2 * 2 * 512 * (64 * 256 + 256 * 128 + 128 * 2)
+GPROJ_FLOPS_PER_STEP = 2 * 2 * 1024 * 256
+METRIC = 'segmented_points_per_sec'
+UNIT = 'points/s'
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json'))), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'sm_max_mhz': 1965.0}, 'fallback'
+
+
+def make_workload(n_rooms, seed_base, cache=True):
+    """Synthetic rooms -> 13-D features + seed order (host feature prep; SURVEY 8f-1 is the device version)."""
+    from learn_region_grow_b200 import rooms
+    path = '/tmp/lrg_bench_rooms_%d_%d.npz' % (n_rooms, seed_base)
+    if cache and os.path.exists(path):
+        z = np.load(path)
+        return z['offsets'], z['points'], z['order'], z['raw_counts']
+    pts, orders, raw = [], [], []
+    for r in range(n_rooms):
+        room = rooms.generate_room(seed_base + r)
+        f = rooms.prepare_features(room, 0.1)
+        pts.append(f['points'])
+        orders.append(f['order'].astype(np.int32))
+        raw.append(len(room))
+    offsets = np.zeros(n_rooms + 1, np.int64)
+    np.cumsum([len(p) for p in pts], out=offsets[1:])
+    out = (offsets, np.ascontiguousarray(np.concatenate(pts), np.float32), np.ascontiguousarray(np.concatenate(orders), np.int32),
+           np.array(raw, np.int64))
+    if cache:
+        try:
+            np.savez(path, offsets=out[0], points=out[1], order=out[2], raw_counts=out[3])
+        except Exception:
+            pass
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def pinned_array(lib_mod, shape, dtype):
+    import ctypes as C
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    lib_mod.check(lib_mod.lib().lrg_host_alloc(C.byref(p), max(n, 1)))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+# ----------------------------------------------------------------------------------------------- CPU arms
+def cpu_sample(weights, points, order, n_steps, literal, room_id=0):
+    """Time `n_steps` grow steps of the oracle driver (port of the reference) on one room.  TEST INFRA used as baseline."""
+    from oracle import lrg_driver, lrg_forward
+    fwd = lambda a, b: lrg_forward.forward(weights, a, b)
+    g = lrg_driver.RoomGrower(points, order, fwd, lrg_driver.PhiloxRng(0), room_id=room_id, literal_update=literal)
+    t0 = time.perf_counter()
+    for seed_id in np.arange(len(points))[order]:
+        if g.visited[seed_id]:
+            continue
+        g.begin_region(seed_id)
+        while g.total_steps < n_steps:
+            st = g.prepare_step()
+            if st is None:
+                break
+            add, rmv = fwd(st['inlier'], st['neighbor'])
+            if g.apply_step(add[0], rmv[0]) is not None:
+                break
+        if g.total_steps >= n_steps:
+            break
+    return g.total_steps, time.perf_counter() - t0
+
+
+def load_weights():
+    with np.load(os.path.join(REPO, 'tests', 'golden', 'lrgnet_model5.npz')) as z:
+        return {k: z[k] for k in z.files}
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path (port: oracle/lrg_driver.py with the literal
+    per-point update loop of test_region_grow.py:282-287 + numpy forward on all host threads); the Python reference cannot
+    travel to the GPU box (TensorFlow/h5py absent), so this is the oracle port."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    offsets, points, order, raw_counts = make_workload(args.rooms, 1000)
+    weights = load_weights()
+    steps_per_room = None
+    sample_steps = args.ref_sample_steps
+    times, nsteps = [], []
+    for it in range(args.warmup + args.steps):
+        room = it % args.rooms
+        p = points[offsets[room]:offsets[room + 1]]
+        o = order[offsets[room]:offsets[room + 1]]
+        n, dt = cpu_sample(weights, p, o, sample_steps if it >= args.warmup else max(5, sample_steps // 10), literal=True, room_id=room)
+        if it >= args.warmup:
+            times.append(dt)
+            nsteps.append(n)
+    steps_per_s = sum(nsteps) / sum(times)
+    # points/s = steps/s x (raw points per grow step of this workload); the ratio comes from the workload statistics file
+    # written by the GPU arm when available, else from the reference logs (~948 steps per ~20k-point room)
+    pts_per_step = workload_points_per_step(args.rooms, raw_counts)
+    value = steps_per_s * pts_per_step
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * float(np.mean(times)), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'area5_synthetic_%d_rooms_20k_raw' % args.rooms, 'rooms': args.rooms, 'resolution': 0.1,
+                   'scope': 'grow driver + LrgNet forward on precomputed 13-D features'},
+        'grow_steps_per_sec': steps_per_s,
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+                         'sample': '%d grow steps per timed step on one room (literal per-point update loop, numpy forward); points/s = steps/s x %.2f raw points per grow step' % (sample_steps, pts_per_step)},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_points_per_step(n_rooms, raw_counts):
+    path = '/tmp/lrg_bench_stats_%d.json' % n_rooms
+    try:
+        s = json.load(open(path))
+        return float(s['raw_points']) / float(s['grow_steps'])
+    except Exception:
+        return float(np.mean(raw_counts)) / 948.0
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--rooms', type=int, default=68, help='rooms per GPU (Area 5 has 68)')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--ref-sample-steps', type=int, default=120)
+    ap.add_argument('--cpu-baseline-steps', type=int, default=150)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--slots', type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    import torch
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', local_rank))
+
+    from learn_region_grow_b200 import _lib, parallel
+    from learn_region_grow_b200.engine import Engine
+    peaks, peaks_src = load_peaks()
+    weights = load_weights()
+    # weak scaling: every rank grows its own Area-5-sized set of rooms (different seeds)
+    offsets, points, order, raw_counts = make_workload(args.rooms, 1000 + rank * args.rooms)
+    total_raw = int(raw_counts.sum())
+    eng = Engine(1, 1, 512, 512, 13, 0, device=local_rank)
+    eng.load_weights(weights)
+    params = dict(resolution=0.1, seed=0, max_slots=args.slots, room_id_base=rank * args.rooms)
+
+    # pinned host buffers for the end-to-end arm
+    h_points = pinned_array(_lib, points.shape, np.float32); h_points[...] = points
+    h_order = pinned_array(_lib, order.shape, np.int32); h_order[...] = order
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')      # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lengths = [int(offsets[-1])] * world      # every rank has the same room sizes only by seed; gather actual below
+    if dist is not None:
+        t = torch.tensor([int(offsets[-1])], device='cuda')
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        lengths = [int(x.item()) for x in allt]
+
+    def gather_labels():
+        if dist is None:
+            return
+        local = torch.as_tensor(parallel.DeviceArray(eng.labels_device_ptr(True), int(offsets[-1])), device='cuda')
+        parallel.allgather_labels(local, lengths)
+
+    # ---- resident arm: `value`
+    eng.upload_concatenated(offsets, points, order, 0.1)
+    launches = 0
+    stats = None
+    dev_ms = []
+    for it in range(args.warmup + args.steps):
+        flush.fill_(it & 0xFF)
+        if it == args.warmup:
+            barrier()
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            wall0 = time.perf_counter()
+        stats = eng.segment_resident(**params)
+        t_ag0 = time.perf_counter()
+        gather_labels()
+        torch.cuda.synchronize()
+        t_ag = time.perf_counter() - t_ag0
+        if it >= args.warmup:
+            pr = eng.profile()
+            dev_ms.append(pr['grow_ms'] + pr['fill_ms'] + (1e3 * t_ag if dist is not None else 0.0))
+            launches += pr['kernel_launches']
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    total_ms = float(sum(dev_ms))
+    if dist is not None:
+        t = torch.tensor([total_ms, wall], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, wall = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    grow_steps = int(stats['grow_steps'].sum())
+    value = world * total_raw / (ms_per_step * 1e-3)
+
+    # ---- kernel timing pass (same workload, CUDA events around every kernel of the lock-step loop)
+    eng.segment_resident(flags=_lib.FLAG_KERNEL_TIMING, **params)
+    kt = eng.profile()
+    branch_s = kt['branch_kernel_ms'] * 1e-3
+    achieved_tf = grow_steps * BRANCH_FLOPS_PER_STEP / branch_s / 1e12 if branch_s > 0 else 0.0
+    sm_mhz = clocks.get('sm_mhz') or peaks.get('sm_max_mhz', 1965.0)
+    fp32_peak_tf = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    peak_tf = peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops'))
+    roofline = {
+        'kernel': 'lrg_branch_kernel', 'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
+        'frac': achieved_tf / peak_tf if peak_tf else None, 'traffic': None, 'peak_source': peaks_src + ' bf16 sustained',
+        'pipe': 'fp32 FMA (parity bar is the fp32 TF graph)', 'fp32_fma_peak_tflops': fp32_peak_tf,
+        'frac_of_fp32_fma': achieved_tf / fp32_peak_tf if fp32_peak_tf else None,
+        'launches': kt['iterations'], 'avg_launch_ms': kt['branch_kernel_ms'] / max(kt['iterations'], 1),
+        'algorithmic_flops_per_launch': grow_steps * BRANCH_FLOPS_PER_STEP / max(kt['iterations'], 1),
+        'kernel_ms_share': {k: kt[k] for k in ('step_kernel_ms', 'branch_kernel_ms', 'gproj_kernel_ms', 'head_kernel_ms')},
+    }
+
+    # ---- end-to-end arm: host buffers in, labels out, copies inside the timed region
+    h2d = h_points.nbytes + h_order.nbytes + offsets.nbytes
+    d2h = int(offsets[-1]) * 4 + args.rooms * 32
+    for it in range(2):
+        eng.segment_concatenated(offsets, h_points, h_order, **params)
+    barrier()
+    e0 = time.perf_counter()
+    for it in range(args.steps):
+        labels, _ = eng.segment_concatenated(offsets, h_points, h_order, **params)
+        gather_labels()
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_value = world * total_raw * args.steps / e2e_s
+
+    if rank == 0:
+        try:
+            json.dump({'raw_points': total_raw, 'grow_steps': grow_steps}, open('/tmp/lrg_bench_stats_%d.json' % args.rooms, 'w'))
+        except Exception:
+            pass
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        p0, o0 = points[offsets[0]:offsets[1]], order[offsets[0]:offsets[1]]
+        pts_per_step = total_raw / grow_steps
+        n_lit, t_lit = cpu_sample(weights, p0, o0, args.cpu_baseline_steps, literal=True)
+        n_vec, t_vec = cpu_sample(weights, p0, o0, args.cpu_baseline_steps * 2, literal=False)
+        cpu_baseline = {'value': n_lit / t_lit * pts_per_step, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+                        'sample': 'first %d grow steps of room 0 (%d pts), oracle port with the reference\'s literal per-point update loop, numpy forward on all host threads; points/s = steps/s x %.2f raw points per grow step of this workload' % (n_lit, len(p0), pts_per_step),
+                        'grow_steps_per_sec': n_lit / t_lit,
+                        'vectorised_port': {'value': n_vec / t_vec * pts_per_step, 'grow_steps_per_sec': n_vec / t_vec}}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': 'area5_synthetic_%d_rooms_20k_raw' % args.rooms, 'rooms_per_gpu': args.rooms, 'resolution': 0.1,
+                       'equalized_points_per_gpu': int(offsets[-1]), 'raw_points_per_gpu': total_raw, 'l2': 'flushed between steps (256 MB fill)',
+                       'scope': 'grow driver + LrgNet forward + fill on precomputed 13-D features', 'rng': 'philox4x32-10 seed 0',
+                       'weights': 'lrgnet_model5 (golden)'},
+            'grow_steps_per_sec': world * grow_steps / (ms_per_step * 1e-3), 'grow_steps_per_pass': grow_steps,
+            'lockstep_iterations_per_pass': kt['iterations'],
+            'wall_s_timed_region': wall, 'clocks': clocks, 'gpu_launches': int(launches),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+            'roofline': roofline, 'cpu_baseline': cpu_baseline,
+            'flops_per_grow_step': FLOPS_PER_STEP,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

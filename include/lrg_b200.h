@@ -119,6 +119,13 @@ int lrg_segment_rooms_host(LrgEngine* e, int n_rooms, const int64_t* room_offset
 int lrg_last_segment_profile(LrgEngine* e, float* grow_ms, float* fill_ms, int64_t* iterations,
                              int64_t* kernel_launches, float* forward_ms);
 
+/* With LRG_FLAG_KERNEL_TIMING: summed CUDA-event durations (ms) of the four kernels of the lock-step loop over the
+ * last lrg_segment_resident call: out[0] step (driver), out[1] branch MLPs, out[2] pooled projection, out[3] heads. */
+int lrg_last_kernel_times(LrgEngine* e, float out_ms[4]);
+/* Device pointer of the (sum N) int32 label array (filled != 0: after the fill), valid until the next upload;
+ * lets the host hand the labels to NCCL without a copy. */
+int lrg_labels_device_ptr(LrgEngine* e, int filled, void** d_ptr);
+
 /* ------------------------------------------------------------------------------------------------------
  * tf_ops primitives.  Same argument lists as the reference's C++ launchers plus a trailing stream; all
  * pointers are DEVICE pointers (the reference receives TF-allocated device buffers).

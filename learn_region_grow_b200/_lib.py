@@ -60,6 +60,8 @@ _SIGNATURES = {
     'lrg_segment_rooms_host': (_I, [_P, _I, _P, _P, _P, C.POINTER(GrowParams), _P, _P]),
     'lrg_last_segment_profile': (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int64),
                                       C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
+    'lrg_last_kernel_times': (_I, [_P, C.POINTER(C.c_float * 4)]),
+    'lrg_labels_device_ptr': (_I, [_P, _I, C.POINTER(_P)]),
     'lrg_farthest_point_sampling': (_I, [_I, _I, _I, _P, _P, _P, _P]),
     'lrg_gather_point': (_I, [_I, _I, _I, _P, _P, _P, _P]),
     'lrg_scatter_add_point': (_I, [_I, _I, _I, _P, _P, _P, _P]),

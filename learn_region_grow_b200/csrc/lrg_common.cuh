@@ -68,6 +68,8 @@ struct ForwardArgs {
 };
 
 int launch_forward(const NetDesc& net, const ForwardArgs& fa, cudaStream_t stream);
+// same launches with an event recorded before the branch kernel and after each of the three kernels (ev[0..3])
+int launch_forward_timed(const NetDesc& net, const ForwardArgs& fa, cudaStream_t stream, cudaEvent_t* ev);
 size_t forward_smem_branch(const NetDesc& net);
 size_t forward_smem_head(const NetDesc& net);
 int forward_configure(const NetDesc& net);

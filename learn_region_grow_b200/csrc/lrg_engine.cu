@@ -84,9 +84,10 @@ struct LrgEngine {
   int* h_done = nullptr;           // mapped pinned
   int* d_done = nullptr;
   LrgStepTrace* d_trace = nullptr;
-  int trace_capacity = 0;
+  int trace_capacity = 0, trace_rooms = 0;
   // profile of the last segment call
   float grow_ms = 0, fill_ms = 0, forward_ms = 0;
+  float kernel_ms[4] = {0, 0, 0, 0};
   long long iterations = 0, launches = 0;
 };
 
@@ -407,7 +408,17 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   n_slots = std::max(1, std::min(n_slots, std::max(n_rooms, 1)));
   LRG_TRY(ensure_slots(e, n_slots));
   cudaStream_t st = e->stream;
-  // reset per-run state
+  cudaEvent_t ev0, ev1, ev2;
+  LRG_CUDA(cudaEventCreate(&ev0)); LRG_CUDA(cudaEventCreate(&ev1)); LRG_CUDA(cudaEventCreate(&ev2));
+  if (params->trace_capacity > 0 && (e->d_trace == nullptr || e->trace_capacity != params->trace_capacity || e->trace_rooms < n_rooms)) {
+    cudaFree(e->d_trace);
+    e->d_trace = nullptr;
+    LRG_TRY(dev_alloc(&e->d_trace, (size_t)std::max(n_rooms, 1) * params->trace_capacity));
+    e->trace_rooms = n_rooms;
+  }
+  *e->h_done = 0;
+  LRG_CUDA(cudaEventRecord(ev0, st));
+  // reset per-run state (inside the timed region: it is part of one pass over the rooms)
   LRG_CUDA(cudaMemsetAsync(e->d_state, 0, T, st));
   LRG_CUDA(cudaMemsetAsync(e->d_label, 0, T * sizeof(int), st));
   LRG_CUDA(cudaMemsetAsync(e->d_stats, 0, sizeof(LrgRoomStats) * std::max(n_rooms, 1), st));
@@ -417,16 +428,11 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   for (auto& s : init) s.room = -1;
   LRG_CUDA(cudaMemcpyAsync(e->d_slots, init.data(), sizeof(SlotState) * n_slots, cudaMemcpyHostToDevice, st));
   if (params->trace_capacity > 0) {
-    cudaFree(e->d_trace);
-    e->d_trace = nullptr;
-    LRG_TRY(dev_alloc(&e->d_trace, (size_t)std::max(n_rooms, 1) * params->trace_capacity));
     LRG_CUDA(cudaMemsetAsync(e->d_trace, 0, sizeof(LrgStepTrace) * (size_t)std::max(n_rooms, 1) * params->trace_capacity, st));
     e->trace_capacity = params->trace_capacity;
   } else {
     e->trace_capacity = 0;
   }
-  *e->h_done = 0;
-  LRG_CUDA(cudaStreamSynchronize(st));   // init is out of the timed region
 
   DriverArgs da{};
   da.n_rooms = n_rooms; da.room_off = e->d_room_off; da.pts = e->d_pts; da.vox = e->d_vox; da.state = e->d_state;
@@ -449,12 +455,10 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   fa.logits[0] = e->s_logits[0]; fa.logits[1] = e->s_logits[1];
   fa.active = &e->d_slots[0].active; fa.active_stride = (int)(sizeof(SlotState) / sizeof(int)); fa.B = n_slots;
 
-  cudaEvent_t ev0, ev1, ev2;
-  LRG_CUDA(cudaEventCreate(&ev0)); LRG_CUDA(cudaEventCreate(&ev1)); LRG_CUDA(cudaEventCreate(&ev2));
   e->iterations = 0; e->launches = 0; e->forward_ms = 0;
+  for (int i = 0; i < 4; ++i) e->kernel_ms[i] = 0;
   const bool kernel_timing = (params->flags & LRG_FLAG_KERNEL_TIMING) != 0;
   const bool use_graph = !kernel_timing && !(params->flags & LRG_FLAG_NO_GRAPH);
-  LRG_CUDA(cudaEventRecord(ev0, st));
   int rc = LRG_OK;
   if (n_rooms > 0) {
     if (use_graph) {
@@ -491,23 +495,26 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
       cudaEventDestroy(evq[0]); cudaEventDestroy(evq[1]);
       cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
     } else {
-      cudaEvent_t ka, kb;
-      LRG_CUDA(cudaEventCreate(&ka)); LRG_CUDA(cudaEventCreate(&kb));
+      cudaEvent_t kev[5];
+      for (auto& k : kev) LRG_CUDA(cudaEventCreate(&k));
       while (rc == LRG_OK) {
+        if (kernel_timing) cudaEventRecord(kev[0], st);
         rc = launch_step(da, st);
         if (rc != LRG_OK) break;
-        if (kernel_timing) cudaEventRecord(ka, st);
-        rc = launch_forward(e->net, fa, st);
-        if (kernel_timing) cudaEventRecord(kb, st);
+        if (kernel_timing) rc = launch_forward_timed(e->net, fa, st, kev + 1);
+        else rc = launch_forward(e->net, fa, st);
         e->iterations += 1; e->launches += 4;
         if (kernel_timing || (e->iterations % 16) == 0) {
           cudaError_t se = cudaStreamSynchronize(st);
           if (se != cudaSuccess) { set_error("grow loop -> %s", cudaGetErrorString(se)); rc = LRG_E_CUDA; break; }
-          if (kernel_timing) { float ms = 0; cudaEventElapsedTime(&ms, ka, kb); e->forward_ms += ms; }
+          if (kernel_timing) {
+            for (int i = 0; i < 4; ++i) { float ms = 0; cudaEventElapsedTime(&ms, kev[i], kev[i + 1]); e->kernel_ms[i] += ms; }
+            e->forward_ms = e->kernel_ms[1] + e->kernel_ms[2] + e->kernel_ms[3];
+          }
           if (*(volatile int*)e->h_done) break;
         }
       }
-      cudaEventDestroy(ka); cudaEventDestroy(kb);
+      for (auto& k : kev) cudaEventDestroy(k);
     }
   }
   if (rc != LRG_OK) return rc;
@@ -564,6 +571,18 @@ int lrg_last_segment_profile(LrgEngine* e, float* grow_ms, float* fill_ms, int64
   if (iterations) *iterations = e->iterations;
   if (kernel_launches) *kernel_launches = e->launches;
   if (forward_ms) *forward_ms = e->forward_ms;
+  return LRG_OK;
+}
+
+int lrg_last_kernel_times(LrgEngine* e, float out_ms[4]) {
+  LRG_REQUIRE(e != nullptr && out_ms != nullptr, "NULL argument");
+  for (int i = 0; i < 4; ++i) out_ms[i] = e->kernel_ms[i];
+  return LRG_OK;
+}
+
+int lrg_labels_device_ptr(LrgEngine* e, int filled, void** d_ptr) {
+  LRG_REQUIRE(e != nullptr && d_ptr != nullptr, "NULL argument");
+  *d_ptr = filled ? (void*)e->d_label_filled : (void*)e->d_label;
   return LRG_OK;
 }
 

@@ -317,17 +317,25 @@ int forward_configure(const NetDesc& net) {
 }
 
 // pooled must be zero for the active tile pairs on entry.
-int launch_forward(const NetDesc& net, const ForwardArgs& fa, cudaStream_t stream) {
+int launch_forward_timed(const NetDesc& net, const ForwardArgs& fa, cudaStream_t stream, cudaEvent_t* ev) {
   if (fa.B <= 0) return LRG_OK;
   const int nmax = fa.n_pts[0] > fa.n_pts[1] ? fa.n_pts[0] : fa.n_pts[1];
   const int tiles = (nmax + kTileRows - 1) / kTileRows;
   dim3 grid(tiles, 2, fa.B);
+  if (ev) cudaEventRecord(ev[0], stream);
   lrg_branch_kernel<<<grid, kThreads, forward_smem_branch(net), stream>>>(net, fa);
+  if (ev) cudaEventRecord(ev[1], stream);
   dim3 ggrid(net.H0 / 64, 2, (fa.B + 7) / 8);
   lrg_gproj_kernel<<<ggrid, 256, gproj_smem(net), stream>>>(net, fa);
+  if (ev) cudaEventRecord(ev[2], stream);
   lrg_head_kernel<<<grid, kThreads, forward_smem_head(net), stream>>>(net, fa);
+  if (ev) cudaEventRecord(ev[3], stream);
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;
+}
+
+int launch_forward(const NetDesc& net, const ForwardArgs& fa, cudaStream_t stream) {
+  return launch_forward_timed(net, fa, stream, nullptr);
 }
 
 }  // namespace lrg

@@ -172,7 +172,15 @@ class Engine:
         g, f, fw = C.c_float(0), C.c_float(0), C.c_float(0)
         it, ln = C.c_int64(0), C.c_int64(0)
         _lib.check(self.lib.lrg_last_segment_profile(self._h, C.byref(g), C.byref(f), C.byref(it), C.byref(ln), C.byref(fw)))
-        return dict(grow_ms=g.value, fill_ms=f.value, iterations=it.value, kernel_launches=ln.value, forward_ms=fw.value)
+        k = (C.c_float * 4)()
+        _lib.check(self.lib.lrg_last_kernel_times(self._h, C.byref(k)))
+        return dict(grow_ms=g.value, fill_ms=f.value, iterations=it.value, kernel_launches=ln.value, forward_ms=fw.value,
+                    step_kernel_ms=k[0], branch_kernel_ms=k[1], gproj_kernel_ms=k[2], head_kernel_ms=k[3])
+
+    def labels_device_ptr(self, filled=True):
+        p = C.c_void_p()
+        _lib.check(self.lib.lrg_labels_device_ptr(self._h, 1 if filled else 0, C.byref(p)))
+        return p.value
 
     def segment_rooms(self, rooms_points, rooms_order, resolution=0.1, **kw):
         """End-to-end call on host arrays: upload, grow, fill, download.  Returns (labels per room, stats)."""

@@ -81,7 +81,7 @@ class RoomGrower:
     """
 
     def __init__(self, points, order, forward_fn, rng, resolution=0.1, num_inlier=512, num_neighbor=512,
-                 cluster_threshold=10, room_id=0, max_steps_per_region=None):
+                 cluster_threshold=10, room_id=0, max_steps_per_region=None, literal_update=False):
         self.points = np.ascontiguousarray(points, dtype=np.float32)
         self.order = np.asarray(order)
         self.forward_fn = forward_fn
@@ -91,6 +91,7 @@ class RoomGrower:
         self.cluster_threshold = cluster_threshold
         self.room_id = room_id
         self.max_steps_per_region = max_steps_per_region
+        self.literal_update = literal_update      # True: the reference's per-point python loop (:282-287), for CPU timing
         n = len(self.points)
         self.point_voxels = voxelize(self.points[:, :3], resolution)              # :175
         self.cluster_label = np.zeros(n, dtype=int)                               # :176
@@ -175,10 +176,22 @@ class RoomGrower:
         rmvPoints = st['inlier'][0, :, :][st['rmv_mask']]                         # :274-277
         rmvPoints[:, :2] += center[:2]
         rmvVoxels = voxelize(rmvPoints[:, :3], self.resolution)
-        in_add = _rows_in(self.point_voxels, addVoxels)                           # :282-287 (set membership)
-        in_rmv = _rows_in(self.point_voxels, rmvVoxels)
-        updated = bool(np.any(np.logical_and(~self.currentMask, in_add)))
-        self.currentMask = np.logical_and(np.logical_or(self.currentMask, in_add), ~in_rmv)
+        if self.literal_update:
+            addSet = set([tuple(p) for p in addVoxels])                           # :273,277
+            rmvSet = set([tuple(p) for p in rmvVoxels])
+            updated = False
+            point_voxels, currentMask = self.point_voxels, self.currentMask
+            for i in range(len(point_voxels)):                                    # :282-287, as written
+                if not currentMask[i] and tuple(point_voxels[i]) in addSet:
+                    currentMask[i] = True
+                    updated = True
+                if tuple(point_voxels[i]) in rmvSet:
+                    currentMask[i] = False
+        else:
+            in_add = _rows_in(self.point_voxels, addVoxels)                       # same set membership, vectorised
+            in_rmv = _rows_in(self.point_voxels, rmvVoxels)
+            updated = bool(np.any(np.logical_and(~self.currentMask, in_add)))
+            self.currentMask = np.logical_and(np.logical_or(self.currentMask, in_add), ~in_rmv)
         self.steps += 1                                                           # :288
         self.total_steps += 1
         if self.trace is not None:

@@ -37,3 +37,15 @@ def test_driver_replays_reference_trace(seed, golden_weights):
     for line, (seed_id, steps, size, reason, _) in zip(lines, labelled):
         tok = line.split()
         assert int(tok[6]) == steps and int(tok[7].split('/')[0]) == size and tok[-1] == reason
+
+
+def test_literal_update_loop_equals_vectorised(golden_weights):
+    """The per-point python loop of test_region_grow.py:282-287 (used for the CPU timing) and its vectorised form."""
+    g = np.load(os.path.join(GOLDEN, 'driver_trace_1000.npz'))
+    fwd = lambda a, b: lrg_forward.forward(golden_weights, a, b, dtype=np.float64)
+    out = []
+    for literal in (False, True):
+        gr = lrg_driver.RoomGrower(g['points'], g['order'], fwd, lrg_driver.PhiloxRng(4), literal_update=literal)
+        gr.run()
+        out.append((gr.cluster_label.copy(), gr.total_steps, list(gr.regions)))
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1:] == out[1][1:]
