@@ -52,6 +52,15 @@ size_t lrg_engine_weight_count(const LrgEngine* e);
  * checkpoint-V2 files and hands over one flat float32 blob in the order above. */
 int lrg_engine_load_weights(LrgEngine* e, const float* blob, size_t n_floats);
 
+/* Which kernels evaluate the network.  AUTO = TENSOR when the model is the full one (lite=0), FMA otherwise.
+ *   LRG_FORWARD_TENSOR  tcgen05 tensor cores, every contraction as 3xTF32 (hi/lo split operands, fp32 accumulation)
+ *   LRG_FORWARD_FMA     fp32 FMA pipe (all lite variants; A/B reference for the tensor path)
+ * No reference equivalent (TF picks its own conv kernels). */
+enum { LRG_FORWARD_AUTO = 0, LRG_FORWARD_FMA = 1, LRG_FORWARD_TENSOR = 2 };
+int lrg_engine_set_forward_mode(LrgEngine* e, int mode);
+/* The mode forward calls currently take (LRG_FORWARD_FMA or LRG_FORWARD_TENSOR; valid after load_weights). */
+int lrg_engine_forward_mode(const LrgEngine* e);
+
 /* Replaces sess.run([net.add_output, net.remove_output], {inlier_pl, neighbor_pl}) (test_region_grow.py:257-258).
  * inlier (B, Ni, F), neighbor (B, Nj, F) float32 row-major; add_out (B, Nj, 2), remove_out (B, Ni, 2).
  * _host: synchronous, host buffers, H2D/D2H inside.  _device: asynchronous on `stream` (0 = engine stream). */

@@ -38,6 +38,7 @@ STEP_TRACE_DTYPE = np.dtype([('seed_point', '<i4'), ('step_in_region', '<i4'), (
 ROOM_STATS_DTYPE = np.dtype([(n, '<i4') for n, _ in RoomStats._fields_])
 assert STEP_TRACE_DTYPE.itemsize == C.sizeof(StepTrace) and ROOM_STATS_DTYPE.itemsize == C.sizeof(RoomStats)
 
+FORWARD_AUTO, FORWARD_FMA, FORWARD_TENSOR = 0, 1, 2
 FLAG_KERNEL_TIMING = 1
 FLAG_NO_GRAPH = 2
 
@@ -51,6 +52,8 @@ _SIGNATURES = {
     'lrg_engine_destroy': (_I, [_P]),
     'lrg_engine_weight_count': (C.c_size_t, [_P]),
     'lrg_engine_load_weights': (_I, [_P, _P, C.c_size_t]),
+    'lrg_engine_set_forward_mode': (_I, [_P, _I]),
+    'lrg_engine_forward_mode': (_I, [_P]),
     'lrg_forward_host': (_I, [_P, _I, _P, _P, _P, _P]),
     'lrg_forward_device': (_I, [_P, _I, _P, _P, _P, _P, _P]),
     'lrg_rooms_upload': (_I, [_P, _I, _P, _P, _P, C.c_float]),

@@ -7,6 +7,8 @@
 #include <vector>
 
 #include "lrg_driver.cuh"
+#include "lrg_tc.cuh"
+#include "lrg_umma.cuh"
 
 namespace lrg {
 
@@ -55,6 +57,12 @@ struct LrgEngine {
   NetDesc net{};
   float* d_weights = nullptr;      // packed/padded device copy
   size_t packed_floats = 0;
+  // tensor-core path (full model only): operand images + descriptor
+  bool tc_available = false;
+  int forward_mode = LRG_FORWARD_AUTO;
+  float* d_tc_img = nullptr;
+  TcNet tcnet{};
+  float *d_gpart = nullptr, *s_gpart = nullptr;   // pooled-projection partials: user forward / slots
   // forward workspaces for max_batch tile pairs (user-facing forward)
   int ws_batch = 0;
   float *d_x[2] = {nullptr, nullptr}, *d_h1[2] = {nullptr, nullptr}, *d_pooled = nullptr, *d_gproj = nullptr,
@@ -117,8 +125,8 @@ static size_t count_weights(const LrgEngine* e) {
 
 static void free_forward_ws(LrgEngine* e) {
   for (int i = 0; i < 2; ++i) { cudaFree(e->d_x[i]); cudaFree(e->d_h1[i]); cudaFree(e->d_logits[i]); e->d_x[i] = e->d_h1[i] = e->d_logits[i] = nullptr; }
-  cudaFree(e->d_pooled); cudaFree(e->d_gproj);
-  e->d_pooled = e->d_gproj = nullptr;
+  cudaFree(e->d_pooled); cudaFree(e->d_gproj); cudaFree(e->d_gpart);
+  e->d_pooled = e->d_gproj = e->d_gpart = nullptr;
   e->ws_batch = 0;
 }
 
@@ -133,6 +141,7 @@ static int ensure_forward_ws(LrgEngine* e, int B) {
   }
   LRG_TRY(dev_alloc(&e->d_pooled, (size_t)B * 2 * e->net.Clast));
   LRG_TRY(dev_alloc(&e->d_gproj, (size_t)B * 2 * e->net.H0));
+  LRG_TRY(dev_alloc(&e->d_gpart, (size_t)kGprojSplits * B * 2 * 256));
   e->ws_batch = B;
   return LRG_OK;
 }
@@ -153,7 +162,8 @@ static void free_slots(LrgEngine* e) {
     cudaFree(e->d_tile[i]); cudaFree(e->d_tileidx[i]); cudaFree(e->s_h1[i]); cudaFree(e->s_logits[i]);
     e->d_tile[i] = nullptr; e->d_tileidx[i] = nullptr; e->s_h1[i] = nullptr; e->s_logits[i] = nullptr;
   }
-  cudaFree(e->s_pooled); cudaFree(e->s_gproj);
+  cudaFree(e->s_pooled); cudaFree(e->s_gproj); cudaFree(e->s_gpart);
+  e->s_gpart = nullptr;
   e->d_slots = nullptr; e->d_listI = e->d_listJ = nullptr; e->d_keyI = e->d_keyJ = nullptr; e->s_pooled = e->s_gproj = nullptr;
   e->n_slots = 0; e->slots_maxN = 0;
 }
@@ -176,9 +186,35 @@ static int ensure_slots(LrgEngine* e, int n_slots) {
   }
   LRG_TRY(dev_alloc(&e->s_pooled, S * 2 * e->net.Clast));
   LRG_TRY(dev_alloc(&e->s_gproj, S * 2 * e->net.H0));
+  LRG_TRY(dev_alloc(&e->s_gpart, (size_t)kGprojSplits * S * 2 * 256));
   e->n_slots = n_slots;
   e->slots_maxN = (int)M;
   return LRG_OK;
+}
+
+static bool use_tc(const LrgEngine* e) {
+  return e->tc_available && e->forward_mode != LRG_FORWARD_FMA;
+}
+
+// The LrgNet forward over fa.B tile pairs on `stream`: tensor-core kernels for the full model, fp32-FMA kernels otherwise.
+static int run_forward(LrgEngine* e, const ForwardArgs& fa, float* gpart, cudaStream_t stream, cudaEvent_t* ev) {
+  if (use_tc(e)) return launch_forward_tc(e->tcnet, fa, gpart, stream, ev);
+  return launch_forward_timed(e->net, fa, stream, ev);
+}
+
+// Operand image of W[k0:k0+Kc, n0:n0+Nc] (row-major [K][N] source) in the UMMA canonical no-swizzle K-major layout:
+// element (n, k) at float offset (k/4)*(Nc*4) + n*4 + k%4; hi image followed by lo image.  Rows k >= K are zero.
+static void pack_chunk(std::vector<float>& out, const float* W, int K, int N, int k0, int Kc, int n0, int Nc) {
+  const size_t base = out.size();
+  out.resize(base + (size_t)2 * Nc * Kc, 0.f);
+  float* hi = out.data() + base;
+  float* lo = hi + (size_t)Nc * Kc;
+  for (int k = 0; k < Kc; ++k)
+    for (int n = 0; n < Nc; ++n) {
+      const float w = (k0 + k < K) ? W[(size_t)(k0 + k) * N + n0 + n] : 0.f;
+      const size_t off = (size_t)(k / 4) * (Nc * 4) + (size_t)n * 4 + (k % 4);
+      umma::split_tf32(w, hi[off], lo[off]);
+    }
 }
 
 }  // namespace lrg
@@ -228,7 +264,7 @@ int lrg_engine_destroy(LrgEngine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   free_forward_ws(e); free_rooms(e); free_slots(e);
-  cudaFree(e->d_weights); cudaFree(e->d_counters); cudaFree(e->d_trace);
+  cudaFree(e->d_weights); cudaFree(e->d_tc_img); cudaFree(e->d_counters); cudaFree(e->d_trace);
   cudaFreeHost(e->h_done);
   cudaStreamDestroy(e->stream);
   delete e;
@@ -236,6 +272,22 @@ int lrg_engine_destroy(LrgEngine* e) {
 }
 
 size_t lrg_engine_weight_count(const LrgEngine* e) { return e ? e->n_weights : 0; }
+
+int lrg_engine_set_forward_mode(LrgEngine* e, int mode) {
+  LRG_REQUIRE(e != nullptr, "engine is NULL");
+  LRG_REQUIRE(mode == LRG_FORWARD_AUTO || mode == LRG_FORWARD_FMA || mode == LRG_FORWARD_TENSOR, "unknown forward mode %d", mode);
+  if (mode == LRG_FORWARD_TENSOR && e->weights_loaded && !e->tc_available) {
+    set_error("the tensor-core forward covers the full model only (lite=0, feature_size<=16)");
+    return LRG_E_STATE;
+  }
+  e->forward_mode = mode;
+  return LRG_OK;
+}
+
+int lrg_engine_forward_mode(const LrgEngine* e) {
+  if (e == nullptr) return LRG_E_INVALID;
+  return use_tc(e) ? LRG_FORWARD_TENSOR : LRG_FORWARD_FMA;
+}
 
 int lrg_engine_load_weights(LrgEngine* e, const float* blob, size_t n_floats) {
   LRG_REQUIRE(e != nullptr && blob != nullptr, "engine/blob is NULL");
@@ -312,6 +364,68 @@ int lrg_engine_load_weights(LrgEngine* e, const float* blob, size_t n_floats) {
     net.out[h] = L(outl[h]);
   }
   LRG_TRY(forward_configure(net));
+  // tensor-core path: pre-packed hi/lo operand images of the full model (lrg_forward_tc.cu)
+  e->tc_available = false;
+  if (e->lite == 0 && e->F <= 16) {
+    std::vector<float> img;
+    img.reserve(2 * kBranchImgFloats + 2 * kHeadImgFloats);
+    size_t branch_off[2], head_off[2];
+    const float* q = blob;
+    for (int br = 0; br < 2; ++br) {
+      const float* Wl[kMaxConv];
+      for (int i = 0; i < nc; ++i) {
+        const int K = i == 0 ? e->F : e->conv[i - 1];
+        Wl[i] = q;
+        q += (size_t)K * e->conv[i] + e->conv[i];
+      }
+      branch_off[br] = img.size();
+      pack_chunk(img, Wl[0], e->F, 64, 0, 16, 0, 64);
+      pack_chunk(img, Wl[1], 64, 64, 0, 64, 0, 64);
+      pack_chunk(img, Wl[2], 64, 64, 0, 64, 0, 64);
+      pack_chunk(img, Wl[3], 64, 128, 0, 32, 0, 128);
+      pack_chunk(img, Wl[3], 64, 128, 32, 32, 0, 128);
+      for (int nb = 0; nb < 4; ++nb)
+        for (int kc = 0; kc < 4; ++kc) pack_chunk(img, Wl[4], 128, 512, kc * 32, 32, nb * 128, 128);
+      if (img.size() - branch_off[br] != kBranchImgFloats) { set_error("internal: branch image size"); return LRG_E_INVALID; }
+    }
+    for (int hb = 0; hb < 2; ++hb) {
+      const int h = hb == 0 ? 1 : 0;                       // blob: add head first; device index 1 = add
+      const float* K0local = q + (size_t)1024 * 256;       // rows 1024.. of kernel0: the per-point part [64][256]
+      q += (size_t)1088 * 256 + 256;
+      const float* K1 = q;                                 // [256][128]
+      q += (size_t)256 * 128 + 128;
+      q += 128 * 2 + 2;
+      head_off[h] = img.size();
+      auto W0 = [&](int nb) { pack_chunk(img, K0local, 64, 256, 0, 64, nb * 64, 64); };
+      auto W1 = [&](int kc) {
+        pack_chunk(img, K1, 256, 128, kc * 64, 32, 0, 128);
+        pack_chunk(img, K1, 256, 128, kc * 64 + 32, 32, 0, 128);
+      };
+      W0(0); W0(1); W1(0); W0(2); W1(1); W0(3); W1(2); W1(3);   // the order lrg_tc_head_kernel consumes them in
+      if (img.size() - head_off[h] != kHeadImgFloats) { set_error("internal: head image size"); return LRG_E_INVALID; }
+    }
+    cudaFree(e->d_tc_img);
+    e->d_tc_img = nullptr;
+    LRG_TRY(dev_alloc(&e->d_tc_img, img.size()));
+    LRG_CUDA(cudaMemcpy(e->d_tc_img, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+    TcNet& t = e->tcnet;
+    memset(&t, 0, sizeof(t));
+    t.F = e->F;
+    for (int br = 0; br < 2; ++br) {
+      t.branch_img[br] = e->d_tc_img + branch_off[br];
+      for (int i = 0; i < 5; ++i) t.conv_bias[br][i] = net.conv[br][i].bias;
+    }
+    for (int h = 0; h < 2; ++h) {
+      t.W0g[h] = net.W0g[h];
+      t.head_img[h] = e->d_tc_img + head_off[h];
+      t.head_bias0[h] = net.head0_local[h].bias;
+      t.head_bias1[h] = net.hidden[h][0].bias;
+      t.head_W2[h] = net.out[h].W;
+      t.head_bias2[h] = net.out[h].bias;
+    }
+    LRG_TRY(tc_forward_configure());
+    e->tc_available = true;
+  }
   e->weights_loaded = true;
   return LRG_OK;
 }
@@ -333,7 +447,7 @@ int lrg_forward_device(LrgEngine* e, int B, const float* d_inlier, const float* 
   fa.logits[0] = d_remove_out; fa.logits[1] = d_add_out;
   fa.active = nullptr; fa.active_stride = 0; fa.B = B;
   LRG_CUDA(cudaMemsetAsync(e->d_pooled, 0, sizeof(float) * (size_t)B * 2 * e->net.Clast, st));
-  return launch_forward(e->net, fa, st);
+  return run_forward(e, fa, e->d_gpart, st, nullptr);
 }
 
 int lrg_forward_host(LrgEngine* e, int B, const float* inlier, const float* neighbor, float* add_out, float* remove_out) {
@@ -468,7 +582,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
       LRG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       for (int it = 0; it < kIterPerGraph && rc == LRG_OK; ++it) {
         rc = launch_step(da, st);
-        if (rc == LRG_OK) rc = launch_forward(e->net, fa, st);
+        if (rc == LRG_OK) rc = run_forward(e, fa, e->s_gpart, st, nullptr);
       }
       cudaError_t cerr = cudaStreamEndCapture(st, &graph);
       if (rc != LRG_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -501,8 +615,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
         if (kernel_timing) cudaEventRecord(kev[0], st);
         rc = launch_step(da, st);
         if (rc != LRG_OK) break;
-        if (kernel_timing) rc = launch_forward_timed(e->net, fa, st, kev + 1);
-        else rc = launch_forward(e->net, fa, st);
+        rc = run_forward(e, fa, e->s_gpart, st, kernel_timing ? kev + 1 : nullptr);
         e->iterations += 1; e->launches += 4;
         if (kernel_timing || (e->iterations % 16) == 0) {
           cudaError_t se = cudaStreamSynchronize(st);

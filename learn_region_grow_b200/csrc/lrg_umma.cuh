@@ -1,0 +1,137 @@
+// Thin inline-PTX layer over the sm_100a primitives the tensor-core kernels use: mbarrier, 1-D bulk async copy (TMA
+// without a tensor map), tcgen05 (TMEM allocation, MMA kind::tf32, commit, TMEM load, fences) and the shared-memory
+// matrix / instruction descriptors.  Field layouts follow the PTX ISA "tcgen05 matrix descriptor" / "instruction
+// descriptor" tables (the same bit positions CuTe's UMMA::SmemDescriptor / InstrDescriptor unions encode).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+namespace lrg {
+namespace umma {
+
+// ------------------------------------------------------------------------------------------------ 3xTF32 split
+// x ~= hi + lo with hi = x rounded to nearest TF32 (10 explicit mantissa bits) and lo = (x - hi) rounded to nearest TF32.
+// The tensor core reads only the top 19 bits of each operand (truncation), so both parts are made TF32-exact here:
+// rounding lo to nearest instead of letting the hardware truncate it keeps the residual unbiased.
+// hi.hi + lo.hi + hi.lo then carries ~21 mantissa bits per product.
+__host__ __device__ inline void split_tf32(float x, float& hi, float& lo) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(x);
+  hi = __uint_as_float((u + 0x1000u) & 0xFFFFE000u);
+  lo = __uint_as_float((__float_as_uint(__fsub_rn(x, hi)) + 0x1000u) & 0xFFFFE000u);
+#else
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  memcpy(&hi, &u, 4);
+  lo = x - hi;
+  memcpy(&u, &lo, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  memcpy(&lo, &u, 4);
+#endif
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ------------------------------------------------------------------------------------------------ mbarrier
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Waits for the phase with the given parity to complete.  A wait that lasts longer than ~2 s is a protocol bug: trap
+// (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) asm volatile("trap;");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ async copies / proxies
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// Makes this thread's prior generic-proxy shared-memory writes visible to the async proxy (tensor core / TMA reads).
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ tcgen05
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Whole warp.  ncols: power of two >= 32.  The TMEM base address is written to *dst_smem.
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t tmem, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ncols) : "memory");
+}
+
+// Shared-memory matrix descriptor, no swizzle, K-major canonical layout: core matrix = 8 rows x 16 bytes stored as 128
+// contiguous bytes; lbo = byte distance between core matrices adjacent in K, sbo = between adjacent 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);          // bits [0,14)  start address >> 4
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;     // bits [16,30) leading-dimension byte offset >> 4
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;     // bits [32,46) stride-dimension byte offset >> 4
+  d |= (uint64_t)1 << 46;                                // bits [46,48) descriptor version (1 on sm_100)
+  return d;                                              // base offset 0, lbo mode 0, layout type 0 = SWIZZLE_NONE
+}
+// Instruction descriptor for kind::tf32: D = f32, A = B = tf32, both K-major, dense, no negate.
+__host__ __device__ inline uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, one K-step of 8 tf32 elements; issued by ONE thread for the CTA.
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// The mbarrier receives one arrival when every tcgen05 operation issued so far by this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Warp w%4 reads TMEM lanes 32*(w%4)..+31: thread t gets lane 32*(w%4)+t, 32 consecutive columns starting at the address.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+#endif  // __CUDACC__
+
+}  // namespace umma
+}  // namespace lrg

@@ -6,6 +6,7 @@ a checkpoint or a dict of variables, ``forward`` on host arrays, and -- the part
 ``segment_rooms`` which grows every room on the device without a host round trip per step.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -54,7 +55,7 @@ def pack_weights(tensors, feature_size=13, lite=0):
 
 class Engine:
     def __init__(self, batch_size=1, seq_len=1, num_inlier_points=512, num_neighbor_points=512, feature_size=13,
-                 lite=0, device=0):
+                 lite=0, device=0, forward_mode=None):
         self.lib = _lib.lib()
         _lib.require_gpu()
         self.B = batch_size * seq_len
@@ -66,6 +67,17 @@ class Engine:
                                               num_neighbor_points, self.lite, self.B))
         self._weights = None
         self._room_offsets = None
+        if forward_mode is None:
+            forward_mode = {'': 0, 'auto': 0, 'fma': 1, 'tensor': 2}[os.environ.get('LRG_FORWARD_MODE', '').lower()]
+        if forward_mode:
+            self.set_forward_mode(forward_mode)
+
+    def set_forward_mode(self, mode):
+        """0 auto, 1 fp32-FMA kernels, 2 tcgen05 3xTF32 kernels (full model only)."""
+        _lib.check(self.lib.lrg_engine_set_forward_mode(self._h, int(mode)))
+
+    def forward_mode(self):
+        return self.lib.lrg_engine_forward_mode(self._h)
 
     def close(self):
         if getattr(self, '_h', None) is not None and self._h.value:

@@ -1,0 +1,90 @@
+"""Tensor-core (tcgen05, 3xTF32) forward vs the fp32-FMA kernels and the CPU oracle, through the C ABI.
+
+Stated tolerance: 2e-4 absolute on logits of magnitude <= ~15 against the float64 evaluation of the reference graph
+(learn_region_grow_util.py:106-162) -- the same bar the fp32-FMA kernels are held to (tests/test_forward_gpu.py)."""
+import numpy as np
+import pytest
+
+from oracle import lrg_driver, lrg_forward
+from test_forward_gpu import _driver_tiles
+
+pytestmark = pytest.mark.gpu
+ATOL = 2e-4
+
+
+def _engine(weights, mode, Ni=512, Nj=512, F=13):
+    from learn_region_grow_b200.engine import Engine
+    e = Engine(1, 1, Ni, Nj, F, 0, forward_mode=mode)
+    e.load_weights(weights)
+    return e
+
+
+def test_auto_mode_is_tensor_for_the_full_model(golden_weights):
+    from learn_region_grow_b200 import _lib
+    e = _engine(golden_weights, 0)
+    assert e.forward_mode() == _lib.FORWARD_TENSOR
+    e.close()
+    from learn_region_grow_b200.engine import Engine
+    lite = Engine(1, 1, 512, 512, 13, 1)
+    lite.load_weights(lrg_forward.random_weights(13, 1, seed=1))
+    assert lite.forward_mode() == _lib.FORWARD_FMA
+    with pytest.raises(_lib.LrgError):
+        lite.set_forward_mode(_lib.FORWARD_TENSOR)
+    lite.close()
+
+
+def test_tensor_forward_matches_oracle_and_fma(golden_weights):
+    from learn_region_grow_b200 import _lib
+    inlier, neighbor = _driver_tiles(golden_weights, n_tiles=8)
+    tc, fma = _engine(golden_weights, _lib.FORWARD_TENSOR), _engine(golden_weights, _lib.FORWARD_FMA)
+    add_t, rmv_t = tc.forward(inlier, neighbor)
+    add_f, rmv_f = fma.forward(inlier, neighbor)
+    add64, rmv64 = lrg_forward.forward(golden_weights, inlier, neighbor, dtype=np.float64)
+    err_t = max(np.abs(add_t - add64).max(), np.abs(rmv_t - rmv64).max())
+    err_f = max(np.abs(add_f - add64).max(), np.abs(rmv_f - rmv64).max())
+    print('max |logit - f64|: tensor 3xTF32 %.3e, fp32 FMA %.3e (|logit| max %.2f)' % (err_t, err_f, np.abs(add64).max()))
+    assert err_t < ATOL and err_f < ATOL
+    flips = 0
+    for b in range(len(inlier)):
+        for got, ref, s in ((add_t[b], add64[b], 7), (rmv_t[b], rmv64[b], 8)):
+            u = np.random.RandomState(s).random_sample(512)
+            c_got, c_ref = lrg_driver.confidence(got), lrg_driver.confidence(ref.astype(np.float32))
+            differ = (u < c_got) != (u < c_ref)
+            assert np.all(np.abs(u[differ] - c_ref[differ]) < 1e-4)
+            flips += int(differ.sum())
+    assert flips <= 2
+    tc.close()
+    fma.close()
+
+
+def test_tensor_forward_random_inputs_and_batching(golden_weights):
+    from learn_region_grow_b200 import _lib
+    rng = np.random.RandomState(11)
+    inlier = rng.randn(7, 512, 13).astype(np.float32)
+    neighbor = rng.randn(7, 512, 13).astype(np.float32)
+    tc = _engine(golden_weights, _lib.FORWARD_TENSOR)
+    add, rmv = tc.forward(inlier, neighbor)
+    add64, rmv64 = lrg_forward.forward(golden_weights, inlier, neighbor, dtype=np.float64)
+    scale = max(np.abs(add64).max(), np.abs(rmv64).max())
+    assert np.abs(add - add64).max() < 1e-5 * scale + ATOL and np.abs(rmv - rmv64).max() < 1e-5 * scale + ATOL
+    for b in (0, 3, 6):
+        a1, r1 = tc.forward(inlier[b:b + 1], neighbor[b:b + 1])
+        np.testing.assert_array_equal(a1[0], add[b])
+        np.testing.assert_array_equal(r1[0], rmv[b])
+    tc.close()
+
+
+@pytest.mark.parametrize('F,Ni,Nj', [(9, 256, 256), (6, 128, 128), (12, 512, 256), (13, 200, 77), (16, 512, 512)])
+def test_tensor_forward_shapes(F, Ni, Nj):
+    """feature_size / set-size variants of the full model (test_region_grow.py:70-83), including ragged last tiles."""
+    from learn_region_grow_b200 import _lib
+    w = lrg_forward.random_weights(F, 0, seed=100 + F)
+    e = _engine(w, _lib.FORWARD_TENSOR, Ni, Nj, F)
+    rng = np.random.RandomState(2)
+    inlier = rng.randn(3, Ni, F).astype(np.float32)
+    neighbor = rng.randn(3, Nj, F).astype(np.float32)
+    add, rmv = e.forward(inlier, neighbor)
+    add64, rmv64 = lrg_forward.forward(w, inlier, neighbor, lite=0, dtype=np.float64)
+    assert add.shape == (3, Nj, 2) and rmv.shape == (3, Ni, 2)
+    assert np.abs(add - add64).max() < ATOL and np.abs(rmv - rmv64).max() < ATOL
+    e.close()
