@@ -85,7 +85,9 @@ typedef struct LrgGrowParams {
 
 enum {
   LRG_FLAG_KERNEL_TIMING = 1,  /* time the forward kernels separately with CUDA events (no graph; slower) */
-  LRG_FLAG_NO_GRAPH = 2        /* launch kernels directly instead of replaying a CUDA graph */
+  LRG_FLAG_NO_GRAPH = 2,       /* lock-step loop with direct kernel launches instead of a CUDA graph */
+  LRG_FLAG_LOCKSTEP = 4        /* lock-step loop (one {step, branch, gproj, head} kernel quartet per iteration, CUDA graph)
+                                  instead of the persistent grow kernel; implied by the two flags above and by FMA mode */
 };
 
 typedef struct LrgRoomStats {
@@ -127,6 +129,11 @@ int lrg_segment_rooms_host(LrgEngine* e, int n_rooms, const int64_t* room_offset
  * lock-step iterations it ran and the kernels it launched. */
 int lrg_last_segment_profile(LrgEngine* e, float* grow_ms, float* fill_ms, int64_t* iterations,
                              int64_t* kernel_launches, float* forward_ms);
+
+/* Persistent grow kernel (default when the tensor-core forward is in use): whether the last lrg_segment_resident call
+ * ran as one persistent launch, and per work-item type (step, branch tile, pooled-projection block, head tile) the summed
+ * handler time over all CTAs in ms and the number of items handled. */
+int lrg_last_grow_profile(LrgEngine* e, int* persistent, double busy_ms[4], int64_t items[4]);
 
 /* With LRG_FLAG_KERNEL_TIMING: summed CUDA-event durations (ms) of the four kernels of the lock-step loop over the
  * last lrg_segment_resident call: out[0] step (driver), out[1] branch MLPs, out[2] pooled projection, out[3] heads. */

@@ -41,6 +41,7 @@ assert STEP_TRACE_DTYPE.itemsize == C.sizeof(StepTrace) and ROOM_STATS_DTYPE.ite
 FORWARD_AUTO, FORWARD_FMA, FORWARD_TENSOR = 0, 1, 2
 FLAG_KERNEL_TIMING = 1
 FLAG_NO_GRAPH = 2
+FLAG_LOCKSTEP = 4
 
 _P = C.c_void_p
 _I = C.c_int
@@ -63,6 +64,7 @@ _SIGNATURES = {
     'lrg_segment_rooms_host': (_I, [_P, _I, _P, _P, _P, C.POINTER(GrowParams), _P, _P]),
     'lrg_last_segment_profile': (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int64),
                                       C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
+    'lrg_last_grow_profile': (_I, [_P, C.POINTER(_I), C.POINTER(C.c_double * 4), C.POINTER(C.c_int64 * 4)]),
     'lrg_last_kernel_times': (_I, [_P, C.POINTER(C.c_float * 4)]),
     'lrg_labels_device_ptr': (_I, [_P, _I, C.POINTER(_P)]),
     'lrg_farthest_point_sampling': (_I, [_I, _I, _I, _P, _P, _P, _P]),

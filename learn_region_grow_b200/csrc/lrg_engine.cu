@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "lrg_driver.cuh"
+#include "lrg_persistent.cuh"
 #include "lrg_tc.cuh"
 #include "lrg_umma.cuh"
 
@@ -62,7 +63,6 @@ struct LrgEngine {
   int forward_mode = LRG_FORWARD_AUTO;
   float* d_tc_img = nullptr;
   TcNet tcnet{};
-  float *d_gpart = nullptr, *s_gpart = nullptr;   // pooled-projection partials: user forward / slots
   // forward workspaces for max_batch tile pairs (user-facing forward)
   int ws_batch = 0;
   float *d_x[2] = {nullptr, nullptr}, *d_h1[2] = {nullptr, nullptr}, *d_pooled = nullptr, *d_gproj = nullptr,
@@ -93,6 +93,16 @@ struct LrgEngine {
   int* d_done = nullptr;
   LrgStepTrace* d_trace = nullptr;
   int trace_capacity = 0, trace_rooms = 0;
+  // persistent grow kernel: work queue, per-slot stage counters, busy-time counters
+  int sm_count = 0;
+  unsigned long long* d_qring = nullptr;
+  unsigned q_capacity = 0;
+  unsigned* d_qctr = nullptr;            // [0] head, [1] tail
+  SlotSync* d_sync = nullptr;
+  int sync_slots = 0;
+  unsigned long long* d_busy = nullptr;  // [16]
+  unsigned long long h_busy[16] = {0};
+  bool last_persistent = false;
   // profile of the last segment call
   float grow_ms = 0, fill_ms = 0, forward_ms = 0;
   float kernel_ms[4] = {0, 0, 0, 0};
@@ -125,8 +135,8 @@ static size_t count_weights(const LrgEngine* e) {
 
 static void free_forward_ws(LrgEngine* e) {
   for (int i = 0; i < 2; ++i) { cudaFree(e->d_x[i]); cudaFree(e->d_h1[i]); cudaFree(e->d_logits[i]); e->d_x[i] = e->d_h1[i] = e->d_logits[i] = nullptr; }
-  cudaFree(e->d_pooled); cudaFree(e->d_gproj); cudaFree(e->d_gpart);
-  e->d_pooled = e->d_gproj = e->d_gpart = nullptr;
+  cudaFree(e->d_pooled); cudaFree(e->d_gproj);
+  e->d_pooled = e->d_gproj = nullptr;
   e->ws_batch = 0;
 }
 
@@ -141,7 +151,6 @@ static int ensure_forward_ws(LrgEngine* e, int B) {
   }
   LRG_TRY(dev_alloc(&e->d_pooled, (size_t)B * 2 * e->net.Clast));
   LRG_TRY(dev_alloc(&e->d_gproj, (size_t)B * 2 * e->net.H0));
-  LRG_TRY(dev_alloc(&e->d_gpart, (size_t)kGprojSplits * B * 2 * 256));
   e->ws_batch = B;
   return LRG_OK;
 }
@@ -162,8 +171,7 @@ static void free_slots(LrgEngine* e) {
     cudaFree(e->d_tile[i]); cudaFree(e->d_tileidx[i]); cudaFree(e->s_h1[i]); cudaFree(e->s_logits[i]);
     e->d_tile[i] = nullptr; e->d_tileidx[i] = nullptr; e->s_h1[i] = nullptr; e->s_logits[i] = nullptr;
   }
-  cudaFree(e->s_pooled); cudaFree(e->s_gproj); cudaFree(e->s_gpart);
-  e->s_gpart = nullptr;
+  cudaFree(e->s_pooled); cudaFree(e->s_gproj);
   e->d_slots = nullptr; e->d_listI = e->d_listJ = nullptr; e->d_keyI = e->d_keyJ = nullptr; e->s_pooled = e->s_gproj = nullptr;
   e->n_slots = 0; e->slots_maxN = 0;
 }
@@ -186,7 +194,6 @@ static int ensure_slots(LrgEngine* e, int n_slots) {
   }
   LRG_TRY(dev_alloc(&e->s_pooled, S * 2 * e->net.Clast));
   LRG_TRY(dev_alloc(&e->s_gproj, S * 2 * e->net.H0));
-  LRG_TRY(dev_alloc(&e->s_gpart, (size_t)kGprojSplits * S * 2 * 256));
   e->n_slots = n_slots;
   e->slots_maxN = (int)M;
   return LRG_OK;
@@ -197,8 +204,8 @@ static bool use_tc(const LrgEngine* e) {
 }
 
 // The LrgNet forward over fa.B tile pairs on `stream`: tensor-core kernels for the full model, fp32-FMA kernels otherwise.
-static int run_forward(LrgEngine* e, const ForwardArgs& fa, float* gpart, cudaStream_t stream, cudaEvent_t* ev) {
-  if (use_tc(e)) return launch_forward_tc(e->tcnet, fa, gpart, stream, ev);
+static int run_forward(LrgEngine* e, const ForwardArgs& fa, cudaStream_t stream, cudaEvent_t* ev) {
+  if (use_tc(e)) return launch_forward_tc(e->tcnet, fa, stream, ev);
   return launch_forward_timed(e->net, fa, stream, ev);
 }
 
@@ -250,6 +257,7 @@ int lrg_engine_create(LrgEngine** out, int device, int feature_size, int num_inl
   if (err == cudaSuccess) err = cudaHostAlloc((void**)&e->h_done, sizeof(int), cudaHostAllocMapped);
   if (err == cudaSuccess) err = cudaHostGetDevicePointer((void**)&e->d_done, e->h_done, 0);
   if (err == cudaSuccess) err = cudaMalloc((void**)&e->d_counters, 2 * sizeof(int));
+  if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (err != cudaSuccess) {
     set_error("engine create: %s", cudaGetErrorString(err));
     delete e;
@@ -265,6 +273,7 @@ int lrg_engine_destroy(LrgEngine* e) {
   cudaStreamSynchronize(e->stream);
   free_forward_ws(e); free_rooms(e); free_slots(e);
   cudaFree(e->d_weights); cudaFree(e->d_tc_img); cudaFree(e->d_counters); cudaFree(e->d_trace);
+  cudaFree(e->d_qring); cudaFree(e->d_qctr); cudaFree(e->d_sync); cudaFree(e->d_busy);
   cudaFreeHost(e->h_done);
   cudaStreamDestroy(e->stream);
   delete e;
@@ -424,6 +433,7 @@ int lrg_engine_load_weights(LrgEngine* e, const float* blob, size_t n_floats) {
       t.head_bias2[h] = net.out[h].bias;
     }
     LRG_TRY(tc_forward_configure());
+    LRG_TRY(grow_configure());
     e->tc_available = true;
   }
   e->weights_loaded = true;
@@ -447,7 +457,7 @@ int lrg_forward_device(LrgEngine* e, int B, const float* d_inlier, const float* 
   fa.logits[0] = d_remove_out; fa.logits[1] = d_add_out;
   fa.active = nullptr; fa.active_stride = 0; fa.B = B;
   LRG_CUDA(cudaMemsetAsync(e->d_pooled, 0, sizeof(float) * (size_t)B * 2 * e->net.Clast, st));
-  return run_forward(e, fa, e->d_gpart, st, nullptr);
+  return run_forward(e, fa, st, nullptr);
 }
 
 int lrg_forward_host(LrgEngine* e, int B, const float* inlier, const float* neighbor, float* add_out, float* remove_out) {
@@ -573,16 +583,63 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   for (int i = 0; i < 4; ++i) e->kernel_ms[i] = 0;
   const bool kernel_timing = (params->flags & LRG_FLAG_KERNEL_TIMING) != 0;
   const bool use_graph = !kernel_timing && !(params->flags & LRG_FLAG_NO_GRAPH);
+  const bool persistent = use_tc(e) && use_graph && !(params->flags & LRG_FLAG_LOCKSTEP) && n_slots <= kMaxGrowSlots;
+  e->last_persistent = persistent && n_rooms > 0;
   int rc = LRG_OK;
   if (n_rooms > 0) {
-    if (use_graph) {
+    if (persistent) {
+      // one launch for the whole run: every slot starts with a STEP item, the device queue does the rest
+      unsigned cap = 1024;
+      while (cap < (unsigned)n_slots * 16u + 1024u) cap <<= 1;
+      if (cap > e->q_capacity) {
+        cudaFree(e->d_qring);
+        e->d_qring = nullptr;
+        e->q_capacity = 0;
+        LRG_TRY(dev_alloc(&e->d_qring, cap));
+        e->q_capacity = cap;
+      }
+      if (e->d_qctr == nullptr) LRG_TRY(dev_alloc(&e->d_qctr, 2));
+      if (e->d_busy == nullptr) LRG_TRY(dev_alloc(&e->d_busy, 16));
+      if (n_slots > e->sync_slots) {
+        cudaFree(e->d_sync);
+        e->d_sync = nullptr;
+        e->sync_slots = 0;
+        LRG_TRY(dev_alloc(&e->d_sync, (size_t)n_slots));
+        e->sync_slots = n_slots;
+      }
+      std::vector<unsigned long long> first(n_slots);
+      for (int s = 0; s < n_slots; ++s) first[s] = (1ull << 32) | make_item(ITEM_STEP, s, 0, 0);
+      const unsigned ctr[2] = {0u, (unsigned)n_slots};
+      LRG_CUDA(cudaMemsetAsync(e->d_qring, 0, sizeof(unsigned long long) * e->q_capacity, st));
+      LRG_CUDA(cudaMemcpyAsync(e->d_qring, first.data(), sizeof(unsigned long long) * n_slots, cudaMemcpyHostToDevice, st));
+      LRG_CUDA(cudaMemcpyAsync(e->d_qctr, ctr, sizeof(ctr), cudaMemcpyHostToDevice, st));
+      LRG_CUDA(cudaMemsetAsync(e->d_busy, 0, sizeof(unsigned long long) * 16, st));
+      LRG_CUDA(cudaMemsetAsync(e->d_sync, 0, sizeof(SlotSync) * n_slots, st));
+      GrowArgs ga{};
+      ga.da = da;
+      ga.da.done_flag = nullptr;
+      ga.fa = fa;
+      ga.fa.active = nullptr;
+      ga.net = e->tcnet;
+      ga.q.ring = e->d_qring; ga.q.cap_mask = e->q_capacity - 1; ga.q.head = e->d_qctr; ga.q.tail = e->d_qctr + 1;
+      ga.sync = e->d_sync;
+      ga.busy_ns = e->d_busy;
+      rc = launch_grow(ga, e->sm_count > 0 ? e->sm_count : 148, st);
+      if (rc == LRG_OK) {
+        cudaError_t se = cudaStreamSynchronize(st);
+        if (se != cudaSuccess) { set_error("persistent grow kernel -> %s", cudaGetErrorString(se)); rc = LRG_E_CUDA; }
+      }
+      if (rc == LRG_OK) LRG_CUDA(cudaMemcpy(e->h_busy, e->d_busy, sizeof(e->h_busy), cudaMemcpyDeviceToHost));
+      e->iterations = 0;
+      e->launches = 1;
+    } else if (use_graph) {
       constexpr int kIterPerGraph = 8;
       cudaGraph_t graph = nullptr;
       cudaGraphExec_t exec = nullptr;
       LRG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       for (int it = 0; it < kIterPerGraph && rc == LRG_OK; ++it) {
         rc = launch_step(da, st);
-        if (rc == LRG_OK) rc = run_forward(e, fa, e->s_gpart, st, nullptr);
+        if (rc == LRG_OK) rc = run_forward(e, fa, st, nullptr);
       }
       cudaError_t cerr = cudaStreamEndCapture(st, &graph);
       if (rc != LRG_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -615,7 +672,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
         if (kernel_timing) cudaEventRecord(kev[0], st);
         rc = launch_step(da, st);
         if (rc != LRG_OK) break;
-        rc = run_forward(e, fa, e->s_gpart, st, kernel_timing ? kev + 1 : nullptr);
+        rc = run_forward(e, fa, st, kernel_timing ? kev + 1 : nullptr);
         e->iterations += 1; e->launches += 4;
         if (kernel_timing || (e->iterations % 16) == 0) {
           cudaError_t se = cudaStreamSynchronize(st);
@@ -684,6 +741,17 @@ int lrg_last_segment_profile(LrgEngine* e, float* grow_ms, float* fill_ms, int64
   if (iterations) *iterations = e->iterations;
   if (kernel_launches) *kernel_launches = e->launches;
   if (forward_ms) *forward_ms = e->forward_ms;
+  return LRG_OK;
+}
+
+int lrg_last_grow_profile(LrgEngine* e, int* persistent, double busy_ms[4], int64_t items[4]) {
+  LRG_REQUIRE(e != nullptr, "engine is NULL");
+  if (persistent) *persistent = e->last_persistent ? 1 : 0;
+  const int types[4] = {ITEM_STEP, ITEM_BRANCH, ITEM_GPROJ, ITEM_HEAD};
+  for (int i = 0; i < 4; ++i) {
+    if (busy_ms) busy_ms[i] = e->last_persistent ? (double)e->h_busy[types[i]] * 1e-6 : 0.0;
+    if (items) items[i] = e->last_persistent ? (int64_t)e->h_busy[8 + types[i]] : 0;
+  }
   return LRG_OK;
 }
 

@@ -1,0 +1,157 @@
+// The persistent grow kernel: the whole region-growing run of every uploaded room as ONE launch, one CTA per SM.
+//
+// The lock-step loop (lrg_engine.cu) advances all rooms together, one {step, branch, gproj, head} kernel quartet per
+// iteration, so every iteration costs the slowest room's step plus four launch boundaries, and the run lasts as many
+// iterations as the longest room has steps.  Here each room slot instead walks its own dependency chain
+//
+//     STEP(slot) -> 8 x BRANCH(slot, branch, tile) -> 8 x GPROJ(slot, head, column block) -> 8 x HEAD(slot, head, tile) -> STEP(slot) ...
+//
+// through a device-side work queue: CTAs pop items, run the same device bodies the stand-alone kernels use
+// (lrg_step_body.cuh, lrg_tc_tiles.cuh) and the CTA that retires the last item of a stage publishes the next stage.
+// Items are only published when they are runnable, so a CTA never waits on another item (no deadlock by construction);
+// rooms progress independently (a slow step of one room no longer stalls the others) and nothing is launched per step.
+//
+// Memory ordering: producers finish their global writes, __syncthreads(), then one thread does __threadfence() and
+// the atomic / queue store that publishes; the consumer's popping thread spins on the volatile queue entry, does
+// __threadfence() (acquire: drops stale L1 lines) and the CTA barrier hands the ordering to the other threads.
+// Data produced inside the launch is additionally read with ld.global.cg where it is consumed (never via ld.global.nc).
+#include "lrg_persistent.cuh"
+#include "lrg_step_body.cuh"
+#include "lrg_tc_tiles.cuh"
+
+namespace lrg {
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Multi-producer / multi-consumer ticket ring.  Entry = (generation << 32) | item; generation = ticket / capacity + 1.
+__device__ __forceinline__ void queue_push(const GrowQueue& q, const unsigned* items, int n) {
+  const unsigned t = atomicAdd(q.tail, (unsigned)n);
+  for (int i = 0; i < n; ++i) {
+    const unsigned idx = t + (unsigned)i;
+    const unsigned long long gen = (unsigned long long)(idx / (q.cap_mask + 1u)) + 1ull;
+    *reinterpret_cast<volatile unsigned long long*>(q.ring + (idx & q.cap_mask)) = (gen << 32) | items[i];
+  }
+}
+
+__device__ __forceinline__ unsigned queue_pop(const GrowQueue& q) {
+  const unsigned h = atomicAdd(q.head, 1u);
+  const unsigned long long gen = (unsigned long long)(h / (q.cap_mask + 1u)) + 1ull;
+  const volatile unsigned long long* e = q.ring + (h & q.cap_mask);
+  unsigned long long v = *e;
+  if ((v >> 32) != gen) {
+    const long long t0 = clock64();
+    while (((v = *e) >> 32) != gen) {
+      __nanosleep(100);
+      if (clock64() - t0 > 60000000000ll) asm volatile("trap;");   // ~30 s without work: the run is wedged, fail loudly
+    }
+  }
+  __threadfence();
+  return (unsigned)v;
+}
+
+__global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_constant__ GrowArgs ga) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(16) TcStatic st;
+  __shared__ uint32_t tmem_base;
+  __shared__ unsigned s_item;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 4) tmem_alloc(smem_u32(&tmem_base), kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_base;
+  // the driver's scratch aliases the tensor tiles' activation region: a CTA runs one item at a time
+  StepShared& sh = *reinterpret_cast<StepShared*>(smem);
+  float* const sP = reinterpret_cast<float*>(smem);
+  float* const sR = sP + 1024;
+  const int tilesI = (ga.fa.n_pts[0] + 127) / 128, tilesJ = (ga.fa.n_pts[1] + 127) / 128;
+
+  while (true) {
+    if (tid == 0) s_item = queue_pop(ga.q);
+    __syncthreads();
+    const unsigned item = s_item;
+    const int type = (int)(item & 7u), slot = (int)((item >> 3) & 0x1FFFu), a = (int)((item >> 16) & 15u), t = (int)((item >> 20) & 15u);
+    if (type == ITEM_EXIT) break;
+    const unsigned long long t0 = (tid == 0) ? global_ns() : 0ull;
+    SlotSync* sy = ga.sync + slot;
+    unsigned next[16];
+    int n_next = 0;
+    if (type == ITEM_STEP) {
+      step_body<kGrowThreads>(ga.da, slot, sh);
+      __syncthreads();
+      if (tid == 0) {
+        if (sh.all_done) {
+          // the last slot has retired: nothing is in flight any more, release every CTA
+          for (unsigned left = gridDim.x; left > 0;) {
+            const int n = left > 16u ? 16 : (int)left;
+            for (int i = 0; i < n; ++i) next[i] = make_item(ITEM_EXIT, 0, 0, 0);
+            __threadfence();
+            queue_push(ga.q, next, n);
+            left -= (unsigned)n;
+          }
+        } else if (sh.S.active && !sh.S.finished) {
+          sy->branch_left = tilesI + tilesJ;
+          sy->gproj_left = 8;
+          sy->head_left = tilesI + tilesJ;
+          for (int i = 0; i < tilesI; ++i) next[n_next++] = make_item(ITEM_BRANCH, slot, 0, i);
+          for (int i = 0; i < tilesJ; ++i) next[n_next++] = make_item(ITEM_BRANCH, slot, 1, i);
+        }
+      }
+    } else if (type == ITEM_BRANCH) {
+      tc_branch_tile(ga.net, ga.fa, slot, a, t, smem, st, tmem);
+      if (tid == 0) {
+        __threadfence();
+        if (atomicSub(&sy->branch_left, 1) == 1)
+          for (int h = 0; h < 2; ++h)
+            for (int cb = 0; cb < 4; ++cb) next[n_next++] = make_item(ITEM_GPROJ, slot, h, cb);
+      }
+    } else if (type == ITEM_GPROJ) {
+      tc_gproj_block(ga.net, ga.fa, slot, a, t, sP, sR);
+      if (tid == 0) {
+        __threadfence();
+        if (atomicSub(&sy->gproj_left, 1) == 1) {
+          for (int i = 0; i < tilesI; ++i) next[n_next++] = make_item(ITEM_HEAD, slot, 0, i);
+          for (int i = 0; i < tilesJ; ++i) next[n_next++] = make_item(ITEM_HEAD, slot, 1, i);
+        }
+      }
+    } else if (type == ITEM_HEAD) {
+      tc_head_tile(ga.net, ga.fa, slot, a, t, smem, st, tmem);
+      if (tid == 0) {
+        __threadfence();
+        if (atomicSub(&sy->head_left, 1) == 1) next[n_next++] = make_item(ITEM_STEP, slot, 0, 0);
+      }
+    }
+    if (tid == 0) {
+      if (n_next > 0) {
+        __threadfence();
+        queue_push(ga.q, next, n_next);
+      }
+      if (ga.busy_ns != nullptr) {
+        atomicAdd(ga.busy_ns + type, global_ns() - t0);
+        atomicAdd(ga.busy_ns + 8 + type, 1ull);
+      }
+    }
+    __syncthreads();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, kTmemCols);
+}
+
+int grow_configure() {
+  LRG_CUDA(cudaFuncSetAttribute(lrg_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  return LRG_OK;
+}
+
+int launch_grow(const GrowArgs& ga, int n_ctas, cudaStream_t stream) {
+  static_assert(sizeof(StepShared) <= kActBytes, "driver scratch must fit the activation region it aliases");
+  lrg_grow_kernel<<<n_ctas, kGrowThreads, kTcSmem, stream>>>(ga);
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
+}
+
+}  // namespace lrg

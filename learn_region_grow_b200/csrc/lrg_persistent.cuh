@@ -1,0 +1,38 @@
+// Persistent grow kernel: work items, queue and launch arguments (internal).
+#pragma once
+#include "lrg_driver.cuh"
+#include "lrg_tc.cuh"
+
+namespace lrg {
+
+constexpr int kGrowThreads = 512;
+enum { ITEM_STEP = 1, ITEM_BRANCH = 2, ITEM_GPROJ = 3, ITEM_HEAD = 4, ITEM_EXIT = 7 };
+
+// type: bits [0,3); slot: bits [3,16); a (branch / head index): bits [16,20); t (tile / column block): bits [20,24)
+__host__ __device__ inline unsigned make_item(int type, int slot, int a, int t) {
+  return (unsigned)type | ((unsigned)slot << 3) | ((unsigned)a << 16) | ((unsigned)t << 20);
+}
+constexpr int kMaxGrowSlots = 8192;
+
+struct GrowQueue {
+  unsigned long long* ring;     // capacity entries, zero-initialised; entry = (generation << 32) | item
+  unsigned cap_mask;            // capacity - 1 (capacity is a power of two > the items that can be outstanding)
+  unsigned* head;               // next ticket to pop
+  unsigned* tail;               // next ticket to push
+};
+
+struct SlotSync { int branch_left, gproj_left, head_left, pad; };
+
+struct GrowArgs {
+  DriverArgs da;
+  ForwardArgs fa;
+  TcNet net;
+  GrowQueue q;
+  SlotSync* sync;               // (n_slots)
+  unsigned long long* busy_ns;  // [16]: [type] = summed handler time in ns, [8 + type] = items handled; may be NULL
+};
+
+int grow_configure();
+int launch_grow(const GrowArgs& ga, int n_ctas, cudaStream_t stream);
+
+}  // namespace lrg

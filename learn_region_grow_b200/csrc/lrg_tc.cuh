@@ -6,7 +6,6 @@ namespace lrg {
 
 constexpr int kBranchChunks = 21;   // L0 (8 KB) + L1 + L2 + 2 (L3, K halves) + 16 (L4: 4 column blocks x 4 K quarters), 32 KB each
 constexpr int kHeadChunks = 12;     // 4 x W0 column block [64x64] interleaved with 4 x 2 W1 K-halves [128x32]
-constexpr int kGprojSplits = 16;    // K splits of the pooled projection (1024 = 16 x 64)
 constexpr size_t kBranchImgFloats = 2048 + 20 * 8192;
 constexpr size_t kHeadImgFloats = 12 * 8192;
 
@@ -24,6 +23,6 @@ struct TcNet {
 };
 
 int tc_forward_configure();
-int launch_forward_tc(const TcNet& net, const ForwardArgs& fa, float* gproj_part, cudaStream_t stream, cudaEvent_t* ev);
+int launch_forward_tc(const TcNet& net, const ForwardArgs& fa, cudaStream_t stream, cudaEvent_t* ev);
 
 }  // namespace lrg

@@ -186,8 +186,14 @@ class Engine:
         _lib.check(self.lib.lrg_last_segment_profile(self._h, C.byref(g), C.byref(f), C.byref(it), C.byref(ln), C.byref(fw)))
         k = (C.c_float * 4)()
         _lib.check(self.lib.lrg_last_kernel_times(self._h, C.byref(k)))
+        pers = C.c_int(0)
+        busy = (C.c_double * 4)()
+        items = (C.c_int64 * 4)()
+        _lib.check(self.lib.lrg_last_grow_profile(self._h, C.byref(pers), C.byref(busy), C.byref(items)))
         return dict(grow_ms=g.value, fill_ms=f.value, iterations=it.value, kernel_launches=ln.value, forward_ms=fw.value,
-                    step_kernel_ms=k[0], branch_kernel_ms=k[1], gproj_kernel_ms=k[2], head_kernel_ms=k[3])
+                    step_kernel_ms=k[0], branch_kernel_ms=k[1], gproj_kernel_ms=k[2], head_kernel_ms=k[3],
+                    persistent=bool(pers.value), busy_ms=dict(zip(('step', 'branch', 'gproj', 'head'), busy)),
+                    items=dict(zip(('step', 'branch', 'gproj', 'head'), items)))
 
     def labels_device_ptr(self, filled=True):
         p = C.c_void_p()
