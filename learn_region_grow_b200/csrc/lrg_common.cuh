@@ -64,8 +64,19 @@ struct ForwardArgs {
   float* logits[2];      // [0] remove_output (B, N0, 2), [1] add_output (B, N1, 2)
   const int* active;     // optional (B) flags; NULL = all active
   int active_stride;     // stride in ints between consecutive flags
+  // optional: n_valid[b * n_valid_stride + s] = rows of set s (0 inlier, 1 neighbor) of tile pair b that carry distinct
+  // points; rows beyond are padding duplicates (test_region_grow.py:239-240,251-252) and are not evaluated.  NULL = all rows.
+  const int* n_valid;
+  int n_valid_stride;
   int B;
 };
+
+__device__ __forceinline__ int forward_valid_rows(const ForwardArgs& fa, int b, int s) {
+  const int n = fa.n_pts[s];
+  if (fa.n_valid == nullptr) return n;
+  const int v = __ldcg(fa.n_valid + (size_t)b * fa.n_valid_stride + s);
+  return v < n ? v : n;
+}
 
 int launch_forward(const NetDesc& net, const ForwardArgs& fa, cudaStream_t stream);
 // same launches with an event recorded before the branch kernel and after each of the three kernels (ev[0..3])

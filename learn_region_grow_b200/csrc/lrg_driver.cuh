@@ -41,6 +41,7 @@ struct DriverArgs {
   unsigned* keyJ;
   float* tile[2];               // [0] inlier (n_slots, Ni, F), [1] neighbor (n_slots, Nj, F)
   int* tileidx[2];              // (n_slots, 512) source point of every tile row
+  int* tilesrc[2];              // (n_slots, 512) tile row whose logits row r uses: r itself, or the row it duplicates
   const float* logits[2];       // [0] remove_output (n_slots, Ni, 2), [1] add_output (n_slots, Nj, 2)
   float* pooled;                // (n_slots, pooled_per_slot) zeroed here for the next forward
   int pooled_per_slot;

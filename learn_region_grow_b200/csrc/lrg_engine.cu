@@ -1,6 +1,7 @@
 // Host side of liblrg_b200.so: engine object (weights, workspaces, stream, CUDA graph of the lock-step grow loop) and
 // the extern "C" entry points of include/lrg_b200.h that concern LrgNet and the region-grow driver.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -87,6 +88,7 @@ struct LrgEngine {
   unsigned *d_keyI = nullptr, *d_keyJ = nullptr;
   float* d_tile[2] = {nullptr, nullptr};
   int* d_tileidx[2] = {nullptr, nullptr};
+  int* d_tilesrc[2] = {nullptr, nullptr};
   float *s_h1[2] = {nullptr, nullptr}, *s_pooled = nullptr, *s_gproj = nullptr, *s_logits[2] = {nullptr, nullptr};
   int* d_counters = nullptr;       // [0] next_room, [1] finished_slots
   int* h_done = nullptr;           // mapped pinned
@@ -103,6 +105,7 @@ struct LrgEngine {
   unsigned long long* d_busy = nullptr;  // [16]
   unsigned long long h_busy[16] = {0};
   bool last_persistent = false;
+  unsigned long long* d_tile_dbg = nullptr;   // [32] tile-stage cycle counters (diagnostics, LRG_TILE_TIMING=1)
   // profile of the last segment call
   float grow_ms = 0, fill_ms = 0, forward_ms = 0;
   float kernel_ms[4] = {0, 0, 0, 0};
@@ -168,8 +171,8 @@ static void free_rooms(LrgEngine* e) {
 static void free_slots(LrgEngine* e) {
   cudaFree(e->d_slots); cudaFree(e->d_listI); cudaFree(e->d_listJ); cudaFree(e->d_keyI); cudaFree(e->d_keyJ);
   for (int i = 0; i < 2; ++i) {
-    cudaFree(e->d_tile[i]); cudaFree(e->d_tileidx[i]); cudaFree(e->s_h1[i]); cudaFree(e->s_logits[i]);
-    e->d_tile[i] = nullptr; e->d_tileidx[i] = nullptr; e->s_h1[i] = nullptr; e->s_logits[i] = nullptr;
+    cudaFree(e->d_tile[i]); cudaFree(e->d_tileidx[i]); cudaFree(e->d_tilesrc[i]); cudaFree(e->s_h1[i]); cudaFree(e->s_logits[i]);
+    e->d_tile[i] = nullptr; e->d_tileidx[i] = nullptr; e->d_tilesrc[i] = nullptr; e->s_h1[i] = nullptr; e->s_logits[i] = nullptr;
   }
   cudaFree(e->s_pooled); cudaFree(e->s_gproj);
   e->d_slots = nullptr; e->d_listI = e->d_listJ = nullptr; e->d_keyI = e->d_keyJ = nullptr; e->s_pooled = e->s_gproj = nullptr;
@@ -189,6 +192,7 @@ static int ensure_slots(LrgEngine* e, int n_slots) {
   for (int i = 0; i < 2; ++i) {
     LRG_TRY(dev_alloc(&e->d_tile[i], S * n[i] * e->F));
     LRG_TRY(dev_alloc(&e->d_tileidx[i], S * kMaxTilePts));
+    LRG_TRY(dev_alloc(&e->d_tilesrc[i], S * kMaxTilePts));
     LRG_TRY(dev_alloc(&e->s_h1[i], S * n[i] * e->net.C1));
     LRG_TRY(dev_alloc(&e->s_logits[i], S * n[i] * 2));
   }
@@ -273,7 +277,7 @@ int lrg_engine_destroy(LrgEngine* e) {
   cudaStreamSynchronize(e->stream);
   free_forward_ws(e); free_rooms(e); free_slots(e);
   cudaFree(e->d_weights); cudaFree(e->d_tc_img); cudaFree(e->d_counters); cudaFree(e->d_trace);
-  cudaFree(e->d_qring); cudaFree(e->d_qctr); cudaFree(e->d_sync); cudaFree(e->d_busy);
+  cudaFree(e->d_qring); cudaFree(e->d_qctr); cudaFree(e->d_sync); cudaFree(e->d_busy); cudaFree(e->d_tile_dbg);
   cudaFreeHost(e->h_done);
   cudaStreamDestroy(e->stream);
   delete e;
@@ -432,6 +436,11 @@ int lrg_engine_load_weights(LrgEngine* e, const float* blob, size_t n_floats) {
       t.head_W2[h] = net.out[h].W;
       t.head_bias2[h] = net.out[h].bias;
     }
+    if (getenv("LRG_TILE_TIMING") != nullptr && e->d_tile_dbg == nullptr) {
+      LRG_TRY(dev_alloc(&e->d_tile_dbg, 32));
+      LRG_CUDA(cudaMemset(e->d_tile_dbg, 0, 32 * sizeof(unsigned long long)));
+    }
+    t.dbg = e->d_tile_dbg;
     LRG_TRY(tc_forward_configure());
     LRG_TRY(grow_configure());
     e->tc_available = true;
@@ -563,6 +572,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   da.label = e->d_label; da.order = e->d_order; da.slots = e->d_slots; da.n_slots = n_slots; da.maxN = e->slots_maxN;
   da.listI = e->d_listI; da.listJ = e->d_listJ; da.keyI = e->d_keyI; da.keyJ = e->d_keyJ;
   da.tile[0] = e->d_tile[0]; da.tile[1] = e->d_tile[1]; da.tileidx[0] = e->d_tileidx[0]; da.tileidx[1] = e->d_tileidx[1];
+  da.tilesrc[0] = e->d_tilesrc[0]; da.tilesrc[1] = e->d_tilesrc[1];
   da.logits[0] = e->s_logits[0]; da.logits[1] = e->s_logits[1];
   da.pooled = e->s_pooled; da.pooled_per_slot = 2 * e->net.Clast;
   da.Ni = e->Ni; da.Nj = e->Nj; da.F = e->F;
@@ -578,6 +588,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   fa.pooled = e->s_pooled; fa.gproj = e->s_gproj;
   fa.logits[0] = e->s_logits[0]; fa.logits[1] = e->s_logits[1];
   fa.active = &e->d_slots[0].active; fa.active_stride = (int)(sizeof(SlotState) / sizeof(int)); fa.B = n_slots;
+  fa.n_valid = &e->d_slots[0].n_in; fa.n_valid_stride = fa.active_stride;   // n_in, n_nb are adjacent in SlotState
 
   e->iterations = 0; e->launches = 0; e->forward_ms = 0;
   for (int i = 0; i < 4; ++i) e->kernel_ms[i] = 0;
@@ -752,6 +763,15 @@ int lrg_last_grow_profile(LrgEngine* e, int* persistent, double busy_ms[4], int6
     if (busy_ms) busy_ms[i] = e->last_persistent ? (double)e->h_busy[types[i]] * 1e-6 : 0.0;
     if (items) items[i] = e->last_persistent ? (int64_t)e->h_busy[8 + types[i]] : 0;
   }
+  return LRG_OK;
+}
+
+int lrg_tile_timing(LrgEngine* e, uint64_t out[32], int reset) {
+  LRG_REQUIRE(e != nullptr && out != nullptr, "NULL argument");
+  if (e->d_tile_dbg == nullptr) { set_error("tile timing is off (set LRG_TILE_TIMING=1 before load_weights)"); return LRG_E_STATE; }
+  LRG_CUDA(cudaSetDevice(e->device));
+  LRG_CUDA(cudaMemcpy(out, e->d_tile_dbg, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (reset) LRG_CUDA(cudaMemset(e->d_tile_dbg, 0, 32 * sizeof(uint64_t)));
   return LRG_OK;
 }
 

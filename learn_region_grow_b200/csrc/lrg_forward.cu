@@ -171,9 +171,10 @@ lrg_branch_kernel(const __grid_constant__ NetDesc net, const __grid_constant__ F
   const int b = blockIdx.z, br = blockIdx.y, tile = blockIdx.x;
   if (fa.active != nullptr && fa.active[(size_t)b * fa.active_stride] == 0) return;
   const int n = fa.n_pts[br];
+  const int nv = forward_valid_rows(fa, b, br);
   const int row0 = tile * kTileRows;
-  if (row0 >= n) return;
-  const int rows = min(kTileRows, n - row0);
+  if (row0 >= nv) return;
+  const int rows = min(kTileRows, nv - row0);
   const int tid = threadIdx.x;
 
   extern __shared__ __align__(16) float smem[];
@@ -253,9 +254,10 @@ lrg_head_kernel(const __grid_constant__ NetDesc net, const __grid_constant__ For
   const int b = blockIdx.z, h = blockIdx.y, tile = blockIdx.x;   // h: 0 = remove head on inlier rows, 1 = add head on neighbor rows
   if (fa.active != nullptr && fa.active[(size_t)b * fa.active_stride] == 0) return;
   const int n = fa.n_pts[h];
+  const int nv = forward_valid_rows(fa, b, h);
   const int row0 = tile * kTileRows;
-  if (row0 >= n) return;
-  const int rows = min(kTileRows, n - row0);
+  if (row0 >= nv) return;
+  const int rows = min(kTileRows, nv - row0);
   const int tid = threadIdx.x;
 
   extern __shared__ __align__(16) float smem[];

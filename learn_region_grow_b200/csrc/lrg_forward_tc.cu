@@ -31,7 +31,8 @@ constexpr int kTcThreads = 192;
 __global__ void __launch_bounds__(kTcThreads, 1) lrg_tc_branch_kernel(const __grid_constant__ TcNet net, const __grid_constant__ ForwardArgs fa) {
   const int b = blockIdx.z, br = blockIdx.y, tile = blockIdx.x;
   if (fa.active != nullptr && fa.active[(size_t)b * fa.active_stride] == 0) return;
-  if (tile * 128 >= fa.n_pts[br]) return;
+  const int nvalid = forward_valid_rows(fa, b, br);
+  if (tile * 128 >= nvalid) return;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(16) TcStatic st;
   __shared__ uint32_t tmem_base;
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) lrg_tc_branch_kernel(const __gr
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_base;
-  tc_branch_tile(net, fa, b, br, tile, smem, st, tmem);
+  tc_branch_tile(net, fa, b, br, tile, nvalid, smem, st, tmem);
   if ((threadIdx.x >> 5) == 4) tmem_dealloc(tmem, kTmemCols);
 }
 
@@ -55,7 +56,8 @@ __global__ void __launch_bounds__(512) lrg_tc_gproj_kernel(const __grid_constant
 __global__ void __launch_bounds__(kTcThreads, 1) lrg_tc_head_kernel(const __grid_constant__ TcNet net, const __grid_constant__ ForwardArgs fa) {
   const int b = blockIdx.z, h = blockIdx.y, tile = blockIdx.x;   // h: 0 = remove head on inlier rows, 1 = add head on neighbor rows
   if (fa.active != nullptr && fa.active[(size_t)b * fa.active_stride] == 0) return;
-  if (tile * 128 >= fa.n_pts[h]) return;
+  const int nvalid = forward_valid_rows(fa, b, h);
+  if (tile * 128 >= nvalid) return;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(16) TcStatic st;
   __shared__ uint32_t tmem_base;
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) lrg_tc_head_kernel(const __grid
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_base;
-  tc_head_tile(net, fa, b, h, tile, smem, st, tmem);
+  tc_head_tile(net, fa, b, h, tile, nvalid, smem, st, tmem);
   if ((threadIdx.x >> 5) == 4) tmem_dealloc(tmem, kTmemCols);
 }
 

@@ -64,11 +64,10 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_base;
-  // the driver's scratch aliases the tensor tiles' activation region: a CTA runs one item at a time
+  // the driver scratch aliases the weight ring of the tensor tiles: a CTA runs one item at a time
   StepShared& sh = *reinterpret_cast<StepShared*>(smem);
   float* const sP = reinterpret_cast<float*>(smem);
   float* const sR = sP + 1024;
-  const int tilesI = (ga.fa.n_pts[0] + 127) / 128, tilesJ = (ga.fa.n_pts[1] + 127) / 128;
 
   while (true) {
     if (tid == 0) s_item = queue_pop(ga.q);
@@ -94,15 +93,19 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
             left -= (unsigned)n;
           }
         } else if (sh.S.active && !sh.S.finished) {
+          // only rows that carry distinct points are evaluated (the rest are padding duplicates of them)
+          const int tilesI = (min(sh.S.n_in, ga.fa.n_pts[0]) + 127) / 128, tilesJ = (min(sh.S.n_nb, ga.fa.n_pts[1]) + 127) / 128;
           sy->branch_left = tilesI + tilesJ;
           sy->gproj_left = 8;
           sy->head_left = tilesI + tilesJ;
+          sy->tiles[0] = tilesI;
+          sy->tiles[1] = tilesJ;
           for (int i = 0; i < tilesI; ++i) next[n_next++] = make_item(ITEM_BRANCH, slot, 0, i);
           for (int i = 0; i < tilesJ; ++i) next[n_next++] = make_item(ITEM_BRANCH, slot, 1, i);
         }
       }
     } else if (type == ITEM_BRANCH) {
-      tc_branch_tile(ga.net, ga.fa, slot, a, t, smem, st, tmem);
+      tc_branch_tile(ga.net, ga.fa, slot, a, t, forward_valid_rows(ga.fa, slot, a), smem, st, tmem);
       if (tid == 0) {
         __threadfence();
         if (atomicSub(&sy->branch_left, 1) == 1)
@@ -114,12 +117,13 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
       if (tid == 0) {
         __threadfence();
         if (atomicSub(&sy->gproj_left, 1) == 1) {
+          const int tilesI = __ldcg(&sy->tiles[0]), tilesJ = __ldcg(&sy->tiles[1]);
           for (int i = 0; i < tilesI; ++i) next[n_next++] = make_item(ITEM_HEAD, slot, 0, i);
           for (int i = 0; i < tilesJ; ++i) next[n_next++] = make_item(ITEM_HEAD, slot, 1, i);
         }
       }
     } else if (type == ITEM_HEAD) {
-      tc_head_tile(ga.net, ga.fa, slot, a, t, smem, st, tmem);
+      tc_head_tile(ga.net, ga.fa, slot, a, t, forward_valid_rows(ga.fa, slot, a), smem, st, tmem);
       if (tid == 0) {
         __threadfence();
         if (atomicSub(&sy->head_left, 1) == 1) next[n_next++] = make_item(ITEM_STEP, slot, 0, 0);
@@ -148,7 +152,7 @@ int grow_configure() {
 }
 
 int launch_grow(const GrowArgs& ga, int n_ctas, cudaStream_t stream) {
-  static_assert(sizeof(StepShared) <= kActBytes, "driver scratch must fit the activation region it aliases");
+  static_assert(sizeof(StepShared) <= kTcSmem, "driver scratch must fit the shared memory it aliases");
   lrg_grow_kernel<<<n_ctas, kGrowThreads, kTcSmem, stream>>>(ga);
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;

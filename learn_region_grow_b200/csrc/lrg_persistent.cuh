@@ -21,7 +21,7 @@ struct GrowQueue {
   unsigned* tail;               // next ticket to push
 };
 
-struct SlotSync { int branch_left, gproj_left, head_left, pad; };
+struct SlotSync { int branch_left, gproj_left, head_left, pad; int tiles[2]; int pad2[2]; };
 
 struct GrowArgs {
   DriverArgs da;

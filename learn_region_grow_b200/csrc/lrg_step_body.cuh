@@ -288,7 +288,9 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       bool m = false;
       int p = -1;
       if (r < nrows) {
-        const float2 lg = __ldcg(reinterpret_cast<const float2*>(da.logits[is_add ? 1 : 0] + ((size_t)slot * nrows + r) * 2));
+        // padding rows duplicate a distinct row (:239-240,251-252): same input, same logits, own uniform draw
+        const int src = __ldcg(da.tilesrc[is_add ? 1 : 0] + (size_t)slot * kMaxTilePts + r);
+        const float2 lg = __ldcg(reinterpret_cast<const float2*>(da.logits[is_add ? 1 : 0] + ((size_t)slot * nrows + src) * 2));
         const float conf = confidence(lg.x, lg.y);
         const unsigned draw = philox_draw(da.seed, room_rng, step_rng, is_add ? kStreamAddUniform : kStreamRemoveUniform, r);
         const float u = (float)(draw >> 8) * (1.0f / 16777216.0f);
@@ -560,15 +562,20 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
         const int nrows = is_nb ? da.Nj : da.Ni;
         unsigned crc_term = 0;
         if (r < nrows) {
-          const int p = (is_nb ? listJ : listI)[sh.sel[is_nb ? 1 : 0][r]];
-          const float* row = pts + (size_t)p * 16;
-          float* out = da.tile[is_nb ? 1 : 0] + ((size_t)slot * nrows + r) * da.F;
-          for (int c = 0; c < da.F; ++c) {
-            float v = row[c];
-            if (c < 2 || c >= 6) v = __fsub_rn(v, S.center[c]);
-            out[c] = v;
+          const int nset = is_nb ? n_nb : n_in;
+          const int pos = sh.sel[is_nb ? 1 : 0][r];
+          const int p = (is_nb ? listJ : listI)[pos];
+          if (r < nset) {                                    // a distinct point: materialise its tile row
+            const float* row = pts + (size_t)p * 16;
+            float* out = da.tile[is_nb ? 1 : 0] + ((size_t)slot * nrows + r) * da.F;
+            for (int c = 0; c < da.F; ++c) {
+              float v = row[c];
+              if (c < 2 || c >= 6) v = __fsub_rn(v, S.center[c]);
+              out[c] = v;
+            }
           }
           da.tileidx[is_nb ? 1 : 0][(size_t)slot * kMaxTilePts + r] = p;
+          da.tilesrc[is_nb ? 1 : 0][(size_t)slot * kMaxTilePts + r] = r < nset ? r : pos;   // padding: pos < nset is the row it copies
           crc_term = (unsigned)(r + 1) * (unsigned)p;
         }
         if (tracing) {

@@ -20,6 +20,9 @@ struct TcNet {
   const float* head_bias1[2];       // [128]
   const float* head_W2[2];          // [128][2]
   const float* head_bias2[2];       // [2]
+  // diagnostics (NULL = off): summed clock64 cycles per tile stage, [0..15] branch tile, [16..31] head tile;
+  // the last entry of each half counts tiles
+  unsigned long long* dbg;
 };
 
 int tc_forward_configure();

@@ -4,7 +4,7 @@
 //
 // Calling convention: every thread of the CTA calls the function (blockDim.x >= 192, a multiple of 32); warps 0-3 are the
 // epilogue warps (warp w owns TMEM lanes 32w..32w+31 = tile rows), warp 4 issues the MMAs, warp 5 streams the weights,
-// further warps only take part in the CTA barriers.  `tmem` is the base of 256 allocated TMEM columns.  Data produced by
+// further warps only take part in the CTA barriers.  `tmem` is the base of 512 allocated TMEM columns.  Data produced by
 // other CTAs during the same launch (tiles, h1, pooled, gproj) is read with ld.global.cg, never through the
 // non-coherent path.
 #pragma once
@@ -17,18 +17,26 @@ namespace lrg {
 using namespace umma;
 
 constexpr uint32_t kSlotBytes = 32768;
-constexpr uint32_t kActBytes = 131072;                 // two 64 KB activation regions (or one 128-channel hi/lo pair)
-constexpr uint32_t kTcSmem = kActBytes + 3 * kSlotBytes;
-constexpr uint32_t kKdir = 2048;                       // bytes between K-adjacent core matrices of a 128-row operand
-constexpr uint32_t kMNdir = 128;                       // bytes between 8-row groups
-constexpr uint32_t kTmemCols = 256;
+constexpr int kRingSlots = 6;                          // weight-operand ring: the only dynamic shared memory the tiles use
+constexpr uint32_t kTcSmem = kRingSlots * kSlotBytes;
+constexpr uint32_t kMNdir = 128;                       // bytes between 8-row groups of a K-major operand image
+constexpr uint32_t kTmemCols = 512;
+// Tensor-memory map (columns).  Activations are the A operand of the next layer and live in TMEM (tcgen05.mma with A in
+// tensor memory: A[m][k] = lane m, column base + k; settled by tools/umma_probe.cu), written in place by the epilogue
+// with tcgen05.st: only the weights (B operand) go through shared memory, which halves the shared-memory traffic per
+// MMA and leaves the whole 192 KB ring to the weight stream.
+//   branch: [0,128) / [128,256) accumulator ping-pong; [256,384) activation hi; [384,512) activation lo
+//   head:   [0,64) / [64,128) layer-0 accumulators; [128,256) layer-1 accumulator; [256,320) / [320,384) h1 tile hi / lo;
+//           [384,448) / [448,512) 64-channel slice of the hidden layer hi / lo
+constexpr uint32_t kTmAhi = 256, kTmAlo = 384;
+constexpr uint32_t kTmH1hi = 256, kTmH1lo = 320, kTmChi = 384, kTmClo = 448;
 
 struct TcBarriers {
-  uint64_t full[3], empty[3];
+  uint64_t full[kRingSlots], empty[kRingSlots];
   uint64_t acc_full[2], acc_empty[2];
-  uint64_t act_ready;          // branch: activations of the next layer written; head: h1 tile + sG written
-  uint64_t c_ready, c_free;    // head only
-  uint64_t acc1_full;          // head only
+  uint64_t act_ready;               // branch: activations of the next layer written; head: h1 tile + vec[] written
+  uint64_t c_ready[2], c_free[2];   // head only: the two 32-channel halves of the hidden-layer slice
+  uint64_t acc1_full;               // head only
 };
 constexpr int kTcBarrierCount = sizeof(TcBarriers) / 8;
 
@@ -39,49 +47,72 @@ struct TcStatic {
   float vec[648];
 };
 
-__device__ __forceinline__ void mbar_inval(uint32_t bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
-
-// One weight chunk = hi image + lo image of an [Nc x Kc] K-major operand; D[tmem] (+)= A(hi,lo)[128 x Kc] . chunk^T.
-__device__ __forceinline__ void mma_chunk(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, int Nc, int Kc, uint32_t d_tmem,
-                                          uint32_t idesc, bool first) {
-  const uint32_t b_lo = b_hi + (uint32_t)(Nc * Kc * 4);
-  const uint32_t kdirB = (uint32_t)Nc * 16;
-  uint32_t acc = first ? 0u : 1u;
-#pragma unroll
-  for (int term = 0; term < 3; ++term) {
-    const uint32_t a0 = (term == 1) ? a_lo : a_hi;
-    const uint32_t b0 = (term == 2) ? b_lo : b_hi;
-    for (int ks = 0; ks < Kc / 8; ++ks) {
-      umma_tf32(d_tmem, make_desc(a0 + ks * 2 * kKdir, kKdir, kMNdir), make_desc(b0 + ks * 2 * kdirB, kdirB, kMNdir), idesc, acc);
-      acc = 1u;
-    }
+// diagnostics: thread 0 adds the cycles since *t to dbg[stage] and restarts the interval
+__device__ __forceinline__ void tc_stamp(unsigned long long* dbg, int stage, long long& t) {
+  if (dbg != nullptr && threadIdx.x == 0) {
+    const long long now = clock64();
+    atomicAdd(dbg + stage, (unsigned long long)(now - t));
+    t = now;
   }
 }
 
-// bias + ReLU + hi/lo split of 32 accumulator columns of this thread's row, written as 8 canonical 16-byte chunks.
-__device__ __forceinline__ void store_act32(const uint32_t (&v)[32], const float* s_bias, float* s_hi, float* s_lo, int chunk0,
-                                            int r, float* g_row) {
+__device__ __forceinline__ void mbar_inval(uint32_t bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory"); }
+
+// One weight chunk = hi image + lo image of an [Nc x Kc] K-major operand in shared memory; the activations' hi / lo parts
+// sit in TMEM columns a_hi.. / a_lo..:  D[tmem] (+)= A(hi,lo)[128 x Kc] . chunk^T as hi.hi + lo.hi + hi.lo.
+// Fully unrolled with compile-time shapes: the single issuing thread must sustain one tcgen05.mma per <= 32..64 cycles,
+// so per instruction there is only a descriptor add (the start-address field advances by a constant) left to do.
+template <int Nc, int Kc>
+__device__ __forceinline__ void mma_chunk(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t d_tmem, bool first) {
+  constexpr uint32_t kdirB = (uint32_t)Nc * 16;                 // bytes between K-adjacent core matrices of the image
+  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint64_t bd_hi = make_desc(b_hi, kdirB, kMNdir);
+  const uint64_t bd_lo = make_desc(b_hi + (uint32_t)(Nc * Kc * 4), kdirB, kMNdir);
+#pragma unroll
+  for (int term = 0; term < 3; ++term) {
+    const uint32_t a0 = (term == 1) ? a_lo : a_hi;
+    const uint64_t bd = (term == 2) ? bd_lo : bd_hi;
+#pragma unroll
+    for (int ks = 0; ks < Kc / 8; ++ks)
+      umma_tf32_ts(d_tmem, a0 + ks * 8, bd + (uint64_t)((ks * 2 * kdirB) >> 4), idesc, (term == 0 && ks == 0 && first) ? 0u : 1u);
+  }
+}
+
+// hi = x rounded to TF32; lo = x - hi (exact; the tensor core truncates it to TF32, an error of 2^-23 relative to x)
+__device__ __forceinline__ void split_fast(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  lo = __float_as_uint(__fsub_rn(x, __uint_as_float(hi)));
+}
+
+// bias + ReLU + hi/lo split of 32 accumulator columns of this thread's row, stored as the A operand of the next layer
+// (TMEM columns t_hi.. / t_lo..); optionally mirrored to global memory as fp32.
+__device__ __forceinline__ void store_act32(uint32_t (&v)[32], const float* s_bias, uint32_t t_hi, uint32_t t_lo, float* g_row) {
+  uint32_t lo[32];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(s_bias + q * 4);
-    float4 x, hi, lo;
+    float4 x;
     x.x = fmaxf(__uint_as_float(v[q * 4 + 0]) + b.x, 0.f);
     x.y = fmaxf(__uint_as_float(v[q * 4 + 1]) + b.y, 0.f);
     x.z = fmaxf(__uint_as_float(v[q * 4 + 2]) + b.z, 0.f);
     x.w = fmaxf(__uint_as_float(v[q * 4 + 3]) + b.w, 0.f);
-    split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
-    *reinterpret_cast<float4*>(s_hi + (chunk0 + q) * 512 + r * 4) = hi;
-    *reinterpret_cast<float4*>(s_lo + (chunk0 + q) * 512 + r * 4) = lo;
     if (g_row != nullptr) *reinterpret_cast<float4*>(g_row + q * 4) = x;
+    split_fast(x.x, v[q * 4 + 0], lo[q * 4 + 0]); split_fast(x.y, v[q * 4 + 1], lo[q * 4 + 1]);
+    split_fast(x.z, v[q * 4 + 2], lo[q * 4 + 2]); split_fast(x.w, v[q * 4 + 3], lo[q * 4 + 3]);
   }
+  tmem_st32(t_hi, v);
+  tmem_st32(t_lo, lo);
 }
 
 __device__ __forceinline__ void tc_init_barriers(TcBarriers& bars, bool head) {
-  for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&bars.full[i]), 1); mbar_init(smem_u32(&bars.empty[i]), 1); }
-  for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars.acc_full[i]), 1); mbar_init(smem_u32(&bars.acc_empty[i]), 128); }
+  for (int i = 0; i < kRingSlots; ++i) { mbar_init(smem_u32(&bars.full[i]), 1); mbar_init(smem_u32(&bars.empty[i]), 1); }
+  for (int i = 0; i < 2; ++i) {
+    mbar_init(smem_u32(&bars.acc_full[i]), 1);
+    mbar_init(smem_u32(&bars.acc_empty[i]), 128);
+    mbar_init(smem_u32(&bars.c_ready[i]), 128);
+    mbar_init(smem_u32(&bars.c_free[i]), 1);
+  }
   mbar_init(smem_u32(&bars.act_ready), head ? 128 + 32 : 128);   // head: 128 rows of h1 + the 32 loader lanes that fill vec[]
-  mbar_init(smem_u32(&bars.c_ready), 128);
-  mbar_init(smem_u32(&bars.c_free), 1);
   mbar_init(smem_u32(&bars.acc1_full), 1);
   fence_barrier_init();
 }
@@ -90,19 +121,33 @@ __device__ __forceinline__ void tc_inval_barriers(TcBarriers& bars) {
   for (int i = 0; i < kTcBarrierCount; ++i) mbar_inval(smem_u32(p + i));
 }
 
+// Weight loader (one thread): streams chunks [first, n_chunks) of the operand image through the ring; chunk 0 may be short.
+__device__ __forceinline__ void tc_stream_weights(TcBarriers& bars, uint32_t ring_u32, const float* img, int first, int n_chunks,
+                                                  uint32_t bytes0) {
+  size_t off = 0;
+  for (int i = 0; i < first; ++i) off += ((i == 0) ? bytes0 : kSlotBytes) / 4;
+  for (int i = first; i < n_chunks; ++i) {
+    const int slot = i % kRingSlots;
+    const uint32_t bytes = (i == 0) ? bytes0 : kSlotBytes;
+    mbar_wait(smem_u32(&bars.empty[slot]), ((uint32_t)(i / kRingSlots) & 1u) ^ 1u);
+    mbar_expect_tx(smem_u32(&bars.full[slot]), bytes);
+    bulk_g2s(ring_u32 + slot * kSlotBytes, img + off, bytes, smem_u32(&bars.full[slot]));
+    off += bytes / 4;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------ branch tile
 // x (rows x F) -> 64 -> 64 -> 64 -> 128 -> 512 -> column max merged into pooled (learn_region_grow_util.py:106-123).
-__device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardArgs& fa, int b, int br, int tile,
+__device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardArgs& fa, int b, int br, int tile, int nvalid,
                                                unsigned char* smem, TcStatic& st, uint32_t tmem) {
   const int n = fa.n_pts[br];
   const int row0 = tile * 128;
-  const int rows = min(128, n - row0);
+  const int rows = min(128, nvalid - row0);       // rows >= nvalid are padding duplicates: never read, never pooled
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   TcBarriers& bars = st.bars;
-  float* const act = reinterpret_cast<float*>(smem);
-  const uint32_t act_u32 = smem_u32(smem);
-  const uint32_t ring_u32 = act_u32 + kActBytes;
+  const uint32_t ring_u32 = smem_u32(smem);
 
+  long long tstamp = clock64();
   if (tid == 0) tc_init_barriers(bars, false);
   if (tid >= 192 && tid < 192 + 80) {                  // biases of layers 0-3 (64,64,64,128) -> st.vec[0..320)
     const int i = (tid - 192) * 4;
@@ -116,32 +161,28 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
     *reinterpret_cast<float4*>(&st.vec[i]) = __ldg(reinterpret_cast<const float4*>(net.conv_bias[br][l] + o));
   }
   __syncthreads();
-
-  // activation regions (float offsets): 64-channel tensors use hi = region, lo = region + 8192 floats (32 KB);
-  // x (16 channels) uses hi = 0, lo = 2048 floats; h3 (128 channels) uses hi = 0, lo = 16384 floats (64 KB).
-  constexpr int kR0 = 0, kR1 = 16384, kLo64 = 8192, kLoX = 2048, kLo128 = 16384;
+  tc_stamp(net.dbg, 0, tstamp);
 
   if (warp < 4) {
-    // ===================================================================== epilogue warps: thread = tile row
+    // ===================================================================== epilogue warps: thread = tile row = TMEM lane
     const int r = tid;
     const bool valid = r < rows;
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
     {
       const float* xrow = fa.x[br] + ((size_t)b * n + row0 + r) * net.F;
-      float xv[16];
+      uint32_t hi[32], lo[32];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) xv[c] = (valid && c < net.F) ? __ldcg(xrow + c) : 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float4 hi, lo;
-        split_tf32(xv[q * 4 + 0], hi.x, lo.x); split_tf32(xv[q * 4 + 1], hi.y, lo.y);
-        split_tf32(xv[q * 4 + 2], hi.z, lo.z); split_tf32(xv[q * 4 + 3], hi.w, lo.w);
-        *reinterpret_cast<float4*>(act + kR0 + q * 512 + r * 4) = hi;
-        *reinterpret_cast<float4*>(act + kR0 + kLoX + q * 512 + r * 4) = lo;
+      for (int c = 0; c < 32; ++c) {
+        const float xv = (c < 16 && valid && c < net.F) ? __ldcg(xrow + c) : 0.f;
+        split_fast(xv, hi[c], lo[c]);
       }
-      fence_proxy_async();
+      tmem_st32(tlane + kTmAhi, hi);
+      tmem_st32(tlane + kTmAlo, lo);
+      tmem_st_wait();
+      tcgen05_fence_before();
       mbar_arrive(smem_u32(&bars.act_ready));
+      tc_stamp(net.dbg, 1, tstamp);
     }
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
     float* g_h1 = valid ? fa.h1[br] + ((size_t)b * n + row0 + r) * 64 : nullptr;
 #pragma unroll 1
     for (int l = 0; l < 4; ++l) {
@@ -149,19 +190,18 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
       mbar_wait(smem_u32(&bars.acc_full[buf]), (uint32_t)(l >> 1) & 1u);
       tcgen05_fence_after();
       const int N = (l == 3) ? 128 : 64;
-      float* s_hi = act + ((l == 0 || l == 2) ? kR1 : kR0);
-      float* s_lo = s_hi + ((l == 3) ? kLo128 : kLo64);
       const float* s_bias = st.vec + l * 64;
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tlane + buf * 128 + c0, v);
         tmem_ld_wait();
-        store_act32(v, s_bias + c0, s_hi, s_lo, c0 / 4, r, (l == 1 && g_h1 != nullptr) ? g_h1 + c0 : nullptr);
+        store_act32(v, s_bias + c0, tlane + kTmAhi + c0, tlane + kTmAlo + c0, (l == 1 && g_h1 != nullptr) ? g_h1 + c0 : nullptr);
       }
+      tmem_st_wait();
       tcgen05_fence_before();
       mbar_arrive(smem_u32(&bars.acc_empty[buf]));
-      fence_proxy_async();
       mbar_arrive(smem_u32(&bars.act_ready));
+      tc_stamp(net.dbg, 2 + l, tstamp);
     }
     // last layer: column max over the tile's rows, bias and ReLU after the max (both monotone)
     int* gmax = reinterpret_cast<int*>(fa.pooled) + (size_t)b * 1024 + br * 512;
@@ -198,65 +238,71 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
       }
       tcgen05_fence_before();
       mbar_arrive(smem_u32(&bars.acc_empty[buf]));
+      tc_stamp(net.dbg, 6 + nb, tstamp);
     }
   } else if (warp == 4) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc64 = make_idesc_tf32(128, 64), idesc128 = make_idesc_tf32(128, 128);
       int chunk = 0;
-      auto next_chunk = [&](uint32_t a_hi, uint32_t a_lo, int Nc, int Kc, uint32_t d, uint32_t idesc, bool first) {
-        const int slot = chunk % 3;
-        mbar_wait(smem_u32(&bars.full[slot]), (uint32_t)(chunk / 3) & 1u);
+      long long w_full = 0, w_acc = 0, w_act = 0;      // diagnostics: cycles this thread waited for weights / TMEM / activations
+      const bool timing = net.dbg != nullptr;
+      auto timed_wait = [&](uint32_t bar, uint32_t parity, long long& acc) {
+        if (timing) { const long long t0 = clock64(); mbar_wait(bar, parity); acc += clock64() - t0; }
+        else mbar_wait(bar, parity);
+      };
+      auto wait_chunk = [&]() {
+        const int slot = chunk % kRingSlots;
+        timed_wait(smem_u32(&bars.full[slot]), (uint32_t)(chunk / kRingSlots) & 1u, w_full);
         tcgen05_fence_after();
-        mma_chunk(a_hi, a_lo, ring_u32 + slot * kSlotBytes, Nc, Kc, d, idesc, first);
-        umma_commit(smem_u32(&bars.empty[slot]));
+        return ring_u32 + slot * kSlotBytes;
+      };
+      auto done_chunk = [&]() {
+        umma_commit(smem_u32(&bars.empty[chunk % kRingSlots]));
         ++chunk;
       };
-      const uint32_t R0 = act_u32, R1 = act_u32 + kR1 * 4;
+      const uint32_t a_hi = tmem + kTmAhi, a_lo = tmem + kTmAlo;
       for (int l = 0; l < 4; ++l) {
         const int buf = l & 1;
-        mbar_wait(smem_u32(&bars.act_ready), (uint32_t)l & 1u);
-        mbar_wait(smem_u32(&bars.acc_empty[buf]), ((uint32_t)(l >> 1) & 1u) ^ 1u);
+        timed_wait(smem_u32(&bars.act_ready), (uint32_t)l & 1u, w_act);
+        timed_wait(smem_u32(&bars.acc_empty[buf]), ((uint32_t)(l >> 1) & 1u) ^ 1u, w_acc);
         tcgen05_fence_after();
         const uint32_t d = tmem + buf * 128;
-        if (l == 0) next_chunk(R0, R0 + kLoX * 4, 64, 16, d, idesc64, true);
-        else if (l == 1) next_chunk(R1, R1 + kLo64 * 4, 64, 64, d, idesc64, true);
-        else if (l == 2) next_chunk(R0, R0 + kLo64 * 4, 64, 64, d, idesc64, true);
+        if (l == 0) { mma_chunk<64, 16>(a_hi, a_lo, wait_chunk(), d, true); done_chunk(); }
+        else if (l < 3) { mma_chunk<64, 64>(a_hi, a_lo, wait_chunk(), d, true); done_chunk(); }
         else {
-          next_chunk(R1, R1 + kLo64 * 4, 128, 32, d, idesc128, true);
-          next_chunk(R1 + 8 * kKdir, R1 + kLo64 * 4 + 8 * kKdir, 128, 32, d, idesc128, false);
+          mma_chunk<128, 32>(a_hi, a_lo, wait_chunk(), d, true); done_chunk();
+          mma_chunk<128, 32>(a_hi + 32, a_lo + 32, wait_chunk(), d, false); done_chunk();
         }
         umma_commit(smem_u32(&bars.acc_full[buf]));
       }
-      mbar_wait(smem_u32(&bars.act_ready), 0u);        // h3 (fifth completion of act_ready)
+      timed_wait(smem_u32(&bars.act_ready), 0u, w_act);   // h3 (fifth completion of act_ready)
       tcgen05_fence_after();
       for (int nb = 0; nb < 4; ++nb) {
         const int j = 4 + nb, buf = nb & 1;
-        mbar_wait(smem_u32(&bars.acc_empty[buf]), ((uint32_t)(j >> 1) & 1u) ^ 1u);
+        timed_wait(smem_u32(&bars.acc_empty[buf]), ((uint32_t)(j >> 1) & 1u) ^ 1u, w_acc);
         tcgen05_fence_after();
-        for (int kc = 0; kc < 4; ++kc)
-          next_chunk(act_u32 + kc * 8 * kKdir, act_u32 + kLo128 * 4 + kc * 8 * kKdir, 128, 32, tmem + buf * 128, idesc128, kc == 0);
+#pragma unroll 1
+        for (int kc = 0; kc < 4; ++kc) {
+          mma_chunk<128, 32>(a_hi + kc * 32, a_lo + kc * 32, wait_chunk(), tmem + buf * 128, kc == 0);
+          done_chunk();
+        }
         umma_commit(smem_u32(&bars.acc_full[buf]));
+      }
+      if (timing) {
+        atomicAdd(net.dbg + 11, (unsigned long long)w_full);
+        atomicAdd(net.dbg + 12, (unsigned long long)w_acc);
+        atomicAdd(net.dbg + 13, (unsigned long long)w_act);
       }
     }
   } else if (warp == 5) {
     // ===================================================================== weight loader
-    if (lane == 0) {
-      const float* img = net.branch_img[br];
-      size_t off = 0;
-      for (int i = 0; i < kBranchChunks; ++i) {
-        const int slot = i % 3;
-        const uint32_t bytes = (i == 0) ? 8192u : kSlotBytes;
-        mbar_wait(smem_u32(&bars.empty[slot]), ((uint32_t)(i / 3) & 1u) ^ 1u);
-        mbar_expect_tx(smem_u32(&bars.full[slot]), bytes);
-        bulk_g2s(ring_u32 + slot * kSlotBytes, img + off, bytes, smem_u32(&bars.full[slot]));
-        off += bytes / 4;
-      }
-    }
+    if (lane == 0) tc_stream_weights(bars, ring_u32, net.branch_img[br], 0, kBranchChunks, 8192u);
   }
   tcgen05_fence_before();
   __syncthreads();
   if (tid == 0) tc_inval_barriers(bars);
+  tc_stamp(net.dbg, 10, tstamp);
+  if (net.dbg != nullptr && tid == 0) atomicAdd(net.dbg + 15, 1ull);
 }
 
 // ------------------------------------------------------------------------------------------------------ pooled projection
@@ -265,15 +311,30 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
 __device__ __forceinline__ void tc_gproj_block(const TcNet& net, const ForwardArgs& fa, int b, int h, int cb, float* sP, float* sR) {
   const int tid = threadIdx.x, col = tid & 63, kg = tid >> 6;
   for (int i = tid; i < 1024; i += 512) sP[i] = __ldcg(fa.pooled + (size_t)b * 1024 + i);
-  __syncthreads();
   const float* W = net.W0g[h] + (size_t)(kg * 128) * 256 + cb * 64 + col;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll 4
-  for (int k = 0; k < 128; k += 4) {
-    acc0 = fmaf(sP[kg * 128 + k + 0], __ldg(W + (size_t)(k + 0) * 256), acc0);
-    acc1 = fmaf(sP[kg * 128 + k + 1], __ldg(W + (size_t)(k + 1) * 256), acc1);
-    acc2 = fmaf(sP[kg * 128 + k + 2], __ldg(W + (size_t)(k + 2) * 256), acc2);
-    acc3 = fmaf(sP[kg * 128 + k + 3], __ldg(W + (size_t)(k + 3) * 256), acc3);
+  float w[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) w[i] = __ldg(W + (size_t)i * 256);      // first quarter in flight while pooled lands
+  __syncthreads();
+#pragma unroll 1
+  for (int k0 = 0; k0 < 128; k0 += 32) {
+    float wn[32];
+    if (k0 + 32 < 128) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) wn[i] = __ldg(W + (size_t)(k0 + 32 + i) * 256);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      acc0 = fmaf(sP[kg * 128 + k0 + i + 0], w[i + 0], acc0);
+      acc1 = fmaf(sP[kg * 128 + k0 + i + 1], w[i + 1], acc1);
+      acc2 = fmaf(sP[kg * 128 + k0 + i + 2], w[i + 2], acc2);
+      acc3 = fmaf(sP[kg * 128 + k0 + i + 3], w[i + 3], acc3);
+    }
+    if (k0 + 32 < 128) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) w[i] = wn[i];
+    }
   }
   sR[kg * 64 + col] = (acc0 + acc1) + (acc2 + acc3);
   __syncthreads();
@@ -288,59 +349,74 @@ __device__ __forceinline__ void tc_gproj_block(const TcNet& net, const ForwardAr
 
 // ------------------------------------------------------------------------------------------------------ head tile
 // [gproj row as bias] + h1 . W0[1024:] -> ReLU -> 256 -> 128 -> ReLU -> 2 (learn_region_grow_util.py:138-162).
-__device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs& fa, int b, int h, int tile,
+// The 256-wide hidden layer is produced as four 64-channel slices; each slice is handed to the 256->128 layer as two
+// 32-channel K-chunks the moment its epilogue has written them (c_ready / c_free per half).
+__device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs& fa, int b, int h, int tile, int nvalid,
                                              unsigned char* smem, TcStatic& st, uint32_t tmem) {
   const int n = fa.n_pts[h];
   const int row0 = tile * 128;
-  const int rows = min(128, n - row0);
+  const int rows = min(128, nvalid - row0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   TcBarriers& bars = st.bars;
-  float* const act = reinterpret_cast<float*>(smem);
-  const uint32_t act_u32 = smem_u32(smem);
-  const uint32_t ring_u32 = act_u32 + kActBytes;
-  constexpr int kA0 = 0, kC = 16384, kLo64 = 8192;
+  const uint32_t ring_u32 = smem_u32(smem);
   float* const sG = st.vec;            // [256] bias0 + pooled . W0[:1024]
   float* const sB1 = st.vec + 256;     // [128]
   float* const sW2 = st.vec + 384;     // [128][2]
   float* const sB2 = st.vec + 640;     // [2]
 
+  long long tstamp = clock64();
   if (tid == 0) tc_init_barriers(bars, true);
   __syncthreads();
+  tc_stamp(net.dbg, 16, tstamp);
 
   if (warp < 4) {
     const int r = tid;
     const bool valid = r < rows;
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
     {
       const float4* hrow = reinterpret_cast<const float4*>(fa.h1[h] + ((size_t)b * n + row0 + r) * 64);
-#pragma unroll 4
-      for (int q = 0; q < 16; ++q) {
-        float4 x = valid ? __ldcg(hrow + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 hi, lo;
-        split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
-        *reinterpret_cast<float4*>(act + kA0 + q * 512 + r * 4) = hi;
-        *reinterpret_cast<float4*>(act + kA0 + kLo64 + q * 512 + r * 4) = lo;
+      float4 x[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) x[q] = valid ? __ldcg(hrow + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 v = x[half * 8 + q];
+          split_fast(v.x, hi[q * 4 + 0], lo[q * 4 + 0]); split_fast(v.y, hi[q * 4 + 1], lo[q * 4 + 1]);
+          split_fast(v.z, hi[q * 4 + 2], lo[q * 4 + 2]); split_fast(v.w, hi[q * 4 + 3], lo[q * 4 + 3]);
+        }
+        tmem_st32(tlane + kTmH1hi + half * 32, hi);
+        tmem_st32(tlane + kTmH1lo + half * 32, lo);
       }
-      fence_proxy_async();
+      tmem_st_wait();
+      tcgen05_fence_before();
       mbar_arrive(smem_u32(&bars.act_ready));
     }
     mbar_wait(smem_u32(&bars.act_ready), 0u);          // st.vec is complete as well
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    tc_stamp(net.dbg, 17, tstamp);
 #pragma unroll 1
     for (int nb = 0; nb < 4; ++nb) {
       const int buf = nb & 1;
       mbar_wait(smem_u32(&bars.acc_full[buf]), (uint32_t)(nb >> 1) & 1u);
-      if (nb >= 1) mbar_wait(smem_u32(&bars.c_free), (uint32_t)(nb - 1) & 1u);   // H1(nb-1) has consumed the C buffer
       tcgen05_fence_after();
-      for (int c0 = 0; c0 < 64; c0 += 32) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
-        tmem_ld32(tlane + buf * 64 + c0, v);
+        tmem_ld32(tlane + buf * 64 + half * 32, v);
         tmem_ld_wait();
-        store_act32(v, sG + nb * 64 + c0, act + kC, act + kC + kLo64, c0 / 4, r, nullptr);
+        if (nb >= 1) {                                 // the previous slice's K-chunk of this half has been consumed
+          mbar_wait(smem_u32(&bars.c_free[half]), (uint32_t)(nb - 1) & 1u);
+          tcgen05_fence_after();
+        }
+        store_act32(v, sG + nb * 64 + half * 32, tlane + kTmChi + half * 32, tlane + kTmClo + half * 32, nullptr);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        if (half == 1) mbar_arrive(smem_u32(&bars.acc_empty[buf]));
+        mbar_arrive(smem_u32(&bars.c_ready[half]));
       }
-      tcgen05_fence_before();
-      mbar_arrive(smem_u32(&bars.acc_empty[buf]));
-      fence_proxy_async();
-      mbar_arrive(smem_u32(&bars.c_ready));
+      tc_stamp(net.dbg, 18 + nb, tstamp);
     }
     // hidden layer 2 (+bias, ReLU) and the 128 -> 2 output layer in registers (util.py:145-149 / :158-162)
     mbar_wait(smem_u32(&bars.acc1_full), 0u);
@@ -359,32 +435,37 @@ __device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs
       }
     }
     if (valid) *reinterpret_cast<float2*>(fa.logits[h] + ((size_t)b * n + row0 + r) * 2) = make_float2(o0, o1);
+    tc_stamp(net.dbg, 22, tstamp);
   } else if (warp == 4) {
     if (lane == 0) {
-      const uint32_t idesc64 = make_idesc_tf32(128, 64), idesc128 = make_idesc_tf32(128, 128);
       int chunk = 0;
-      auto next_chunk = [&](uint32_t a_hi, uint32_t a_lo, int Nc, int Kc, uint32_t d, uint32_t idesc, bool first) {
-        const int slot = chunk % 3;
-        mbar_wait(smem_u32(&bars.full[slot]), (uint32_t)(chunk / 3) & 1u);
+      auto wait_chunk = [&]() {
+        const int slot = chunk % kRingSlots;
+        mbar_wait(smem_u32(&bars.full[slot]), (uint32_t)(chunk / kRingSlots) & 1u);
         tcgen05_fence_after();
-        mma_chunk(a_hi, a_lo, ring_u32 + slot * kSlotBytes, Nc, Kc, d, idesc, first);
-        umma_commit(smem_u32(&bars.empty[slot]));
+        return ring_u32 + slot * kSlotBytes;
+      };
+      auto done_chunk = [&]() {
+        umma_commit(smem_u32(&bars.empty[chunk % kRingSlots]));
         ++chunk;
       };
-      const uint32_t A0 = act_u32 + kA0 * 4, Cb = act_u32 + kC * 4;
       auto H0 = [&](int nb) {
         const int buf = nb & 1;
         mbar_wait(smem_u32(&bars.acc_empty[buf]), ((uint32_t)(nb >> 1) & 1u) ^ 1u);
         tcgen05_fence_after();
-        next_chunk(A0, A0 + kLo64 * 4, 64, 64, tmem + buf * 64, idesc64, true);
+        mma_chunk<64, 64>(tmem + kTmH1hi, tmem + kTmH1lo, wait_chunk(), tmem + buf * 64, true);
+        done_chunk();
         umma_commit(smem_u32(&bars.acc_full[buf]));
       };
       auto H1 = [&](int kc) {
-        mbar_wait(smem_u32(&bars.c_ready), (uint32_t)kc & 1u);
-        tcgen05_fence_after();
-        next_chunk(Cb, Cb + kLo64 * 4, 128, 32, tmem + 128, idesc128, kc == 0);
-        next_chunk(Cb + 8 * kKdir, Cb + kLo64 * 4 + 8 * kKdir, 128, 32, tmem + 128, idesc128, false);
-        umma_commit(smem_u32(&bars.c_free));
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(smem_u32(&bars.c_ready[half]), (uint32_t)kc & 1u);
+          tcgen05_fence_after();
+          mma_chunk<128, 32>(tmem + kTmChi + half * 32, tmem + kTmClo + half * 32, wait_chunk(), tmem + 128, kc == 0 && half == 0);
+          done_chunk();
+          umma_commit(smem_u32(&bars.c_free[half]));
+        }
         if (kc == 3) umma_commit(smem_u32(&bars.acc1_full));
       };
       mbar_wait(smem_u32(&bars.act_ready), 0u);
@@ -395,29 +476,34 @@ __device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs
     // loader warp: first fill the ring, then stage the small vectors, then keep the ring fed
     const float* img = net.head_img[h];
     if (lane == 0) {
-      for (int i = 0; i < 3; ++i) {
+      for (int i = 0; i < kRingSlots; ++i) {
         mbar_expect_tx(smem_u32(&bars.full[i]), kSlotBytes);
         bulk_g2s(ring_u32 + i * kSlotBytes, img + (size_t)i * (kSlotBytes / 4), kSlotBytes, smem_u32(&bars.full[i]));
       }
     }
     const float* g = fa.gproj + ((size_t)b * 2 + h) * 256;
-    for (int c = lane; c < 256; c += 32) sG[c] = __ldcg(g + c);
-    for (int c = lane; c < 128; c += 32) sB1[c] = __ldg(net.head_bias1[h] + c);
-    for (int c = lane; c < 256; c += 32) sW2[c] = __ldg(net.head_W2[h] + c);
+    float tg[8], tb[4], tw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tg[i] = __ldcg(g + lane + 32 * i);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tb[i] = __ldg(net.head_bias1[h] + lane + 32 * i);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tw[i] = __ldg(net.head_W2[h] + lane + 32 * i);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sG[lane + 32 * i] = tg[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sB1[lane + 32 * i] = tb[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sW2[lane + 32 * i] = tw[i];
     if (lane < 2) sB2[lane] = __ldg(net.head_bias2[h] + lane);
     mbar_arrive(smem_u32(&bars.act_ready));
-    if (lane == 0) {
-      for (int i = 3; i < kHeadChunks; ++i) {
-        const int slot = i % 3;
-        mbar_wait(smem_u32(&bars.empty[slot]), ((uint32_t)(i / 3) & 1u) ^ 1u);
-        mbar_expect_tx(smem_u32(&bars.full[slot]), kSlotBytes);
-        bulk_g2s(ring_u32 + slot * kSlotBytes, img + (size_t)i * (kSlotBytes / 4), kSlotBytes, smem_u32(&bars.full[slot]));
-      }
-    }
+    if (lane == 0) tc_stream_weights(bars, ring_u32, img, kRingSlots, kHeadChunks, kSlotBytes);
   }
   tcgen05_fence_before();
   __syncthreads();
   if (tid == 0) tc_inval_barriers(bars);
+  tc_stamp(net.dbg, 23, tstamp);
+  if (net.dbg != nullptr && tid == 0) atomicAdd(net.dbg + 31, 1ull);
 }
 
 }  // namespace lrg

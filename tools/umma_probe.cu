@@ -21,7 +21,7 @@ struct ProbeArgs {
   const float* A;      // [128][K] row-major fp32
   const float* Bimg;   // hi image then lo image, canonical layout, N*K floats each
   float* D;            // [128][N]
-  int K, N, variant, terms;
+  int K, N, variant, terms;   // variant 0: A from shared memory; variant 2: A from tensor memory (written with tcgen05.st)
 };
 
 __global__ void __launch_bounds__(192, 1) probe_kernel(ProbeArgs pa) {
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(192, 1) probe_kernel(ProbeArgs pa) {
     mbar_init(bar_d, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(&tmem_base_smem), 128);
+  if (warp == 4) tmem_alloc(smem_u32(&tmem_base_smem), 256);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -55,6 +55,21 @@ __global__ void __launch_bounds__(192, 1) probe_kernel(ProbeArgs pa) {
       split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
       *reinterpret_cast<float4*>(sA_hi + k4 * 512 + r * 4) = hi;
       *reinterpret_cast<float4*>(sA_lo + k4 * 512 + r * 4) = lo;
+    }
+    if (pa.variant == 2) {
+      // A operand in TMEM: hi at columns 128.., lo at columns 192.. (K <= 64), thread = row = lane
+      for (int k0 = 0; k0 < K; k0 += 32) {
+        uint32_t vh[32], vl[32];
+        for (int j = 0; j < 32; ++j) {
+          float hi = 0.f, lo = 0.f;
+          if (k0 + j < K) split_tf32(pa.A[(size_t)r * K + k0 + j], hi, lo);
+          vh[j] = __float_as_uint(hi); vl[j] = __float_as_uint(lo);
+        }
+        tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + 128 + k0, vh);
+        tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + 192 + k0, vl);
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
     }
     fence_proxy_async();
     mbar_arrive(bar_a);
@@ -87,10 +102,9 @@ __global__ void __launch_bounds__(192, 1) probe_kernel(ProbeArgs pa) {
         const uint32_t a0 = (t == 1) ? a_lo : a_hi, b0 = (t == 2) ? b_lo : b_hi;
         for (int ks = 0; ks < K / 8; ++ks) {
           const uint32_t aaddr = a0 + ks * 2 * kdirA, baddr = b0 + ks * 2 * kdirB;
-          uint64_t da, db;
-          if (pa.variant == 0) { da = make_desc(aaddr, kdirA, mndir); db = make_desc(baddr, kdirB, mndir); }
-          else { da = make_desc(aaddr, mndir, kdirA); db = make_desc(baddr, mndir, kdirB); }
-          umma_tf32(tmem, da, db, idesc, acc);
+          const uint64_t da = make_desc(aaddr, kdirA, mndir), db = make_desc(baddr, kdirB, mndir);
+          if (pa.variant == 2) umma_tf32_ts(tmem, tmem + ((t == 1) ? 192 : 128) + ks * 8, db, idesc, acc);
+          else umma_tf32(tmem, da, db, idesc, acc);
           acc = 1;
         }
       }
@@ -98,7 +112,45 @@ __global__ void __launch_bounds__(192, 1) probe_kernel(ProbeArgs pa) {
     }
   }
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 128);
+  if (warp == 4) tmem_dealloc(tmem, 256);
+}
+
+// ---------------------------------------------------------------------------------------------- MMA rate probe
+// One thread issues `reps` x 8 tf32 MMAs (M=128, N, K=8) with A in TMEM and B in shared memory, either all into one
+// accumulator or alternating between two, then commits and waits; cycles per MMA tell whether back-to-back MMAs into
+// the same accumulator run at the nominal N/2 cycles.
+__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int alternate, int reps, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_smem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 16384; i += 128) reinterpret_cast<float*>(smem)[i] = 0.f;    // 64 KB of zeros as the B operand
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+  fence_proxy_async();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_base_smem;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_tf32(128, N);
+    const uint32_t kdirB = (uint32_t)N * 16;
+    const uint64_t bd = make_desc(smem_u32(smem), kdirB, 128);
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t d = tmem + ((alternate && (ks & 1)) ? 256u : 0u);
+        umma_tf32_ts(d, tmem + 448 + ks * 8, bd + (uint64_t)(((ks & 3) * 2 * kdirB) >> 4), idesc, 1u);
+      }
+    }
+    umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    out[0] = clock64() - t0;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 static void pack_image(const std::vector<float>& W /* [N][K] */, int N, int K, float* hi, float* lo) {
@@ -138,7 +190,7 @@ int main() {
     cudaMemcpy(dB, img.data(), img.size() * 4, cudaMemcpyHostToDevice);
     const size_t smem = (size_t)(2 * 128 * K + 2 * N * K) * 4;
     cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    for (int variant = 0; variant < 1; ++variant)   // variant 1 (fields swapped) faults with an illegal address: settled
+    for (int variant = 0; variant <= 2; variant += 2)   // (variant 1, descriptor fields swapped, faults with an illegal address: settled)
       for (int terms = 1; terms <= 3; terms += 2) {
         cudaMemset(dD, 0xff, D.size() * 4);
         ProbeArgs pa{dA, dB, dD, K, N, variant, terms};
@@ -154,10 +206,27 @@ int main() {
         }
         const bool ok = terms == 3 ? e < 1e-4 : e < 5e-2;
         printf("K=%3d N=%3d variant=%d terms=%d  max|D-ref64| = %.3e   (fp32 fmaf chain: %.3e)  %s\n", K, N, variant, terms, e, e32, ok ? "OK" : "MISMATCH");
-        if (variant == 0 && !ok) ++fails;
+        if (!ok) ++fails;
       }
     cudaFree(dA); cudaFree(dB); cudaFree(dD);
   }
-  printf(fails ? "probe: variant 0 FAILED in %d case(s)\n" : "probe: variant 0 passes everywhere (LBO = K-direction stride, SBO = M/N-direction stride)\n", fails);
+  {
+    long long* d_out;
+    cudaMalloc(&d_out, 8);
+    cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    const int cases[][2] = {{64, 0}, {64, 1}, {128, 0}, {128, 1}, {256, 0}, {256, 1}};
+    for (auto& c : cases) {
+      long long cyc = 0;
+      for (int it = 0; it < 2; ++it) {
+        rate_kernel<<<1, 128, 65536>>>(c[0], c[1], 64, d_out);
+        cudaError_t err = cudaDeviceSynchronize();
+        if (err != cudaSuccess) { printf("rate probe N=%d: CUDA error %s\n", c[0], cudaGetErrorString(err)); return 3; }
+        cudaMemcpy(&cyc, d_out, 8, cudaMemcpyDeviceToHost);
+      }
+      printf("rate: M=128 N=%3d K=8 tf32, %s accumulator(s): %.1f cycles per MMA (nominal %d)\n", c[0], c[1] ? "two alternating" : "one", cyc / 512.0, c[0] / 2);
+    }
+    cudaFree(d_out);
+  }
+  printf(fails ? "probe: FAILED in %d case(s)\n" : "probe: all cases pass (LBO = K-direction stride, SBO = M/N-direction stride; A from TMEM: lane = row, column = k)\n", fails);
   return fails ? 1 : 0;
 }
