@@ -25,6 +25,8 @@ FLOPS_PER_STEP = 271712256                     # BASELINE.md section 4 (algorith
 BRANCH_FLOPS_PER_STEP = 2 * 2 * 512 * 82752    # both branches, 512 points, 82,752 MAC per point
 HEAD_FLOPS_PER_STEP = 2 * 2 * 512 * (64 * 256 + 256 * 128 + 128 * 2)
 GPROJ_FLOPS_PER_STEP = 2 * 2 * 1024 * 256
+BRANCH_TILE_FLOPS = 2 * 128 * 82752                      # one 128-row tile of one branch
+HEAD_TILE_FLOPS = 2 * 128 * (64 * 256 + 256 * 128)       # tensor part of one 128-row head tile (128->2 runs on the FMA pipe)
 METRIC = 'segmented_points_per_sec'
 UNIT = 'points/s'
 
@@ -201,6 +203,7 @@ def main():
     ap.add_argument('--cpu-baseline-steps', type=int, default=150)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--slots', type=int, default=0)
+    ap.add_argument('--lockstep-timing', action='store_true', help='also time the lock-step loop kernel by kernel')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -256,6 +259,7 @@ def main():
     launches = 0
     stats = None
     dev_ms = []
+    grow_ms_list = []
     for it in range(args.warmup + args.steps):
         flush.fill_(it & 0xFF)
         if it == args.warmup:
@@ -271,6 +275,7 @@ def main():
         if it >= args.warmup:
             pr = eng.profile()
             dev_ms.append(pr['grow_ms'] + pr['fill_ms'] + (1e3 * t_ag if dist is not None else 0.0))
+            grow_ms_list.append(pr['grow_ms'])
             launches += pr['kernel_launches']
     barrier()
     wall = time.perf_counter() - wall0
@@ -284,23 +289,42 @@ def main():
     grow_steps = int(stats['grow_steps'].sum())
     value = world * total_raw / (ms_per_step * 1e-3)
 
-    # ---- kernel timing pass (same workload, CUDA events around every kernel of the lock-step loop)
-    eng.segment_resident(flags=_lib.FLAG_KERNEL_TIMING, **params)
-    kt = eng.profile()
-    branch_s = kt['branch_kernel_ms'] * 1e-3
-    achieved_tf = grow_steps * BRANCH_FLOPS_PER_STEP / branch_s / 1e12 if branch_s > 0 else 0.0
+    # ---- roofline of the dominant kernel: the persistent grow kernel (one launch per pass; CUDA events on the engine stream)
+    pr = eng.profile()
     sm_mhz = clocks.get('sm_mhz') or peaks.get('sm_max_mhz', 1965.0)
-    fp32_peak_tf = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
     peak_tf = peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops'))
+    grow_ms = float(np.mean(grow_ms_list))
+    achieved_tf = grow_steps * FLOPS_PER_STEP / (grow_ms * 1e-3) / 1e12
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(REPO, 'profiles', 'grow_kernel_traffic.json')))['dram_bytes_per_launch']
+    except Exception:
+        pass
     roofline = {
-        'kernel': 'lrg_branch_kernel', 'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-        'frac': achieved_tf / peak_tf if peak_tf else None, 'traffic': None, 'peak_source': peaks_src + ' bf16 sustained',
-        'pipe': 'fp32 FMA (parity bar is the fp32 TF graph)', 'fp32_fma_peak_tflops': fp32_peak_tf,
-        'frac_of_fp32_fma': achieved_tf / fp32_peak_tf if fp32_peak_tf else None,
-        'launches': kt['iterations'], 'avg_launch_ms': kt['branch_kernel_ms'] / max(kt['iterations'], 1),
-        'algorithmic_flops_per_launch': grow_steps * BRANCH_FLOPS_PER_STEP / max(kt['iterations'], 1),
-        'kernel_ms_share': {k: kt[k] for k in ('step_kernel_ms', 'branch_kernel_ms', 'gproj_kernel_ms', 'head_kernel_ms')},
+        'kernel': 'lrg_grow_kernel' if pr['persistent'] else 'lock-step kernels', 'bound': 'tensor', 'achieved': achieved_tf, 'peak': peak_tf,
+        'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf if peak_tf else None, 'traffic': traffic, 'peak_source': peaks_src + ' bf16 sustained',
+        'launches_per_pass': 1 if pr['persistent'] else None, 'avg_launch_ms': grow_ms,
+        'algorithmic_flops_per_launch': grow_steps * FLOPS_PER_STEP,
+        'note': 'algorithmic = 271.7 MFLOP per grow step (512+512 rows, factored heads); the kernel evaluates only distinct rows '
+                '(padding duplicates reuse logits) as 3xTF32 on tcgen05; the run is latency-bound by the longest room',
     }
+    if pr['persistent']:
+        items, busy = pr['items'], pr['busy_ms']
+        executed = 3.0 * (items['branch'] * BRANCH_TILE_FLOPS + items['head'] * HEAD_TILE_FLOPS)
+        roofline.update({
+            'items_per_pass': items, 'busy_ms_by_item': busy,
+            'avg_us_per_item': {k: (1e3 * busy[k] / items[k] if items[k] else None) for k in items},
+            'sm_busy_frac': sum(busy.values()) / (148.0 * grow_ms),
+            'executed_tf32_tflops': executed / (grow_ms * 1e-3) / 1e12,
+            'frac_of_tf32_peak_executed': executed / (grow_ms * 1e-3) / 1e12 / (peak_tf / 2.0) if peak_tf else None,
+            'tensor_tile_busy_tflops': executed / ((busy['branch'] + busy['head']) * 1e-3 / 148.0) / 1e12 if (busy['branch'] + busy['head']) > 0 else None,
+        })
+    if args.lockstep_timing:
+        # per-kernel CUDA-event times of the lock-step loop (the A/B path; one {step, branch, gproj, head} quartet per iteration)
+        eng.segment_resident(flags=_lib.FLAG_KERNEL_TIMING, **params)
+        kt = eng.profile()
+        roofline['lockstep_kernel_ms'] = {k: kt[k] for k in ('step_kernel_ms', 'branch_kernel_ms', 'gproj_kernel_ms', 'head_kernel_ms')}
+        roofline['lockstep_iterations'] = kt['iterations']
 
     # ---- end-to-end arm: host buffers in, labels out, copies inside the timed region
     h2d = h_points.nbytes + h_order.nbytes + offsets.nbytes
@@ -346,7 +370,7 @@ def main():
                        'scope': 'grow driver + LrgNet forward + fill on precomputed 13-D features', 'rng': 'philox4x32-10 seed 0',
                        'weights': 'lrgnet_model5 (golden)'},
             'grow_steps_per_sec': world * grow_steps / (ms_per_step * 1e-3), 'grow_steps_per_pass': grow_steps,
-            'lockstep_iterations_per_pass': kt['iterations'],
+            'longest_room_steps': int(stats['grow_steps'].max()),
             'wall_s_timed_region': wall, 'clocks': clocks, 'gpu_launches': int(launches),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             'roofline': roofline, 'cpu_baseline': cpu_baseline,

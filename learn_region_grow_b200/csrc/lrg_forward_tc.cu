@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) lrg_tc_branch_kernel(const __gr
 
 __global__ void __launch_bounds__(512) lrg_tc_gproj_kernel(const __grid_constant__ TcNet net, const __grid_constant__ ForwardArgs fa) {
   __shared__ float sP[1024];
-  __shared__ float sR[8 * 64];
+  __shared__ float sR[32 * 64];
   const int cb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   if (fa.active != nullptr && fa.active[(size_t)b * fa.active_stride] == 0) return;
   tc_gproj_block(net, fa, b, h, cb, sP, sR);

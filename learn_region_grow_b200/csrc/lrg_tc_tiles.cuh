@@ -306,42 +306,40 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
 }
 
 // ------------------------------------------------------------------------------------------------------ pooled projection
-// gproj[b][h][cb*64 + c] = bias0_h[c] + sum_k pooled[b][k] * W0g_h[k][c], k summed in 8 groups of 128 combined in fixed
-// order (deterministic).  Needs blockDim.x == 512 and 4 KB + 2 KB of scratch (float sP[1024], float sR[8][64]).
+// gproj[b][h][cb*64 + c] = bias0_h[c] + sum_k pooled[b][k] * W0g_h[k][c]: 512 threads = 16 column quads x 32 K-groups of
+// 32 rows; every thread keeps 16-32 128-bit weight loads in flight (the item is ~two L2 round trips + 256 KB of traffic), partial sums are combined in fixed order (deterministic).  Scratch: float sP[1024], float sR[32][64].
 __device__ __forceinline__ void tc_gproj_block(const TcNet& net, const ForwardArgs& fa, int b, int h, int cb, float* sP, float* sR) {
-  const int tid = threadIdx.x, col = tid & 63, kg = tid >> 6;
+  const int tid = threadIdx.x, c4 = tid & 15, kg = tid >> 4;
+  const float4* W = reinterpret_cast<const float4*>(net.W0g[h] + (size_t)(kg * 32) * 256 + cb * 64) + c4;
+  float4 w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i] = __ldg(W + (size_t)i * 64);
   for (int i = tid; i < 1024; i += 512) sP[i] = __ldcg(fa.pooled + (size_t)b * 1024 + i);
-  const float* W = net.W0g[h] + (size_t)(kg * 128) * 256 + cb * 64 + col;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-  float w[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) w[i] = __ldg(W + (size_t)i * 256);      // first quarter in flight while pooled lands
   __syncthreads();
-#pragma unroll 1
-  for (int k0 = 0; k0 < 128; k0 += 32) {
-    float wn[32];
-    if (k0 + 32 < 128) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) wn[i] = __ldg(W + (size_t)(k0 + 32 + i) * 256);
+  for (int half = 0; half < 2; ++half) {
+    float4 wn[16];
+    if (half == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) wn[i] = __ldg(W + (size_t)(16 + i) * 64);
     }
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      acc0 = fmaf(sP[kg * 128 + k0 + i + 0], w[i + 0], acc0);
-      acc1 = fmaf(sP[kg * 128 + k0 + i + 1], w[i + 1], acc1);
-      acc2 = fmaf(sP[kg * 128 + k0 + i + 2], w[i + 2], acc2);
-      acc3 = fmaf(sP[kg * 128 + k0 + i + 3], w[i + 3], acc3);
+    for (int i = 0; i < 16; ++i) {
+      const float p = sP[kg * 32 + half * 16 + i];
+      acc.x = fmaf(p, w[i].x, acc.x); acc.y = fmaf(p, w[i].y, acc.y); acc.z = fmaf(p, w[i].z, acc.z); acc.w = fmaf(p, w[i].w, acc.w);
     }
-    if (k0 + 32 < 128) {
+    if (half == 0) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) w[i] = wn[i];
+      for (int i = 0; i < 16; ++i) w[i] = wn[i];
     }
   }
-  sR[kg * 64 + col] = (acc0 + acc1) + (acc2 + acc3);
+  *reinterpret_cast<float4*>(sR + kg * 64 + c4 * 4) = acc;
   __syncthreads();
   if (tid < 64) {
     float s = __ldg(net.head_bias0[h] + cb * 64 + tid);
 #pragma unroll
-    for (int g = 0; g < 8; ++g) s += sR[g * 64 + tid];
+    for (int g = 0; g < 32; ++g) s += sR[g * 64 + tid];
     fa.gproj[((size_t)b * 2 + h) * 256 + cb * 64 + tid] = s;
   }
   __syncthreads();
