@@ -279,7 +279,6 @@ def main():
             launches += pr['kernel_launches']
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
     total_ms = float(sum(dev_ms))
     if dist is not None:
         t = torch.tensor([total_ms, wall], device='cuda', dtype=torch.float64)
@@ -291,7 +290,6 @@ def main():
 
     # ---- roofline of the dominant kernel: the persistent grow kernel (one launch per pass; CUDA events on the engine stream)
     pr = eng.profile()
-    sm_mhz = clocks.get('sm_mhz') or peaks.get('sm_max_mhz', 1965.0)
     peak_tf = peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops'))
     grow_ms = float(np.mean(grow_ms_list))
     achieved_tf = grow_steps * FLOPS_PER_STEP / (grow_ms * 1e-3) / 1e12
@@ -333,11 +331,15 @@ def main():
         eng.segment_concatenated(offsets, h_points, h_order, **params)
     barrier()
     e0 = time.perf_counter()
+    e2e_ms = []
     for it in range(args.steps):
+        t_it = time.perf_counter()
         labels, _ = eng.segment_concatenated(offsets, h_points, h_order, **params)
         gather_labels()
+        e2e_ms.append(1e3 * (time.perf_counter() - t_it))
     barrier()
     e2e_s = time.perf_counter() - e0
+    clocks = sampler.stop()          # nvidia-smi keeps sampling through both timed regions
     if dist is not None:
         t = torch.tensor([e2e_s], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -372,7 +374,8 @@ def main():
             'grow_steps_per_sec': world * grow_steps / (ms_per_step * 1e-3), 'grow_steps_per_pass': grow_steps,
             'longest_room_steps': int(stats['grow_steps'].max()),
             'wall_s_timed_region': wall, 'clocks': clocks, 'gpu_launches': int(launches),
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                    'ms_per_step': [round(x, 2) for x in e2e_ms]},
             'roofline': roofline, 'cpu_baseline': cpu_baseline,
             'flops_per_grow_step': FLOPS_PER_STEP,
         }

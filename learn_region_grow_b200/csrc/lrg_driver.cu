@@ -6,35 +6,86 @@
 namespace lrg {
 
 // ----------------------------------------------------------------------------------------------------- pack
-__global__ void lrg_pack_kernel(const float* __restrict__ points, int F, long long total, float res,
-                                float* __restrict__ pts16, int4* __restrict__ vox) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  float row[16];
+// One CTA per room: voxelise (numpy.round(xyz / resolution), :175), find the room's voxel origin, then write the padded
+// 16-float feature rows and the packed state words (coordinates relative to the origin, flags clear, padding VISITED).
+__global__ void __launch_bounds__(1024) lrg_pack_kernel(const float* __restrict__ points, int F, const long long* __restrict__ room_off,
+                                                        const long long* __restrict__ pw_off, float res, float* __restrict__ pts16,
+                                                        unsigned* __restrict__ pw, int4* __restrict__ room_vmin, int* err) {
+  __shared__ int s_mn[3], s_mx[3];
+  const int room = blockIdx.x, tid = threadIdx.x;
+  const long long base = room_off[room];
+  const int N = (int)(room_off[room + 1] - base);
+  if (tid < 3) { s_mn[tid] = INT_MAX; s_mx[tid] = INT_MIN; }
+  __syncthreads();
+  int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+  for (int i = tid; i < N; i += 1024)
 #pragma unroll
-  for (int c = 0; c < 16; ++c) row[c] = c < F ? points[i * F + c] : 0.f;
+    for (int a = 0; a < 3; ++a) {
+      const int v = voxel_of(points[(base + i) * F + a], res);
+      mn[a] = min(mn[a], v); mx[a] = max(mx[a], v);
+    }
 #pragma unroll
-  for (int c = 0; c < 16; c += 4)
-    *reinterpret_cast<float4*>(pts16 + i * 16 + c) = make_float4(row[c], row[c + 1], row[c + 2], row[c + 3]);
-  vox[i] = make_int4(voxel_of(row[0], res), voxel_of(row[1], res), voxel_of(row[2], res), 0);
+  for (int a = 0; a < 3; ++a) { atomicMin(&s_mn[a], mn[a]); atomicMax(&s_mx[a], mx[a]); }
+  __syncthreads();
+  const int o0 = s_mn[0], o1 = s_mn[1], o2 = s_mn[2];
+  if (tid == 0) {
+    room_vmin[room] = make_int4(N ? o0 : 0, N ? o1 : 0, N ? o2 : 0, 0);
+    if (N > 0 && (s_mx[0] - o0 > 1022 || s_mx[1] - o1 > 1022 || s_mx[2] - o2 > 1022)) atomicCAS(err, 0, room + 1);
+  }
+  unsigned* w = pw + pw_off[room];
+  const int n4 = (N + 3) & ~3;
+  for (int i = tid; i < n4; i += 1024) {
+    if (i >= N) { w[i] = PW_VIS; continue; }
+    float row[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) row[c] = c < F ? points[(base + i) * F + c] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; c += 4)
+      *reinterpret_cast<float4*>(pts16 + (base + i) * 16 + c) = make_float4(row[c], row[c + 1], row[c + 2], row[c + 3]);
+    const unsigned x = (unsigned)(voxel_of(row[0], res) - o0) & 1023u, y = (unsigned)(voxel_of(row[1], res) - o1) & 1023u,
+                   z = (unsigned)(voxel_of(row[2], res) - o2) & 1023u;
+    w[i] = x | (y << 10) | (z << 20);
+  }
 }
 
-int launch_pack(const float* d_points, int F, long long total, float resolution, float* d_pts16, int4* d_vox,
-                cudaStream_t stream) {
-  if (total <= 0) return LRG_OK;
-  lrg_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_points, F, total, resolution, d_pts16, d_vox);
+__global__ void __launch_bounds__(1024) lrg_reset_words_kernel(const long long* __restrict__ room_off, const long long* __restrict__ pw_off,
+                                                               unsigned* __restrict__ pw) {
+  const int room = blockIdx.x;
+  const int N = (int)(room_off[room + 1] - room_off[room]);
+  unsigned* w = pw + pw_off[room];
+  for (int i = threadIdx.x; i < N; i += 1024) w[i] &= PW_XYZ;
+}
+
+int launch_pack(const float* d_points, int F, int n_rooms, const long long* d_room_off, const long long* d_pw_off, float resolution,
+                float* d_pts16, unsigned* d_pw, int4* d_room_vmin, int* d_err, cudaStream_t stream) {
+  if (n_rooms <= 0) return LRG_OK;
+  lrg_pack_kernel<<<n_rooms, 1024, 0, stream>>>(d_points, F, d_room_off, d_pw_off, resolution, d_pts16, d_pw, d_room_vmin, d_err);
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
+}
+
+int launch_reset_words(int n_rooms, const long long* d_room_off, const long long* d_pw_off, unsigned* d_pw, cudaStream_t stream) {
+  if (n_rooms <= 0) return LRG_OK;
+  lrg_reset_words_kernel<<<n_rooms, 1024, 0, stream>>>(d_room_off, d_pw_off, d_pw);
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;
 }
 
 // ----------------------------------------------------------------------------------------------------- step
 __global__ void __launch_bounds__(kStepThreads, 1) lrg_step_kernel(const __grid_constant__ DriverArgs da) {
-  __shared__ StepShared sh;
-  step_body<kStepThreads>(da, blockIdx.x, sh);
+  extern __shared__ __align__(16) unsigned char step_smem[];
+  step_body<kStepThreads>(da, blockIdx.x, *reinterpret_cast<StepShared*>(step_smem));
 }
 
+size_t step_smem_bytes() { return sizeof(StepShared); }
+
 int launch_step(const DriverArgs& da, cudaStream_t stream) {
-  lrg_step_kernel<<<da.n_slots, kStepThreads, 0, stream>>>(da);
+  static bool configured = false;
+  if (!configured) {
+    LRG_CUDA(cudaFuncSetAttribute(lrg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepShared)));
+    configured = true;
+  }
+  lrg_step_kernel<<<da.n_slots, kStepThreads, sizeof(StepShared), stream>>>(da);
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;
 }

@@ -28,8 +28,9 @@ struct DriverArgs {
   int n_rooms;
   const long long* room_off;    // (n_rooms+1)
   const float* pts;             // (T,16) padded feature rows
-  const int4* vox;              // (T) voxel coordinates (:175)
-  unsigned char* state;         // (T) ST_CUR | ST_VISITED
+  unsigned* pw;                 // per-point state words: 10+10+10 bits of room-relative voxel coordinates (:175), bit 30 CURRENT, bit 31 VISITED
+  const long long* pw_off;      // (n_rooms+1) word offset of every room in pw (rooms padded to a multiple of 4 words)
+  const int4* room_vmin;        // (n_rooms) voxel coordinates the words are relative to
   int* label;                   // (T) cluster_label (:176)
   const int* order;             // (T) room-local seed order (:183)
   SlotState* slots;
@@ -57,6 +58,7 @@ struct DriverArgs {
   LrgRoomStats* stats;          // (n_rooms)
   LrgStepTrace* trace;          // (n_rooms, trace_capacity) or NULL
   int trace_capacity;
+  unsigned long long* dbg;      // diagnostics (NULL = off): summed clock64 cycles per step stage [0..14], steps in [15]
 };
 
 struct FillArgs {
@@ -72,8 +74,12 @@ struct FillArgs {
   int F;
 };
 
-int launch_pack(const float* d_points, int F, long long total, float resolution, float* d_pts16, int4* d_vox,
-                cudaStream_t stream);
+// feature rows -> padded 16-float rows + state words; *d_err is set to a room index + 1 if a room spans > 1022 voxels
+int launch_pack(const float* d_points, int F, int n_rooms, const long long* d_room_off, const long long* d_pw_off, float resolution,
+                float* d_pts16, unsigned* d_pw, int4* d_room_vmin, int* d_err, cudaStream_t stream);
+// clears the CURRENT / VISITED flags of every room (start of a run)
+int launch_reset_words(int n_rooms, const long long* d_room_off, const long long* d_pw_off, unsigned* d_pw, cudaStream_t stream);
+size_t step_smem_bytes();
 int launch_step(const DriverArgs& da, cudaStream_t stream);
 int launch_fill(const FillArgs& fa, cudaStream_t stream);
 

@@ -76,8 +76,10 @@ struct LrgEngine {
   std::vector<long long> h_room_off;
   long long* d_room_off = nullptr;
   float* d_pts = nullptr;
-  int4* d_vox = nullptr;
-  unsigned char* d_state = nullptr;
+  unsigned* d_pw = nullptr;              // packed per-point state words (rooms padded to 4 words)
+  long long* d_pw_off = nullptr;
+  int4* d_room_vmin = nullptr;
+  long long total_words = 0;
   int *d_label = nullptr, *d_label_filled = nullptr, *d_order = nullptr;
   int *d_lab_list = nullptr, *d_unl_list = nullptr, *d_n_lab = nullptr, *d_n_unl = nullptr;
   LrgRoomStats* d_stats = nullptr;
@@ -159,10 +161,10 @@ static int ensure_forward_ws(LrgEngine* e, int B) {
 }
 
 static void free_rooms(LrgEngine* e) {
-  cudaFree(e->d_room_off); cudaFree(e->d_pts); cudaFree(e->d_vox); cudaFree(e->d_state); cudaFree(e->d_label);
+  cudaFree(e->d_room_off); cudaFree(e->d_pts); cudaFree(e->d_pw); cudaFree(e->d_pw_off); cudaFree(e->d_room_vmin); cudaFree(e->d_label);
   cudaFree(e->d_label_filled); cudaFree(e->d_order); cudaFree(e->d_lab_list); cudaFree(e->d_unl_list);
   cudaFree(e->d_n_lab); cudaFree(e->d_n_unl); cudaFree(e->d_stats);
-  e->d_room_off = nullptr; e->d_pts = nullptr; e->d_vox = nullptr; e->d_state = nullptr; e->d_label = nullptr;
+  e->d_room_off = nullptr; e->d_pts = nullptr; e->d_pw = nullptr; e->d_pw_off = nullptr; e->d_room_vmin = nullptr; e->d_label = nullptr;
   e->d_label_filled = nullptr; e->d_order = nullptr; e->d_lab_list = e->d_unl_list = e->d_n_lab = e->d_n_unl = nullptr;
   e->d_stats = nullptr;
   e->n_rooms = 0; e->total_pts = 0; e->maxN = 0;
@@ -437,8 +439,8 @@ int lrg_engine_load_weights(LrgEngine* e, const float* blob, size_t n_floats) {
       t.head_bias2[h] = net.out[h].bias;
     }
     if (getenv("LRG_TILE_TIMING") != nullptr && e->d_tile_dbg == nullptr) {
-      LRG_TRY(dev_alloc(&e->d_tile_dbg, 32));
-      LRG_CUDA(cudaMemset(e->d_tile_dbg, 0, 32 * sizeof(unsigned long long)));
+      LRG_TRY(dev_alloc(&e->d_tile_dbg, 48));
+      LRG_CUDA(cudaMemset(e->d_tile_dbg, 0, 48 * sizeof(unsigned long long)));
     }
     t.dbg = e->d_tile_dbg;
     LRG_TRY(tc_forward_configure());
@@ -506,8 +508,13 @@ int lrg_rooms_upload(LrgEngine* e, int n_rooms, const int64_t* room_offsets, con
   const size_t T = (size_t)total;
   LRG_TRY(dev_alloc(&e->d_room_off, (size_t)n_rooms + 1));
   LRG_TRY(dev_alloc(&e->d_pts, T * 16));
-  LRG_TRY(dev_alloc(&e->d_vox, T));
-  LRG_TRY(dev_alloc(&e->d_state, T));
+  std::vector<long long> h_pw_off((size_t)n_rooms + 1, 0);
+  for (int r = 0; r < n_rooms; ++r) h_pw_off[r + 1] = h_pw_off[r] + ((room_offsets[r + 1] - room_offsets[r] + 3) / 4) * 4;
+  e->total_words = h_pw_off[n_rooms];
+  LRG_TRY(dev_alloc(&e->d_pw, (size_t)e->total_words));
+  LRG_TRY(dev_alloc(&e->d_pw_off, (size_t)n_rooms + 1));
+  LRG_TRY(dev_alloc(&e->d_room_vmin, (size_t)std::max(n_rooms, 1)));
+  LRG_CUDA(cudaMemcpyAsync(e->d_pw_off, h_pw_off.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice, e->stream));
   LRG_TRY(dev_alloc(&e->d_label, T));
   LRG_TRY(dev_alloc(&e->d_label_filled, T));
   LRG_TRY(dev_alloc(&e->d_order, T));
@@ -522,10 +529,14 @@ int lrg_rooms_upload(LrgEngine* e, int n_rooms, const int64_t* room_offsets, con
     LRG_TRY(dev_alloc(&d_raw, T * e->F));
     LRG_CUDA(cudaMemcpyAsync(d_raw, points, sizeof(float) * T * e->F, cudaMemcpyHostToDevice, e->stream));
     LRG_CUDA(cudaMemcpyAsync(e->d_order, seed_order, sizeof(int) * T, cudaMemcpyHostToDevice, e->stream));
-    int rc = launch_pack(d_raw, e->F, total, resolution, e->d_pts, e->d_vox, e->stream);
+    LRG_CUDA(cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(int), e->stream));
+    int rc = launch_pack(d_raw, e->F, n_rooms, e->d_room_off, e->d_pw_off, resolution, e->d_pts, e->d_pw, e->d_room_vmin, e->d_counters, e->stream);
+    int bad_room = 0;
+    if (rc == LRG_OK && cudaMemcpyAsync(&bad_room, e->d_counters, sizeof(int), cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) rc = LRG_E_CUDA;
     cudaStreamSynchronize(e->stream);
     cudaFree(d_raw);
     LRG_TRY(rc);
+    LRG_REQUIRE(bad_room == 0, "room %d spans more than 1022 voxels along an axis at resolution %g (state words hold 10 bits per axis)", bad_room - 1, (double)resolution);
   }
   LRG_CUDA(cudaStreamSynchronize(e->stream));
   return LRG_OK;
@@ -552,7 +563,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   *e->h_done = 0;
   LRG_CUDA(cudaEventRecord(ev0, st));
   // reset per-run state (inside the timed region: it is part of one pass over the rooms)
-  LRG_CUDA(cudaMemsetAsync(e->d_state, 0, T, st));
+  LRG_TRY(launch_reset_words(n_rooms, e->d_room_off, e->d_pw_off, e->d_pw, st));
   LRG_CUDA(cudaMemsetAsync(e->d_label, 0, T * sizeof(int), st));
   LRG_CUDA(cudaMemsetAsync(e->d_stats, 0, sizeof(LrgRoomStats) * std::max(n_rooms, 1), st));
   LRG_CUDA(cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(int), st));
@@ -568,7 +579,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   }
 
   DriverArgs da{};
-  da.n_rooms = n_rooms; da.room_off = e->d_room_off; da.pts = e->d_pts; da.vox = e->d_vox; da.state = e->d_state;
+  da.n_rooms = n_rooms; da.room_off = e->d_room_off; da.pts = e->d_pts; da.pw = e->d_pw; da.pw_off = e->d_pw_off; da.room_vmin = e->d_room_vmin;
   da.label = e->d_label; da.order = e->d_order; da.slots = e->d_slots; da.n_slots = n_slots; da.maxN = e->slots_maxN;
   da.listI = e->d_listI; da.listJ = e->d_listJ; da.keyI = e->d_keyI; da.keyJ = e->d_keyJ;
   da.tile[0] = e->d_tile[0]; da.tile[1] = e->d_tile[1]; da.tileidx[0] = e->d_tileidx[0]; da.tileidx[1] = e->d_tileidx[1];
@@ -579,6 +590,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   da.resolution = e->resolution; da.cluster_threshold = params->cluster_threshold; da.seed = params->seed;
   da.max_steps = params->max_steps_per_region; da.room_id_base = params->room_id_base;
   da.next_room = e->d_counters; da.finished_slots = e->d_counters + 1; da.done_flag = e->d_done;
+  da.dbg = e->d_tile_dbg ? e->d_tile_dbg + 32 : nullptr;
   da.stats = e->d_stats; da.trace = e->trace_capacity > 0 ? e->d_trace : nullptr; da.trace_capacity = e->trace_capacity;
 
   ForwardArgs fa{};
@@ -766,12 +778,12 @@ int lrg_last_grow_profile(LrgEngine* e, int* persistent, double busy_ms[4], int6
   return LRG_OK;
 }
 
-int lrg_tile_timing(LrgEngine* e, uint64_t out[32], int reset) {
+int lrg_tile_timing(LrgEngine* e, uint64_t out[48], int reset) {
   LRG_REQUIRE(e != nullptr && out != nullptr, "NULL argument");
   if (e->d_tile_dbg == nullptr) { set_error("tile timing is off (set LRG_TILE_TIMING=1 before load_weights)"); return LRG_E_STATE; }
   LRG_CUDA(cudaSetDevice(e->device));
-  LRG_CUDA(cudaMemcpy(out, e->d_tile_dbg, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-  if (reset) LRG_CUDA(cudaMemset(e->d_tile_dbg, 0, 32 * sizeof(uint64_t)));
+  LRG_CUDA(cudaMemcpy(out, e->d_tile_dbg, 48 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (reset) LRG_CUDA(cudaMemset(e->d_tile_dbg, 0, 48 * sizeof(uint64_t)));
   return LRG_OK;
 }
 

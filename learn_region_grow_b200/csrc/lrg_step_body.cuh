@@ -4,6 +4,11 @@
 // 9-channel median, sample 512+512 points and gather the centred tiles for the next forward.
 // Templated on the CTA size NT (a multiple of 32 that divides 1024) so that both the stand-alone lock-step kernel
 // (1024 threads) and the persistent grow kernel (512 threads) run the same code.
+//
+// A step is a chain of dependent phases, so it is built for latency: the per-point state is ONE packed 32-bit word
+// (10+10+10 bits of room-relative voxel coordinates, CURRENT and VISITED flags) that a whole-room scan reads with every
+// 128-bit load in flight at once (one L2 round trip per scan), the lists are produced by a single ordered block
+// compaction per scan, and the median works on keys staged once in shared memory.
 #pragma once
 #include <limits.h>
 
@@ -175,7 +180,74 @@ __device__ void block_select_smallest(int n, const unsigned* __restrict__ keys, 
   }
 }
 
+// ----------------------------------------------------------------------------------------------------- packed state words
+constexpr unsigned PW_CUR = 1u << 30, PW_VIS = 1u << 31, PW_XYZ = 0x3FFFFFFFu;
+__device__ __forceinline__ int pw_x(unsigned w) { return (int)(w & 1023u); }
+__device__ __forceinline__ int pw_y(unsigned w) { return (int)((w >> 10) & 1023u); }
+__device__ __forceinline__ int pw_z(unsigned w) { return (int)((w >> 20) & 1023u); }
+
+// Ordered block-wide compaction over a room's state words: out[] receives, ascending, every i with pred(word_i);
+// visit(word) is called for each selected word (bounding boxes).  Every thread issues all of its 128-bit loads of a
+// 32*NT-point chunk before using any (one memory round trip per chunk); warp w owns a contiguous run of the chunk, so
+// a per-warp scan plus one scan of the warp totals gives the global order.  The array is padded to a multiple of four
+// words with VISITED words that no predicate selects.  s_scan: 33 ints.  Returns the count to every thread.
+// (Plain loads on purpose: the words are rewritten by this CTA between scans and by other CTAs between steps; the
+// CTA barrier orders the former, the acquire fence at the start of a work item drops stale L1 lines for the latter.)
+template <int NT, class Pred, class Visit>
+__device__ int scan_words(const unsigned* pw, int N, Pred pred, Visit visit, int* out, int* s_scan) {
+  constexpr int U = 8;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n4 = (N + 3) >> 2;
+  int running = 0;
+  for (int c4 = 0; c4 < n4; c4 += NT * U) {
+    const int q0 = c4 + warp * 32 * U + lane;
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int q = q0 + u * 32;
+      v[u] = q < n4 ? reinterpret_cast<const uint4*>(pw)[q] : make_uint4(PW_VIS, PW_VIS, PW_VIS, PW_VIS);
+    }
+    unsigned flags = 0;
+    int offs[U], wtotal = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      unsigned f = 0;
+      if (pred(v[u].x)) f |= 1u;
+      if (pred(v[u].y)) f |= 2u;
+      if (pred(v[u].z)) f |= 4u;
+      if (pred(v[u].w)) f |= 8u;
+      flags |= f << (4 * u);
+      const int cnt = __popc(f);
+      const int incl = warp_incl_scan(cnt, lane);
+      offs[u] = wtotal + incl - cnt;
+      wtotal += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) s_scan[warp] = wtotal;
+    __syncthreads();
+    scan_warp_totals<NT>(s_scan, warp, lane);
+    __syncthreads();
+    const int wbase = running + s_scan[warp];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned f = (flags >> (4 * u)) & 15u;
+      if (f) {
+        int o = wbase + offs[u];
+        const int i0 = (q0 + u * 32) * 4;
+        if (f & 1u) { out[o++] = i0; visit(v[u].x); }
+        if (f & 2u) { out[o++] = i0 + 1; visit(v[u].y); }
+        if (f & 4u) { out[o++] = i0 + 2; visit(v[u].z); }
+        if (f & 8u) { out[o++] = i0 + 3; visit(v[u].w); }
+      }
+    }
+    running += s_scan[32];
+    __syncthreads();
+  }
+  return running;
+}
+
 // ----------------------------------------------------------------------------------------------------- step
+constexpr int kMedianCap = 2048;   // inlier sets up to this size have their 9 median channels staged in shared memory
+
 struct StepShared {
   SlotState S;
   int scan[68];
@@ -188,6 +260,8 @@ struct StepShared {
   int red[32 * 6];
   int flag;
   int all_done;                 // set when this call retired the last slot of the run
+  unsigned nextkey[16];         // median: smallest key above the lower median, per channel
+  unsigned mkeys[9][kMedianCap];
 };
 
 enum { MODE_NEW_REGION = 0, MODE_SCAN = 1 };
@@ -199,6 +273,131 @@ __device__ __forceinline__ float confidence(float l0, float l1) {
   return e / (1.f + e);
 }
 
+// Median of one channel by ONE warp, keys in shared memory (n <= 32*E): bitwise radix select of rank (n-1)/2 from the
+// most significant bit down, counting with ballots (no atomics, no block barriers), keys and candidate flags held in
+// registers; for even n the upper median is the same key again if it has a further duplicate, else the smallest key
+// above it.  Returns numpy.median's two middle keys in lo / hi (equal for odd n).
+template <int E>
+__device__ __forceinline__ void warp_median(const unsigned* __restrict__ keys, int n, unsigned& lo, unsigned& hi) {
+  const int lane = threadIdx.x & 31;
+  unsigned k[E];
+  unsigned alive = 0;                               // bit e: element lane + 32*e is still a candidate
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int j = lane + 32 * e;
+    k[e] = j < n ? keys[j] : 0u;
+    if (j < n) alive |= 1u << e;
+  }
+  int rank = (n - 1) >> 1;
+  unsigned prefix = 0;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    int zeros = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) zeros += __popc(__ballot_sync(0xffffffffu, ((alive >> e) & 1u) && !((k[e] >> bit) & 1u)));
+    const bool take_ones = rank >= zeros;           // warp-uniform
+    if (take_ones) { rank -= zeros; prefix |= 1u << bit; }
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if ((((k[e] >> bit) & 1u) != 0) != take_ones) alive &= ~(1u << e);
+  }
+  lo = prefix;
+  hi = prefix;
+  if ((n & 1) == 0) {
+    // candidates left = keys equal to prefix; `rank` = position of the lower median inside that run
+    int equal = 0;
+    unsigned above = 0xFFFFFFFFu;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      equal += __popc(__ballot_sync(0xffffffffu, (alive >> e) & 1u));
+      const int j = lane + 32 * e;
+      if (j < n && k[e] > prefix) above = min(above, k[e]);
+    }
+    if (rank + 1 >= equal) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) above = min(above, __shfl_xor_sync(0xffffffffu, above, d));
+      hi = above;
+    }
+  }
+}
+
+// numpy.median over n keys per channel (mean of the two middle values for even n, :241): block radix select of rank
+// (n-1)/2 in every channel at once -- histogram updates are aggregated per warp with match.any, because the leading
+// byte of a feature channel is nearly constant over a region -- then, for even n, the next key in sorted order is either
+// the same value again (when the selected key has further duplicates) or the smallest key above it (one extra pass).
+// keyfn(j, k[9]) yields the sortable keys of inlier j.  On return s_prefix[c] = lower median key, s_next[c] = upper.
+template <int NT, class KeyFn>
+__device__ void block_median9(int n, int nch, KeyFn keyfn, unsigned* s_prefix, int* s_rank, int* s_hist, unsigned* s_next) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 9) { s_prefix[tid] = 0; s_rank[tid] = (n - 1) / 2; }
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 9 * 256; i += NT) s_hist[i] = 0;
+    __syncthreads();
+    const unsigned himask = (shift == 24) ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int j0 = 0; j0 < n; j0 += NT) {             // whole warps iterate together (match.any needs the full warp)
+      const int j = j0 + tid;
+      unsigned k[9];
+      if (j < n) keyfn(j, k);
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        const bool on = j < n && c < nch && ((k[c] ^ s_prefix[c]) & himask) == 0;
+        const unsigned bin = on ? ((k[c] >> shift) & 255u) : 256u;
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (on && lane == __ffs(peers) - 1) atomicAdd(&s_hist[c * 256 + bin], __popc(peers));
+      }
+    }
+    __syncthreads();
+    for (int c = warp; c < nch; c += NT / 32) {
+      int cnt[8], sum = 0;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { cnt[t] = s_hist[c * 256 + lane * 8 + t]; sum += cnt[t]; }
+      const int incl = warp_incl_scan(sum, lane);
+      int acc = incl - sum;
+      const int rank = s_rank[c];
+      if (acc <= rank && rank < incl) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          if (rank < acc + cnt[t]) {
+            s_prefix[c] |= (unsigned)(lane * 8 + t) << shift;
+            s_rank[c] = rank - acc;
+            if (shift == 0) s_rank[9 + c] = cnt[t];      // how many keys equal the selected one
+            break;
+          }
+          acc += cnt[t];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // upper median (rank n/2) for even n
+  if (tid < 9) s_next[tid] = 0xFFFFFFFFu;
+  __syncthreads();
+  if ((n & 1) == 0) {
+    unsigned best[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) best[c] = 0xFFFFFFFFu;
+    for (int j = tid; j < n; j += NT) {
+      unsigned k[9];
+      keyfn(j, k);
+#pragma unroll
+      for (int c = 0; c < 9; ++c)
+        if (k[c] > s_prefix[c] && k[c] < best[c]) best[c] = k[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+      unsigned b = best[c];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) b = min(b, __shfl_xor_sync(0xffffffffu, b, d));
+      if (lane == 0 && c < nch && b != 0xFFFFFFFFu) atomicMin(&s_next[c], b);
+    }
+    __syncthreads();
+    if (tid < nch && s_rank[tid] + 1 < s_rank[9 + tid]) s_next[tid] = s_prefix[tid];   // a duplicate of the lower median follows it
+  } else if (tid < 9) {
+    s_next[tid] = s_prefix[tid];
+  }
+  __syncthreads();
+}
+
 // On return sh.S holds the slot's state (also written back): S.active != 0 means tiles are ready for a forward,
 // S.finished != 0 means the slot has retired (no rooms left).
 template <int NT>
@@ -206,6 +405,14 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
   constexpr int VT = 2 * kMaxTilePts / NT;       // tile rows (512 inlier + 512 neighbor) handled per thread
   static_assert(VT * NT == 2 * kMaxTilePts, "NT must divide 1024");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  long long tstamp = clock64();
+  auto stamp = [&](int stage) {
+    if (da.dbg != nullptr && tid == 0) {
+      const long long now = clock64();
+      atomicAdd(da.dbg + stage, (unsigned long long)(now - tstamp));
+      tstamp = now;
+    }
+  };
   SlotState* gS = da.slots + slot;
   for (int i = tid; i < (int)(sizeof(SlotState) / 4); i += NT)
     reinterpret_cast<int*>(&sh.S)[i] = __ldcg(reinterpret_cast<const int*>(gS) + i);
@@ -224,36 +431,28 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
   long long base = 0;
   int N = 0;
   const float* pts = nullptr;
-  const int4* vox = nullptr;
-  unsigned char* state = nullptr;
+  unsigned* pw = nullptr;
+  int vmin0 = 0, vmin1 = 0, vmin2 = 0;            // voxel coordinates in the state words are relative to these
   auto bind_room = [&]() {
     base = da.room_off[S.room];
     N = (int)(da.room_off[S.room + 1] - base);
     pts = da.pts + base * 16;
-    vox = da.vox + base;
-    state = da.state + base;
+    pw = da.pw + da.pw_off[S.room];
+    const int4 vm = da.room_vmin[S.room];
+    vmin0 = vm.x; vmin1 = vm.y; vmin2 = vm.z;
   };
   if (S.room >= 0) bind_room();
 
-  // stop_growing (:210-217): visited |= current; label when the region is larger than the threshold
-  auto stop_region = [&](int reason) {
-    int cnt = 0;
-    for (int i = tid; i < N; i += NT) cnt += (state[i] & ST_CUR) ? 1 : 0;
-    int w = cnt;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) w += __shfl_xor_sync(0xffffffffu, w, d);
-    if (lane == 0) sh.red[warp] = w;
-    __syncthreads();
-    int total = 0;
-    for (int i = 0; i < NT / 32; ++i) total += sh.red[i];
-    const bool labelled = total > da.cluster_threshold;
+  // stop_growing (:210-217): visited |= current; label when the region is larger than the threshold.
+  // listI[0..n_cur) holds the current region.
+  auto stop_region = [&](int reason, int n_cur) {
+    const bool labelled = n_cur > da.cluster_threshold;
     int* label = da.label + base;
-    for (int i = tid; i < N; i += NT) {
-      unsigned char st = state[i];
-      if (st & ST_CUR) {
-        state[i] = ST_VISITED;
-        if (labelled) label[i] = S.cluster_id;
-      }
+    const int cid = S.cluster_id;
+    for (int j = tid; j < n_cur; j += NT) {
+      const int i = listI[j];
+      pw[i] = (pw[i] & PW_XYZ) | PW_VIS;
+      if (labelled) label[i] = cid;
     }
     __syncthreads();
     if (tid == 0) {
@@ -264,10 +463,10 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       S.active = 0;
     }
     __syncthreads();
-    return total;
   };
 
   int mode = MODE_NEW_REGION;
+  stamp(0);
 
   // ------------------------------------------------------------------ apply the pending step (:262-306)
   if (S.active) {
@@ -276,26 +475,45 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     LrgStepTrace* tr = nullptr;
     if (da.trace != nullptr && S.total_steps < da.trace_capacity)
       tr = da.trace + (size_t)S.room * da.trace_capacity + S.total_steps;
-    bool m_[VT], normal_[VT];
-    int p_[VT];
-    int upd = 0;
+    // every row's metadata first (independent loads), then the dependent loads (logits, point, state word)
+    int p_[VT], src_[VT];
 #pragma unroll
     for (int k = 0; k < VT; ++k) {
       const int vt = tid + k * NT;                        // virtual thread: 0..511 inlier rows (remove), 512.. neighbor rows (add)
       const bool is_add = vt >= kMaxTilePts;
       const int r = is_add ? vt - kMaxTilePts : vt;
+      const bool on = r < (is_add ? da.Nj : da.Ni);
+      // padding rows duplicate a distinct row (:239-240,251-252): same input, same logits, own uniform draw
+      src_[k] = on ? __ldcg(da.tilesrc[is_add ? 1 : 0] + (size_t)slot * kMaxTilePts + r) : 0;
+      p_[k] = on ? __ldcg(da.tileidx[is_add ? 1 : 0] + (size_t)slot * kMaxTilePts + r) : -1;
+    }
+    float2 lg_[VT], xy_[VT];
+    unsigned w_[VT];
+#pragma unroll
+    for (int k = 0; k < VT; ++k) {
+      const int vt = tid + k * NT;
+      const bool is_add = vt >= kMaxTilePts;
       const int nrows = is_add ? da.Nj : da.Ni;
+      if (p_[k] >= 0) {
+        lg_[k] = __ldcg(reinterpret_cast<const float2*>(da.logits[is_add ? 1 : 0] + ((size_t)slot * nrows + src_[k]) * 2));
+        xy_[k] = *reinterpret_cast<const float2*>(pts + (size_t)p_[k] * 16);
+        w_[k] = pw[p_[k]];
+      }
+    }
+    bool m_[VT], normal_[VT];
+    int upd = 0;
+#pragma unroll
+    for (int k = 0; k < VT; ++k) {
+      const int vt = tid + k * NT;
+      const bool is_add = vt >= kMaxTilePts;
+      const int r = is_add ? vt - kMaxTilePts : vt;
+      const int p = p_[k];
       bool m = false;
-      int p = -1;
-      if (r < nrows) {
-        // padding rows duplicate a distinct row (:239-240,251-252): same input, same logits, own uniform draw
-        const int src = __ldcg(da.tilesrc[is_add ? 1 : 0] + (size_t)slot * kMaxTilePts + r);
-        const float2 lg = __ldcg(reinterpret_cast<const float2*>(da.logits[is_add ? 1 : 0] + ((size_t)slot * nrows + src) * 2));
-        const float conf = confidence(lg.x, lg.y);
+      if (p >= 0) {
+        const float conf = confidence(lg_[k].x, lg_[k].y);
         const unsigned draw = philox_draw(da.seed, room_rng, step_rng, is_add ? kStreamAddUniform : kStreamRemoveUniform, r);
         const float u = (float)(draw >> 8) * (1.0f / 16777216.0f);
         m = u < conf;                                          // :266-267
-        p = __ldcg(da.tileidx[is_add ? 1 : 0] + (size_t)slot * kMaxTilePts + r);
       }
       const unsigned bal = __ballot_sync(0xffffffffu, m);
       if (tr != nullptr && lane == 0) {
@@ -307,63 +525,60 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       bool normal = false;
       if (m) {
         const float cx = S.center[0], cy = S.center[1];
-        const float x = __fadd_rn(__fsub_rn(pts[(size_t)p * 16 + 0], cx), cx);
-        const float y = __fadd_rn(__fsub_rn(pts[(size_t)p * 16 + 1], cy), cy);
-        const int4 v = vox[p];
-        const int vx = voxel_of(x, res), vy = voxel_of(y, res);
-        normal = (vx == v.x && vy == v.y);
+        const float x = __fadd_rn(__fsub_rn(xy_[k].x, cx), cx);
+        const float y = __fadd_rn(__fsub_rn(xy_[k].y, cy), cy);
+        const int vx = voxel_of(x, res) - vmin0, vy = voxel_of(y, res) - vmin1;
+        normal = (vx == pw_x(w_[k]) && vy == pw_y(w_[k]));
         if (!normal) {
           int o = atomicAdd(&sh.n_odd, 1);
-          sh.odd[o] = make_int4(vx, vy, v.z, is_add ? 1 : 0);
+          sh.odd[o] = make_int4(vx, vy, pw_z(w_[k]), is_add ? 1 : 0);
         }
       }
       // adds first, removes second (:283-286)
-      if (m && normal && is_add) { state[p] = (unsigned char)(state[p] | ST_CUR); upd = 1; }
-      m_[k] = m; normal_[k] = normal; p_[k] = p;
+      if (m && normal && is_add) { pw[p] = w_[k] | PW_CUR; upd = 1; }      // (a neighbour row is never CURRENT before this)
+      m_[k] = m; normal_[k] = normal;
     }
     __syncthreads();
     const int n_odd = sh.n_odd;
     if (n_odd > 0) {
       for (int i = tid; i < N; i += NT) {
-        const int4 v = vox[i];
+        const unsigned w = pw[i];
         bool hit = false;
-        for (int o = 0; o < n_odd; ++o) hit |= (sh.odd[o].w == 1 && sh.odd[o].x == v.x && sh.odd[o].y == v.y && sh.odd[o].z == v.z);
-        if (hit && !(state[i] & ST_CUR)) { state[i] = (unsigned char)(state[i] | ST_CUR); upd = 1; }
+        for (int o = 0; o < n_odd; ++o) hit |= (sh.odd[o].w == 1 && sh.odd[o].x == pw_x(w) && sh.odd[o].y == pw_y(w) && sh.odd[o].z == pw_z(w));
+        if (hit && !(w & PW_CUR)) { pw[i] = w | PW_CUR; upd = 1; }
       }
     }
     const int updated = __syncthreads_or(upd);
 #pragma unroll
     for (int k = 0; k < VT; ++k) {
       const bool is_add = (tid + k * NT) >= kMaxTilePts;
-      if (m_[k] && normal_[k] && !is_add) state[p_[k]] = (unsigned char)(state[p_[k]] & ~ST_CUR);
+      if (m_[k] && normal_[k] && !is_add) pw[p_[k]] = w_[k] & ~PW_CUR;      // (an inlier row is CURRENT and not VISITED)
     }
     if (n_odd > 0) {
       __syncthreads();
       for (int i = tid; i < N; i += NT) {
-        const int4 v = vox[i];
+        const unsigned w = pw[i];
         bool hit = false;
-        for (int o = 0; o < n_odd; ++o) hit |= (sh.odd[o].w == 0 && sh.odd[o].x == v.x && sh.odd[o].y == v.y && sh.odd[o].z == v.z);
-        if (hit) state[i] = (unsigned char)(state[i] & ~ST_CUR);
+        for (int o = 0; o < n_odd; ++o) hit |= (sh.odd[o].w == 0 && sh.odd[o].x == pw_x(w) && sh.odd[o].y == pw_y(w) && sh.odd[o].z == pw_z(w));
+        if (hit) pw[i] = w & ~PW_CUR;
       }
     }
     __syncthreads();
     if (tid == 0) { S.steps += 1; S.total_steps += 1; }     // :288
-    __syncthreads();
+    stamp(1);
 
+    // inlier list + bounding box of the updated region (:292-293); also what stop_growing marks when the region ends
+    int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+    const int n_in = scan_words<NT>(pw, N, [](unsigned w) { return (w & PW_CUR) != 0; },
+                                    [&](unsigned w) {
+                                      const int x = pw_x(w), y = pw_y(w), z = pw_z(w);
+                                      mn[0] = min(mn[0], x); mn[1] = min(mn[1], y); mn[2] = min(mn[2], z);
+                                      mx[0] = max(mx[0], x); mx[1] = max(mx[1], y); mx[2] = max(mx[2], z);
+                                    }, listI, sh.scan);
     int reason = STOP_NONE;
-    int size_after = -1;
     if (!updated) {
-      reason = STOP_NOEXPAND;                                // :304-306
+      reason = STOP_NOEXPAND;                                // :304-306 (removals alone do not count)
     } else {
-      // inlier list + bounding box of the updated region (:292-293)
-      int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
-      const int n_in = block_compact<NT>(N, [&](int i) {
-        if (!(state[i] & ST_CUR)) return false;
-        const int4 v = vox[i];
-        mn[0] = min(mn[0], v.x); mn[1] = min(mn[1], v.y); mn[2] = min(mn[2], v.z);
-        mx[0] = max(mx[0], v.x); mx[1] = max(mx[1], v.y); mx[2] = max(mx[2], v.z);
-        return true;
-      }, listI, sh.scan);
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1)
 #pragma unroll
@@ -374,7 +589,6 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       if (lane == 0)
         for (int a = 0; a < 3; ++a) { sh.red[warp * 6 + a] = mn[a]; sh.red[warp * 6 + 3 + a] = mx[a]; }
       __syncthreads();
-      size_after = n_in;
       if (tid == 0) {
         S.n_in = n_in;
         if (n_in > 0) {
@@ -402,16 +616,17 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       reason = sh.flag;
       __syncthreads();
     }
-    if (tr != nullptr && tid == 0) { tr->stop_reason = reason; tr->size_after = size_after; }
+    if (tr != nullptr && tid == 0) { tr->stop_reason = reason; tr->size_after = n_in; }
+    stamp(2);
     if (reason != STOP_NONE) {
-      int total = stop_region(reason);
-      if (tr != nullptr && tid == 0 && size_after < 0) tr->size_after = total;
+      stop_region(reason, n_in);
       mode = MODE_NEW_REGION;
     } else {
       mode = MODE_SCAN;
     }
   }
 
+  stamp(3);
   // ------------------------------------------------------------------ find the next region that needs a forward
   while (true) {
     if (mode == MODE_NEW_REGION) {
@@ -421,7 +636,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
         const int* order = da.order + base;
         for (int start = S.cursor; start < N; start += NT) {
           const int pos = start + tid;
-          const bool ok = pos < N && !(state[order[pos]] & ST_VISITED);
+          const bool ok = pos < N && !(pw[order[pos]] & PW_VIS);
           const unsigned bal = __ballot_sync(0xffffffffu, ok);
           if (lane == 0) sh.red[warp] = bal ? (start + warp * 32 + __ffs(bal) - 1) : INT_MAX;
           __syncthreads();
@@ -464,34 +679,36 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       // begin a region at the seed (:189-205)
       const int seed = da.order[base + found];
       if (tid == 0) {
-        const int4 v = vox[seed];
+        const unsigned w = pw[seed];
         S.cursor = found + 1;
         S.seed = seed;
-        S.minD[0] = S.maxD[0] = S.seqMin[0] = S.seqMax[0] = v.x;
-        S.minD[1] = S.maxD[1] = S.seqMin[1] = S.seqMax[1] = v.y;
-        S.minD[2] = S.maxD[2] = S.seqMin[2] = S.seqMax[2] = v.z;
+        S.minD[0] = S.maxD[0] = S.seqMin[0] = S.seqMax[0] = pw_x(w);
+        S.minD[1] = S.maxD[1] = S.seqMin[1] = S.seqMax[1] = pw_y(w);
+        S.minD[2] = S.maxD[2] = S.seqMin[2] = S.seqMax[2] = pw_z(w);
         S.stuck = 0; S.steps = 0; S.n_in = 1;
-        state[seed] = (unsigned char)(state[seed] | ST_CUR);
+        pw[seed] = w | PW_CUR;
         listI[0] = seed;
       }
       __syncthreads();
       mode = MODE_SCAN;
     }
+    stamp(4);
     // neighbour shell: bbox +- 1 voxel, not current, not visited (:222-229)
     const int lo0 = S.minD[0] - 1, lo1 = S.minD[1] - 1, lo2 = S.minD[2] - 1;
     const int hi0 = S.maxD[0] + 1, hi1 = S.maxD[1] + 1, hi2 = S.maxD[2] + 1;
-    const int n_nb = block_compact<NT>(N, [&](int i) {
-      if (state[i] & (ST_CUR | ST_VISITED)) return false;
-      const int4 v = vox[i];
-      return v.x >= lo0 && v.x <= hi0 && v.y >= lo1 && v.y <= hi1 && v.z >= lo2 && v.z <= hi2;
-    }, listJ, sh.scan);
+    const int n_nb = scan_words<NT>(pw, N, [&](unsigned w) {
+      if (w & (PW_CUR | PW_VIS)) return false;
+      const int x = pw_x(w), y = pw_y(w), z = pw_z(w);
+      return x >= lo0 && x <= hi0 && y >= lo1 && y <= hi1 && z >= lo2 && z <= hi2;
+    }, [](unsigned) {}, listJ, sh.scan);
     if (n_nb == 0) {                                          // :233-235
-      stop_region(STOP_NONEIGHBOR);
+      stop_region(STOP_NONEIGHBOR, S.n_in);
       mode = MODE_NEW_REGION;
       continue;
     }
     if (tid == 0) S.n_nb = n_nb;
     __syncthreads();
+    stamp(5);
     break;
   }
 
@@ -502,9 +719,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     const unsigned step_rng = (unsigned)S.total_steps;
     // median of every centred channel over ALL current points (:241): channels 0,1 and 6..F-1
     const int nch = 2 + (da.F > 6 ? da.F - 6 : 0);
-    if (tid < 18) sh.rank[tid] = (tid & 1) ? (n_in / 2) : ((n_in - 1) / 2);
-    __syncthreads();
-    block_radix_select<NT, 9, 2>(n_in, [&](int j, unsigned (&k)[9], bool (&valid)[9]) {
+    auto row_keys = [&](int j, unsigned (&k)[9]) {
       const float* row = pts + (size_t)listI[j] * 16;
       const float4 a = *reinterpret_cast<const float4*>(row);
       const float4 b = *reinterpret_cast<const float4*>(row + 4);
@@ -512,18 +727,47 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       const float4 d = *reinterpret_cast<const float4*>(row + 12);
       const float vals[9] = {a.x, a.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x};
 #pragma unroll
-      for (int s = 0; s < 9; ++s) { k[s] = sortable(vals[s]); valid[s] = s < nch; }
-    }, sh.prefix, sh.rank, sh.hist);
+      for (int s = 0; s < 9; ++s) k[s] = sortable(vals[s]);
+    };
+    if (n_in <= kMedianCap) {
+      for (int j = tid; j < n_in; j += NT) {
+        unsigned k[9];
+        row_keys(j, k);
+#pragma unroll
+        for (int s = 0; s < 9; ++s) sh.mkeys[s][j] = k[s];
+      }
+      __syncthreads();
+    }
+    if (n_in <= 1024) {
+      // one warp per channel, no atomics and no block barriers (most regions are small: median n_in ~ 50)
+      for (int c = warp; c < nch; c += NT / 32) {
+        unsigned lo, hi;
+        if (n_in <= 64) warp_median<2>(sh.mkeys[c], n_in, lo, hi);
+        else if (n_in <= 256) warp_median<8>(sh.mkeys[c], n_in, lo, hi);
+        else warp_median<32>(sh.mkeys[c], n_in, lo, hi);
+        if (lane == 0) { sh.prefix[c] = lo; sh.nextkey[c] = hi; }
+      }
+      __syncthreads();
+    } else if (n_in <= kMedianCap) {
+      block_median9<NT>(n_in, nch, [&](int j, unsigned (&k)[9]) {
+#pragma unroll
+        for (int s = 0; s < 9; ++s) k[s] = sh.mkeys[s][j];
+      }, sh.prefix, sh.rank, sh.hist, sh.nextkey);
+    } else {
+      __syncthreads();
+      block_median9<NT>(n_in, nch, row_keys, sh.prefix, sh.rank, sh.hist, sh.nextkey);
+    }
     if (tid < 16) {
       float cval = 0.f;
       const int ch = tid < 2 ? tid : tid - 4;                 // feature column -> median channel
       if ((tid < 2 || tid >= 6) && tid < da.F) {
-        const float lo = unsortable(sh.prefix[ch * 2]), hi = unsortable(sh.prefix[ch * 2 + 1]);
+        const float lo = unsortable(sh.prefix[ch]), hi = unsortable(sh.nextkey[ch]);
         cval = (n_in & 1) ? lo : __fmul_rn(__fadd_rn(lo, hi), 0.5f);   // numpy.median: mean of the two middle values
       }
       S.center[tid] = cval;
     }
     __syncthreads();
+    stamp(6);
 
     // sampling (:237-240, :249-252) with the Philox stream of oracle/lrg_driver.py PhiloxRng
     const bool fullI = n_in >= da.Ni, fullJ = n_nb >= da.Nj;
@@ -551,6 +795,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
         sh.sel[1][r] = r < n_nb ? r : (int)__umulhi(philox_draw(da.seed, room_rng, step_rng, kStreamNeighborPad, r - n_nb), (unsigned)n_nb);
     __syncthreads();
 
+    stamp(7);
     // gather + centre (:242-247, :253): columns 0:2 and 6: are centred, z and the room coordinates are not
     {
       const bool tracing = da.trace != nullptr && S.total_steps < da.trace_capacity;
@@ -599,10 +844,13 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     }
     for (int i = tid; i < da.pooled_per_slot; i += NT) da.pooled[(size_t)slot * da.pooled_per_slot + i] = 0.f;
     if (tid == 0) S.active = 1;
+    stamp(8);
   }
   __syncthreads();
   for (int i = tid; i < (int)(sizeof(SlotState) / 4); i += NT)
     reinterpret_cast<int*>(gS)[i] = reinterpret_cast<const int*>(&sh.S)[i];
+  stamp(9);
+  if (da.dbg != nullptr && tid == 0) atomicAdd(da.dbg + 15, 1ull);
 }
 
 }  // namespace lrg
