@@ -183,9 +183,15 @@ def run_reference_arm(args):
 
 
 def workload_points_per_step(n_rooms, raw_counts):
-    path = '/tmp/lrg_bench_stats_%d.json' % n_rooms
+    """Raw points per grow step of the workload: from the GPU arm's last run on this box if there was one, else from the
+    committed statistics of the same deterministic workload (profiles/workload_stats.json), else from the reference logs."""
     try:
-        s = json.load(open(path))
+        s = json.load(open('/tmp/lrg_bench_stats_%d.json' % n_rooms))
+        return float(s['raw_points']) / float(s['grow_steps'])
+    except Exception:
+        pass
+    try:
+        s = json.load(open(os.path.join(REPO, 'profiles', 'workload_stats.json')))['area5_synthetic_%d_rooms_20k_raw' % n_rooms]
         return float(s['raw_points']) / float(s['grow_steps'])
     except Exception:
         return float(np.mean(raw_counts)) / 948.0
