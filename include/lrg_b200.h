@@ -86,6 +86,8 @@ typedef struct LrgGrowParams {
 enum {
   LRG_FLAG_KERNEL_TIMING = 1,  /* time the forward kernels separately with CUDA events (no graph; slower) */
   LRG_FLAG_NO_GRAPH = 2,       /* lock-step loop with direct kernel launches instead of a CUDA graph */
+  LRG_FLAG_PRIORITY = 8,       /* persistent kernel: serve the slots with the most unvisited points from a high-priority ring
+                                  (off by default: +5% against the plain FIFO, measured, but costs as much in polling) */
   LRG_FLAG_LOCKSTEP = 4        /* lock-step loop (one {step, branch, gproj, head} kernel quartet per iteration, CUDA graph)
                                   instead of the persistent grow kernel; implied by the two flags above and by FMA mode */
 };
@@ -134,6 +136,8 @@ int lrg_last_segment_profile(LrgEngine* e, float* grow_ms, float* fill_ms, int64
  * ran as one persistent launch, and per work-item type (step, branch tile, pooled-projection block, head tile) the summed
  * handler time over all CTAs in ms and the number of items handled. */
 int lrg_last_grow_profile(LrgEngine* e, int* persistent, double busy_ms[4], int64_t items[4]);
+/* Summed time (ms) the items of each type waited in the device queue between publication and pick-up (same order). */
+int lrg_last_grow_queue_delay(LrgEngine* e, double delay_ms[4]);
 
 /* Diagnostics: with LRG_TILE_TIMING=1 in the environment at load_weights time the tensor tiles add the SM cycles of each
  * of their stages to counters (out[0..13] branch tile stages, out[15] branch tiles; out[16..23] head tile stages,

@@ -42,6 +42,7 @@ FORWARD_AUTO, FORWARD_FMA, FORWARD_TENSOR = 0, 1, 2
 FLAG_KERNEL_TIMING = 1
 FLAG_NO_GRAPH = 2
 FLAG_LOCKSTEP = 4
+FLAG_PRIORITY = 8
 
 _P = C.c_void_p
 _I = C.c_int
@@ -66,6 +67,7 @@ _SIGNATURES = {
                                       C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     'lrg_last_grow_profile': (_I, [_P, C.POINTER(_I), C.POINTER(C.c_double * 4), C.POINTER(C.c_int64 * 4)]),
     'lrg_tile_timing': (_I, [_P, C.POINTER(C.c_uint64 * 48), _I]),
+    'lrg_last_grow_queue_delay': (_I, [_P, C.POINTER(C.c_double * 4)]),
     'lrg_last_kernel_times': (_I, [_P, C.POINTER(C.c_float * 4)]),
     'lrg_labels_device_ptr': (_I, [_P, _I, C.POINTER(_P)]),
     'lrg_farthest_point_sampling': (_I, [_I, _I, _I, _P, _P, _P, _P]),

@@ -21,6 +21,7 @@ struct SlotState {
   int n_in, n_nb;
   int cluster_id;      // :177
   int regions, stops[4];
+  int visited;         // points of the current room already assigned to a finished region (scheduling hint)
   float center[16];    // :241
 };
 

@@ -101,11 +101,12 @@ struct LrgEngine {
   int sm_count = 0;
   unsigned long long* d_qring = nullptr;
   unsigned q_capacity = 0;
-  unsigned* d_qctr = nullptr;            // [0] head, [1] tail
+  unsigned* d_qctr = nullptr;            // [0] head, [1] tail of the high-priority ring, [2], [3] of the normal ring
+  int* d_remaining = nullptr;
   SlotSync* d_sync = nullptr;
   int sync_slots = 0;
-  unsigned long long* d_busy = nullptr;  // [16]
-  unsigned long long h_busy[16] = {0};
+  unsigned long long* d_busy = nullptr;  // [24]
+  unsigned long long h_busy[24] = {0};
   bool last_persistent = false;
   unsigned long long* d_tile_dbg = nullptr;   // [32] tile-stage cycle counters (diagnostics, LRG_TILE_TIMING=1)
   // profile of the last segment call
@@ -279,7 +280,7 @@ int lrg_engine_destroy(LrgEngine* e) {
   cudaStreamSynchronize(e->stream);
   free_forward_ws(e); free_rooms(e); free_slots(e);
   cudaFree(e->d_weights); cudaFree(e->d_tc_img); cudaFree(e->d_counters); cudaFree(e->d_trace);
-  cudaFree(e->d_qring); cudaFree(e->d_qctr); cudaFree(e->d_sync); cudaFree(e->d_busy); cudaFree(e->d_tile_dbg);
+  cudaFree(e->d_qring); cudaFree(e->d_qctr); cudaFree(e->d_sync); cudaFree(e->d_busy); cudaFree(e->d_tile_dbg); cudaFree(e->d_remaining);
   cudaFreeHost(e->h_done);
   cudaStreamDestroy(e->stream);
   delete e;
@@ -618,35 +619,43 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
         cudaFree(e->d_qring);
         e->d_qring = nullptr;
         e->q_capacity = 0;
-        LRG_TRY(dev_alloc(&e->d_qring, cap));
+        LRG_TRY(dev_alloc(&e->d_qring, (size_t)2 * cap));     // two rings: high priority, normal
         e->q_capacity = cap;
       }
-      if (e->d_qctr == nullptr) LRG_TRY(dev_alloc(&e->d_qctr, 2));
-      if (e->d_busy == nullptr) LRG_TRY(dev_alloc(&e->d_busy, 16));
+      if (e->d_qctr == nullptr) LRG_TRY(dev_alloc(&e->d_qctr, 4));
+      if (e->d_busy == nullptr) LRG_TRY(dev_alloc(&e->d_busy, 24));
       if (n_slots > e->sync_slots) {
-        cudaFree(e->d_sync);
-        e->d_sync = nullptr;
+        cudaFree(e->d_sync); cudaFree(e->d_remaining);
+        e->d_sync = nullptr; e->d_remaining = nullptr;
         e->sync_slots = 0;
         LRG_TRY(dev_alloc(&e->d_sync, (size_t)n_slots));
+        LRG_TRY(dev_alloc(&e->d_remaining, (size_t)n_slots));
         e->sync_slots = n_slots;
       }
       std::vector<unsigned long long> first(n_slots);
       for (int s = 0; s < n_slots; ++s) first[s] = (1ull << 32) | make_item(ITEM_STEP, s, 0, 0);
-      const unsigned ctr[2] = {0u, (unsigned)n_slots};
-      LRG_CUDA(cudaMemsetAsync(e->d_qring, 0, sizeof(unsigned long long) * e->q_capacity, st));
-      LRG_CUDA(cudaMemcpyAsync(e->d_qring, first.data(), sizeof(unsigned long long) * n_slots, cudaMemcpyHostToDevice, st));
+      const unsigned ctr[4] = {0u, 0u, 0u, (unsigned)n_slots};
+      LRG_CUDA(cudaMemsetAsync(e->d_qring, 0, sizeof(unsigned long long) * 2 * e->q_capacity, st));
+      LRG_CUDA(cudaMemcpyAsync(e->d_qring + e->q_capacity, first.data(), sizeof(unsigned long long) * n_slots, cudaMemcpyHostToDevice, st));
       LRG_CUDA(cudaMemcpyAsync(e->d_qctr, ctr, sizeof(ctr), cudaMemcpyHostToDevice, st));
-      LRG_CUDA(cudaMemsetAsync(e->d_busy, 0, sizeof(unsigned long long) * 16, st));
+      LRG_CUDA(cudaMemsetAsync(e->d_busy, 0, sizeof(unsigned long long) * 24, st));
       LRG_CUDA(cudaMemsetAsync(e->d_sync, 0, sizeof(SlotSync) * n_slots, st));
+      LRG_CUDA(cudaMemsetAsync(e->d_remaining, 0, sizeof(int) * n_slots, st));
       GrowArgs ga{};
       ga.da = da;
       ga.da.done_flag = nullptr;
       ga.fa = fa;
       ga.fa.active = nullptr;
       ga.net = e->tcnet;
-      ga.q.ring = e->d_qring; ga.q.cap_mask = e->q_capacity - 1; ga.q.head = e->d_qctr; ga.q.tail = e->d_qctr + 1;
+      for (int k = 0; k < 2; ++k) {
+        ga.q[k].ring = e->d_qring + (size_t)k * e->q_capacity; ga.q[k].cap_mask = e->q_capacity - 1;
+        ga.q[k].head = e->d_qctr + 2 * k; ga.q[k].tail = e->d_qctr + 2 * k + 1;
+      }
       ga.sync = e->d_sync;
       ga.busy_ns = e->d_busy;
+      ga.remaining = e->d_remaining;
+      ga.hi_slots = params->flags & LRG_FLAG_PRIORITY ? std::max(2, n_slots / 8) : 0;
+      ga.tune = getenv("LRG_TUNE") ? atoi(getenv("LRG_TUNE")) : 2;   // measured (profiles/README.md): splitting costs more than it saves; overlap +3%
       rc = launch_grow(ga, e->sm_count > 0 ? e->sm_count : 148, st);
       if (rc == LRG_OK) {
         cudaError_t se = cudaStreamSynchronize(st);
@@ -764,6 +773,13 @@ int lrg_last_segment_profile(LrgEngine* e, float* grow_ms, float* fill_ms, int64
   if (iterations) *iterations = e->iterations;
   if (kernel_launches) *kernel_launches = e->launches;
   if (forward_ms) *forward_ms = e->forward_ms;
+  return LRG_OK;
+}
+
+int lrg_last_grow_queue_delay(LrgEngine* e, double delay_ms[4]) {
+  LRG_REQUIRE(e != nullptr && delay_ms != nullptr, "NULL argument");
+  const int types[4] = {ITEM_STEP, ITEM_BRANCH, ITEM_GPROJ, ITEM_HEAD};
+  for (int i = 0; i < 4; ++i) delay_ms[i] = e->last_persistent ? (double)e->h_busy[16 + types[i]] * 1e-6 : 0.0;
   return LRG_OK;
 }
 

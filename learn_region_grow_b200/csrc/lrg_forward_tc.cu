@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) lrg_tc_branch_kernel(const __gr
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_base;
-  tc_branch_tile(net, fa, b, br, tile, nvalid, smem, st, tmem);
+  tc_branch_tile(net, fa, b, br, tile, nvalid, 0, 4, smem, st, tmem);
   if ((threadIdx.x >> 5) == 4) tmem_dealloc(tmem, kTmemCols);
 }
 
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) lrg_tc_head_kernel(const __grid
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_base;
-  tc_head_tile(net, fa, b, h, tile, nvalid, smem, st, tmem);
+  tc_head_tile(net, fa, b, h, tile, nvalid, nullptr, smem, st, tmem);
   if ((threadIdx.x >> 5) == 4) tmem_dealloc(tmem, kTmemCols);
 }
 

@@ -37,6 +37,7 @@ __device__ __forceinline__ void queue_push(const GrowQueue& q, const unsigned* i
   }
 }
 
+// Blocking pop of the normal ring: take a ticket, spin on that ticket's own entry (idle CTAs poll distinct addresses).
 __device__ __forceinline__ unsigned queue_pop(const GrowQueue& q) {
   const unsigned h = atomicAdd(q.head, 1u);
   const unsigned long long gen = (unsigned long long)(h / (q.cap_mask + 1u)) + 1ull;
@@ -51,6 +52,24 @@ __device__ __forceinline__ unsigned queue_pop(const GrowQueue& q) {
   }
   __threadfence();
   return (unsigned)v;
+}
+
+// Non-blocking pop of the high-priority ring: claims a ticket only if an item has been published for it (CAS, never
+// over-claims).  Called once per item a CTA retires, never in a spin loop (every CTA would hammer the same two words).
+__device__ __forceinline__ bool queue_try_pop(const GrowQueue& q, unsigned& item) {
+  while (true) {
+    const unsigned h = *reinterpret_cast<volatile unsigned*>(q.head);
+    const unsigned t = *reinterpret_cast<volatile unsigned*>(q.tail);
+    if ((int)(t - h) <= 0) return false;
+    if (atomicCAS(q.head, h, h + 1u) != h) continue;  // lost the race for this ticket: look again
+    const unsigned long long gen = (unsigned long long)(h / (q.cap_mask + 1u)) + 1ull;
+    const volatile unsigned long long* e = q.ring + (h & q.cap_mask);
+    unsigned long long v;
+    while (((v = *e) >> 32) != gen) {}               // the producer bumped tail first and is writing the entry right now
+    __threadfence();
+    item = (unsigned)v;
+    return true;
+  }
 }
 
 __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_constant__ GrowArgs ga) {
@@ -69,61 +88,114 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
   float* const sP = reinterpret_cast<float*>(smem);
   float* const sR = sP + 1024;
 
+  // Scheduling: items of the high-priority slots go to ring 0 and a WAKE token goes to ring 1 with them; a CTA blocks on
+  // ring 1 only, and before running what it popped there it drains ring 0.  Under load every retiring CTA therefore serves
+  // the high-priority ring first; when idle, the token wakes a CTA that finds the item.
+  unsigned deferred = 0;                              // the ring-1 item to run once ring 0 is empty (0 = none)
   while (true) {
-    if (tid == 0) s_item = queue_pop(ga.q);
+    if (tid == 0) {
+      unsigned it = 0;
+      if (ga.hi_slots <= 0) it = queue_pop(ga.q[1]);    // priorities off: one FIFO
+      else if (!queue_try_pop(ga.q[0], it)) {
+        if (deferred != 0) { it = deferred; deferred = 0; }
+        else {
+          it = queue_pop(ga.q[1]);
+          unsigned hi_item = 0;
+          if (queue_try_pop(ga.q[0], hi_item)) { deferred = it; it = hi_item; }
+        }
+      }
+      s_item = it;
+    }
     __syncthreads();
     const unsigned item = s_item;
     const int type = (int)(item & 7u), slot = (int)((item >> 3) & 0x1FFFu), a = (int)((item >> 16) & 15u), t = (int)((item >> 20) & 15u);
     if (type == ITEM_EXIT) break;
+    if (type == ITEM_WAKE) { __syncthreads(); continue; }
     const unsigned long long t0 = (tid == 0) ? global_ns() : 0ull;
     SlotSync* sy = ga.sync + slot;
-    unsigned next[16];
+    if (tid == 0 && ga.busy_ns != nullptr) {
+      // diagnostics: how long the item sat between being published and being picked up
+      const unsigned long long tp = *reinterpret_cast<volatile unsigned long long*>(&sy->t_pub);
+      if (tp != 0 && t0 > tp) atomicAdd(ga.busy_ns + 16 + type, t0 - tp);
+    }
+    unsigned next[32];
     int n_next = 0;
     if (type == ITEM_STEP) {
       step_body<kGrowThreads>(ga.da, slot, sh);
       __syncthreads();
       if (tid == 0) {
+        if (sh.S.finished) *reinterpret_cast<volatile int*>(ga.remaining + slot) = 0;
         if (sh.all_done) {
           // the last slot has retired: nothing is in flight any more, release every CTA
           for (unsigned left = gridDim.x; left > 0;) {
             const int n = left > 16u ? 16 : (int)left;
             for (int i = 0; i < n; ++i) next[i] = make_item(ITEM_EXIT, 0, 0, 0);
             __threadfence();
-            queue_push(ga.q, next, n);
+            queue_push(ga.q[1], next, n);
             left -= (unsigned)n;
           }
         } else if (sh.S.active && !sh.S.finished) {
+          // scheduling (optional): the run ends with the rooms that have the most work left; rank this slot by unvisited points
+          sy->prio = 1;
+          if (ga.hi_slots > 0) {
+            const int mine = (int)(ga.da.room_off[sh.S.room + 1] - ga.da.room_off[sh.S.room]) - sh.S.visited;
+            *reinterpret_cast<volatile int*>(ga.remaining + slot) = mine;
+            int ahead = 0;
+            for (int i = 0; i < ga.da.n_slots; ++i) ahead += (*reinterpret_cast<volatile int*>(ga.remaining + i) > mine) ? 1 : 0;
+            if (ahead < ga.hi_slots) sy->prio = 0;
+          }
           // only rows that carry distinct points are evaluated (the rest are padding duplicates of them)
           const int tilesI = (min(sh.S.n_in, ga.fa.n_pts[0]) + 127) / 128, tilesJ = (min(sh.S.n_nb, ga.fa.n_pts[1]) + 127) / 128;
-          sy->branch_left = tilesI + tilesJ;
+          // When SMs are idle (short backlog) every branch tile is split over 2 or 4 CTAs by column block of the last
+          // layer -- each recomputes the cheap first four layers -- which shortens the critical path of the run's tail;
+          // under load tiles stay whole (splitting costs SM time).  a = branch | log2(parts) << 1, t = tile | part << 2.
+          const unsigned backlog = (*reinterpret_cast<volatile unsigned*>(ga.q[0].tail) - *reinterpret_cast<volatile unsigned*>(ga.q[0].head)) +
+                                   (*reinterpret_cast<volatile unsigned*>(ga.q[1].tail) - *reinterpret_cast<volatile unsigned*>(ga.q[1].head));
+          const int lg = !(ga.tune & 1) ? 0 : backlog + 8u * (unsigned)(tilesI + tilesJ) <= gridDim.x / 2 ? 2 : backlog + 4u * (unsigned)(tilesI + tilesJ) <= gridDim.x ? 1 : 0;
+          const int parts = 1 << lg;
+          sy->branch_left = (tilesI + tilesJ) * parts;
           sy->gproj_left = 8;
           sy->head_left = tilesI + tilesJ;
           sy->tiles[0] = tilesI;
           sy->tiles[1] = tilesJ;
-          for (int i = 0; i < tilesI; ++i) next[n_next++] = make_item(ITEM_BRANCH, slot, 0, i);
-          for (int i = 0; i < tilesJ; ++i) next[n_next++] = make_item(ITEM_BRANCH, slot, 1, i);
+          for (int part = 0; part < parts; ++part) {
+            for (int i = 0; i < tilesI; ++i) next[n_next++] = make_item(ITEM_BRANCH, slot, 0 | (lg << 1), i | (part << 2));
+            for (int i = 0; i < tilesJ; ++i) next[n_next++] = make_item(ITEM_BRANCH, slot, 1 | (lg << 1), i | (part << 2));
+          }
         }
       }
     } else if (type == ITEM_BRANCH) {
-      tc_branch_tile(ga.net, ga.fa, slot, a, t, forward_valid_rows(ga.fa, slot, a), smem, st, tmem);
+      {
+        const int br = a & 1, part = t >> 2, nbs = 4 >> (a >> 1);
+        tc_branch_tile(ga.net, ga.fa, slot, br, t & 3, forward_valid_rows(ga.fa, slot, br), part * nbs, (part + 1) * nbs, smem, st, tmem);
+      }
       if (tid == 0) {
         __threadfence();
-        if (atomicSub(&sy->branch_left, 1) == 1)
+        if (atomicSub(&sy->branch_left, 1) == 1) {
+          // the pooled row is complete: publish the projection blocks and, behind them in the FIFO, the head tiles -- a CTA
+          // that pops a head tile knows every projection block of its slot is already running (or done), so the head's
+          // wait on gproj_left cannot deadlock, and its prologue overlaps the projection
           for (int h = 0; h < 2; ++h)
             for (int cb = 0; cb < 4; ++cb) next[n_next++] = make_item(ITEM_GPROJ, slot, h, cb);
+          if (ga.tune & 2) {
+            const int tilesI = __ldcg(&sy->tiles[0]), tilesJ = __ldcg(&sy->tiles[1]);
+            for (int i = 0; i < tilesI; ++i) next[n_next++] = make_item(ITEM_HEAD, slot, 0, i);
+            for (int i = 0; i < tilesJ; ++i) next[n_next++] = make_item(ITEM_HEAD, slot, 1, i);
+          }
+        }
       }
     } else if (type == ITEM_GPROJ) {
       tc_gproj_block(ga.net, ga.fa, slot, a, t, sP, sR);
       if (tid == 0) {
         __threadfence();
-        if (atomicSub(&sy->gproj_left, 1) == 1) {
+        if (atomicSub(&sy->gproj_left, 1) == 1 && !(ga.tune & 2)) {   // (with tune bit 1 the head tiles are already out, spinning on this)
           const int tilesI = __ldcg(&sy->tiles[0]), tilesJ = __ldcg(&sy->tiles[1]);
           for (int i = 0; i < tilesI; ++i) next[n_next++] = make_item(ITEM_HEAD, slot, 0, i);
           for (int i = 0; i < tilesJ; ++i) next[n_next++] = make_item(ITEM_HEAD, slot, 1, i);
         }
       }
     } else if (type == ITEM_HEAD) {
-      tc_head_tile(ga.net, ga.fa, slot, a, t, forward_valid_rows(ga.fa, slot, a), smem, st, tmem);
+      tc_head_tile(ga.net, ga.fa, slot, a, t, forward_valid_rows(ga.fa, slot, a), &sy->gproj_left, smem, st, tmem);
       if (tid == 0) {
         __threadfence();
         if (atomicSub(&sy->head_left, 1) == 1) next[n_next++] = make_item(ITEM_STEP, slot, 0, 0);
@@ -131,8 +203,13 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
     }
     if (tid == 0) {
       if (n_next > 0) {
+        *reinterpret_cast<volatile unsigned long long*>(&sy->t_pub) = global_ns();
         __threadfence();
-        queue_push(ga.q, next, n_next);
+        if ((sy->prio & 1) == 0) {
+          queue_push(ga.q[0], next, n_next);
+          for (int i = 0; i < n_next; ++i) next[i] = make_item(ITEM_WAKE, 0, 0, 0);
+        }
+        queue_push(ga.q[1], next, n_next);
       }
       if (ga.busy_ns != nullptr) {
         atomicAdd(ga.busy_ns + type, global_ns() - t0);

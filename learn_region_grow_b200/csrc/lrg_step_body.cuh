@@ -458,6 +458,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     if (tid == 0) {
       if (labelled) S.cluster_id += 1;
       S.regions += 1;
+      S.visited += n_cur;
       int slot_r = reason == STOP_NONEIGHBOR ? 0 : reason == STOP_NOEXPAND ? 1 : reason == STOP_STUCK ? 2 : 3;
       S.stops[slot_r] += 1;
       S.active = 0;
@@ -656,7 +657,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
           }
           const int nr = atomicAdd(da.next_room, 1);
           S.room = nr < da.n_rooms ? nr : -1;
-          S.cursor = 0; S.cluster_id = 1; S.total_steps = 0; S.regions = 0;
+          S.cursor = 0; S.cluster_id = 1; S.total_steps = 0; S.regions = 0; S.visited = 0;
           S.stops[0] = S.stops[1] = S.stops[2] = S.stops[3] = 0;
           S.active = 0;
         }

@@ -34,9 +34,10 @@ constexpr uint32_t kTmH1hi = 256, kTmH1lo = 320, kTmChi = 384, kTmClo = 448;
 struct TcBarriers {
   uint64_t full[kRingSlots], empty[kRingSlots];
   uint64_t acc_full[2], acc_empty[2];
-  uint64_t act_ready;               // branch: activations of the next layer written; head: h1 tile + vec[] written
+  uint64_t act_ready;               // branch: activations of the next layer written; head: h1 tile written
   uint64_t c_ready[2], c_free[2];   // head only: the two 32-channel halves of the hidden-layer slice
   uint64_t acc1_full;               // head only
+  uint64_t vec_ready;               // head only: vec[] (pooled projection row, bias1, W2, bias2) staged
 };
 constexpr int kTcBarrierCount = sizeof(TcBarriers) / 8;
 
@@ -44,7 +45,7 @@ constexpr int kTcBarrierCount = sizeof(TcBarriers) / 8;
 // W2 256 + bias2 2 = 642 floats).
 struct TcStatic {
   TcBarriers bars;
-  float vec[648];
+  alignas(16) float vec[648];
 };
 
 // diagnostics: thread 0 adds the cycles since *t to dbg[stage] and restarts the interval
@@ -112,8 +113,10 @@ __device__ __forceinline__ void tc_init_barriers(TcBarriers& bars, bool head) {
     mbar_init(smem_u32(&bars.c_ready[i]), 128);
     mbar_init(smem_u32(&bars.c_free[i]), 1);
   }
-  mbar_init(smem_u32(&bars.act_ready), head ? 128 + 32 : 128);   // head: 128 rows of h1 + the 32 loader lanes that fill vec[]
+  mbar_init(smem_u32(&bars.act_ready), 128);
   mbar_init(smem_u32(&bars.acc1_full), 1);
+  mbar_init(smem_u32(&bars.vec_ready), 32);
+  (void)head;
   fence_barrier_init();
 }
 __device__ __forceinline__ void tc_inval_barriers(TcBarriers& bars) {
@@ -121,25 +124,29 @@ __device__ __forceinline__ void tc_inval_barriers(TcBarriers& bars) {
   for (int i = 0; i < kTcBarrierCount; ++i) mbar_inval(smem_u32(p + i));
 }
 
-// Weight loader (one thread): streams chunks [first, n_chunks) of the operand image through the ring; chunk 0 may be short.
-__device__ __forceinline__ void tc_stream_weights(TcBarriers& bars, uint32_t ring_u32, const float* img, int first, int n_chunks,
-                                                  uint32_t bytes0) {
-  size_t off = 0;
-  for (int i = 0; i < first; ++i) off += ((i == 0) ? bytes0 : kSlotBytes) / 4;
-  for (int i = first; i < n_chunks; ++i) {
+// Weight loader (one thread): streams the operand-image chunks [first, n_head) and [gap_to, gap_to + n_tail) through the
+// ring in that order (the ring position is the running count); chunk 0 of the image may be short (bytes0).
+__device__ __forceinline__ void tc_stream_weights(TcBarriers& bars, uint32_t ring_u32, const float* img, int first, int n_head,
+                                                  int gap_to, int n_tail, uint32_t bytes0) {
+  auto chunk_off = [&](int c) { return c == 0 ? (size_t)0 : (size_t)bytes0 / 4 + (size_t)(c - 1) * (kSlotBytes / 4); };
+  int i = first;                                   // position in the ring sequence
+  const int total = n_head + n_tail;
+  for (; i < total; ++i) {
+    const int c = i < n_head ? i : gap_to + (i - n_head);
     const int slot = i % kRingSlots;
-    const uint32_t bytes = (i == 0) ? bytes0 : kSlotBytes;
+    const uint32_t bytes = (c == 0) ? bytes0 : kSlotBytes;
     mbar_wait(smem_u32(&bars.empty[slot]), ((uint32_t)(i / kRingSlots) & 1u) ^ 1u);
     mbar_expect_tx(smem_u32(&bars.full[slot]), bytes);
-    bulk_g2s(ring_u32 + slot * kSlotBytes, img + off, bytes, smem_u32(&bars.full[slot]));
-    off += bytes / 4;
+    bulk_g2s(ring_u32 + slot * kSlotBytes, img + chunk_off(c), bytes, smem_u32(&bars.full[slot]));
   }
 }
 
 // ------------------------------------------------------------------------------------------------------ branch tile
 // x (rows x F) -> 64 -> 64 -> 64 -> 128 -> 512 -> column max merged into pooled (learn_region_grow_util.py:106-123).
+// nb0..nb1: which 128-column blocks of the last layer this call reduces (a tile may be split over several CTAs, each
+// recomputing the cheap first four layers, to shorten the critical path when SMs are idle); h1 is written when nb0 == 0.
 __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardArgs& fa, int b, int br, int tile, int nvalid,
-                                               unsigned char* smem, TcStatic& st, uint32_t tmem) {
+                                               int nb0, int nb1, unsigned char* smem, TcStatic& st, uint32_t tmem) {
   const int n = fa.n_pts[br];
   const int row0 = tile * 128;
   const int rows = min(128, nvalid - row0);       // rows >= nvalid are padding duplicates: never read, never pooled
@@ -183,7 +190,7 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
       mbar_arrive(smem_u32(&bars.act_ready));
       tc_stamp(net.dbg, 1, tstamp);
     }
-    float* g_h1 = valid ? fa.h1[br] + ((size_t)b * n + row0 + r) * 64 : nullptr;
+    float* g_h1 = (valid && nb0 == 0) ? fa.h1[br] + ((size_t)b * n + row0 + r) * 64 : nullptr;
 #pragma unroll 1
     for (int l = 0; l < 4; ++l) {
       const int buf = l & 1;
@@ -207,8 +214,8 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
     int* gmax = reinterpret_cast<int*>(fa.pooled) + (size_t)b * 1024 + br * 512;
     const float* bias4 = net.conv_bias[br][4];
 #pragma unroll 1
-    for (int nb = 0; nb < 4; ++nb) {
-      const int j = 4 + nb, buf = nb & 1;
+    for (int nb = nb0; nb < nb1; ++nb) {
+      const int j = 4 + (nb - nb0), buf = j & 1;
       float b4[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) b4[c] = __ldg(bias4 + nb * 128 + c * 32 + lane);
@@ -238,7 +245,7 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
       }
       tcgen05_fence_before();
       mbar_arrive(smem_u32(&bars.acc_empty[buf]));
-      tc_stamp(net.dbg, 6 + nb, tstamp);
+      tc_stamp(net.dbg, 6 + (nb - nb0), tstamp);
     }
   } else if (warp == 4) {
     // ===================================================================== MMA issuer
@@ -277,8 +284,8 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
       }
       timed_wait(smem_u32(&bars.act_ready), 0u, w_act);   // h3 (fifth completion of act_ready)
       tcgen05_fence_after();
-      for (int nb = 0; nb < 4; ++nb) {
-        const int j = 4 + nb, buf = nb & 1;
+      for (int nb = nb0; nb < nb1; ++nb) {
+        const int j = 4 + (nb - nb0), buf = j & 1;
         timed_wait(smem_u32(&bars.acc_empty[buf]), ((uint32_t)(j >> 1) & 1u) ^ 1u, w_acc);
         tcgen05_fence_after();
 #pragma unroll 1
@@ -296,7 +303,7 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
     }
   } else if (warp == 5) {
     // ===================================================================== weight loader
-    if (lane == 0) tc_stream_weights(bars, ring_u32, net.branch_img[br], 0, kBranchChunks, 8192u);
+    if (lane == 0) tc_stream_weights(bars, ring_u32, net.branch_img[br], 0, 5, 5 + 4 * nb0, 4 * (nb1 - nb0), 8192u);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -349,8 +356,11 @@ __device__ __forceinline__ void tc_gproj_block(const TcNet& net, const ForwardAr
 // [gproj row as bias] + h1 . W0[1024:] -> ReLU -> 256 -> 128 -> ReLU -> 2 (learn_region_grow_util.py:138-162).
 // The 256-wide hidden layer is produced as four 64-channel slices; each slice is handed to the 256->128 layer as two
 // 32-channel K-chunks the moment its epilogue has written them (c_ready / c_free per half).
+// gproj_pending: optional counter that reaches 0 when this tile pair's pooled projection has been written (the
+// persistent kernel publishes head tiles together with the projection blocks so that the tile's prologue and first MMAs
+// overlap them); NULL = the projection is already there.
 __device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs& fa, int b, int h, int tile, int nvalid,
-                                             unsigned char* smem, TcStatic& st, uint32_t tmem) {
+                                             const int* gproj_pending, unsigned char* smem, TcStatic& st, uint32_t tmem) {
   const int n = fa.n_pts[h];
   const int row0 = tile * 128;
   const int rows = min(128, nvalid - row0);
@@ -392,7 +402,7 @@ __device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs
       tcgen05_fence_before();
       mbar_arrive(smem_u32(&bars.act_ready));
     }
-    mbar_wait(smem_u32(&bars.act_ready), 0u);          // st.vec is complete as well
+    mbar_wait(smem_u32(&bars.vec_ready), 0u);          // st.vec is complete
     tc_stamp(net.dbg, 17, tstamp);
 #pragma unroll 1
     for (int nb = 0; nb < 4; ++nb) {
@@ -482,11 +492,22 @@ __device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs
     const float* g = fa.gproj + ((size_t)b * 2 + h) * 256;
     float tg[8], tb[4], tw[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) tg[i] = __ldcg(g + lane + 32 * i);
-#pragma unroll
     for (int i = 0; i < 4; ++i) tb[i] = __ldg(net.head_bias1[h] + lane + 32 * i);
 #pragma unroll
     for (int i = 0; i < 8; ++i) tw[i] = __ldg(net.head_W2[h] + lane + 32 * i);
+    if (gproj_pending != nullptr) {
+      if (lane == 0) {
+        const long long t0 = clock64();
+        while (*reinterpret_cast<const volatile int*>(gproj_pending) != 0) {
+          __nanosleep(40);
+          if (clock64() - t0 > 4000000000ll) asm volatile("trap;");
+        }
+        __threadfence();
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tg[i] = __ldcg(g + lane + 32 * i);
 #pragma unroll
     for (int i = 0; i < 8; ++i) sG[lane + 32 * i] = tg[i];
 #pragma unroll
@@ -494,8 +515,8 @@ __device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs
 #pragma unroll
     for (int i = 0; i < 8; ++i) sW2[lane + 32 * i] = tw[i];
     if (lane < 2) sB2[lane] = __ldg(net.head_bias2[h] + lane);
-    mbar_arrive(smem_u32(&bars.act_ready));
-    if (lane == 0) tc_stream_weights(bars, ring_u32, img, kRingSlots, kHeadChunks, kSlotBytes);
+    mbar_arrive(smem_u32(&bars.vec_ready));
+    if (lane == 0) tc_stream_weights(bars, ring_u32, img, kRingSlots, kHeadChunks, 0, 0, kSlotBytes);
   }
   tcgen05_fence_before();
   __syncthreads();

@@ -190,9 +190,11 @@ class Engine:
         busy = (C.c_double * 4)()
         items = (C.c_int64 * 4)()
         _lib.check(self.lib.lrg_last_grow_profile(self._h, C.byref(pers), C.byref(busy), C.byref(items)))
+        delay = (C.c_double * 4)()
+        _lib.check(self.lib.lrg_last_grow_queue_delay(self._h, C.byref(delay)))
         return dict(grow_ms=g.value, fill_ms=f.value, iterations=it.value, kernel_launches=ln.value, forward_ms=fw.value,
                     step_kernel_ms=k[0], branch_kernel_ms=k[1], gproj_kernel_ms=k[2], head_kernel_ms=k[3],
-                    persistent=bool(pers.value), busy_ms=dict(zip(('step', 'branch', 'gproj', 'head'), busy)),
+                    persistent=bool(pers.value), queue_delay_ms=dict(zip(('step', 'branch', 'gproj', 'head'), delay)), busy_ms=dict(zip(('step', 'branch', 'gproj', 'head'), busy)),
                     items=dict(zip(('step', 'branch', 'gproj', 'head'), items)))
 
     def labels_device_ptr(self, filled=True):

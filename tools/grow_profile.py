@@ -13,6 +13,7 @@ def main():
     ap.add_argument('--rooms', type=int, default=68)
     ap.add_argument('--repeat', type=int, default=2)
     ap.add_argument('--slots', type=int, default=0)
+    ap.add_argument('--flags', type=int, default=0)
     args = ap.parse_args()
     import bench
     from learn_region_grow_b200.engine import Engine
@@ -21,14 +22,15 @@ def main():
     eng.load_weights(bench.load_weights())
     eng.upload_concatenated(offsets, points, order, 0.1)
     for _ in range(args.repeat):
-        stats = eng.segment_resident(resolution=0.1, seed=0, max_slots=args.slots)
+        stats = eng.segment_resident(resolution=0.1, seed=0, max_slots=args.slots, flags=args.flags)
         pr = eng.profile()
     steps = int(stats['grow_steps'].sum())
     print('rooms %d  grow steps %d (max/room %d)  grow %.1f ms  fill %.1f ms  persistent %s' %
           (args.rooms, steps, int(stats['grow_steps'].max()), pr['grow_ms'], pr['fill_ms'], pr['persistent']))
     for k in ('step', 'branch', 'gproj', 'head'):
         n = max(pr['items'][k], 1)
-        print('  %-7s items %8d  busy %9.1f ms  avg %7.2f us/item' % (k, pr['items'][k], pr['busy_ms'][k], 1e3 * pr['busy_ms'][k] / n))
+        print('  %-7s items %8d  busy %9.1f ms  avg %7.2f us/item   queue delay avg %6.2f us/item' %
+              (k, pr['items'][k], pr['busy_ms'][k], 1e3 * pr['busy_ms'][k] / n, 1e3 * pr['queue_delay_ms'][k] / n))
     tot = sum(pr['busy_ms'].values())
     print('  busy total %.1f ms = %.1f %% of %d SMs x %.1f ms' % (tot, 100 * tot / (148 * pr['grow_ms']), 148, pr['grow_ms']))
     print('  longest room: %.1f us per step end to end' % (1e3 * pr['grow_ms'] / int(stats['grow_steps'].max())))
