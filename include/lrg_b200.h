@@ -141,8 +141,9 @@ int lrg_last_grow_queue_delay(LrgEngine* e, double delay_ms[4]);
 
 /* Diagnostics: with LRG_TILE_TIMING=1 in the environment at load_weights time the tensor tiles add the SM cycles of each
  * of their stages to counters (out[0..13] branch tile stages, out[15] branch tiles; out[16..23] head tile stages,
- * out[31] head tiles; out[32..41] driver step stages, out[47] steps); tools/grow_profile.py prints them. */
-int lrg_tile_timing(LrgEngine* e, uint64_t out[48], int reset);
+ * out[31] head tiles; out[32..41] driver step stages, out[47] steps, out[48..59] median cycles / steps by set-size bucket);
+ * tools/grow_profile.py prints them. */
+int lrg_tile_timing(LrgEngine* e, uint64_t out[64], int reset);
 
 /* With LRG_FLAG_KERNEL_TIMING: summed CUDA-event durations (ms) of the four kernels of the lock-step loop over the
  * last lrg_segment_resident call: out[0] step (driver), out[1] branch MLPs, out[2] pooled projection, out[3] heads. */

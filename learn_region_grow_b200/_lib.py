@@ -66,7 +66,7 @@ _SIGNATURES = {
     'lrg_last_segment_profile': (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int64),
                                       C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     'lrg_last_grow_profile': (_I, [_P, C.POINTER(_I), C.POINTER(C.c_double * 4), C.POINTER(C.c_int64 * 4)]),
-    'lrg_tile_timing': (_I, [_P, C.POINTER(C.c_uint64 * 48), _I]),
+    'lrg_tile_timing': (_I, [_P, C.POINTER(C.c_uint64 * 64), _I]),
     'lrg_last_grow_queue_delay': (_I, [_P, C.POINTER(C.c_double * 4)]),
     'lrg_last_kernel_times': (_I, [_P, C.POINTER(C.c_float * 4)]),
     'lrg_labels_device_ptr': (_I, [_P, _I, C.POINTER(_P)]),

@@ -440,8 +440,8 @@ int lrg_engine_load_weights(LrgEngine* e, const float* blob, size_t n_floats) {
       t.head_bias2[h] = net.out[h].bias;
     }
     if (getenv("LRG_TILE_TIMING") != nullptr && e->d_tile_dbg == nullptr) {
-      LRG_TRY(dev_alloc(&e->d_tile_dbg, 48));
-      LRG_CUDA(cudaMemset(e->d_tile_dbg, 0, 48 * sizeof(unsigned long long)));
+      LRG_TRY(dev_alloc(&e->d_tile_dbg, 64));
+      LRG_CUDA(cudaMemset(e->d_tile_dbg, 0, 64 * sizeof(unsigned long long)));
     }
     t.dbg = e->d_tile_dbg;
     LRG_TRY(tc_forward_configure());
@@ -794,12 +794,12 @@ int lrg_last_grow_profile(LrgEngine* e, int* persistent, double busy_ms[4], int6
   return LRG_OK;
 }
 
-int lrg_tile_timing(LrgEngine* e, uint64_t out[48], int reset) {
+int lrg_tile_timing(LrgEngine* e, uint64_t out[64], int reset) {
   LRG_REQUIRE(e != nullptr && out != nullptr, "NULL argument");
   if (e->d_tile_dbg == nullptr) { set_error("tile timing is off (set LRG_TILE_TIMING=1 before load_weights)"); return LRG_E_STATE; }
   LRG_CUDA(cudaSetDevice(e->device));
-  LRG_CUDA(cudaMemcpy(out, e->d_tile_dbg, 48 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-  if (reset) LRG_CUDA(cudaMemset(e->d_tile_dbg, 0, 48 * sizeof(uint64_t)));
+  LRG_CUDA(cudaMemcpy(out, e->d_tile_dbg, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if (reset) LRG_CUDA(cudaMemset(e->d_tile_dbg, 0, 64 * sizeof(uint64_t)));
   return LRG_OK;
 }
 

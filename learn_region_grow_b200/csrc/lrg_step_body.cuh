@@ -190,11 +190,12 @@ __device__ __forceinline__ int pw_z(unsigned w) { return (int)((w >> 20) & 1023u
 // visit(word) is called for each selected word (bounding boxes).  Every thread issues all of its 128-bit loads of a
 // 32*NT-point chunk before using any (one memory round trip per chunk); warp w owns a contiguous run of the chunk, so
 // a per-warp scan plus one scan of the warp totals gives the global order.  The array is padded to a multiple of four
-// words with VISITED words that no predicate selects.  s_scan: 33 ints.  Returns the count to every thread.
+// words with VISITED words that no predicate selects.  The first cap_s entries are mirrored in shared memory (out_s) so
+// that the phases that follow do not pay a global round trip for the list.  s_scan: 33 ints.  Returns the count to every thread.
 // (Plain loads on purpose: the words are rewritten by this CTA between scans and by other CTAs between steps; the
 // CTA barrier orders the former, the acquire fence at the start of a work item drops stale L1 lines for the latter.)
 template <int NT, class Pred, class Visit>
-__device__ int scan_words(const unsigned* pw, int N, Pred pred, Visit visit, int* out, int* s_scan) {
+__device__ int scan_words(const unsigned* pw, int N, Pred pred, Visit visit, int* out, int* out_s, int cap_s, int* s_scan) {
   constexpr int U = 8;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n4 = (N + 3) >> 2;
@@ -233,10 +234,10 @@ __device__ int scan_words(const unsigned* pw, int N, Pred pred, Visit visit, int
       if (f) {
         int o = wbase + offs[u];
         const int i0 = (q0 + u * 32) * 4;
-        if (f & 1u) { out[o++] = i0; visit(v[u].x); }
-        if (f & 2u) { out[o++] = i0 + 1; visit(v[u].y); }
-        if (f & 4u) { out[o++] = i0 + 2; visit(v[u].z); }
-        if (f & 8u) { out[o++] = i0 + 3; visit(v[u].w); }
+        if (f & 1u) { out[o] = i0; if (o < cap_s) out_s[o] = i0; ++o; visit(v[u].x); }
+        if (f & 2u) { out[o] = i0 + 1; if (o < cap_s) out_s[o] = i0 + 1; ++o; visit(v[u].y); }
+        if (f & 4u) { out[o] = i0 + 2; if (o < cap_s) out_s[o] = i0 + 2; ++o; visit(v[u].z); }
+        if (f & 8u) { out[o] = i0 + 3; if (o < cap_s) out_s[o] = i0 + 3; ++o; visit(v[u].w); }
       }
     }
     running += s_scan[32];
@@ -247,13 +248,13 @@ __device__ int scan_words(const unsigned* pw, int N, Pred pred, Visit visit, int
 
 // ----------------------------------------------------------------------------------------------------- step
 constexpr int kMedianCap = 2048;   // inlier sets up to this size have their 9 median channels staged in shared memory
+constexpr int kListCap = 1024;     // leading entries of the inlier / neighbour lists mirrored in shared memory
 
 struct StepShared {
   SlotState S;
   int scan[68];
   unsigned prefix[32];
   int rank[32];
-  int hist[18 * 256];
   int sel[2][kMaxTilePts];      // sampled list positions: [0] inlier, [1] neighbor
   int4 odd[2 * kMaxTilePts];    // re-rounded voxels that do not match their source point (x, y, z, kind)
   int n_odd;
@@ -261,7 +262,11 @@ struct StepShared {
   int flag;
   int all_done;                 // set when this call retired the last slot of the run
   unsigned nextkey[16];         // median: smallest key above the lower median, per channel
-  unsigned mkeys[9][kMedianCap];
+  int listI_s[kListCap], listJ_s[kListCap];
+  union {                        // the histograms of the radix selects are never live together with the staged median keys
+    unsigned mkeys[9][kMedianCap];
+    int hist[18 * 256];
+  };
 };
 
 enum { MODE_NEW_REGION = 0, MODE_SCAN = 1 };
@@ -273,50 +278,63 @@ __device__ __forceinline__ float confidence(float l0, float l1) {
   return e / (1.f + e);
 }
 
-// Median of one channel by ONE warp, keys in shared memory (n <= 32*E): bitwise radix select of rank (n-1)/2 from the
-// most significant bit down, counting with ballots (no atomics, no block barriers), keys and candidate flags held in
-// registers; for even n the upper median is the same key again if it has a further duplicate, else the smallest key
-// above it.  Returns numpy.median's two middle keys in lo / hi (equal for odd n).
-template <int E>
+// Median of one channel by ONE warp, keys in shared memory (n <= 1024 * G): bit-sliced radix select.  First the keys
+// are transposed into bit planes with ballots -- lane s ends up owning slot s (the 32 keys s*32..s*32+31) as 32 words,
+// P[b] = bit b of those 32 keys -- which are independent instructions that pipeline.  The select of rank (n-1)/2 then
+// walks the bits from the top with one popc + one warp reduction per bit (not per key): zeros = sum over slots of
+// popc(alive & ~P[b]).  For even n the upper median is the same key again if it has a further duplicate, else the
+// smallest key above it.  Returns numpy.median's two middle keys in lo / hi (equal for odd n).
+template <int G>
 __device__ __forceinline__ void warp_median(const unsigned* __restrict__ keys, int n, unsigned& lo, unsigned& hi) {
   const int lane = threadIdx.x & 31;
-  unsigned k[E];
-  unsigned alive = 0;                               // bit e: element lane + 32*e is still a candidate
+  const int nslots = (n + 31) >> 5;
+  unsigned P[G][32], alive[G];
 #pragma unroll
-  for (int e = 0; e < E; ++e) {
-    const int j = lane + 32 * e;
-    k[e] = j < n ? keys[j] : 0u;
-    if (j < n) alive |= 1u << e;
+  for (int g = 0; g < G; ++g) {
+    alive[g] = 0;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) P[g][b] = 0;
+    const int ns = min(32, nslots - 32 * g);
+    for (int s = 0; s < ns; ++s) {
+      const int j = (s + 32 * g) * 32 + lane;
+      const unsigned key = j < n ? keys[j] : 0u;
+      const unsigned av = __ballot_sync(0xffffffffu, j < n);
+      if (lane == s) alive[g] = av;
+#pragma unroll
+      for (int b = 0; b < 32; ++b) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (key >> b) & 1u);
+        if (lane == s) P[g][b] = bal;
+      }
+    }
   }
   int rank = (n - 1) >> 1;
   unsigned prefix = 0;
-#pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
-    int zeros = 0;
 #pragma unroll
-    for (int e = 0; e < E; ++e) zeros += __popc(__ballot_sync(0xffffffffu, ((alive >> e) & 1u) && !((k[e] >> bit) & 1u)));
-    const bool take_ones = rank >= zeros;           // warp-uniform
-    if (take_ones) { rank -= zeros; prefix |= 1u << bit; }
+  for (int b = 31; b >= 0; --b) {
+    unsigned z = 0;
 #pragma unroll
-    for (int e = 0; e < E; ++e)
-      if ((((k[e] >> bit) & 1u) != 0) != take_ones) alive &= ~(1u << e);
+    for (int g = 0; g < G; ++g) z += __popc(alive[g] & ~P[g][b]);
+    const int zeros = (int)__reduce_add_sync(0xffffffffu, z);
+    const bool take_ones = rank >= zeros;            // warp-uniform
+    if (take_ones) { rank -= zeros; prefix |= 1u << b; }
+#pragma unroll
+    for (int g = 0; g < G; ++g) alive[g] &= take_ones ? P[g][b] : ~P[g][b];
   }
   lo = prefix;
   hi = prefix;
   if ((n & 1) == 0) {
     // candidates left = keys equal to prefix; `rank` = position of the lower median inside that run
-    int equal = 0;
-    unsigned above = 0xFFFFFFFFu;
+    unsigned eq = 0;
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      equal += __popc(__ballot_sync(0xffffffffu, (alive >> e) & 1u));
-      const int j = lane + 32 * e;
-      if (j < n && k[e] > prefix) above = min(above, k[e]);
-    }
+    for (int g = 0; g < G; ++g) eq += __popc(alive[g]);
+    const int equal = (int)__reduce_add_sync(0xffffffffu, eq);
     if (rank + 1 >= equal) {
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) above = min(above, __shfl_xor_sync(0xffffffffu, above, d));
-      hi = above;
+      unsigned above = 0xFFFFFFFFu;
+      for (int j = lane; j < n; j += 32) {
+        const unsigned k = keys[j];
+        if (k > prefix) above = min(above, k);
+      }
+      hi = __reduce_min_sync(0xffffffffu, above);
     }
   }
 }
@@ -575,7 +593,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
                                       const int x = pw_x(w), y = pw_y(w), z = pw_z(w);
                                       mn[0] = min(mn[0], x); mn[1] = min(mn[1], y); mn[2] = min(mn[2], z);
                                       mx[0] = max(mx[0], x); mx[1] = max(mx[1], y); mx[2] = max(mx[2], z);
-                                    }, listI, sh.scan);
+                                    }, listI, sh.listI_s, kListCap, sh.scan);
     int reason = STOP_NONE;
     if (!updated) {
       reason = STOP_NOEXPAND;                                // :304-306 (removals alone do not count)
@@ -689,6 +707,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
         S.stuck = 0; S.steps = 0; S.n_in = 1;
         pw[seed] = w | PW_CUR;
         listI[0] = seed;
+        sh.listI_s[0] = seed;
       }
       __syncthreads();
       mode = MODE_SCAN;
@@ -701,7 +720,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       if (w & (PW_CUR | PW_VIS)) return false;
       const int x = pw_x(w), y = pw_y(w), z = pw_z(w);
       return x >= lo0 && x <= hi0 && y >= lo1 && y <= hi1 && z >= lo2 && z <= hi2;
-    }, [](unsigned) {}, listJ, sh.scan);
+    }, [](unsigned) {}, listJ, sh.listJ_s, kListCap, sh.scan);
     if (n_nb == 0) {                                          // :233-235
       stop_region(STOP_NONEIGHBOR, S.n_in);
       mode = MODE_NEW_REGION;
@@ -721,7 +740,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     // median of every centred channel over ALL current points (:241): channels 0,1 and 6..F-1
     const int nch = 2 + (da.F > 6 ? da.F - 6 : 0);
     auto row_keys = [&](int j, unsigned (&k)[9]) {
-      const float* row = pts + (size_t)listI[j] * 16;
+      const float* row = pts + (size_t)(j < kListCap ? sh.listI_s[j] : listI[j]) * 16;
       const float4 a = *reinterpret_cast<const float4*>(row);
       const float4 b = *reinterpret_cast<const float4*>(row + 4);
       const float4 c = *reinterpret_cast<const float4*>(row + 8);
@@ -738,22 +757,15 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
         for (int s = 0; s < 9; ++s) sh.mkeys[s][j] = k[s];
       }
       __syncthreads();
-    }
-    if (n_in <= 1024) {
-      // one warp per channel, no atomics and no block barriers (most regions are small: median n_in ~ 50)
+      // one warp per channel, no atomics and no block barriers (a bitonic sort of the nine rows by the whole CTA was
+      // measured 3-4x slower, a histogram select with shared-memory atomics 2x slower)
       for (int c = warp; c < nch; c += NT / 32) {
         unsigned lo, hi;
-        if (n_in <= 64) warp_median<2>(sh.mkeys[c], n_in, lo, hi);
-        else if (n_in <= 256) warp_median<8>(sh.mkeys[c], n_in, lo, hi);
-        else warp_median<32>(sh.mkeys[c], n_in, lo, hi);
+        if (n_in <= 1024) warp_median<1>(sh.mkeys[c], n_in, lo, hi);
+        else warp_median<2>(sh.mkeys[c], n_in, lo, hi);
         if (lane == 0) { sh.prefix[c] = lo; sh.nextkey[c] = hi; }
       }
       __syncthreads();
-    } else if (n_in <= kMedianCap) {
-      block_median9<NT>(n_in, nch, [&](int j, unsigned (&k)[9]) {
-#pragma unroll
-        for (int s = 0; s < 9; ++s) k[s] = sh.mkeys[s][j];
-      }, sh.prefix, sh.rank, sh.hist, sh.nextkey);
     } else {
       __syncthreads();
       block_median9<NT>(n_in, nch, row_keys, sh.prefix, sh.rank, sh.hist, sh.nextkey);
@@ -768,6 +780,11 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       S.center[tid] = cval;
     }
     __syncthreads();
+    if (da.dbg != nullptr && tid == 0) {   // median cost by set size: [16 + 2b] cycles, [17 + 2b] steps; b = size bucket
+      const int bkt = n_in <= 64 ? 0 : n_in <= 256 ? 1 : n_in <= 512 ? 2 : n_in <= 1024 ? 3 : n_in <= 2048 ? 4 : 5;
+      atomicAdd(da.dbg + 16 + 2 * bkt, (unsigned long long)(clock64() - tstamp));
+      atomicAdd(da.dbg + 17 + 2 * bkt, 1ull);
+    }
     stamp(6);
 
     // sampling (:237-240, :249-252) with the Philox stream of oracle/lrg_driver.py PhiloxRng
@@ -810,7 +827,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
         if (r < nrows) {
           const int nset = is_nb ? n_nb : n_in;
           const int pos = sh.sel[is_nb ? 1 : 0][r];
-          const int p = (is_nb ? listJ : listI)[pos];
+          const int p = pos < kListCap ? (is_nb ? sh.listJ_s : sh.listI_s)[pos] : (is_nb ? listJ : listI)[pos];
           if (r < nset) {                                    // a distinct point: materialise its tile row
             const float* row = pts + (size_t)p * 16;
             float* out = da.tile[is_nb ? 1 : 0] + ((size_t)slot * nrows + r) * da.F;

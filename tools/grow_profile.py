@@ -37,7 +37,7 @@ def main():
     if os.environ.get('LRG_TILE_TIMING'):
         import ctypes as C
         from learn_region_grow_b200 import _lib
-        out = (C.c_uint64 * 48)()
+        out = (C.c_uint64 * 64)()
         _lib.check(eng.lib.lrg_tile_timing(eng._h, C.byref(out), 0))
         names_b = ['init+bias', 'x tile', 'epi L0', 'epi L1', 'epi L2', 'epi L3', 'L4 nb0', 'L4 nb1', 'L4 nb2', 'L4 nb3', 'teardown']
         names_h = ['init', 'h1 tile+vec', 'epi nb0', 'epi nb1', 'epi nb2', 'epi nb3', 'final', 'teardown']
@@ -49,6 +49,8 @@ def main():
         ns = max(out[47], 1)
         print('  step stages        (cycles/step, thread 0):', ', '.join('%s %d' % (n, out[32 + i] // ns) for i, n in enumerate(names_s)),
               '| total', sum(out[32 + i] for i in range(10)) // ns)
+        bn = ['<=64', '<=256', '<=512', '<=1024', '<=2048', '>2048']
+        print('  median by inlier-set size: ' + ', '.join('%s: %d steps x %d cyc' % (bn[b], out[49 + 2 * b], out[48 + 2 * b] // max(out[49 + 2 * b], 1)) for b in range(6)))
         print('  head tile stages   (cycles/tile, thread 0):', ', '.join('%s %d' % (n, out[16 + i] // nh) for i, n in enumerate(names_h)),
               '| total', sum(out[16 + i] for i in range(8)) // nh)
 
