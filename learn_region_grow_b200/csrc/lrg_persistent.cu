@@ -46,12 +46,11 @@ __device__ __forceinline__ unsigned queue_pop(const GrowQueue& q) {
   if ((v >> 32) != gen) {
     const long long t0 = clock64();
     while (((v = *e) >> 32) != gen) {
-      __nanosleep(100);
+      __nanosleep(32);
       if (clock64() - t0 > 60000000000ll) asm volatile("trap;");   // ~30 s without work: the run is wedged, fail loudly
     }
   }
-  __threadfence();
-  return (unsigned)v;
+  return (unsigned)v;                                // (the caller issues the acquire fence where the item needs one)
 }
 
 // Non-blocking pop of the high-priority ring: claims a ticket only if an item has been published for it (CAS, never
@@ -66,7 +65,6 @@ __device__ __forceinline__ bool queue_try_pop(const GrowQueue& q, unsigned& item
     const volatile unsigned long long* e = q.ring + (h & q.cap_mask);
     unsigned long long v;
     while (((v = *e) >> 32) != gen) {}               // the producer bumped tail first and is writing the entry right now
-    __threadfence();
     item = (unsigned)v;
     return true;
   }
@@ -92,18 +90,25 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
   // ring 1 only, and before running what it popped there it drains ring 0.  Under load every retiring CTA therefore serves
   // the high-priority ring first; when idle, the token wakes a CTA that finds the item.
   unsigned deferred = 0;                              // the ring-1 item to run once ring 0 is empty (0 = none)
+  unsigned chained = 0;                               // item this CTA hands to itself (the STEP that follows the last head tile)
   while (true) {
     if (tid == 0) {
-      unsigned it = 0;
-      if (ga.hi_slots <= 0) it = queue_pop(ga.q[1]);    // priorities off: one FIFO
-      else if (!queue_try_pop(ga.q[0], it)) {
-        if (deferred != 0) { it = deferred; deferred = 0; }
-        else {
-          it = queue_pop(ga.q[1]);
-          unsigned hi_item = 0;
-          if (queue_try_pop(ga.q[0], hi_item)) { deferred = it; it = hi_item; }
+      unsigned it = chained;
+      chained = 0;
+      if (it == 0) {
+        if (ga.hi_slots <= 0) it = queue_pop(ga.q[1]);    // priorities off: one FIFO
+        else if (!queue_try_pop(ga.q[0], it)) {
+          if (deferred != 0) { it = deferred; deferred = 0; }
+          else {
+            it = queue_pop(ga.q[1]);
+            unsigned hi_item = 0;
+            if (queue_try_pop(ga.q[0], hi_item)) { deferred = it; it = hi_item; }
+          }
         }
       }
+      // acquire: the driver step reads state other CTAs wrote with plain stores (drop stale L1 lines); the tensor tiles and
+      // the projection read everything produced in this launch with ld.global.cg and need no fence
+      if ((it & 7u) == ITEM_STEP) __threadfence();
       s_item = it;
     }
     __syncthreads();
@@ -198,18 +203,26 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
       tc_head_tile(ga.net, ga.fa, slot, a, t, forward_valid_rows(ga.fa, slot, a), &sy->gproj_left, smem, st, tmem);
       if (tid == 0) {
         __threadfence();
-        if (atomicSub(&sy->head_left, 1) == 1) next[n_next++] = make_item(ITEM_STEP, slot, 0, 0);
+        // the CTA that retires the slot's last head tile runs the slot's next driver step itself: no queue hop, and under
+        // load the step does not wait behind other slots' tiles
+        if (atomicSub(&sy->head_left, 1) == 1) chained = make_item(ITEM_STEP, slot, 0, 0);
       }
     }
     if (tid == 0) {
-      if (n_next > 0) {
+      // keep the first successor for this CTA (a branch tile after a STEP, a projection block after the last branch tile:
+      // neither ever waits on another item), publish the rest
+      int first = 0;
+      if (n_next > 0 && (type == ITEM_STEP || type == ITEM_BRANCH)) { chained = next[0]; first = 1; }
+      if (n_next > first) {
         *reinterpret_cast<volatile unsigned long long*>(&sy->t_pub) = global_ns();
-        __threadfence();
-        if ((sy->prio & 1) == 0) {
-          queue_push(ga.q[0], next, n_next);
-          for (int i = 0; i < n_next; ++i) next[i] = make_item(ITEM_WAKE, 0, 0, 0);
+        // release: a STEP publishes the counters it just wrote; the tile / projection finishers already fenced before the
+        // atomic that made them last (the push is control-dependent on that atomic's result)
+        if (type == ITEM_STEP) __threadfence();
+        if ((*reinterpret_cast<volatile int*>(&sy->prio) & 1) == 0) {
+          queue_push(ga.q[0], next + first, n_next - first);
+          for (int i = first; i < n_next; ++i) next[i] = make_item(ITEM_WAKE, 0, 0, 0);
         }
-        queue_push(ga.q[1], next, n_next);
+        queue_push(ga.q[1], next + first, n_next - first);
       }
       if (ga.busy_ns != nullptr) {
         atomicAdd(ga.busy_ns + type, global_ns() - t0);
