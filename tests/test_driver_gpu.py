@@ -145,3 +145,48 @@ def test_resolution_and_threshold_parameters(engine, golden_weights):
     shell = np.all(np.abs(vox - vox[seed]) <= 1, axis=1)
     shell[seed] = False
     assert trace[0]['seed_point'] == seed and trace[0]['n_neighbor'] == shell.sum()
+
+
+def test_large_room_replays_on_oracle(engine, golden_weights):
+    """A room larger than one scan chunk (N > 16,384 state words) with a floor region of several thousand inliers:
+    multi-chunk scans, the >1024 and >2048 median paths and full 512-of-n sampling, replayed step by step on the oracle."""
+    from learn_region_grow_b200 import rooms as R
+    f = R.prepare_features(R.generate_room(4242, n_raw=70000, n_boxes=6, dims=np.array([9.0, 9.0, 2.4])))
+    points, order = f['points'], f['order']
+    assert len(points) > 16384
+    engine.upload_rooms([points], [order], resolution=0.1)
+    stats = engine.segment_resident(resolution=0.1, seed=5, trace_capacity=16384)
+    trace, n_steps = engine.trace(0, 16384)
+    assert n_steps == stats['grow_steps'][0] and n_steps <= 16384
+    assert trace['n_inlier'].max() > 2048 and trace['n_neighbor'].max() >= 512
+    g, adopted = _replay(points, order, golden_weights, trace, n_steps, 5)
+    assert adopted <= 8
+    np.testing.assert_array_equal(engine.labels(filled=False)[0], g.cluster_label)
+    np.testing.assert_array_equal(engine.labels(filled=True)[0], g.fill())
+
+
+def test_scheduling_variants_give_identical_labels(engine):
+    """Lock-step loop, persistent kernel, persistent kernel with the priority ring: same computation, same labels."""
+    from learn_region_grow_b200 import _lib, rooms as R
+    feats = [R.prepare_features(R.generate_room(1100 + i, n_raw=6000 + 2000 * i, n_boxes=6)) for i in range(5)]
+    pts, orders = [f['points'] for f in feats], [f['order'] for f in feats]
+    ref, st0 = engine.segment_rooms(pts, orders, resolution=0.1, seed=3)
+    assert engine.profile()['persistent']
+    for flags in (_lib.FLAG_LOCKSTEP, _lib.FLAG_PRIORITY, _lib.FLAG_NO_GRAPH):
+        got, st = engine.segment_rooms(pts, orders, resolution=0.1, seed=3, flags=flags)
+        assert engine.profile()['persistent'] == (flags == _lib.FLAG_PRIORITY)
+        for a, b in zip(ref, got):
+            np.testing.assert_array_equal(a, b)
+        assert st['grow_steps'].tolist() == st0['grow_steps'].tolist()
+
+
+def test_room_span_limit(engine):
+    """The packed state words hold 10 bits of voxel coordinate per axis: a room spanning more is rejected at upload."""
+    from learn_region_grow_b200._lib import LrgError
+    pts = np.zeros((4, 13), np.float32)
+    pts[:, 0] = [0.0, 50.0, 100.0, 102.5]          # 1025 voxels at 0.1 m
+    with pytest.raises(LrgError):
+        engine.upload_rooms([pts], [np.arange(4)], resolution=0.1)
+    pts[:, 0] = [0.0, 50.0, 100.0, 102.0]          # 1020 voxels: fine
+    labels, stats = engine.segment_rooms([pts], [np.arange(4)], resolution=0.1, seed=0)
+    assert stats['n_points'][0] == 4 and labels[0].shape == (4,)
