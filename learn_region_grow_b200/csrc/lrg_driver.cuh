@@ -6,7 +6,6 @@ namespace lrg {
 
 constexpr int kStepThreads = 1024;
 constexpr int kMaxTilePts = 512;       // NUM_INLIER_POINT / NUM_NEIGHBOR_POINT upper bound (test_region_grow.py:22-23)
-enum : unsigned char { ST_CUR = 1, ST_VISITED = 2 };
 enum { STOP_NONE = 0, STOP_NONEIGHBOR = 1, STOP_NOEXPAND = 2, STOP_STUCK = 3, STOP_MAXSTEPS = 4, STOP_EMPTY = 5 };
 
 // Per-slot grow state (one slot = one room in flight).  `active` is read by the forward kernels.
