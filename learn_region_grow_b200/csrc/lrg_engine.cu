@@ -655,7 +655,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
       ga.busy_ns = e->d_busy;
       ga.remaining = e->d_remaining;
       ga.hi_slots = params->flags & LRG_FLAG_PRIORITY ? std::max(2, n_slots / 8) : 0;
-      ga.tune = getenv("LRG_TUNE") ? atoi(getenv("LRG_TUNE")) : 2;   // measured (profiles/README.md): splitting costs more than it saves; overlap +3%
+      ga.tune = getenv("LRG_TUNE") ? atoi(getenv("LRG_TUNE")) : 3;   // both measured positive (profiles/README.md)
       rc = launch_grow(ga, e->sm_count > 0 ? e->sm_count : 148, st);
       if (rc == LRG_OK) {
         cudaError_t se = cudaStreamSynchronize(st);

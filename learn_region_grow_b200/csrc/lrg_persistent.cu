@@ -151,12 +151,13 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
           }
           // only rows that carry distinct points are evaluated (the rest are padding duplicates of them)
           const int tilesI = (min(sh.S.n_in, ga.fa.n_pts[0]) + 127) / 128, tilesJ = (min(sh.S.n_nb, ga.fa.n_pts[1]) + 127) / 128;
-          // When SMs are idle (short backlog) every branch tile is split over 2 or 4 CTAs by column block of the last
+          // When enough CTAs are idle every branch tile is split over 2 or 4 CTAs by column block of the last
           // layer -- each recomputes the cheap first four layers -- which shortens the critical path of the run's tail;
           // under load tiles stay whole (splitting costs SM time).  a = branch | log2(parts) << 1, t = tile | part << 2.
-          const unsigned backlog = (*reinterpret_cast<volatile unsigned*>(ga.q[0].tail) - *reinterpret_cast<volatile unsigned*>(ga.q[0].head)) +
-                                   (*reinterpret_cast<volatile unsigned*>(ga.q[1].tail) - *reinterpret_cast<volatile unsigned*>(ga.q[1].head));
-          const int lg = !(ga.tune & 1) ? 0 : backlog + 8u * (unsigned)(tilesI + tilesJ) <= gridDim.x / 2 ? 2 : backlog + 4u * (unsigned)(tilesI + tilesJ) <= gridDim.x ? 1 : 0;
+          // (idle CTAs hold tickets ahead of the tail, so tail - head is negative when the machine has spare SMs)
+          const int b1 = (int)(*reinterpret_cast<volatile unsigned*>(ga.q[1].tail) - *reinterpret_cast<volatile unsigned*>(ga.q[1].head));
+          const int idle = b1 < 0 ? -b1 : 0;               // CTAs waiting for work right now
+          const int lg = !(ga.tune & 1) ? 0 : idle >= 8 * (tilesI + tilesJ) ? 2 : idle >= 4 * (tilesI + tilesJ) ? 1 : 0;
           const int parts = 1 << lg;
           sy->branch_left = (tilesI + tilesJ) * parts;
           sy->gproj_left = 8;
