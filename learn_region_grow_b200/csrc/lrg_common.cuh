@@ -56,7 +56,8 @@ struct NetDesc {
 
 // Launch description of one forward over `B` tile pairs.
 struct ForwardArgs {
-  const float* x[2];     // [0] inlier (B, N0, F), [1] neighbor (B, N1, F)
+  const float* x[2];     // [0] inlier (B, N0, x_stride), [1] neighbor (B, N1, x_stride): rows of F features
+  int x_stride;          // floats between consecutive rows: F for user tensors, 16 (padded, 16-byte aligned) for slot tiles
   int n_pts[2];
   float* h1[2];          // (B, n_pts, C1) scratch
   float* pooled;         // (B, 2*Clast) as int-ordered floats, must be zero on entry

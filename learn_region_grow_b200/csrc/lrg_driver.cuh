@@ -40,7 +40,7 @@ struct DriverArgs {
   int* listJ;                   // (n_slots, maxN) ascending indices of the neighbour shell
   unsigned* keyI;               // (n_slots, maxN) sampling keys
   unsigned* keyJ;
-  float* tile[2];               // [0] inlier (n_slots, Ni, F), [1] neighbor (n_slots, Nj, F)
+  float* tile[2];               // [0] inlier (n_slots, Ni, 16), [1] neighbor (n_slots, Nj, 16): rows padded to 16 floats
   int* tileidx[2];              // (n_slots, 512) source point of every tile row
   int* tilesrc[2];              // (n_slots, 512) tile row whose logits row r uses: r itself, or the row it duplicates
   const float* logits[2];       // [0] remove_output (n_slots, Ni, 2), [1] add_output (n_slots, Nj, 2)

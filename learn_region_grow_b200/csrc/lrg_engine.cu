@@ -193,7 +193,7 @@ static int ensure_slots(LrgEngine* e, int n_slots) {
   LRG_TRY(dev_alloc(&e->d_keyJ, S * M));
   const int n[2] = {e->Ni, e->Nj};
   for (int i = 0; i < 2; ++i) {
-    LRG_TRY(dev_alloc(&e->d_tile[i], S * n[i] * e->F));
+    LRG_TRY(dev_alloc(&e->d_tile[i], S * n[i] * 16));     // slot tiles: rows padded to 16 floats
     LRG_TRY(dev_alloc(&e->d_tileidx[i], S * kMaxTilePts));
     LRG_TRY(dev_alloc(&e->d_tilesrc[i], S * kMaxTilePts));
     LRG_TRY(dev_alloc(&e->s_h1[i], S * n[i] * e->net.C1));
@@ -462,7 +462,7 @@ int lrg_forward_device(LrgEngine* e, int B, const float* d_inlier, const float* 
   LRG_TRY(ensure_forward_ws(e, std::max(B, e->max_batch)));
   cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
   ForwardArgs fa{};
-  fa.x[0] = d_inlier; fa.x[1] = d_neighbor;
+  fa.x[0] = d_inlier; fa.x[1] = d_neighbor; fa.x_stride = e->F;
   fa.n_pts[0] = e->Ni; fa.n_pts[1] = e->Nj;
   fa.h1[0] = e->d_h1[0]; fa.h1[1] = e->d_h1[1];
   fa.pooled = e->d_pooled; fa.gproj = e->d_gproj;
@@ -595,7 +595,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   da.stats = e->d_stats; da.trace = e->trace_capacity > 0 ? e->d_trace : nullptr; da.trace_capacity = e->trace_capacity;
 
   ForwardArgs fa{};
-  fa.x[0] = e->d_tile[0]; fa.x[1] = e->d_tile[1];
+  fa.x[0] = e->d_tile[0]; fa.x[1] = e->d_tile[1]; fa.x_stride = 16;
   fa.n_pts[0] = e->Ni; fa.n_pts[1] = e->Nj;
   fa.h1[0] = e->s_h1[0]; fa.h1[1] = e->s_h1[1];
   fa.pooled = e->s_pooled; fa.gproj = e->s_gproj;

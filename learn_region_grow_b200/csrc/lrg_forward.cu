@@ -185,10 +185,10 @@ lrg_branch_kernel(const __grid_constant__ NetDesc net, const __grid_constant__ F
   int* sMax = reinterpret_cast<int*>(sW + kStages * kStageFloats);
 
   // input tile, zero padded to 16 features and 128 rows (row-major, ld 20)
-  const float* x = fa.x[br] + ((size_t)b * n + row0) * net.F;
+  const float* x = fa.x[br] + ((size_t)b * n + row0) * fa.x_stride;
   for (int idx = tid; idx < kTileRows * 16; idx += kThreads) {
     int r = idx >> 4, c = idx & 15;
-    buf0[r * 20 + c] = (r < rows && c < net.F) ? x[(size_t)r * net.F + c] : 0.f;
+    buf0[r * 20 + c] = (r < rows && c < net.F) ? x[(size_t)r * fa.x_stride + c] : 0.f;
   }
   const float* cur = buf0;
   int ld = 20;

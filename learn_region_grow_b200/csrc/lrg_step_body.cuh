@@ -188,19 +188,26 @@ __device__ __forceinline__ int pw_z(unsigned w) { return (int)((w >> 20) & 1023u
 
 // Ordered block-wide compaction over a room's state words: out[] receives, ascending, every i with pred(word_i);
 // visit(word) is called for each selected word (bounding boxes).  Every thread issues all of its 128-bit loads of a
-// 32*NT-point chunk before using any (one memory round trip per chunk); warp w owns a contiguous run of the chunk, so
-// a per-warp scan plus one scan of the warp totals gives the global order.  The array is padded to a multiple of four
-// words with VISITED words that no predicate selects.  The first cap_s entries are mirrored in shared memory (out_s) so
-// that the phases that follow do not pay a global round trip for the list.  s_scan: 33 ints.  Returns the count to every thread.
+// 32*NT-point chunk before using any (one memory round trip per chunk); warp w owns a contiguous run of the chunk, read
+// lane-interleaved so the loads coalesce (a thread-contiguous assignment needs one warp scan instead of eight but its
+// 32-lines-per-instruction loads were measured 4k cycles slower); per-warp scans plus one scan of the warp totals give
+// the global order.  The
+// array is padded to a multiple of four words with VISITED words that no predicate selects.  The first cap_s entries are
+// mirrored in shared memory (out_s) so that the phases that follow do not pay a global round trip for the list.
+// (Keeping the words in registers for the second scan of a step was tried: the 32 extra live registers spill and cost more
+// than the L2 round trip they save.)
+// s_scan: 33 ints.  Returns the count to every thread.
 // (Plain loads on purpose: the words are rewritten by this CTA between scans and by other CTAs between steps; the
 // CTA barrier orders the former, the acquire fence at the start of a work item drops stale L1 lines for the latter.)
+constexpr int kScanU = 8;
 template <int NT, class Pred, class Visit>
 __device__ int scan_words(const unsigned* pw, int N, Pred pred, Visit visit, int* out, int* out_s, int cap_s, int* s_scan) {
-  constexpr int U = 8;
+  constexpr int U = kScanU;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n4 = (N + 3) >> 2;
   int running = 0;
   for (int c4 = 0; c4 < n4; c4 += NT * U) {
+    // warp w owns the 32*U consecutive 128-bit words from q0 - lane; lane-interleaved so that every load is coalesced
     const int q0 = c4 + warp * 32 * U + lane;
     uint4 v[U];
 #pragma unroll
@@ -228,16 +235,18 @@ __device__ int scan_words(const unsigned* pw, int N, Pred pred, Visit visit, int
     scan_warp_totals<NT>(s_scan, warp, lane);
     __syncthreads();
     const int wbase = running + s_scan[warp];
+    if (flags) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const unsigned f = (flags >> (4 * u)) & 15u;
-      if (f) {
-        int o = wbase + offs[u];
-        const int i0 = (q0 + u * 32) * 4;
-        if (f & 1u) { out[o] = i0; if (o < cap_s) out_s[o] = i0; ++o; visit(v[u].x); }
-        if (f & 2u) { out[o] = i0 + 1; if (o < cap_s) out_s[o] = i0 + 1; ++o; visit(v[u].y); }
-        if (f & 4u) { out[o] = i0 + 2; if (o < cap_s) out_s[o] = i0 + 2; ++o; visit(v[u].z); }
-        if (f & 8u) { out[o] = i0 + 3; if (o < cap_s) out_s[o] = i0 + 3; ++o; visit(v[u].w); }
+      for (int u = 0; u < U; ++u) {
+        const unsigned f = (flags >> (4 * u)) & 15u;
+        if (f) {
+          int o = wbase + offs[u];
+          const int i0 = (q0 + u * 32) * 4;
+          if (f & 1u) { out[o] = i0; if (o < cap_s) out_s[o] = i0; ++o; visit(v[u].x); }
+          if (f & 2u) { out[o] = i0 + 1; if (o < cap_s) out_s[o] = i0 + 1; ++o; visit(v[u].y); }
+          if (f & 4u) { out[o] = i0 + 2; if (o < cap_s) out_s[o] = i0 + 2; ++o; visit(v[u].z); }
+          if (f & 8u) { out[o] = i0 + 3; if (o < cap_s) out_s[o] = i0 + 3; ++o; visit(v[u].w); }
+        }
       }
     }
     running += s_scan[32];
@@ -431,6 +440,19 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       tstamp = now;
     }
   };
+  // metadata of the pending step's tile rows: addressed by the slot alone, so these loads go out together with the slot
+  // state (one round trip); they are only meaningful -- and only used -- when a forward is pending
+  int p_[VT], src_[VT];
+#pragma unroll
+  for (int k = 0; k < VT; ++k) {
+    const int vt = tid + k * NT;                        // virtual thread: 0..511 inlier rows (remove), 512.. neighbor rows (add)
+    const bool is_add = vt >= kMaxTilePts;
+    const int r = is_add ? vt - kMaxTilePts : vt;
+    const bool on = r < (is_add ? da.Nj : da.Ni);
+    // padding rows duplicate a distinct row (:239-240,251-252): same input, same logits, own uniform draw
+    src_[k] = on ? __ldcg(da.tilesrc[is_add ? 1 : 0] + (size_t)slot * kMaxTilePts + r) : 0;
+    p_[k] = on ? __ldcg(da.tileidx[is_add ? 1 : 0] + (size_t)slot * kMaxTilePts + r) : -1;
+  }
   SlotState* gS = da.slots + slot;
   for (int i = tid; i < (int)(sizeof(SlotState) / 4); i += NT)
     reinterpret_cast<int*>(&sh.S)[i] = __ldcg(reinterpret_cast<const int*>(gS) + i);
@@ -494,18 +516,6 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     LrgStepTrace* tr = nullptr;
     if (da.trace != nullptr && S.total_steps < da.trace_capacity)
       tr = da.trace + (size_t)S.room * da.trace_capacity + S.total_steps;
-    // every row's metadata first (independent loads), then the dependent loads (logits, point, state word)
-    int p_[VT], src_[VT];
-#pragma unroll
-    for (int k = 0; k < VT; ++k) {
-      const int vt = tid + k * NT;                        // virtual thread: 0..511 inlier rows (remove), 512.. neighbor rows (add)
-      const bool is_add = vt >= kMaxTilePts;
-      const int r = is_add ? vt - kMaxTilePts : vt;
-      const bool on = r < (is_add ? da.Nj : da.Ni);
-      // padding rows duplicate a distinct row (:239-240,251-252): same input, same logits, own uniform draw
-      src_[k] = on ? __ldcg(da.tilesrc[is_add ? 1 : 0] + (size_t)slot * kMaxTilePts + r) : 0;
-      p_[k] = on ? __ldcg(da.tileidx[is_add ? 1 : 0] + (size_t)slot * kMaxTilePts + r) : -1;
-    }
     float2 lg_[VT], xy_[VT];
     unsigned w_[VT];
 #pragma unroll
@@ -828,14 +838,17 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
           const int nset = is_nb ? n_nb : n_in;
           const int pos = sh.sel[is_nb ? 1 : 0][r];
           const int p = pos < kListCap ? (is_nb ? sh.listJ_s : sh.listI_s)[pos] : (is_nb ? listJ : listI)[pos];
-          if (r < nset) {                                    // a distinct point: materialise its tile row
-            const float* row = pts + (size_t)p * 16;
-            float* out = da.tile[is_nb ? 1 : 0] + ((size_t)slot * nrows + r) * da.F;
-            for (int c = 0; c < da.F; ++c) {
-              float v = row[c];
-              if (c < 2 || c >= 6) v = __fsub_rn(v, S.center[c]);
-              out[c] = v;
-            }
+          if (r < nset) {                                    // a distinct point: materialise its tile row (16 floats, zero padded)
+            const float4* row = reinterpret_cast<const float4*>(pts + (size_t)p * 16);
+            float4* out = reinterpret_cast<float4*>(da.tile[is_nb ? 1 : 0] + ((size_t)slot * nrows + r) * 16);
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float4 t = row[q]; v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w; }
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+              if ((c < 2 || c >= 6) && c < da.F) v[c] = __fsub_rn(v[c], S.center[c]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) out[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
           }
           da.tileidx[is_nb ? 1 : 0][(size_t)slot * kMaxTilePts + r] = p;
           da.tilesrc[is_nb ? 1 : 0][(size_t)slot * kMaxTilePts + r] = r < nset ? r : pos;   // padding: pos < nset is the row it copies

@@ -176,12 +176,22 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
     const bool valid = r < rows;
     const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
     {
-      const float* xrow = fa.x[br] + ((size_t)b * n + row0 + r) * net.F;
+      const float* xrow = fa.x[br] + ((size_t)b * n + row0 + r) * fa.x_stride;
+      float xv[16];
+      if (fa.x_stride == 16) {                       // slot tiles: padded rows, four 128-bit loads
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t = valid ? __ldcg(reinterpret_cast<const float4*>(xrow) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xv[q * 4 + 0] = t.x; xv[q * 4 + 1] = t.y; xv[q * 4 + 2] = t.z; xv[q * 4 + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) xv[c] = (valid && c < net.F) ? __ldcg(xrow + c) : 0.f;
+      }
       uint32_t hi[32], lo[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        const float xv = (c < 16 && valid && c < net.F) ? __ldcg(xrow + c) : 0.f;
-        split_fast(xv, hi[c], lo[c]);
+        if (c < 16) split_fast(xv[c], hi[c], lo[c]); else { hi[c] = 0u; lo[c] = 0u; }
       }
       tmem_st32(tlane + kTmAhi, hi);
       tmem_st32(tlane + kTmAlo, lo);
