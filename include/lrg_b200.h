@@ -116,6 +116,23 @@ typedef struct LrgStepTrace {
  * room-local indices.  Replaces the numpy arrays the driver keeps per room (:175-183). */
 int lrg_rooms_upload(LrgEngine* e, int n_rooms, const int64_t* room_offsets, const float* points,
                      const int32_t* seed_order, float resolution);
+/* Upload rooms as RAW points and prepare the features on the device: replaces test_region_grow.py:119-173 (equalise to one
+ * point per voxel in first-seen order, room-normalised coordinates, normal + curvature from the covariance of the raw
+ * points in the 27 surrounding voxels, curvature / max, seed order = argsort(curvatures)).  raw_points: (sum Nr, n_cols)
+ * float32 rows x y z r g b [...] as stored in the reference's H5 files (learn_region_grow_util.py:13-20); the engine's
+ * feature_size selects the columns like the driver's ablation switches (6: xyz + room xyz, 9: + rgb, 12: + normal, 13: +
+ * curvature).  A room may hold at most 1,048,575 raw points. */
+int lrg_rooms_upload_raw(LrgEngine* e, int n_rooms, const int64_t* raw_offsets, const float* raw_points, int n_cols,
+                         float resolution);
+/* After an upload: (n_rooms+1) prefix sums of the equalised room sizes. */
+int lrg_rooms_equalized_offsets(LrgEngine* e, int64_t* eq_offsets);
+/* After lrg_rooms_upload_raw: the prepared features (sum Neq, F), the seed order, equalized_idx (sum Neq: raw index of every
+ * equalised point, room-local) and unequalized_idx (sum Nr: equalised index of every raw point, :130); any pointer may be NULL. */
+int lrg_rooms_features_download(LrgEngine* e, float* points, int32_t* seed_order, int32_t* equalized_idx,
+                                int32_t* unequalized_idx);
+/* cluster_label[unequalized_idx] (:366): the labels of lrg_labels_download mapped back to the raw points (sum Nr). */
+int lrg_labels_download_raw(LrgEngine* e, int32_t* labels_raw, int filled);
+
 /* Grow every uploaded room to completion on the device (no host round trip per step), then fill unlabeled
  * points (:308-316).  stats may be NULL or n_rooms entries. */
 int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats* stats);

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "lrg_driver.cuh"
+#include "lrg_featprep.cuh"
 #include "lrg_persistent.cuh"
 #include "lrg_tc.cuh"
 #include "lrg_umma.cuh"
@@ -83,6 +84,13 @@ struct LrgEngine {
   int *d_label = nullptr, *d_label_filled = nullptr, *d_order = nullptr;
   int *d_lab_list = nullptr, *d_unl_list = nullptr, *d_n_lab = nullptr, *d_n_unl = nullptr;
   LrgRoomStats* d_stats = nullptr;
+  // rooms uploaded as raw points (device feature preparation): maps between raw and equalised points, dense features
+  bool raw_mode = false;
+  long long total_raw = 0;
+  std::vector<long long> h_raw_off;
+  long long* d_raw_off = nullptr;
+  int *d_equalized_idx = nullptr, *d_unequalized_idx = nullptr;
+  float* d_feat = nullptr;
   // slots
   int n_slots = 0, slots_maxN = 0;
   SlotState* d_slots = nullptr;
@@ -165,6 +173,8 @@ static void free_rooms(LrgEngine* e) {
   cudaFree(e->d_room_off); cudaFree(e->d_pts); cudaFree(e->d_pw); cudaFree(e->d_pw_off); cudaFree(e->d_room_vmin); cudaFree(e->d_label);
   cudaFree(e->d_label_filled); cudaFree(e->d_order); cudaFree(e->d_lab_list); cudaFree(e->d_unl_list);
   cudaFree(e->d_n_lab); cudaFree(e->d_n_unl); cudaFree(e->d_stats);
+  cudaFree(e->d_raw_off); cudaFree(e->d_equalized_idx); cudaFree(e->d_unequalized_idx); cudaFree(e->d_feat);
+  e->d_raw_off = nullptr; e->d_equalized_idx = e->d_unequalized_idx = nullptr; e->d_feat = nullptr; e->raw_mode = false; e->total_raw = 0;
   e->d_room_off = nullptr; e->d_pts = nullptr; e->d_pw = nullptr; e->d_pw_off = nullptr; e->d_room_vmin = nullptr; e->d_label = nullptr;
   e->d_label_filled = nullptr; e->d_order = nullptr; e->d_lab_list = e->d_unl_list = e->d_n_lab = e->d_n_unl = nullptr;
   e->d_stats = nullptr;
@@ -488,11 +498,8 @@ int lrg_forward_host(LrgEngine* e, int B, const float* inlier, const float* neig
   return LRG_OK;
 }
 
-int lrg_rooms_upload(LrgEngine* e, int n_rooms, const int64_t* room_offsets, const float* points, const int32_t* seed_order,
-                     float resolution) {
-  LRG_REQUIRE(e != nullptr, "engine is NULL");
-  LRG_REQUIRE(n_rooms >= 0 && room_offsets != nullptr, "bad room table");
-  LRG_REQUIRE(resolution > 0.f, "resolution must be > 0");
+// Allocates the per-room arrays for rooms of the given (equalised) sizes; frees whatever was uploaded before.
+static int alloc_rooms(LrgEngine* e, int n_rooms, const int64_t* room_offsets, float resolution) {
   LRG_REQUIRE(room_offsets[0] == 0, "room_offsets[0] must be 0");
   long long total = room_offsets[n_rooms];
   int maxN = 0;
@@ -501,8 +508,6 @@ int lrg_rooms_upload(LrgEngine* e, int n_rooms, const int64_t* room_offsets, con
     LRG_REQUIRE(n >= 0 && n < (1ll << 30), "room %d has an invalid point count", r);
     maxN = std::max(maxN, (int)n);
   }
-  LRG_REQUIRE(total == 0 || (points != nullptr && seed_order != nullptr), "NULL points/seed_order");
-  LRG_CUDA(cudaSetDevice(e->device));
   free_rooms(e);
   e->n_rooms = n_rooms; e->total_pts = total; e->maxN = maxN; e->resolution = resolution;
   e->h_room_off.assign(room_offsets, room_offsets + n_rooms + 1);
@@ -515,7 +520,7 @@ int lrg_rooms_upload(LrgEngine* e, int n_rooms, const int64_t* room_offsets, con
   LRG_TRY(dev_alloc(&e->d_pw, (size_t)e->total_words));
   LRG_TRY(dev_alloc(&e->d_pw_off, (size_t)n_rooms + 1));
   LRG_TRY(dev_alloc(&e->d_room_vmin, (size_t)std::max(n_rooms, 1)));
-  LRG_CUDA(cudaMemcpyAsync(e->d_pw_off, h_pw_off.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice, e->stream));
+  LRG_CUDA(cudaMemcpy(e->d_pw_off, h_pw_off.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice));
   LRG_TRY(dev_alloc(&e->d_label, T));
   LRG_TRY(dev_alloc(&e->d_label_filled, T));
   LRG_TRY(dev_alloc(&e->d_order, T));
@@ -524,22 +529,160 @@ int lrg_rooms_upload(LrgEngine* e, int n_rooms, const int64_t* room_offsets, con
   LRG_TRY(dev_alloc(&e->d_n_lab, (size_t)n_rooms));
   LRG_TRY(dev_alloc(&e->d_n_unl, (size_t)n_rooms));
   LRG_TRY(dev_alloc(&e->d_stats, (size_t)n_rooms));
-  LRG_CUDA(cudaMemcpyAsync(e->d_room_off, e->h_room_off.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice, e->stream));
+  LRG_CUDA(cudaMemcpy(e->d_room_off, e->h_room_off.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice));
+  return LRG_OK;
+}
+
+// Dense (T, F) device feature rows -> padded rows + packed state words (e->d_order must already hold the seed order).
+static int pack_rooms(LrgEngine* e, const float* d_dense) {
+  if (e->total_pts <= 0) return LRG_OK;
+  LRG_CUDA(cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(int), e->stream));
+  LRG_TRY(launch_pack(d_dense, e->F, e->n_rooms, e->d_room_off, e->d_pw_off, e->resolution, e->d_pts, e->d_pw, e->d_room_vmin, e->d_counters, e->stream));
+  int bad_room = 0;
+  LRG_CUDA(cudaMemcpyAsync(&bad_room, e->d_counters, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  LRG_CUDA(cudaStreamSynchronize(e->stream));
+  LRG_REQUIRE(bad_room == 0, "room %d spans more than 1022 voxels along an axis at resolution %g (state words hold 10 bits per axis)", bad_room - 1, (double)e->resolution);
+  return LRG_OK;
+}
+
+int lrg_rooms_upload(LrgEngine* e, int n_rooms, const int64_t* room_offsets, const float* points, const int32_t* seed_order,
+                     float resolution) {
+  LRG_REQUIRE(e != nullptr, "engine is NULL");
+  LRG_REQUIRE(n_rooms >= 0 && room_offsets != nullptr, "bad room table");
+  LRG_REQUIRE(resolution > 0.f, "resolution must be > 0");
+  const long long total = room_offsets[n_rooms];
+  LRG_REQUIRE(total == 0 || (points != nullptr && seed_order != nullptr), "NULL points/seed_order");
+  LRG_CUDA(cudaSetDevice(e->device));
+  LRG_TRY(alloc_rooms(e, n_rooms, room_offsets, resolution));
   if (total > 0) {
+    const size_t T = (size_t)total;
     float* d_raw = nullptr;     // staging for the dense (T, F) rows; freed after the pack kernel
     LRG_TRY(dev_alloc(&d_raw, T * e->F));
-    LRG_CUDA(cudaMemcpyAsync(d_raw, points, sizeof(float) * T * e->F, cudaMemcpyHostToDevice, e->stream));
-    LRG_CUDA(cudaMemcpyAsync(e->d_order, seed_order, sizeof(int) * T, cudaMemcpyHostToDevice, e->stream));
-    LRG_CUDA(cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(int), e->stream));
-    int rc = launch_pack(d_raw, e->F, n_rooms, e->d_room_off, e->d_pw_off, resolution, e->d_pts, e->d_pw, e->d_room_vmin, e->d_counters, e->stream);
-    int bad_room = 0;
-    if (rc == LRG_OK && cudaMemcpyAsync(&bad_room, e->d_counters, sizeof(int), cudaMemcpyDeviceToHost, e->stream) != cudaSuccess) rc = LRG_E_CUDA;
+    cudaError_t ce = cudaMemcpyAsync(d_raw, points, sizeof(float) * T * e->F, cudaMemcpyHostToDevice, e->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->d_order, seed_order, sizeof(int) * T, cudaMemcpyHostToDevice, e->stream);
+    int rc = ce == cudaSuccess ? pack_rooms(e, d_raw) : LRG_E_CUDA;
+    if (ce != cudaSuccess) set_error("rooms upload -> %s", cudaGetErrorString(ce));
     cudaStreamSynchronize(e->stream);
     cudaFree(d_raw);
     LRG_TRY(rc);
-    LRG_REQUIRE(bad_room == 0, "room %d spans more than 1022 voxels along an axis at resolution %g (state words hold 10 bits per axis)", bad_room - 1, (double)resolution);
   }
   LRG_CUDA(cudaStreamSynchronize(e->stream));
+  return LRG_OK;
+}
+
+int lrg_rooms_upload_raw(LrgEngine* e, int n_rooms, const int64_t* raw_offsets, const float* raw_points, int n_cols, float resolution) {
+  LRG_REQUIRE(e != nullptr, "engine is NULL");
+  LRG_REQUIRE(n_rooms >= 0 && raw_offsets != nullptr && raw_offsets[0] == 0, "bad room table");
+  LRG_REQUIRE(resolution > 0.f, "resolution must be > 0");
+  LRG_REQUIRE(n_cols >= 6, "raw points need at least x y z r g b (got %d columns)", n_cols);
+  LRG_REQUIRE(e->F == 6 || e->F == 9 || e->F == 12 || e->F == 13, "feature_size %d has no definition from raw points (6, 9, 12 or 13)", e->F);
+  const long long total_raw = raw_offsets[n_rooms];
+  LRG_REQUIRE(total_raw == 0 || raw_points != nullptr, "NULL raw_points");
+  LRG_CUDA(cudaSetDevice(e->device));
+  std::vector<long long> sort_off((size_t)n_rooms + 1, 0);
+  for (int r = 0; r < n_rooms; ++r) {
+    const long long n = raw_offsets[r + 1] - raw_offsets[r];
+    LRG_REQUIRE(n >= 0 && n < (1ll << 20), "room %d has %lld raw points (limit 1,048,575)", r, n);
+    long long P = 2;
+    while (P < n) P <<= 1;
+    sort_off[r + 1] = sort_off[r] + P;
+  }
+  cudaStream_t st = e->stream;
+  // workspace (freed before returning)
+  float* d_raw = nullptr; long long *d_raw_off = nullptr, *d_sort_off = nullptr, *d_eq_off = nullptr;
+  unsigned long long *d_keys = nullptr, *d_keys2 = nullptr; int4* d_vmin = nullptr; int *d_neq = nullptr, *d_err = nullptr;
+  unsigned* d_uvox = nullptr; int *d_ustart = nullptr, *d_equ = nullptr, *d_rank = nullptr; double *d_sums = nullptr, *d_curv = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_raw); cudaFree(d_sort_off); cudaFree(d_eq_off); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_vmin); cudaFree(d_neq);
+    cudaFree(d_err); cudaFree(d_uvox); cudaFree(d_ustart); cudaFree(d_equ); cudaFree(d_rank); cudaFree(d_sums); cudaFree(d_curv);
+  };
+  const size_t TR = (size_t)total_raw, TS = (size_t)sort_off[n_rooms];
+  int rc = LRG_OK;
+  auto A = [&](int r) { if (rc == LRG_OK) rc = r; };
+  A(dev_alloc(&d_raw, TR * n_cols)); A(dev_alloc(&d_raw_off, (size_t)n_rooms + 1)); A(dev_alloc(&d_sort_off, (size_t)n_rooms + 1));
+  A(dev_alloc(&d_eq_off, (size_t)n_rooms + 1)); A(dev_alloc(&d_keys, TS)); A(dev_alloc(&d_keys2, TS)); A(dev_alloc(&d_vmin, (size_t)std::max(n_rooms, 1)));
+  A(dev_alloc(&d_neq, (size_t)std::max(n_rooms, 1))); A(dev_alloc(&d_err, 1)); A(dev_alloc(&d_uvox, TR)); A(dev_alloc(&d_ustart, TR));
+  A(dev_alloc(&d_equ, TR)); A(dev_alloc(&d_rank, TR)); A(dev_alloc(&d_sums, TR * 10));
+  if (rc != LRG_OK) { cleanup(); cudaFree(d_raw_off); return rc; }
+  std::vector<long long> h_raw_off(raw_offsets, raw_offsets + n_rooms + 1);
+  cudaMemcpyAsync(d_raw, raw_points, sizeof(float) * TR * n_cols, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_raw_off, h_raw_off.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_sort_off, sort_off.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(d_err, 0, sizeof(int), st);
+  FeatPrepArgs fp{};
+  fp.n_rooms = n_rooms; fp.C = n_cols; fp.F = e->F; fp.res = resolution;
+  fp.raw_off = d_raw_off; fp.raw = d_raw; fp.sort_off = d_sort_off; fp.keys = d_keys; fp.keys2 = d_keys2; fp.raw_vmin = d_vmin;
+  fp.n_eq = d_neq; fp.err = d_err; fp.uniq_vox = d_uvox; fp.uniq_start = d_ustart; fp.eq_of_uniq = d_equ; fp.sums = d_sums; fp.raw_rank = d_rank;
+  rc = launch_featprep_phase1(fp, st);
+  std::vector<int> h_neq(std::max(n_rooms, 1), 0);
+  int bad_room = 0;
+  if (rc == LRG_OK) {
+    cudaMemcpyAsync(h_neq.data(), d_neq, sizeof(int) * n_rooms, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&bad_room, d_err, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaError_t ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) { set_error("feature preparation -> %s", cudaGetErrorString(ce)); rc = LRG_E_CUDA; }
+  }
+  if (rc == LRG_OK && bad_room != 0) {
+    set_error("room %d spans more than 1022 voxels along an axis at resolution %g (state words hold 10 bits per axis)", bad_room - 1, (double)resolution);
+    rc = LRG_E_INVALID;
+  }
+  if (rc != LRG_OK) { cleanup(); cudaFree(d_raw_off); return rc; }
+  std::vector<int64_t> eq_off((size_t)n_rooms + 1, 0);
+  for (int r = 0; r < n_rooms; ++r) eq_off[r + 1] = eq_off[r] + h_neq[r];
+  rc = alloc_rooms(e, n_rooms, eq_off.data(), resolution);
+  const size_t TE = (size_t)eq_off[n_rooms];
+  if (rc == LRG_OK) rc = dev_alloc(&d_curv, TE);
+  if (rc == LRG_OK) rc = dev_alloc(&e->d_feat, TE * e->F);
+  if (rc == LRG_OK) rc = dev_alloc(&e->d_equalized_idx, TE);
+  if (rc == LRG_OK) rc = dev_alloc(&e->d_unequalized_idx, TR);
+  if (rc == LRG_OK) {
+    std::vector<long long> h_eq(eq_off.begin(), eq_off.end());
+    cudaMemcpyAsync(d_eq_off, h_eq.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice, st);
+    fp.eq_off = d_eq_off; fp.feat = e->d_feat; fp.curv = d_curv; fp.order = e->d_order; fp.equalized_idx = e->d_equalized_idx;
+    fp.unequalized_idx = e->d_unequalized_idx;
+    rc = launch_featprep_phase2(fp, st);
+    if (rc == LRG_OK) rc = pack_rooms(e, e->d_feat);
+    cudaError_t ce = cudaStreamSynchronize(st);
+    if (rc == LRG_OK && ce != cudaSuccess) { set_error("feature preparation -> %s", cudaGetErrorString(ce)); rc = LRG_E_CUDA; }
+  }
+  cleanup();
+  if (rc != LRG_OK) { cudaFree(d_raw_off); return rc; }
+  e->raw_mode = true; e->total_raw = total_raw; e->h_raw_off = h_raw_off; e->d_raw_off = d_raw_off;
+  return LRG_OK;
+}
+
+int lrg_rooms_equalized_offsets(LrgEngine* e, int64_t* eq_offsets) {
+  LRG_REQUIRE(e != nullptr && eq_offsets != nullptr, "NULL argument");
+  for (int r = 0; r <= e->n_rooms; ++r) eq_offsets[r] = e->h_room_off.empty() ? 0 : e->h_room_off[r];
+  return LRG_OK;
+}
+
+int lrg_rooms_features_download(LrgEngine* e, float* points, int32_t* seed_order, int32_t* equalized_idx, int32_t* unequalized_idx) {
+  LRG_REQUIRE(e != nullptr, "engine is NULL");
+  if (!e->raw_mode) { set_error("rooms were not uploaded as raw points"); return LRG_E_STATE; }
+  LRG_CUDA(cudaSetDevice(e->device));
+  const size_t TE = (size_t)e->total_pts, TR = (size_t)e->total_raw;
+  if (points && TE) LRG_CUDA(cudaMemcpy(points, e->d_feat, sizeof(float) * TE * e->F, cudaMemcpyDeviceToHost));
+  if (seed_order && TE) LRG_CUDA(cudaMemcpy(seed_order, e->d_order, sizeof(int) * TE, cudaMemcpyDeviceToHost));
+  if (equalized_idx && TE) LRG_CUDA(cudaMemcpy(equalized_idx, e->d_equalized_idx, sizeof(int) * TE, cudaMemcpyDeviceToHost));
+  if (unequalized_idx && TR) LRG_CUDA(cudaMemcpy(unequalized_idx, e->d_unequalized_idx, sizeof(int) * TR, cudaMemcpyDeviceToHost));
+  return LRG_OK;
+}
+
+int lrg_labels_download_raw(LrgEngine* e, int32_t* labels_raw, int filled) {
+  LRG_REQUIRE(e != nullptr && (labels_raw != nullptr || e->total_raw == 0), "engine/labels is NULL");
+  if (!e->raw_mode) { set_error("rooms were not uploaded as raw points"); return LRG_E_STATE; }
+  LRG_CUDA(cudaSetDevice(e->device));
+  if (e->total_raw <= 0) return LRG_OK;
+  int* d_out = nullptr;
+  LRG_TRY(dev_alloc(&d_out, (size_t)e->total_raw));
+  int rc = launch_labels_raw(e->n_rooms, e->d_raw_off, e->d_room_off, e->d_unequalized_idx, filled ? e->d_label_filled : e->d_label, d_out, e->stream);
+  cudaError_t ce = cudaSuccess;
+  if (rc == LRG_OK) ce = cudaMemcpyAsync(labels_raw, d_out, sizeof(int) * (size_t)e->total_raw, cudaMemcpyDeviceToHost, e->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  cudaFree(d_out);
+  LRG_TRY(rc);
+  LRG_CUDA(ce);
   return LRG_OK;
 }
 

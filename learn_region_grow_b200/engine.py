@@ -154,6 +154,49 @@ class Engine:
                                              _lib.ptr(order), C.c_float(resolution)))
         self._room_offsets = np.array(offsets, dtype=np.int64)
 
+    def upload_raw_rooms(self, raw_rooms, resolution=0.1):
+        """raw_rooms: list of (N_r, C>=6) float32 arrays x y z r g b [...] (the rows of the reference's H5 files).  The
+        features of test_region_grow.py:119-173 are prepared on the device.  Returns the equalised room offsets."""
+        counts = [len(r) for r in raw_rooms]
+        raw_off = np.zeros(len(counts) + 1, dtype=np.int64)
+        np.cumsum(counts, out=raw_off[1:])
+        ncols = raw_rooms[0].shape[1] if raw_rooms else 6
+        raw = (np.ascontiguousarray(np.concatenate([np.asarray(r, np.float32) for r in raw_rooms]), dtype=np.float32)
+               if raw_rooms else np.zeros((0, ncols), np.float32))
+        return self.upload_raw_concatenated(raw_off, raw, resolution)
+
+    def upload_raw_concatenated(self, raw_offsets, raw_points, resolution=0.1):
+        n_rooms = len(raw_offsets) - 1
+        _lib.check(self.lib.lrg_rooms_upload_raw(self._h, n_rooms, _lib.ptr(raw_offsets), _lib.ptr(raw_points),
+                                                 int(raw_points.shape[1]), C.c_float(resolution)))
+        eq = np.zeros(n_rooms + 1, dtype=np.int64)
+        _lib.check(self.lib.lrg_rooms_equalized_offsets(self._h, _lib.ptr(eq)))
+        self._room_offsets = eq
+        self._raw_offsets = np.array(raw_offsets, dtype=np.int64)
+        return eq
+
+    def prepared_features(self):
+        """After upload_raw_rooms: dict(points (sum Neq, F), order, equalized_idx, unequalized_idx), concatenated over rooms."""
+        te, tr = int(self._room_offsets[-1]), int(self._raw_offsets[-1])
+        out = dict(points=np.zeros((te, self.F), np.float32), order=np.zeros(te, np.int32),
+                   equalized_idx=np.zeros(te, np.int32), unequalized_idx=np.zeros(tr, np.int32))
+        _lib.check(self.lib.lrg_rooms_features_download(self._h, _lib.ptr(out['points']), _lib.ptr(out['order']),
+                                                        _lib.ptr(out['equalized_idx']), _lib.ptr(out['unequalized_idx'])))
+        return out
+
+    def raw_labels(self, filled=True):
+        """cluster_label[unequalized_idx] per room (test_region_grow.py:366)."""
+        tr = int(self._raw_offsets[-1])
+        out = np.zeros(tr, dtype=np.int32)
+        _lib.check(self.lib.lrg_labels_download_raw(self._h, _lib.ptr(out), 1 if filled else 0))
+        return [out[self._raw_offsets[i]:self._raw_offsets[i + 1]] for i in range(len(self._raw_offsets) - 1)]
+
+    def segment_raw_rooms(self, raw_rooms, resolution=0.1, **kw):
+        """Raw rooms in, per-raw-point instance labels out: feature preparation, growing and fill all on the device."""
+        self.upload_raw_rooms(raw_rooms, resolution)
+        stats = self.segment_resident(resolution=resolution, **kw)
+        return self.raw_labels(True), stats
+
     def make_params(self, resolution=0.1, cluster_threshold=10, seed=0, max_slots=0, max_steps_per_region=0,
                     room_id_base=0, trace_capacity=0, flags=0):
         return GrowParams(resolution, cluster_threshold, seed, max_slots, max_steps_per_region, room_id_base,
