@@ -38,27 +38,33 @@ def load_peaks():
         return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'sm_max_mhz': 1965.0}, 'fallback'
 
 
+RAW_ROOMS = {}      # (n_rooms, seed_base) -> concatenated raw rooms (sum N_raw, 8) float32, filled by make_workload
+
+
 def make_workload(n_rooms, seed_base, cache=True):
     """Synthetic rooms -> 13-D features + seed order (host feature prep; SURVEY 8f-1 is the device version)."""
     from learn_region_grow_b200 import rooms
-    path = '/tmp/lrg_bench_rooms_%d_%d.npz' % (n_rooms, seed_base)
+    path = '/tmp/lrg_bench_rooms_v2_%d_%d.npz' % (n_rooms, seed_base)
     if cache and os.path.exists(path):
         z = np.load(path)
+        RAW_ROOMS[(n_rooms, seed_base)] = z['raw_points']
         return z['offsets'], z['points'], z['order'], z['raw_counts']
-    pts, orders, raw = [], [], []
+    pts, orders, raw, raw_rows = [], [], [], []
     for r in range(n_rooms):
         room = rooms.generate_room(seed_base + r)
         f = rooms.prepare_features(room, 0.1)
         pts.append(f['points'])
         orders.append(f['order'].astype(np.int32))
         raw.append(len(room))
+        raw_rows.append(room)
     offsets = np.zeros(n_rooms + 1, np.int64)
     np.cumsum([len(p) for p in pts], out=offsets[1:])
     out = (offsets, np.ascontiguousarray(np.concatenate(pts), np.float32), np.ascontiguousarray(np.concatenate(orders), np.int32),
            np.array(raw, np.int64))
+    RAW_ROOMS[(n_rooms, seed_base)] = np.ascontiguousarray(np.concatenate(raw_rows), np.float32)
     if cache:
         try:
-            np.savez(path, offsets=out[0], points=out[1], order=out[2], raw_counts=out[3])
+            np.savez(path, offsets=out[0], points=out[1], order=out[2], raw_counts=out[3], raw_points=RAW_ROOMS[(n_rooms, seed_base)])
         except Exception:
             pass
     return out
@@ -345,7 +351,32 @@ def main():
         e2e_ms.append(1e3 * (time.perf_counter() - t_it))
     barrier()
     e2e_s = time.perf_counter() - e0
-    clocks = sampler.stop()          # nvidia-smi keeps sampling through both timed regions
+    # ---- end to end from RAW points (x y z r g b ...): device feature preparation + growing + fill, raw labels out
+    raw_points = RAW_ROOMS[(args.rooms, 1000 + rank * args.rooms)]
+    raw_off = np.zeros(args.rooms + 1, np.int64)
+    np.cumsum(raw_counts, out=raw_off[1:])
+    h_raw = pinned_array(_lib, raw_points.shape, np.float32); h_raw[...] = raw_points
+    raw_ms = []
+    for it in range(1 + args.steps):
+        barrier()
+        t_it = time.perf_counter()
+        eng.upload_raw_concatenated(raw_off, h_raw, 0.1)
+        st_raw = eng.segment_resident(**params)
+        lab_raw = eng.raw_labels(True)
+        gather_labels()
+        barrier()
+        if it >= 1:
+            raw_ms.append(1e3 * (time.perf_counter() - t_it))
+    raw_s = float(np.mean(raw_ms)) * 1e-3
+    if dist is not None:
+        t = torch.tensor([raw_s], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        raw_s = float(t[0])
+    e2e_raw = {'value': world * total_raw / raw_s, 'unit': UNIT, 'ms_per_step': [round(x, 2) for x in raw_ms],
+               'h2d_bytes_per_step': int(h_raw.nbytes + raw_off.nbytes), 'd2h_bytes_per_step': int(total_raw * 4 + args.rooms * 32),
+               'grow_steps_per_pass': int(st_raw['grow_steps'].sum()),
+               'scope': 'raw points (x y z r g b) in pinned host memory -> device feature preparation (test_region_grow.py:119-173) -> grow -> fill -> per-raw-point labels on the host'}
+    clocks = sampler.stop()          # nvidia-smi keeps sampling through the timed regions
     if dist is not None:
         t = torch.tensor([e2e_s], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -382,6 +413,7 @@ def main():
             'wall_s_timed_region': wall, 'clocks': clocks, 'gpu_launches': int(launches),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'ms_per_step': [round(x, 2) for x in e2e_ms]},
+            'e2e_raw': e2e_raw,
             'roofline': roofline, 'cpu_baseline': cpu_baseline,
             'flops_per_grow_step': FLOPS_PER_STEP,
         }

@@ -38,6 +38,10 @@ static int dev_alloc(T** p, size_t count) {
   return LRG_OK;
 }
 
+template <class T>
+static int pool_alloc(LrgEngine* e, T** p, size_t count);
+static void pool_free(LrgEngine* e, void* p);
+
 #define LRG_TRY(expr)            \
   do {                           \
     int rc__ = (expr);           \
@@ -50,8 +54,13 @@ struct HostLayer { int K, N; size_t w_off, b_off; };
 
 using namespace lrg;
 
+struct PoolBlock { void* p; size_t bytes; bool used; };
+
 struct LrgEngine {
   int device = 0;
+  // device-memory pool for the per-upload arrays and workspaces: cudaMalloc / cudaFree cost milliseconds (and synchronise),
+  // which would dominate an upload; blocks are recycled across calls and released when the engine is destroyed
+  std::vector<PoolBlock> pool;
   int F = 13, Ni = 512, Nj = 512, lite = 0, max_batch = 1;
   std::vector<int> conv, conv2;
   size_t n_weights = 0;
@@ -125,6 +134,44 @@ struct LrgEngine {
 
 namespace lrg {
 
+template <class T>
+static int pool_alloc(LrgEngine* e, T** p, size_t count) {
+  *p = nullptr;
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  int best = -1;
+  for (size_t i = 0; i < e->pool.size(); ++i)
+    if (!e->pool[i].used && e->pool[i].bytes >= bytes && e->pool[i].bytes <= 2 * bytes + 4096 &&
+        (best < 0 || e->pool[i].bytes < e->pool[best].bytes))
+      best = (int)i;
+  if (best >= 0) {
+    e->pool[best].used = true;
+    *p = reinterpret_cast<T*>(e->pool[best].p);
+    return LRG_OK;
+  }
+  void* q = nullptr;
+  cudaError_t err = cudaMalloc(&q, bytes);
+  if (err != cudaSuccess) {
+    // release the idle blocks and retry once before giving up
+    for (auto& b : e->pool)
+      if (!b.used && b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+    err = cudaMalloc(&q, bytes);
+  }
+  if (err != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) -> %s", bytes, cudaGetErrorString(err));
+    return LRG_E_NOMEM;
+  }
+  e->pool.push_back(PoolBlock{q, bytes, true});
+  *p = reinterpret_cast<T*>(q);
+  return LRG_OK;
+}
+
+static void pool_free(LrgEngine* e, void* p) {
+  if (p == nullptr) return;
+  for (auto& b : e->pool)
+    if (b.p == p) { b.used = false; return; }
+  cudaFree(p);     // not ours
+}
+
 static void channel_lists(int lite, std::vector<int>& conv, std::vector<int>& conv2) {
   if (lite == 1) { conv = {64, 64}; conv2 = {64}; }
   else if (lite == 2) { conv = {64, 64, 256}; conv2 = {64, 64}; }
@@ -170,10 +217,10 @@ static int ensure_forward_ws(LrgEngine* e, int B) {
 }
 
 static void free_rooms(LrgEngine* e) {
-  cudaFree(e->d_room_off); cudaFree(e->d_pts); cudaFree(e->d_pw); cudaFree(e->d_pw_off); cudaFree(e->d_room_vmin); cudaFree(e->d_label);
-  cudaFree(e->d_label_filled); cudaFree(e->d_order); cudaFree(e->d_lab_list); cudaFree(e->d_unl_list);
-  cudaFree(e->d_n_lab); cudaFree(e->d_n_unl); cudaFree(e->d_stats);
-  cudaFree(e->d_raw_off); cudaFree(e->d_equalized_idx); cudaFree(e->d_unequalized_idx); cudaFree(e->d_feat);
+  pool_free(e, e->d_room_off); pool_free(e, e->d_pts); pool_free(e, e->d_pw); pool_free(e, e->d_pw_off); pool_free(e, e->d_room_vmin); pool_free(e, e->d_label);
+  pool_free(e, e->d_label_filled); pool_free(e, e->d_order); pool_free(e, e->d_lab_list); pool_free(e, e->d_unl_list);
+  pool_free(e, e->d_n_lab); pool_free(e, e->d_n_unl); pool_free(e, e->d_stats);
+  pool_free(e, e->d_raw_off); pool_free(e, e->d_equalized_idx); pool_free(e, e->d_unequalized_idx); pool_free(e, e->d_feat);
   e->d_raw_off = nullptr; e->d_equalized_idx = e->d_unequalized_idx = nullptr; e->d_feat = nullptr; e->raw_mode = false; e->total_raw = 0;
   e->d_room_off = nullptr; e->d_pts = nullptr; e->d_pw = nullptr; e->d_pw_off = nullptr; e->d_room_vmin = nullptr; e->d_label = nullptr;
   e->d_label_filled = nullptr; e->d_order = nullptr; e->d_lab_list = e->d_unl_list = e->d_n_lab = e->d_n_unl = nullptr;
@@ -291,6 +338,8 @@ int lrg_engine_destroy(LrgEngine* e) {
   free_forward_ws(e); free_rooms(e); free_slots(e);
   cudaFree(e->d_weights); cudaFree(e->d_tc_img); cudaFree(e->d_counters); cudaFree(e->d_trace);
   cudaFree(e->d_qring); cudaFree(e->d_qctr); cudaFree(e->d_sync); cudaFree(e->d_busy); cudaFree(e->d_tile_dbg); cudaFree(e->d_remaining);
+  for (auto& b : e->pool) cudaFree(b.p);
+  e->pool.clear();
   cudaFreeHost(e->h_done);
   cudaStreamDestroy(e->stream);
   delete e;
@@ -512,23 +561,23 @@ static int alloc_rooms(LrgEngine* e, int n_rooms, const int64_t* room_offsets, f
   e->n_rooms = n_rooms; e->total_pts = total; e->maxN = maxN; e->resolution = resolution;
   e->h_room_off.assign(room_offsets, room_offsets + n_rooms + 1);
   const size_t T = (size_t)total;
-  LRG_TRY(dev_alloc(&e->d_room_off, (size_t)n_rooms + 1));
-  LRG_TRY(dev_alloc(&e->d_pts, T * 16));
+  LRG_TRY(pool_alloc(e, &e->d_room_off, (size_t)n_rooms + 1));
+  LRG_TRY(pool_alloc(e, &e->d_pts, T * 16));
   std::vector<long long> h_pw_off((size_t)n_rooms + 1, 0);
   for (int r = 0; r < n_rooms; ++r) h_pw_off[r + 1] = h_pw_off[r] + ((room_offsets[r + 1] - room_offsets[r] + 3) / 4) * 4;
   e->total_words = h_pw_off[n_rooms];
-  LRG_TRY(dev_alloc(&e->d_pw, (size_t)e->total_words));
-  LRG_TRY(dev_alloc(&e->d_pw_off, (size_t)n_rooms + 1));
-  LRG_TRY(dev_alloc(&e->d_room_vmin, (size_t)std::max(n_rooms, 1)));
+  LRG_TRY(pool_alloc(e, &e->d_pw, (size_t)e->total_words));
+  LRG_TRY(pool_alloc(e, &e->d_pw_off, (size_t)n_rooms + 1));
+  LRG_TRY(pool_alloc(e, &e->d_room_vmin, (size_t)std::max(n_rooms, 1)));
   LRG_CUDA(cudaMemcpy(e->d_pw_off, h_pw_off.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice));
-  LRG_TRY(dev_alloc(&e->d_label, T));
-  LRG_TRY(dev_alloc(&e->d_label_filled, T));
-  LRG_TRY(dev_alloc(&e->d_order, T));
-  LRG_TRY(dev_alloc(&e->d_lab_list, T));
-  LRG_TRY(dev_alloc(&e->d_unl_list, T));
-  LRG_TRY(dev_alloc(&e->d_n_lab, (size_t)n_rooms));
-  LRG_TRY(dev_alloc(&e->d_n_unl, (size_t)n_rooms));
-  LRG_TRY(dev_alloc(&e->d_stats, (size_t)n_rooms));
+  LRG_TRY(pool_alloc(e, &e->d_label, T));
+  LRG_TRY(pool_alloc(e, &e->d_label_filled, T));
+  LRG_TRY(pool_alloc(e, &e->d_order, T));
+  LRG_TRY(pool_alloc(e, &e->d_lab_list, T));
+  LRG_TRY(pool_alloc(e, &e->d_unl_list, T));
+  LRG_TRY(pool_alloc(e, &e->d_n_lab, (size_t)n_rooms));
+  LRG_TRY(pool_alloc(e, &e->d_n_unl, (size_t)n_rooms));
+  LRG_TRY(pool_alloc(e, &e->d_stats, (size_t)n_rooms));
   LRG_CUDA(cudaMemcpy(e->d_room_off, e->h_room_off.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice));
   return LRG_OK;
 }
@@ -557,13 +606,13 @@ int lrg_rooms_upload(LrgEngine* e, int n_rooms, const int64_t* room_offsets, con
   if (total > 0) {
     const size_t T = (size_t)total;
     float* d_raw = nullptr;     // staging for the dense (T, F) rows; freed after the pack kernel
-    LRG_TRY(dev_alloc(&d_raw, T * e->F));
+    LRG_TRY(pool_alloc(e, &d_raw, T * e->F));
     cudaError_t ce = cudaMemcpyAsync(d_raw, points, sizeof(float) * T * e->F, cudaMemcpyHostToDevice, e->stream);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->d_order, seed_order, sizeof(int) * T, cudaMemcpyHostToDevice, e->stream);
     int rc = ce == cudaSuccess ? pack_rooms(e, d_raw) : LRG_E_CUDA;
     if (ce != cudaSuccess) set_error("rooms upload -> %s", cudaGetErrorString(ce));
     cudaStreamSynchronize(e->stream);
-    cudaFree(d_raw);
+    pool_free(e, d_raw);
     LRG_TRY(rc);
   }
   LRG_CUDA(cudaStreamSynchronize(e->stream));
@@ -593,17 +642,17 @@ int lrg_rooms_upload_raw(LrgEngine* e, int n_rooms, const int64_t* raw_offsets, 
   unsigned long long *d_keys = nullptr, *d_keys2 = nullptr; int4* d_vmin = nullptr; int *d_neq = nullptr, *d_err = nullptr;
   unsigned* d_uvox = nullptr; int *d_ustart = nullptr, *d_equ = nullptr, *d_rank = nullptr; double *d_sums = nullptr, *d_curv = nullptr;
   auto cleanup = [&]() {
-    cudaFree(d_raw); cudaFree(d_sort_off); cudaFree(d_eq_off); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_vmin); cudaFree(d_neq);
-    cudaFree(d_err); cudaFree(d_uvox); cudaFree(d_ustart); cudaFree(d_equ); cudaFree(d_rank); cudaFree(d_sums); cudaFree(d_curv);
+    pool_free(e, d_raw); pool_free(e, d_sort_off); pool_free(e, d_eq_off); pool_free(e, d_keys); pool_free(e, d_keys2); pool_free(e, d_vmin); pool_free(e, d_neq);
+    pool_free(e, d_err); pool_free(e, d_uvox); pool_free(e, d_ustart); pool_free(e, d_equ); pool_free(e, d_rank); pool_free(e, d_sums); pool_free(e, d_curv);
   };
   const size_t TR = (size_t)total_raw, TS = (size_t)sort_off[n_rooms];
   int rc = LRG_OK;
   auto A = [&](int r) { if (rc == LRG_OK) rc = r; };
-  A(dev_alloc(&d_raw, TR * n_cols)); A(dev_alloc(&d_raw_off, (size_t)n_rooms + 1)); A(dev_alloc(&d_sort_off, (size_t)n_rooms + 1));
-  A(dev_alloc(&d_eq_off, (size_t)n_rooms + 1)); A(dev_alloc(&d_keys, TS)); A(dev_alloc(&d_keys2, TS)); A(dev_alloc(&d_vmin, (size_t)std::max(n_rooms, 1)));
-  A(dev_alloc(&d_neq, (size_t)std::max(n_rooms, 1))); A(dev_alloc(&d_err, 1)); A(dev_alloc(&d_uvox, TR)); A(dev_alloc(&d_ustart, TR));
-  A(dev_alloc(&d_equ, TR)); A(dev_alloc(&d_rank, TR)); A(dev_alloc(&d_sums, TR * 10));
-  if (rc != LRG_OK) { cleanup(); cudaFree(d_raw_off); return rc; }
+  A(pool_alloc(e, &d_raw, TR * n_cols)); A(pool_alloc(e, &d_raw_off, (size_t)n_rooms + 1)); A(pool_alloc(e, &d_sort_off, (size_t)n_rooms + 1));
+  A(pool_alloc(e, &d_eq_off, (size_t)n_rooms + 1)); A(pool_alloc(e, &d_keys, TS)); A(pool_alloc(e, &d_keys2, TS)); A(pool_alloc(e, &d_vmin, (size_t)std::max(n_rooms, 1)));
+  A(pool_alloc(e, &d_neq, (size_t)std::max(n_rooms, 1))); A(pool_alloc(e, &d_err, 1)); A(pool_alloc(e, &d_uvox, TR)); A(pool_alloc(e, &d_ustart, TR));
+  A(pool_alloc(e, &d_equ, TR)); A(pool_alloc(e, &d_rank, TR)); A(pool_alloc(e, &d_sums, TR * 10));
+  if (rc != LRG_OK) { cleanup(); pool_free(e, d_raw_off); return rc; }
   std::vector<long long> h_raw_off(raw_offsets, raw_offsets + n_rooms + 1);
   cudaMemcpyAsync(d_raw, raw_points, sizeof(float) * TR * n_cols, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(d_raw_off, h_raw_off.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice, st);
@@ -626,15 +675,15 @@ int lrg_rooms_upload_raw(LrgEngine* e, int n_rooms, const int64_t* raw_offsets, 
     set_error("room %d spans more than 1022 voxels along an axis at resolution %g (state words hold 10 bits per axis)", bad_room - 1, (double)resolution);
     rc = LRG_E_INVALID;
   }
-  if (rc != LRG_OK) { cleanup(); cudaFree(d_raw_off); return rc; }
+  if (rc != LRG_OK) { cleanup(); pool_free(e, d_raw_off); return rc; }
   std::vector<int64_t> eq_off((size_t)n_rooms + 1, 0);
   for (int r = 0; r < n_rooms; ++r) eq_off[r + 1] = eq_off[r] + h_neq[r];
   rc = alloc_rooms(e, n_rooms, eq_off.data(), resolution);
   const size_t TE = (size_t)eq_off[n_rooms];
-  if (rc == LRG_OK) rc = dev_alloc(&d_curv, TE);
-  if (rc == LRG_OK) rc = dev_alloc(&e->d_feat, TE * e->F);
-  if (rc == LRG_OK) rc = dev_alloc(&e->d_equalized_idx, TE);
-  if (rc == LRG_OK) rc = dev_alloc(&e->d_unequalized_idx, TR);
+  if (rc == LRG_OK) rc = pool_alloc(e, &d_curv, TE);
+  if (rc == LRG_OK) rc = pool_alloc(e, &e->d_feat, TE * e->F);
+  if (rc == LRG_OK) rc = pool_alloc(e, &e->d_equalized_idx, TE);
+  if (rc == LRG_OK) rc = pool_alloc(e, &e->d_unequalized_idx, TR);
   if (rc == LRG_OK) {
     std::vector<long long> h_eq(eq_off.begin(), eq_off.end());
     cudaMemcpyAsync(d_eq_off, h_eq.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice, st);
@@ -646,7 +695,7 @@ int lrg_rooms_upload_raw(LrgEngine* e, int n_rooms, const int64_t* raw_offsets, 
     if (rc == LRG_OK && ce != cudaSuccess) { set_error("feature preparation -> %s", cudaGetErrorString(ce)); rc = LRG_E_CUDA; }
   }
   cleanup();
-  if (rc != LRG_OK) { cudaFree(d_raw_off); return rc; }
+  if (rc != LRG_OK) { pool_free(e, d_raw_off); return rc; }
   e->raw_mode = true; e->total_raw = total_raw; e->h_raw_off = h_raw_off; e->d_raw_off = d_raw_off;
   return LRG_OK;
 }
@@ -675,12 +724,12 @@ int lrg_labels_download_raw(LrgEngine* e, int32_t* labels_raw, int filled) {
   LRG_CUDA(cudaSetDevice(e->device));
   if (e->total_raw <= 0) return LRG_OK;
   int* d_out = nullptr;
-  LRG_TRY(dev_alloc(&d_out, (size_t)e->total_raw));
+  LRG_TRY(pool_alloc(e, &d_out, (size_t)e->total_raw));
   int rc = launch_labels_raw(e->n_rooms, e->d_raw_off, e->d_room_off, e->d_unequalized_idx, filled ? e->d_label_filled : e->d_label, d_out, e->stream);
   cudaError_t ce = cudaSuccess;
   if (rc == LRG_OK) ce = cudaMemcpyAsync(labels_raw, d_out, sizeof(int) * (size_t)e->total_raw, cudaMemcpyDeviceToHost, e->stream);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
-  cudaFree(d_out);
+  pool_free(e, d_out);
   LRG_TRY(rc);
   LRG_CUDA(ce);
   return LRG_OK;

@@ -1,0 +1,17 @@
+"""Time the raw-points path: device feature preparation (upload_raw) vs growing, per pass."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import bench
+from learn_region_grow_b200 import _lib
+from learn_region_grow_b200.engine import Engine
+offsets, points, order, raw_counts = bench.make_workload(68, 1000)
+raw = bench.RAW_ROOMS[(68, 1000)]
+raw_off = np.zeros(69, np.int64); np.cumsum(raw_counts, out=raw_off[1:])
+eng = Engine(1, 1, 512, 512, 13, 0); eng.load_weights(bench.load_weights())
+h_raw = bench.pinned_array(_lib, raw.shape, np.float32); h_raw[...] = raw
+for it in range(4):
+    t0 = time.perf_counter(); eng.upload_raw_concatenated(raw_off, h_raw, 0.1); t1 = time.perf_counter()
+    st = eng.segment_resident(resolution=0.1, seed=0); t2 = time.perf_counter()
+    lab = eng.raw_labels(True); t3 = time.perf_counter()
+    print('upload_raw (feature prep) %.1f ms   segment %.1f ms   raw labels %.1f ms' % (1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2)))
