@@ -170,6 +170,36 @@ int lrg_last_kernel_times(LrgEngine* e, float out_ms[4]);
 int lrg_labels_device_ptr(LrgEngine* e, int filled, void** d_ptr);
 
 /* ------------------------------------------------------------------------------------------------------
+ * Per-room segmentation statistics (test_region_grow.py:319-349)
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct LrgRoomMetrics {
+  double nmi;                  /* sklearn normalized_mutual_info_score(obj_id, cluster_label)   (:346) */
+  double ami;                  /* sklearn adjusted_mutual_info_score                            (:347) */
+  double ars;                  /* sklearn adjusted_rand_score                                   (:348) */
+  double prc;                  /* numpy.mean(dt_match): matched clusters / cluster_label.max()  (:342) */
+  double rcl;                  /* gt_match / len(set(obj_id))                                   (:343) */
+  double iou;                  /* mean over objects of the best IoU with an unmatched cluster   (:344) */
+  int32_t n_points;
+  int32_t n_classes;           /* len(set(obj_id)) */
+  int32_t n_clusters;          /* cluster_label.max() */
+  int32_t gt_match;            /* objects matched to a cluster with IoU > 0.5 (:333-335) */
+} LrgRoomMetrics;
+
+/* Replaces the statistics block of test_region_grow.py:319-349 for n_rooms rooms stored back to back: d_obj_id and
+ * d_cluster_label are DEVICE arrays of room_offsets[n_rooms] int32 (room_offsets is host memory and starts at 0).  One
+ * contingency table per room is built on the device, the expected mutual information is evaluated on the device, the
+ * O(classes x clusters) closed forms on the host.  Objects are matched in descending point count; equal counts in the order
+ * of a stable ascending sort reversed (numpy.argsort's tie order at :328 is unspecified).  d_cluster_label2 (optional,
+ * device, same length) receives cluster_label2 (:323,335,339-341).  An empty room yields NaNs. */
+int lrg_segmentation_metrics(int n_rooms, const int64_t* room_offsets, const int32_t* d_obj_id, const int32_t* d_cluster_label,
+                             LrgRoomMetrics* out, int32_t* d_cluster_label2, lrg_stream_t s);
+/* Same on the rooms held by the engine after lrg_segment_resident.  obj_id is HOST memory: the ground-truth object id of
+ * every equalised point (raw == 0, sum Neq values) or of every raw point (raw != 0, sum Nr values, rooms uploaded with
+ * lrg_rooms_upload_raw; gathered with equalized_idx on the device like :136).  filled selects the labels after the
+ * nearest-neighbour fill (what the reference scores) or before it.  cluster_label2 (optional, host, sum Neq). */
+int lrg_room_metrics(LrgEngine* e, const int32_t* obj_id, int raw, int filled, LrgRoomMetrics* out, int32_t* cluster_label2);
+
+/* ------------------------------------------------------------------------------------------------------
  * tf_ops primitives.  Same argument lists as the reference's C++ launchers plus a trailing stream; all
  * pointers are DEVICE pointers (the reference receives TF-allocated device buffers).
  * ------------------------------------------------------------------------------------------------------ */

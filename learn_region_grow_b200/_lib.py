@@ -36,6 +36,8 @@ STEP_TRACE_DTYPE = np.dtype([('seed_point', '<i4'), ('step_in_region', '<i4'), (
                              ('add_mask', '<u4', (16,)), ('remove_mask', '<u4', (16,)),
                              ('inlier_idx_crc', '<u4'), ('neighbor_idx_crc', '<u4')])
 ROOM_STATS_DTYPE = np.dtype([(n, '<i4') for n, _ in RoomStats._fields_])
+ROOM_METRICS_DTYPE = np.dtype([('nmi', '<f8'), ('ami', '<f8'), ('ars', '<f8'), ('prc', '<f8'), ('rcl', '<f8'), ('iou', '<f8'),
+                               ('n_points', '<i4'), ('n_classes', '<i4'), ('n_clusters', '<i4'), ('gt_match', '<i4')])
 assert STEP_TRACE_DTYPE.itemsize == C.sizeof(StepTrace) and ROOM_STATS_DTYPE.itemsize == C.sizeof(RoomStats)
 
 FORWARD_AUTO, FORWARD_FMA, FORWARD_TENSOR = 0, 1, 2
@@ -63,6 +65,8 @@ _SIGNATURES = {
     'lrg_rooms_equalized_offsets': (_I, [_P, _P]),
     'lrg_rooms_features_download': (_I, [_P, _P, _P, _P, _P]),
     'lrg_labels_download_raw': (_I, [_P, _P, _I]),
+    'lrg_segmentation_metrics': (_I, [_I, _P, _P, _P, _P, _P, _P]),
+    'lrg_room_metrics': (_I, [_P, _P, _I, _I, _P, _P]),
     'lrg_segment_resident': (_I, [_P, C.POINTER(GrowParams), _P]),
     'lrg_labels_download': (_I, [_P, _P, _I]),
     'lrg_trace_download': (_I, [_P, _I, _P, _I, C.POINTER(_I)]),

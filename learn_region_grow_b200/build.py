@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'liblrg_b200.so')
-SOURCES = ['lrg_forward.cu', 'lrg_forward_tc.cu', 'lrg_persistent.cu', 'lrg_driver.cu', 'lrg_featprep.cu', 'lrg_engine.cu', 'lrg_tfops.cu']
+SOURCES = ['lrg_forward.cu', 'lrg_forward_tc.cu', 'lrg_persistent.cu', 'lrg_driver.cu', 'lrg_featprep.cu', 'lrg_metrics.cu', 'lrg_engine.cu', 'lrg_tfops.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '--extended-lambda',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
 

@@ -9,6 +9,7 @@
 
 #include "lrg_driver.cuh"
 #include "lrg_featprep.cuh"
+#include "lrg_metrics.cuh"
 #include "lrg_persistent.cuh"
 #include "lrg_tc.cuh"
 #include "lrg_umma.cuh"
@@ -1004,6 +1005,34 @@ int lrg_last_kernel_times(LrgEngine* e, float out_ms[4]) {
 int lrg_labels_device_ptr(LrgEngine* e, int filled, void** d_ptr) {
   LRG_REQUIRE(e != nullptr && d_ptr != nullptr, "NULL argument");
   *d_ptr = filled ? (void*)e->d_label_filled : (void*)e->d_label;
+  return LRG_OK;
+}
+
+int lrg_room_metrics(LrgEngine* e, const int32_t* obj_id, int raw, int filled, LrgRoomMetrics* out, int32_t* cluster_label2) {
+  LRG_REQUIRE(e != nullptr && (out != nullptr || e->n_rooms == 0), "engine/out is NULL");
+  if (e->d_label == nullptr && e->total_pts > 0) { set_error("no rooms uploaded"); return LRG_E_STATE; }
+  if (raw && !e->raw_mode) { set_error("rooms were not uploaded as raw points"); return LRG_E_STATE; }
+  LRG_CUDA(cudaSetDevice(e->device));
+  if (e->n_rooms == 0) return LRG_OK;
+  const size_t TE = (size_t)e->total_pts, TIN = raw ? (size_t)e->total_raw : TE;
+  LRG_REQUIRE(obj_id != nullptr || TIN == 0, "obj_id is NULL");
+  int *d_in = nullptr, *d_eq = nullptr, *d_l2 = nullptr;
+  int rc = pool_alloc(e, &d_in, TIN);
+  if (rc == LRG_OK && raw) rc = pool_alloc(e, &d_eq, TE);
+  if (rc == LRG_OK && cluster_label2 != nullptr) rc = pool_alloc(e, &d_l2, TE);
+  cudaError_t ce = cudaSuccess;
+  if (rc == LRG_OK && TIN > 0) ce = cudaMemcpyAsync(d_in, obj_id, sizeof(int) * TIN, cudaMemcpyHostToDevice, e->stream);
+  if (rc == LRG_OK && ce == cudaSuccess && raw)
+    rc = launch_gather_equalized(e->n_rooms, e->d_raw_off, e->d_room_off, e->d_equalized_idx, d_in, d_eq, e->stream);
+  if (rc == LRG_OK && ce == cudaSuccess)
+    rc = segmentation_metrics(e->n_rooms, reinterpret_cast<const int64_t*>(e->h_room_off.data()), raw ? d_eq : d_in, filled ? e->d_label_filled : e->d_label, out, d_l2, e->stream);
+  if (rc == LRG_OK && ce == cudaSuccess && cluster_label2 != nullptr && TE > 0) {
+    ce = cudaMemcpyAsync(cluster_label2, d_l2, sizeof(int) * TE, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  }
+  pool_free(e, d_in); pool_free(e, d_eq); pool_free(e, d_l2);
+  LRG_TRY(rc);
+  LRG_CUDA(ce);
   return LRG_OK;
 }
 

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 from . import _lib
-from ._lib import GrowParams, LrgError, ROOM_STATS_DTYPE, STEP_TRACE_DTYPE
+from ._lib import GrowParams, LrgError, ROOM_METRICS_DTYPE, ROOM_STATS_DTYPE, STEP_TRACE_DTYPE
 
 
 def channel_lists(lite):
@@ -216,6 +216,23 @@ class Engine:
         out = np.zeros(total, dtype=np.int32)
         _lib.check(self.lib.lrg_labels_download(self._h, _lib.ptr(out), 1 if filled else 0))
         return [out[self._room_offsets[i]:self._room_offsets[i + 1]] for i in range(len(self._room_offsets) - 1)]
+
+    def room_metrics(self, obj_ids, raw=False, filled=True, return_label2=False):
+        """NMI / AMI / ARS / PRC / RCL / IOU of every room (test_region_grow.py:319-349) against ground-truth object ids:
+        ``obj_ids`` = list of per-room int arrays, one id per equalised point, or per raw point with ``raw=True`` (rooms
+        uploaded raw; gathered with equalized_idx on the device, :136).  Returns a structured array (one row per room) and,
+        with ``return_label2``, the per-room cluster_label2 arrays (:323,335,339-341)."""
+        obj = np.ascontiguousarray(np.concatenate([np.asarray(o).astype(np.int32) for o in obj_ids]) if len(obj_ids) else np.zeros(0, np.int32))
+        expect = int((self._raw_offsets if raw else self._room_offsets)[-1])
+        if obj.size != expect:
+            raise ValueError('obj_ids hold %d values, the uploaded rooms have %d %s points' % (obj.size, expect, 'raw' if raw else 'equalised'))
+        n_rooms = len(self._room_offsets) - 1
+        out = np.zeros(n_rooms, dtype=ROOM_METRICS_DTYPE)
+        label2 = np.zeros(int(self._room_offsets[-1]), np.int32) if return_label2 else None
+        _lib.check(self.lib.lrg_room_metrics(self._h, _lib.ptr(obj), 1 if raw else 0, 1 if filled else 0, _lib.ptr(out), _lib.ptr(label2)))
+        if return_label2:
+            return out, [label2[self._room_offsets[i]:self._room_offsets[i + 1]] for i in range(n_rooms)]
+        return out
 
     def trace(self, room, capacity):
         buf = np.zeros(capacity, dtype=STEP_TRACE_DTYPE)

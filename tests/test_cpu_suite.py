@@ -240,3 +240,21 @@ def test_h5_standin_and_loadFromH5(tmp_path):
     finally:
         sys.path.remove(standins)
         sys.modules.pop('h5py', None)
+
+
+@pytest.mark.parametrize('seed', [1000, 1001])
+def test_metrics_oracle_reproduces_the_reference_log(seed):
+    """oracle/metrics.py is pinned by the statistics line the UNMODIFIED reference driver printed for the golden rooms
+    (test_region_grow.py:349): same obj_id (raw column 6 at equalized_idx) and the reference's own final cluster labels."""
+    from oracle import metrics as om
+    from learn_region_grow_b200 import rooms
+    z = np.load(os.path.join(REPO, 'tests', 'golden', 'driver_trace_%d.npz' % seed), allow_pickle=True)
+    room = z['room']
+    f = rooms.prepare_features(room, 0.1)
+    obj_id = room[f['equalized_idx'], 6].astype(int)
+    assert len(obj_id) == len(z['cluster_label'])
+    m = om.room_statistics(obj_id, z['cluster_label'])
+    line = [l for l in str(z['log']).split('\n') if l.startswith('Area 5 room 0 NMI')][0]
+    logged = dict(zip(('nmi', 'ami', 'ars', 'prc', 'rcl', 'iou'), [float(x) for x in re.findall(r': (\d\.\d\d)', line)]))
+    for k, v in logged.items():
+        assert abs(m[k] - v) <= 0.005 + 1e-9, (k, m[k], v)
