@@ -21,7 +21,7 @@ class NumpyLegacyRng:
     def __init__(self, seed=0, state=None):
         self.rs = state if state is not None else np.random.RandomState(seed)
 
-    def begin_step(self, room, step):
+    def begin_step(self, room, step, lane=0):
         pass
 
     def sample(self, count, k, which):
@@ -41,25 +41,27 @@ class PhiloxRng:
         self.seed = int(seed)
         self.room = 0
         self.step = 0
+        self.lane = 0
 
-    def begin_step(self, room, step):
-        self.room, self.step = int(room), int(step)
+    def begin_step(self, room, step, lane=0):
+        # restart lane l (test_random_restart.py) draws from streams 8*l + {0..5}: lanes run side by side on the device
+        self.room, self.step, self.lane = int(room), int(step), int(lane)
 
     def sample(self, count, k, which):
         key_stream = philox.STREAM_INLIER_KEY if which == 'inlier' else philox.STREAM_NEIGHBOR_KEY
         pad_stream = philox.STREAM_INLIER_PAD if which == 'inlier' else philox.STREAM_NEIGHBOR_PAD
         if count >= k:
             # k smallest (key, index) pairs, emitted in ascending index order
-            keys = philox.draw_u32(self.seed, self.room, self.step, key_stream, count)
+            keys = philox.draw_u32(self.seed, self.room, self.step, key_stream + 8 * self.lane, count)
             chosen = np.lexsort((np.arange(count), keys))[:k]
             return np.sort(chosen)
-        r = philox.draw_u32(self.seed, self.room, self.step, pad_stream, k - count).astype(np.uint64)
+        r = philox.draw_u32(self.seed, self.room, self.step, pad_stream + 8 * self.lane, k - count).astype(np.uint64)
         pad = (r * np.uint64(count)) >> np.uint64(32)          # multiply-high range reduction
         return np.concatenate([np.arange(count), pad.astype(np.int64)])
 
     def uniform(self, k, which):
         stream = philox.STREAM_ADD_UNIFORM if which == 'add' else philox.STREAM_REMOVE_UNIFORM
-        return philox.u32_to_unit_float(philox.draw_u32(self.seed, self.room, self.step, stream, k))
+        return philox.u32_to_unit_float(philox.draw_u32(self.seed, self.room, self.step, stream + 8 * self.lane, k))
 
 
 # ----------------------------------------------------------------------------- confidence
@@ -101,6 +103,9 @@ class RoomGrower:
         self.regions = []          # (seed, steps, size, reason, labelled)
         self.trace = None          # optional list of per-step dicts
 
+    def _begin_rng_step(self):
+        self.rng.begin_step(self.room_id, self.total_steps)
+
     # -- region lifecycle ---------------------------------------------------------------------------
     def begin_region(self, seed_id):
         self.seed_id = int(seed_id)
@@ -136,7 +141,7 @@ class RoomGrower:
         if len(expandPoints) == 0:                                                # :233-235
             self.stop_growing('noneighbor')
             return None
-        self.rng.begin_step(self.room_id, self.total_steps)
+        self._begin_rng_step()
         subset_i = self.rng.sample(len(currentPoints), self.Ni, 'inlier')         # :237-240
         center = np.median(currentPoints, axis=0)                                 # :241
         expandPoints[:, :2] -= center[:2]                                         # :243-244
@@ -241,6 +246,72 @@ class RoomGrower:
 
     def fill(self):
         return fill_unlabeled(self.points, self.cluster_label)
+
+
+class RestartRoomGrower(RoomGrower):
+    """One room of /root/reference/test_random_restart.py:141-303: every seed is grown NUM_RESTARTS (:24) times from the
+    same ``visited`` state and the restart that ends with the most points is kept (``restart_scoring = 'np'``, the default
+    :40; numpy.argmax -> the first of equal scores, :177).  Only the kept mask becomes visited / labelled (:178-181).
+
+    ('ml' scoring is not restated: after the first restart the reference resets ``maskLogProb`` to a list (:196), which
+    numpy turns into an empty array on the next ``+=`` (:272), so every later score is empty -- the mode does not work.)
+
+    RNG: with ``NumpyLegacyRng`` the restarts consume the single global stream one after the other like the reference; with
+    ``PhiloxRng`` restart ``l`` is lane ``l`` with its own streams and its own step counter (steps taken by that lane in
+    this room), so that the device can grow the restarts of a seed side by side.
+    """
+
+    def __init__(self, *args, num_restarts=10, **kw):
+        super().__init__(*args, **kw)
+        self.num_restarts = int(num_restarts)
+        self.lane = 0
+        self.lane_steps = [0] * self.num_restarts
+        self.restart_score, self.restart_mask = [], []
+        self.lane_regions = []      # (seed, lane, size, reason) of every restart
+
+    def _begin_rng_step(self):
+        self.rng.begin_step(self.room_id, self.lane_steps[self.lane], self.lane)
+
+    def stop_growing(self, reason):                                               # test_random_restart.py:170-197
+        self.restart_score.append(int(np.sum(self.currentMask)))                  # :174
+        self.restart_mask.append(self.currentMask)
+        self.lane_regions.append((self.seed_id, self.lane, self.restart_score[-1], reason))
+        if len(self.restart_score) == self.num_restarts:
+            best = self.restart_mask[int(np.argmax(self.restart_score))]          # :177
+            self.visited[best] = True
+            size = int(np.sum(best))
+            labelled = size > self.cluster_threshold
+            if labelled:
+                self.cluster_label[best] = self.cluster_id
+                self.cluster_id += 1
+            self.regions.append((self.seed_id, self.seed_steps, size, reason, labelled))
+            self.restart_score, self.restart_mask = [], []
+
+    def apply_step(self, *a, **kw):
+        self.seed_steps += 1                                                      # `steps` is not reset by a restart (:163,:188-196)
+        self.lane_steps[self.lane] += 1
+        return super().apply_step(*a, **kw)
+
+    def run(self):
+        for seed_id in np.arange(len(self.points))[self.order]:
+            if self.visited[seed_id]:
+                continue
+            self.seed_steps = 0
+            for lane in range(self.num_restarts):
+                self.lane = lane
+                self.begin_region(seed_id)                                        # :188-196
+                self.grow_region_from_current()
+        return self.cluster_label
+
+    def grow_region_from_current(self):
+        while True:
+            st = self.prepare_step()
+            if st is None:
+                return 'noneighbor'
+            add, rmv = self.forward_fn(st['inlier'], st['neighbor'])
+            reason = self.apply_step(np.asarray(add)[0], np.asarray(rmv)[0])
+            if reason is not None:
+                return reason
 
 
 def _rows_in(voxels, query):

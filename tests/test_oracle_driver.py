@@ -49,3 +49,30 @@ def test_literal_update_loop_equals_vectorised(golden_weights):
         gr.run()
         out.append((gr.cluster_label.copy(), gr.total_steps, list(gr.regions)))
     assert np.array_equal(out[0][0], out[1][0]) and out[0][1:] == out[1][1:]
+
+
+def test_restart_driver_replays_reference_trace(golden_weights):
+    """oracle RestartRoomGrower vs the UNMODIFIED /root/reference/test_random_restart.py (tests/golden/restart_trace_1000.npz):
+    every tile fed to Session.run over all 10 restarts of every seed, the final labels and the printed region lines."""
+    base = np.load(os.path.join(GOLDEN, 'driver_trace_1000.npz'))
+    g = np.load(os.path.join(GOLDEN, 'restart_trace_1000.npz'))
+    calls = []
+
+    def fwd(inlier, neighbor):
+        calls.append((_crc(inlier), _crc(neighbor)))
+        add, rmv = lrg_forward.forward(golden_weights, inlier, neighbor, dtype=np.float64)
+        return add.astype(np.float32), rmv.astype(np.float32)
+
+    grower = lrg_driver.RestartRoomGrower(base['points'], base['order'], fwd, lrg_driver.NumpyLegacyRng(0), resolution=0.1,
+                                          num_restarts=int(g['num_restarts']))
+    grower.run()
+    assert len(calls) == len(g['inlier_crc'])
+    assert [c[0] for c in calls] == [int(x) for x in g['inlier_crc']]
+    assert [c[1] for c in calls] == [int(x) for x in g['neighbor_crc']]
+    np.testing.assert_array_equal(grower.fill(), g['cluster_label'])
+    lines = [l for l in str(g['log']).split('\n') if l.startswith('room ')]
+    labelled = [r for r in grower.regions if r[4]]
+    assert len(lines) == len(labelled)
+    for line, (seed_id, steps, size, reason, _) in zip(lines, labelled):
+        tok = line.split()
+        assert int(tok[6]) == steps and int(tok[7].split('/')[0]) == size and tok[-1] == reason
