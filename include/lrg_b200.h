@@ -81,6 +81,9 @@ typedef struct LrgGrowParams {
   int room_id_base;            /* added to the local room index in the RNG counter (multi-GPU sharding) */
   int trace_capacity;          /* >0: record up to this many grow steps per room (tests) */
   int flags;                   /* LRG_FLAG_* */
+  int num_restarts;            /* 0/1: test_region_grow.py.  N > 1: test_random_restart.py with NUM_RESTARTS = N (:24) and
+                                  'np' scoring (:40,174): every seed is grown N times from the same visited state, the N
+                                  restarts side by side on the device, and the largest result is kept (max 16) */
 } LrgGrowParams;
 
 enum {
@@ -140,6 +143,8 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
  * otherwise the raw cluster_label with 0 = unlabeled (:176,214). */
 int lrg_labels_download(LrgEngine* e, int32_t* labels, int filled);
 int lrg_trace_download(LrgEngine* e, int room, LrgStepTrace* out, int capacity, int* n_steps);
+/* After a run with num_restarts > 1: the steps restart lane `lane` took in `room` (all seeds, in order). */
+int lrg_trace_download_lane(LrgEngine* e, int room, int lane, LrgStepTrace* out, int capacity, int* n_steps);
 /* Host-buffer convenience: upload + segment + download (the end-to-end call bench.py times). */
 int lrg_segment_rooms_host(LrgEngine* e, int n_rooms, const int64_t* room_offsets, const float* points,
                            const int32_t* seed_order, const LrgGrowParams* params, int32_t* labels_filled,

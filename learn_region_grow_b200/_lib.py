@@ -16,7 +16,7 @@ class LrgError(RuntimeError):
 class GrowParams(C.Structure):
     _fields_ = [('resolution', C.c_float), ('cluster_threshold', C.c_int), ('seed', C.c_uint64),
                 ('max_slots', C.c_int), ('max_steps_per_region', C.c_int), ('room_id_base', C.c_int),
-                ('trace_capacity', C.c_int), ('flags', C.c_int)]
+                ('trace_capacity', C.c_int), ('flags', C.c_int), ('num_restarts', C.c_int)]
 
 
 class RoomStats(C.Structure):
@@ -70,6 +70,7 @@ _SIGNATURES = {
     'lrg_segment_resident': (_I, [_P, C.POINTER(GrowParams), _P]),
     'lrg_labels_download': (_I, [_P, _P, _I]),
     'lrg_trace_download': (_I, [_P, _I, _P, _I, C.POINTER(_I)]),
+    'lrg_trace_download_lane': (_I, [_P, _I, _I, _P, _I, C.POINTER(_I)]),
     'lrg_segment_rooms_host': (_I, [_P, _I, _P, _P, _P, C.POINTER(GrowParams), _P, _P]),
     'lrg_last_segment_profile': (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int64),
                                       C.POINTER(C.c_int64), C.POINTER(C.c_float)]),

@@ -49,11 +49,15 @@ __global__ void __launch_bounds__(1024) lrg_pack_kernel(const float* __restrict_
 }
 
 __global__ void __launch_bounds__(1024) lrg_reset_words_kernel(const long long* __restrict__ room_off, const long long* __restrict__ pw_off,
-                                                               unsigned* __restrict__ pw) {
+                                                               unsigned* __restrict__ pw, int lanes, long long lane_stride) {
   const int room = blockIdx.x;
   const int N = (int)(room_off[room + 1] - room_off[room]);
   unsigned* w = pw + pw_off[room];
-  for (int i = threadIdx.x; i < N; i += 1024) w[i] &= PW_XYZ;
+  const int n4 = (N + 3) & ~3;
+  for (int i = threadIdx.x; i < n4; i += 1024) {
+    const unsigned v = i < N ? (w[i] & PW_XYZ) : PW_VIS;
+    for (int l = 0; l < lanes; ++l) w[(long long)l * lane_stride + i] = v;
+  }
 }
 
 int launch_pack(const float* d_points, int F, int n_rooms, const long long* d_room_off, const long long* d_pw_off, float resolution,
@@ -64,9 +68,10 @@ int launch_pack(const float* d_points, int F, int n_rooms, const long long* d_ro
   return LRG_OK;
 }
 
-int launch_reset_words(int n_rooms, const long long* d_room_off, const long long* d_pw_off, unsigned* d_pw, cudaStream_t stream) {
+int launch_reset_words(int n_rooms, const long long* d_room_off, const long long* d_pw_off, unsigned* d_pw, int lanes, long long lane_stride,
+                       cudaStream_t stream) {
   if (n_rooms <= 0) return LRG_OK;
-  lrg_reset_words_kernel<<<n_rooms, 1024, 0, stream>>>(d_room_off, d_pw_off, d_pw);
+  lrg_reset_words_kernel<<<n_rooms, 1024, 0, stream>>>(d_room_off, d_pw_off, d_pw, lanes < 1 ? 1 : lanes, lane_stride);
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;
 }

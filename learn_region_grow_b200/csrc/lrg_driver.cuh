@@ -22,6 +22,19 @@ struct SlotState {
   int regions, stops[4];
   int visited;         // points of the current room already assigned to a finished region (scheduling hint)
   float center[16];    // :241
+  // random-restart driver only (lanes > 1): this lane has finished the current seed and waits for the other restarts /
+  // the lane was handed a fresh seed by the lane that committed the previous one (skip the seed search)
+  int parked, begin;
+};
+
+// Random-restart driver (test_random_restart.py): the NUM_RESTARTS restarts of a seed are `lanes` consecutive slots (a
+// group) that grow side by side from the same visited state, each on its own copy of the room's state words.  What the
+// reference keeps per room lives here, owned by whichever lane commits a seed (the last one to finish it).
+constexpr int kMaxLanes = 16;
+struct LaneGroup {
+  int done;                // lanes that have finished the current seed
+  int score[kMaxLanes];    // 'np' score of every lane: points in its final region (test_random_restart.py:174)
+  int room, cursor, cluster_id, regions, visited;
 };
 
 struct DriverArgs {
@@ -59,6 +72,11 @@ struct DriverArgs {
   LrgStepTrace* trace;          // (n_rooms, trace_capacity) or NULL
   int trace_capacity;
   unsigned long long* dbg;      // diagnostics (NULL = off): summed clock64 cycles per step stage [0..14], steps in [15]
+  // random restarts (lanes > 1): slot = group * lanes + lane; lane l works on pw + l * pw_lane_stride
+  int lanes;
+  LaneGroup* groups;            // (n_slots / lanes)
+  long long pw_lane_stride;
+  int* lane_steps;              // (n_rooms, lanes) out: grow steps every lane took in the room (trace lengths)
 };
 
 struct FillArgs {
@@ -78,7 +96,9 @@ struct FillArgs {
 int launch_pack(const float* d_points, int F, int n_rooms, const long long* d_room_off, const long long* d_pw_off, float resolution,
                 float* d_pts16, unsigned* d_pw, int4* d_room_vmin, int* d_err, cudaStream_t stream);
 // clears the CURRENT / VISITED flags of every room (start of a run)
-int launch_reset_words(int n_rooms, const long long* d_room_off, const long long* d_pw_off, unsigned* d_pw, cudaStream_t stream);
+// (lanes > 1: also re-creates the copies 1..lanes-1 of the words, lane_stride words apart)
+int launch_reset_words(int n_rooms, const long long* d_room_off, const long long* d_pw_off, unsigned* d_pw, int lanes, long long lane_stride,
+                       cudaStream_t stream);
 size_t step_smem_bytes();
 int launch_step(const DriverArgs& da, cudaStream_t stream);
 int launch_fill(const FillArgs& fa, cudaStream_t stream);

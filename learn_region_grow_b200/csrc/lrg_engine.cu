@@ -115,6 +115,11 @@ struct LrgEngine {
   int* d_done = nullptr;
   LrgStepTrace* d_trace = nullptr;
   int trace_capacity = 0, trace_rooms = 0;
+  // random restarts: per-lane copies of the state words, group records, per-lane step counts of the last run
+  unsigned* d_pw_lanes = nullptr;
+  LaneGroup* d_groups = nullptr;
+  int* d_lane_steps = nullptr;
+  int last_lanes = 1;
   // persistent grow kernel: work queue, per-slot stage counters, busy-time counters
   int sm_count = 0;
   unsigned long long* d_qring = nullptr;
@@ -221,6 +226,8 @@ static void free_rooms(LrgEngine* e) {
   pool_free(e, e->d_room_off); pool_free(e, e->d_pts); pool_free(e, e->d_pw); pool_free(e, e->d_pw_off); pool_free(e, e->d_room_vmin); pool_free(e, e->d_label);
   pool_free(e, e->d_label_filled); pool_free(e, e->d_order); pool_free(e, e->d_lab_list); pool_free(e, e->d_unl_list);
   pool_free(e, e->d_n_lab); pool_free(e, e->d_n_unl); pool_free(e, e->d_stats);
+  pool_free(e, e->d_pw_lanes); pool_free(e, e->d_groups); pool_free(e, e->d_lane_steps);
+  e->d_pw_lanes = nullptr; e->d_groups = nullptr; e->d_lane_steps = nullptr;
   pool_free(e, e->d_raw_off); pool_free(e, e->d_equalized_idx); pool_free(e, e->d_unequalized_idx); pool_free(e, e->d_feat);
   e->d_raw_off = nullptr; e->d_equalized_idx = e->d_unequalized_idx = nullptr; e->d_feat = nullptr; e->raw_mode = false; e->total_raw = 0;
   e->d_room_off = nullptr; e->d_pts = nullptr; e->d_pw = nullptr; e->d_pw_off = nullptr; e->d_room_vmin = nullptr; e->d_label = nullptr;
@@ -742,38 +749,63 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   LRG_CUDA(cudaSetDevice(e->device));
   const int n_rooms = e->n_rooms;
   const size_t T = (size_t)e->total_pts;
-  int n_slots = params->max_slots > 0 ? params->max_slots : 148;
-  n_slots = std::max(1, std::min(n_slots, std::max(n_rooms, 1)));
+  // random restarts (test_random_restart.py): `lanes` consecutive slots grow the restarts of one seed side by side
+  const int lanes = params->num_restarts > 1 ? params->num_restarts : 1;
+  LRG_REQUIRE(lanes <= kMaxLanes, "num_restarts %d exceeds the limit of %d", lanes, kMaxLanes);
+  int n_slots = params->max_slots > 0 ? params->max_slots : (lanes > 1 ? 296 : 148);
+  int n_groups = std::max(1, std::min(n_slots / lanes, std::max(n_rooms, 1)));
+  n_slots = n_groups * lanes;
   LRG_TRY(ensure_slots(e, n_slots));
+  e->last_lanes = lanes;
+  if (lanes > 1) {
+    pool_free(e, e->d_pw_lanes); pool_free(e, e->d_groups); pool_free(e, e->d_lane_steps);
+    e->d_pw_lanes = nullptr; e->d_groups = nullptr; e->d_lane_steps = nullptr;
+    LRG_TRY(pool_alloc(e, &e->d_pw_lanes, (size_t)std::max<long long>(e->total_words, 4) * lanes));
+    LRG_TRY(pool_alloc(e, &e->d_groups, (size_t)n_groups));
+    LRG_TRY(pool_alloc(e, &e->d_lane_steps, (size_t)std::max(n_rooms, 1) * lanes));
+  }
   cudaStream_t st = e->stream;
   cudaEvent_t ev0, ev1, ev2;
   LRG_CUDA(cudaEventCreate(&ev0)); LRG_CUDA(cudaEventCreate(&ev1)); LRG_CUDA(cudaEventCreate(&ev2));
-  if (params->trace_capacity > 0 && (e->d_trace == nullptr || e->trace_capacity != params->trace_capacity || e->trace_rooms < n_rooms)) {
+  if (params->trace_capacity > 0 && (e->d_trace == nullptr || e->trace_capacity != params->trace_capacity || e->trace_rooms < n_rooms * lanes)) {
     cudaFree(e->d_trace);
     e->d_trace = nullptr;
-    LRG_TRY(dev_alloc(&e->d_trace, (size_t)std::max(n_rooms, 1) * params->trace_capacity));
-    e->trace_rooms = n_rooms;
+    LRG_TRY(dev_alloc(&e->d_trace, (size_t)std::max(n_rooms, 1) * lanes * params->trace_capacity));
+    e->trace_rooms = n_rooms * lanes;
   }
   *e->h_done = 0;
   LRG_CUDA(cudaEventRecord(ev0, st));
   // reset per-run state (inside the timed region: it is part of one pass over the rooms)
-  LRG_TRY(launch_reset_words(n_rooms, e->d_room_off, e->d_pw_off, e->d_pw, st));
+  unsigned* d_words = e->d_pw;
+  if (lanes > 1) {
+    d_words = e->d_pw_lanes;
+    if (e->total_words > 0) LRG_CUDA(cudaMemcpyAsync(d_words, e->d_pw, sizeof(unsigned) * (size_t)e->total_words, cudaMemcpyDeviceToDevice, st));
+    std::vector<LaneGroup> ginit(n_groups);
+    memset(ginit.data(), 0, sizeof(LaneGroup) * n_groups);
+    for (auto& g : ginit) { g.room = -1; g.cluster_id = 1; }
+    LRG_CUDA(cudaMemcpyAsync(e->d_groups, ginit.data(), sizeof(LaneGroup) * n_groups, cudaMemcpyHostToDevice, st));
+    LRG_CUDA(cudaMemsetAsync(e->d_lane_steps, 0, sizeof(int) * (size_t)std::max(n_rooms, 1) * lanes, st));
+    LRG_CUDA(cudaStreamSynchronize(st));      // (ginit is a host temporary)
+  }
+  LRG_TRY(launch_reset_words(n_rooms, e->d_room_off, e->d_pw_off, d_words, lanes, e->total_words, st));
   LRG_CUDA(cudaMemsetAsync(e->d_label, 0, T * sizeof(int), st));
   LRG_CUDA(cudaMemsetAsync(e->d_stats, 0, sizeof(LrgRoomStats) * std::max(n_rooms, 1), st));
   LRG_CUDA(cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(int), st));
   std::vector<SlotState> init(n_slots);
   memset(init.data(), 0, sizeof(SlotState) * n_slots);
   for (auto& s : init) s.room = -1;
+  if (lanes > 1)
+    for (int s = 0; s < n_slots; ++s) init[s].parked = (s % lanes) != 0;      // lane 0 of every group takes the first room
   LRG_CUDA(cudaMemcpyAsync(e->d_slots, init.data(), sizeof(SlotState) * n_slots, cudaMemcpyHostToDevice, st));
   if (params->trace_capacity > 0) {
-    LRG_CUDA(cudaMemsetAsync(e->d_trace, 0, sizeof(LrgStepTrace) * (size_t)std::max(n_rooms, 1) * params->trace_capacity, st));
+    LRG_CUDA(cudaMemsetAsync(e->d_trace, 0, sizeof(LrgStepTrace) * (size_t)std::max(n_rooms, 1) * lanes * params->trace_capacity, st));
     e->trace_capacity = params->trace_capacity;
   } else {
     e->trace_capacity = 0;
   }
 
   DriverArgs da{};
-  da.n_rooms = n_rooms; da.room_off = e->d_room_off; da.pts = e->d_pts; da.pw = e->d_pw; da.pw_off = e->d_pw_off; da.room_vmin = e->d_room_vmin;
+  da.n_rooms = n_rooms; da.room_off = e->d_room_off; da.pts = e->d_pts; da.pw = d_words; da.pw_off = e->d_pw_off; da.room_vmin = e->d_room_vmin;
   da.label = e->d_label; da.order = e->d_order; da.slots = e->d_slots; da.n_slots = n_slots; da.maxN = e->slots_maxN;
   da.listI = e->d_listI; da.listJ = e->d_listJ; da.keyI = e->d_keyI; da.keyJ = e->d_keyJ;
   da.tile[0] = e->d_tile[0]; da.tile[1] = e->d_tile[1]; da.tileidx[0] = e->d_tileidx[0]; da.tileidx[1] = e->d_tileidx[1];
@@ -786,6 +818,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   da.next_room = e->d_counters; da.finished_slots = e->d_counters + 1; da.done_flag = e->d_done;
   da.dbg = e->d_tile_dbg ? e->d_tile_dbg + 32 : nullptr;
   da.stats = e->d_stats; da.trace = e->trace_capacity > 0 ? e->d_trace : nullptr; da.trace_capacity = e->trace_capacity;
+  da.lanes = lanes; da.groups = e->d_groups; da.pw_lane_stride = e->total_words; da.lane_steps = lanes > 1 ? e->d_lane_steps : nullptr;
 
   ForwardArgs fa{};
   fa.x[0] = e->d_tile[0]; fa.x[1] = e->d_tile[1]; fa.x_stride = 16;
@@ -825,11 +858,12 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
         LRG_TRY(dev_alloc(&e->d_remaining, (size_t)n_slots));
         e->sync_slots = n_slots;
       }
-      std::vector<unsigned long long> first(n_slots);
-      for (int s = 0; s < n_slots; ++s) first[s] = (1ull << 32) | make_item(ITEM_STEP, s, 0, 0);
-      const unsigned ctr[4] = {0u, 0u, 0u, (unsigned)n_slots};
+      // (random restarts: only lane 0 of every group starts; it wakes the other lanes once it holds a seed)
+      std::vector<unsigned long long> first(n_groups);
+      for (int g = 0; g < n_groups; ++g) first[g] = (1ull << 32) | make_item(ITEM_STEP, g * lanes, 0, 0);
+      const unsigned ctr[4] = {0u, 0u, 0u, (unsigned)n_groups};
       LRG_CUDA(cudaMemsetAsync(e->d_qring, 0, sizeof(unsigned long long) * 2 * e->q_capacity, st));
-      LRG_CUDA(cudaMemcpyAsync(e->d_qring + e->q_capacity, first.data(), sizeof(unsigned long long) * n_slots, cudaMemcpyHostToDevice, st));
+      LRG_CUDA(cudaMemcpyAsync(e->d_qring + e->q_capacity, first.data(), sizeof(unsigned long long) * n_groups, cudaMemcpyHostToDevice, st));
       LRG_CUDA(cudaMemcpyAsync(e->d_qctr, ctr, sizeof(ctr), cudaMemcpyHostToDevice, st));
       LRG_CUDA(cudaMemsetAsync(e->d_busy, 0, sizeof(unsigned long long) * 24, st));
       LRG_CUDA(cudaMemsetAsync(e->d_sync, 0, sizeof(SlotSync) * n_slots, st));
@@ -847,7 +881,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
       ga.sync = e->d_sync;
       ga.busy_ns = e->d_busy;
       ga.remaining = e->d_remaining;
-      ga.hi_slots = params->flags & LRG_FLAG_PRIORITY ? std::max(2, n_slots / 8) : 0;
+      ga.hi_slots = (params->flags & LRG_FLAG_PRIORITY) && lanes == 1 ? std::max(2, n_slots / 8) : 0;
       ga.tune = getenv("LRG_TUNE") ? atoi(getenv("LRG_TUNE")) : 3;   // both measured positive (profiles/README.md)
       rc = launch_grow(ga, e->sm_count > 0 ? e->sm_count : 148, st);
       if (rc == LRG_OK) {
@@ -937,9 +971,26 @@ int lrg_labels_download(LrgEngine* e, int32_t* labels, int filled) {
   return LRG_OK;
 }
 
+int lrg_trace_download_lane(LrgEngine* e, int room, int lane, LrgStepTrace* out, int capacity, int* n_steps) {
+  LRG_REQUIRE(e != nullptr && out != nullptr && n_steps != nullptr, "NULL argument");
+  LRG_REQUIRE(room >= 0 && room < e->n_rooms, "room %d out of range", room);
+  LRG_REQUIRE(lane >= 0 && lane < e->last_lanes, "lane %d out of range (the last run had %d)", lane, e->last_lanes);
+  if (e->last_lanes <= 1) return lrg_trace_download(e, room, out, capacity, n_steps);
+  if (e->trace_capacity <= 0 || e->d_trace == nullptr) { set_error("no trace recorded (trace_capacity was 0)"); return LRG_E_STATE; }
+  LRG_CUDA(cudaSetDevice(e->device));
+  int steps = 0;
+  LRG_CUDA(cudaMemcpy(&steps, e->d_lane_steps + (size_t)room * e->last_lanes + lane, sizeof(int), cudaMemcpyDeviceToHost));
+  const int n = std::min(std::min(steps, e->trace_capacity), capacity);
+  *n_steps = steps;
+  if (n > 0)
+    LRG_CUDA(cudaMemcpy(out, e->d_trace + ((size_t)room * e->last_lanes + lane) * e->trace_capacity, sizeof(LrgStepTrace) * n, cudaMemcpyDeviceToHost));
+  return LRG_OK;
+}
+
 int lrg_trace_download(LrgEngine* e, int room, LrgStepTrace* out, int capacity, int* n_steps) {
   LRG_REQUIRE(e != nullptr && out != nullptr && n_steps != nullptr, "NULL argument");
   LRG_REQUIRE(room >= 0 && room < e->n_rooms, "room %d out of range", room);
+  LRG_REQUIRE(e->last_lanes <= 1, "the last run used %d restart lanes: use lrg_trace_download_lane", e->last_lanes);
   if (e->trace_capacity <= 0 || e->d_trace == nullptr) { set_error("no trace recorded (trace_capacity was 0)"); return LRG_E_STATE; }
   LRG_CUDA(cudaSetDevice(e->device));
   LrgRoomStats st;

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
       const unsigned long long tp = *reinterpret_cast<volatile unsigned long long*>(&sy->t_pub);
       if (tp != 0 && t0 > tp) atomicAdd(ga.busy_ns + 16 + type, t0 - tp);
     }
-    unsigned next[32];
+    unsigned next[32 + kMaxLanes];
     int n_next = 0;
     if (type == ITEM_STEP) {
       step_body<kGrowThreads>(ga.da, slot, sh);
@@ -168,6 +168,12 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
             for (int i = 0; i < tilesI; ++i) next[n_next++] = make_item(ITEM_BRANCH, slot, 0 | (lg << 1), i | (part << 2));
             for (int i = 0; i < tilesJ; ++i) next[n_next++] = make_item(ITEM_BRANCH, slot, 1 | (lg << 1), i | (part << 2));
           }
+        }
+        if (sh.wake && !sh.all_done) {
+          // random restarts: this step committed a seed and started every lane of its group on the next one
+          const int L = ga.da.lanes, first_slot = slot - slot % L;
+          for (int l = 0; l < L; ++l)
+            if (first_slot + l != slot) next[n_next++] = make_item(ITEM_STEP, first_slot + l, 0, 0);
         }
       }
     } else if (type == ITEM_BRANCH) {
@@ -219,7 +225,7 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
         // release: a STEP publishes the counters it just wrote; the tile / projection finishers already fenced before the
         // atomic that made them last (the push is control-dependent on that atomic's result)
         if (type == ITEM_STEP) __threadfence();
-        if ((*reinterpret_cast<volatile int*>(&sy->prio) & 1) == 0) {
+        if (ga.hi_slots > 0 && (*reinterpret_cast<volatile int*>(&sy->prio) & 1) == 0) {
           queue_push(ga.q[0], next + first, n_next - first);
           for (int i = first; i < n_next; ++i) next[i] = make_item(ITEM_WAKE, 0, 0, 0);
         }

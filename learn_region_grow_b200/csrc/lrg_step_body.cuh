@@ -270,6 +270,8 @@ struct StepShared {
   int red[32 * 6];
   int flag;
   int all_done;                 // set when this call retired the last slot of the run
+  int wake;                     // random restarts: this call handed a fresh seed to the other lanes of its group (they need a STEP)
+  LaneGroup G;                  // random restarts: the group's room-level state while this CTA owns it
   unsigned nextkey[16];         // median: smallest key above the lower median, per channel
   int listI_s[kListCap], listJ_s[kListCap];
   union {                        // the histograms of the radix selects are never live together with the staged median keys
@@ -456,10 +458,16 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
   SlotState* gS = da.slots + slot;
   for (int i = tid; i < (int)(sizeof(SlotState) / 4); i += NT)
     reinterpret_cast<int*>(&sh.S)[i] = __ldcg(reinterpret_cast<const int*>(gS) + i);
-  if (tid == 0) { sh.n_odd = 0; sh.flag = 0; sh.all_done = 0; }
+  if (tid == 0) { sh.n_odd = 0; sh.flag = 0; sh.all_done = 0; sh.wake = 0; }
   __syncthreads();
   SlotState& S = sh.S;
   if (S.finished) return;
+  // random restarts (test_random_restart.py): slot = group * L + lane; a parked lane waits for the other restarts of its seed
+  const int L = da.lanes > 1 ? da.lanes : 1;
+  const int lane_id = L > 1 ? slot % L : 0;
+  LaneGroup* const grp = L > 1 ? da.groups + slot / L : nullptr;
+  const unsigned rng_lane = 8u * (unsigned)lane_id;        // lane l draws from the Philox streams 8l + {0..5}
+  if (L > 1 && S.parked) return;
 
   int* listI = da.listI + (size_t)slot * da.maxN;
   int* listJ = da.listJ + (size_t)slot * da.maxN;
@@ -477,15 +485,179 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     base = da.room_off[S.room];
     N = (int)(da.room_off[S.room + 1] - base);
     pts = da.pts + base * 16;
-    pw = da.pw + da.pw_off[S.room];
+    pw = da.pw + (long long)lane_id * da.pw_lane_stride + da.pw_off[S.room];
     const int4 vm = da.room_vmin[S.room];
     vmin0 = vm.x; vmin1 = vm.y; vmin2 = vm.z;
   };
   if (S.room >= 0) bind_room();
 
+  // next unvisited seed in curvature order from position `cursor` (:183-188); -1 when the room is exhausted
+  auto find_seed = [&](int cursor) -> int {
+    const int* order = da.order + base;
+    for (int start = cursor; start < N; start += NT) {
+      const int pos = start + tid;
+      const bool ok = pos < N && !(pw[order[pos]] & PW_VIS);
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) sh.red[warp] = bal ? (start + warp * 32 + __ffs(bal) - 1) : INT_MAX;
+      __syncthreads();
+      int best = INT_MAX;
+      for (int w = 0; w < NT / 32; ++w) best = min(best, sh.red[w]);
+      __syncthreads();
+      if (best != INT_MAX) return best;
+    }
+    return -1;
+  };
+
+  // ---- random restarts (test_random_restart.py:170-197) ---------------------------------------------------------------
+  // A restart that stops does not touch visited / labels: it records its score ('np': points in the region, :174), clears
+  // its CURRENT flags and parks.  The lane that finishes a seed LAST commits it -- the first lane with the highest score
+  // wins (numpy.argmax, :177), its region becomes visited in every lane's copy of the words and is labelled (:178-181) --
+  // and then owns the group: it finds the next seed (or room), starts every lane on it and asks for their STEP items.
+  auto stop_lane = [&](int reason, int n_cur) -> bool {
+    for (int j = tid; j < n_cur; j += NT) {
+      const int i = listI[j];
+      pw[i] &= PW_XYZ;                                       // (a CURRENT point is never VISITED)
+    }
+    if (tid == 0) {
+      const int slot_r = reason == STOP_NONEIGHBOR ? 0 : reason == STOP_NOEXPAND ? 1 : reason == STOP_STUCK ? 2 : 3;
+      S.stops[slot_r] += 1;
+      S.active = 0;
+      S.parked = 1;
+      S.n_in = n_cur;
+    }
+    __syncthreads();
+    for (int i = tid; i < (int)(sizeof(SlotState) / 4); i += NT)
+      reinterpret_cast<int*>(gS)[i] = reinterpret_cast<const int*>(&sh.S)[i];
+    __syncthreads();
+    if (tid == 0) {
+      *reinterpret_cast<volatile int*>(&grp->score[lane_id]) = n_cur;
+      __threadfence();
+      const int done = atomicAdd(&grp->done, 1) + 1;
+      sh.flag = done;
+      if (done == L) {
+        __threadfence();
+        for (int i = 0; i < (int)(sizeof(LaneGroup) / 4); ++i)
+          reinterpret_cast<int*>(&sh.G)[i] = __ldcg(reinterpret_cast<const int*>(grp) + i);
+        int best = 0;
+        for (int l = 1; l < L; ++l)
+          if (sh.G.score[l] > sh.G.score[best]) best = l;
+        sh.red[0] = best;
+        sh.G.done = 0;
+      }
+    }
+    __syncthreads();
+    const bool last = sh.flag == L;
+    const int best = sh.red[0];
+    __syncthreads();
+    if (!last) return false;
+    // commit the best restart of this seed
+    const int n_best = sh.G.score[best];
+    const bool labelled = n_best > da.cluster_threshold;
+    const int cid = sh.G.cluster_id;
+    const int* blist = da.listI + (size_t)(slot - lane_id + best) * da.maxN;
+    int* label = da.label + base;
+    unsigned* pw0 = da.pw + da.pw_off[S.room];
+    for (int j = tid; j < n_best; j += NT) {
+      const int i = best == lane_id ? blist[j] : __ldcg(blist + j);
+      const unsigned w = (pw[i] & PW_XYZ) | PW_VIS;
+      for (int l = 0; l < L; ++l) pw0[(long long)l * da.pw_lane_stride + i] = w;
+      if (labelled) label[i] = cid;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (labelled) sh.G.cluster_id += 1;
+      sh.G.regions += 1;
+      sh.G.visited += n_best;
+      S.parked = 0;
+    }
+    __syncthreads();
+    return true;
+  };
+  // Owner of the group: next seed of the room, else the next room, else retire every lane.  Returns false when retired.
+  auto advance_group = [&]() -> bool {
+    LaneGroup& G = sh.G;
+    while (true) {
+      int found = -1;
+      if (G.room >= 0) found = find_seed(G.cursor);
+      if (found >= 0) {
+        const int seed = da.order[base + found];
+        const unsigned w = pw[seed];
+        if (tid == 0) {
+          G.cursor = found + 1;
+          const int vx = pw_x(w), vy = pw_y(w), vz = pw_z(w);
+          // order: the commit's word / label stores (all threads, before the barrier) and the seed's flags and list heads
+          // become visible before any lane can observe its `begin` flag
+          __threadfence();
+          for (int l = 0; l < L; ++l) {
+            (da.pw + (long long)l * da.pw_lane_stride + da.pw_off[G.room])[seed] = w | PW_CUR;
+            (da.listI + (size_t)(slot - lane_id + l) * da.maxN)[0] = seed;
+          }
+          __threadfence();
+          for (int l = 0; l < L; ++l) {
+            SlotState* o = l == lane_id ? &S : da.slots + (slot - lane_id + l);
+            o->active = 0; o->finished = 0; o->room = G.room; o->seed = seed;
+            o->minD[0] = o->maxD[0] = o->seqMin[0] = o->seqMax[0] = vx;
+            o->minD[1] = o->maxD[1] = o->seqMin[1] = o->seqMax[1] = vy;
+            o->minD[2] = o->maxD[2] = o->seqMin[2] = o->seqMax[2] = vz;
+            o->stuck = 0; o->steps = 0; o->n_in = 1; o->n_nb = 0;
+            o->parked = 0;
+            *reinterpret_cast<volatile int*>(&o->begin) = l == lane_id ? 0 : 1;
+          }
+          sh.listI_s[0] = seed;
+          sh.wake = 1;
+          *grp = G;
+        }
+        __syncthreads();
+        return true;
+      }
+      // room exhausted (or first call): publish its stats and fetch the next room from the queue
+      if (tid == 0) {
+        if (G.room >= 0) {
+          int steps = 0, stops[4] = {0, 0, 0, 0};
+          for (int l = 0; l < L; ++l) {
+            const SlotState* o = da.slots + (slot - lane_id + l);
+            const int ts = l == lane_id ? S.total_steps : __ldcg(&o->total_steps);
+            steps += ts;
+            if (da.lane_steps != nullptr) da.lane_steps[(size_t)G.room * L + l] = ts;
+            for (int k = 0; k < 4; ++k) stops[k] += l == lane_id ? S.stops[k] : __ldcg(&o->stops[k]);
+          }
+          LrgRoomStats& st = da.stats[G.room];
+          st.n_points = N; st.grow_steps = steps; st.regions = G.regions; st.clusters = G.cluster_id - 1;
+          st.stop_noneighbor = stops[0]; st.stop_noexpand = stops[1]; st.stop_stuck = stops[2]; st.stop_other = stops[3];
+        }
+        const int nr = atomicAdd(da.next_room, 1);
+        G.room = nr < da.n_rooms ? nr : -1;
+        G.cursor = 0; G.cluster_id = 1; G.regions = 0; G.visited = 0;
+        for (int l = 0; l < L; ++l) {                      // per-room counters of every lane (the others are parked)
+          SlotState* o = l == lane_id ? &S : da.slots + (slot - lane_id + l);
+          o->total_steps = 0; o->stops[0] = o->stops[1] = o->stops[2] = o->stops[3] = 0;
+        }
+        S.room = G.room; S.active = 0;
+      }
+      __syncthreads();
+      if (G.room < 0) {
+        if (tid == 0) {
+          for (int l = 0; l < L; ++l)
+            if (l != lane_id) *reinterpret_cast<volatile int*>(&da.slots[slot - lane_id + l].finished) = 1;
+          S.finished = 1;
+          *grp = G;
+          const int fin = atomicAdd(da.finished_slots, L) + L;
+          if (fin == da.n_slots) {
+            sh.all_done = 1;
+            if (da.done_flag != nullptr) { *da.done_flag = 1; __threadfence_system(); }
+          }
+        }
+        __syncthreads();
+        return false;
+      }
+      bind_room();
+    }
+  };
+
   // stop_growing (:210-217): visited |= current; label when the region is larger than the threshold.
   // listI[0..n_cur) holds the current region.
-  auto stop_region = [&](int reason, int n_cur) {
+  auto stop_region = [&](int reason, int n_cur) -> bool {
+    if (L > 1) return stop_lane(reason, n_cur);
     const bool labelled = n_cur > da.cluster_threshold;
     int* label = da.label + base;
     const int cid = S.cluster_id;
@@ -504,9 +676,23 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       S.active = 0;
     }
     __syncthreads();
+    return true;
   };
 
   int mode = MODE_NEW_REGION;
+  if (L > 1 && !S.active) {
+    if (S.begin) {                      // a fresh seed handed over by the lane that committed the previous one
+      __threadfence();                  // (acquire: the committing CTA's stores to this lane's words and list)
+      __syncthreads();
+      if (tid == 0) { S.begin = 0; sh.listI_s[0] = S.seed; }      // (the region is the seed alone: list mirror of listI[0])
+      mode = MODE_SCAN;
+    } else {                            // first call of the run (lane 0): take the group
+      if (tid == 0)
+        for (int i = 0; i < (int)(sizeof(LaneGroup) / 4); ++i)
+          reinterpret_cast<int*>(&sh.G)[i] = __ldcg(reinterpret_cast<const int*>(grp) + i);
+    }
+    __syncthreads();
+  }
   stamp(0);
 
   // ------------------------------------------------------------------ apply the pending step (:262-306)
@@ -515,7 +701,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     const unsigned step_rng = (unsigned)S.total_steps;
     LrgStepTrace* tr = nullptr;
     if (da.trace != nullptr && S.total_steps < da.trace_capacity)
-      tr = da.trace + (size_t)S.room * da.trace_capacity + S.total_steps;
+      tr = da.trace + ((size_t)S.room * L + lane_id) * da.trace_capacity + S.total_steps;
     float2 lg_[VT], xy_[VT];
     unsigned w_[VT];
 #pragma unroll
@@ -540,7 +726,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       bool m = false;
       if (p >= 0) {
         const float conf = confidence(lg_[k].x, lg_[k].y);
-        const unsigned draw = philox_draw(da.seed, room_rng, step_rng, is_add ? kStreamAddUniform : kStreamRemoveUniform, r);
+        const unsigned draw = philox_draw(da.seed, room_rng, step_rng, rng_lane + (is_add ? kStreamAddUniform : kStreamRemoveUniform), r);
         const float u = (float)(draw >> 8) * (1.0f / 16777216.0f);
         m = u < conf;                                          // :266-267
       }
@@ -648,7 +834,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     if (tr != nullptr && tid == 0) { tr->stop_reason = reason; tr->size_after = n_in; }
     stamp(2);
     if (reason != STOP_NONE) {
-      stop_region(reason, n_in);
+      if (!stop_region(reason, n_in)) return;              // (random restarts: parked until the seed's other restarts end)
       mode = MODE_NEW_REGION;
     } else {
       mode = MODE_SCAN;
@@ -658,23 +844,13 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
   stamp(3);
   // ------------------------------------------------------------------ find the next region that needs a forward
   while (true) {
-    if (mode == MODE_NEW_REGION) {
+    if (mode == MODE_NEW_REGION && L > 1) {
+      if (!advance_group()) break;
+      mode = MODE_SCAN;
+    } else if (mode == MODE_NEW_REGION) {
       // next unvisited seed in curvature order (:183-188)
       int found = -1;
-      if (S.room >= 0) {
-        const int* order = da.order + base;
-        for (int start = S.cursor; start < N; start += NT) {
-          const int pos = start + tid;
-          const bool ok = pos < N && !(pw[order[pos]] & PW_VIS);
-          const unsigned bal = __ballot_sync(0xffffffffu, ok);
-          if (lane == 0) sh.red[warp] = bal ? (start + warp * 32 + __ffs(bal) - 1) : INT_MAX;
-          __syncthreads();
-          int best = INT_MAX;
-          for (int w = 0; w < NT / 32; ++w) best = min(best, sh.red[w]);
-          __syncthreads();
-          if (best != INT_MAX) { found = best; break; }
-        }
-      }
+      if (S.room >= 0) found = find_seed(S.cursor);
       if (found < 0) {
         // room exhausted (or first launch): publish its stats and fetch the next room from the queue
         if (tid == 0) {
@@ -732,7 +908,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       return x >= lo0 && x <= hi0 && y >= lo1 && y <= hi1 && z >= lo2 && z <= hi2;
     }, [](unsigned) {}, listJ, sh.listJ_s, kListCap, sh.scan);
     if (n_nb == 0) {                                          // :233-235
-      stop_region(STOP_NONEIGHBOR, S.n_in);
+      if (!stop_region(STOP_NONEIGHBOR, S.n_in)) return;
       mode = MODE_NEW_REGION;
       continue;
     }
@@ -799,8 +975,8 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
 
     // sampling (:237-240, :249-252) with the Philox stream of oracle/lrg_driver.py PhiloxRng
     const bool fullI = n_in >= da.Ni, fullJ = n_nb >= da.Nj;
-    if (fullI) for (int j = tid; j < n_in; j += NT) keyI[j] = philox_draw(da.seed, room_rng, step_rng, kStreamInlierKey, j);
-    if (fullJ) for (int j = tid; j < n_nb; j += NT) keyJ[j] = philox_draw(da.seed, room_rng, step_rng, kStreamNeighborKey, j);
+    if (fullI) for (int j = tid; j < n_in; j += NT) keyI[j] = philox_draw(da.seed, room_rng, step_rng, rng_lane + kStreamInlierKey, j);
+    if (fullJ) for (int j = tid; j < n_nb; j += NT) keyJ[j] = philox_draw(da.seed, room_rng, step_rng, rng_lane + kStreamNeighborKey, j);
     if (tid == 0) { sh.rank[0] = da.Ni - 1; sh.rank[1] = da.Nj - 1; }
     __syncthreads();
     if (fullI || fullJ) {
@@ -816,11 +992,11 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     if (fullI) block_select_smallest<NT>(n_in, keyI, TI, EI, sh.sel[0], sh.scan);
     else
       for (int r = tid; r < da.Ni; r += NT)
-        sh.sel[0][r] = r < n_in ? r : (int)__umulhi(philox_draw(da.seed, room_rng, step_rng, kStreamInlierPad, r - n_in), (unsigned)n_in);
+        sh.sel[0][r] = r < n_in ? r : (int)__umulhi(philox_draw(da.seed, room_rng, step_rng, rng_lane + kStreamInlierPad, r - n_in), (unsigned)n_in);
     if (fullJ) block_select_smallest<NT>(n_nb, keyJ, TJ, EJ, sh.sel[1], sh.scan);
     else
       for (int r = tid; r < da.Nj; r += NT)
-        sh.sel[1][r] = r < n_nb ? r : (int)__umulhi(philox_draw(da.seed, room_rng, step_rng, kStreamNeighborPad, r - n_nb), (unsigned)n_nb);
+        sh.sel[1][r] = r < n_nb ? r : (int)__umulhi(philox_draw(da.seed, room_rng, step_rng, rng_lane + kStreamNeighborPad, r - n_nb), (unsigned)n_nb);
     __syncthreads();
 
     stamp(7);
@@ -864,7 +1040,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       if (tracing) {
         __syncthreads();
         if (tid == 0) {
-          LrgStepTrace* tr = da.trace + (size_t)S.room * da.trace_capacity + S.total_steps;
+          LrgStepTrace* tr = da.trace + ((size_t)S.room * L + lane_id) * da.trace_capacity + S.total_steps;
           unsigned ci = 0, cj = 0;
           for (int w2 = 0; w2 < 16; ++w2) { ci += (unsigned)sh.red[w2]; cj += (unsigned)sh.red[16 + w2]; }
           tr->seed_point = S.seed; tr->step_in_region = S.steps; tr->n_inlier = n_in; tr->n_neighbor = n_nb;

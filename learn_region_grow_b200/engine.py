@@ -198,9 +198,10 @@ class Engine:
         return self.raw_labels(True), stats
 
     def make_params(self, resolution=0.1, cluster_threshold=10, seed=0, max_slots=0, max_steps_per_region=0,
-                    room_id_base=0, trace_capacity=0, flags=0):
+                    room_id_base=0, trace_capacity=0, flags=0, num_restarts=0):
+        """``num_restarts`` > 1 selects the random-restart driver (test_random_restart.py, NUM_RESTARTS, 'np' scoring)."""
         return GrowParams(resolution, cluster_threshold, seed, max_slots, max_steps_per_region, room_id_base,
-                          trace_capacity, flags)
+                          trace_capacity, flags, num_restarts)
 
     def segment_resident(self, params=None, **kw):
         """Grow all uploaded rooms on the device; returns the per-room statistics (structured array)."""
@@ -234,10 +235,13 @@ class Engine:
             return out, [label2[self._room_offsets[i]:self._room_offsets[i + 1]] for i in range(n_rooms)]
         return out
 
-    def trace(self, room, capacity):
+    def trace(self, room, capacity, lane=None):
         buf = np.zeros(capacity, dtype=STEP_TRACE_DTYPE)
         n = C.c_int(0)
-        _lib.check(self.lib.lrg_trace_download(self._h, room, _lib.ptr(buf), capacity, C.byref(n)))
+        if lane is None:
+            _lib.check(self.lib.lrg_trace_download(self._h, room, _lib.ptr(buf), capacity, C.byref(n)))
+        else:
+            _lib.check(self.lib.lrg_trace_download_lane(self._h, room, lane, _lib.ptr(buf), capacity, C.byref(n)))
         return buf[:min(n.value, capacity)], n.value
 
     def profile(self):

@@ -1,0 +1,27 @@
+"""Random-restart driver (test_random_restart.py) on the bench workload: time per pass and steps/s for a few lane counts.
+Also prints the segmentation statistics of the plain driver and of the restarts (the reference's reason for restarts)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import bench
+from learn_region_grow_b200.engine import Engine
+
+rooms = int(sys.argv[1]) if len(sys.argv) > 1 else 68
+offsets, points, order, raw_counts = bench.make_workload(rooms, 1000)
+raw = bench.RAW_ROOMS[(rooms, 1000)]
+raw_off = np.zeros(rooms + 1, np.int64); np.cumsum(raw_counts, out=raw_off[1:])
+eng = Engine(1, 1, 512, 512, 13, 0); eng.load_weights(bench.load_weights())
+eng.upload_raw_concatenated(raw_off, raw, 0.1)
+obj_raw = [raw[raw_off[i]:raw_off[i + 1], 6].astype(np.int32) for i in range(rooms)]
+for R in (1, 2, 5, 10):
+    best = None
+    for it in range(2):
+        t0 = time.perf_counter()
+        st = eng.segment_resident(resolution=0.1, seed=0, num_restarts=R)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    m = eng.room_metrics(obj_raw, raw=True)
+    steps = int(st['grow_steps'].sum())
+    print('restarts %2d: %7.1f ms/pass  %8d grow steps  %7.0f k steps/s  %6.2f M raw points/s | NMI %.3f AMI %.3f ARS %.3f PRC %.3f RCL %.3f IOU %.3f' %
+          (R, 1e3 * best, steps, steps / best / 1e3, raw_off[-1] / best / 1e6, m['nmi'].mean(), m['ami'].mean(), m['ars'].mean(),
+           np.nanmean(m['prc']), m['rcl'].mean(), m['iou'].mean()), flush=True)
