@@ -257,6 +257,8 @@ __device__ int scan_words(const unsigned* pw, int N, Pred pred, Visit visit, int
 
 // ----------------------------------------------------------------------------------------------------- step
 constexpr int kMedianCap = 2048;   // inlier sets up to this size have their 9 median channels staged in shared memory
+constexpr int kMedianCapSlots = kMedianCap / 32;
+constexpr int kMedianSmall = 256;  // up to this size the channel's own warp transposes its keys by ballots (cheaper below ~256)
 constexpr int kListCap = 1024;     // leading entries of the inlier / neighbour lists mirrored in shared memory
 
 struct StepShared {
@@ -274,8 +276,10 @@ struct StepShared {
   LaneGroup G;                  // random restarts: the group's room-level state while this CTA owns it
   unsigned nextkey[16];         // median: smallest key above the lower median, per channel
   int listI_s[kListCap], listJ_s[kListCap];
-  union {                        // the histograms of the radix selects are never live together with the staged median keys
-    unsigned mkeys[9][kMedianCap];
+  unsigned malive[kMedianCapSlots];   // median: which keys of every 32-key slot exist
+  union {                        // the histograms of the radix selects are never live together with the staged median bit planes
+    unsigned planes[9][32 * (kMedianCapSlots + 1)];   // [channel][bit][slot]: bit planes of the inlier keys (sets above kMedianSmall)
+    unsigned mkeys[9][kMedianSmall];                  // the keys themselves (sets up to kMedianSmall)
     int hist[18 * 256];
   };
 };
@@ -348,6 +352,58 @@ __device__ __forceinline__ void warp_median(const unsigned* __restrict__ keys, i
       hi = __reduce_min_sync(0xffffffffu, above);
     }
   }
+}
+
+// 32 x 32 bit transpose across a warp (five exchange steps): lane i passes key i; lane b receives the word whose bit i is
+// bit b of key i -- the bit plane b of the warp's 32 keys.
+__device__ __forceinline__ unsigned warp_transpose32(unsigned x, int lane) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    const unsigned m = d == 16 ? 0x0000FFFFu : d == 8 ? 0x00FF00FFu : d == 4 ? 0x0F0F0F0Fu : d == 2 ? 0x33333333u : 0x55555555u;
+    const unsigned y = __shfl_xor_sync(0xffffffffu, x, d);
+    x = (lane & d) ? ((x & ~m) | ((y >> d) & m)) : ((x & m) | ((y << d) & ~m));
+  }
+  return x;
+}
+
+constexpr int kPlaneStride = kMedianCapSlots + 1;      // (+1: the 32 lanes of a warp write one column, bank-conflict free)
+
+// numpy.median's two middle keys of one channel by ONE warp from bit planes staged in shared memory: planes[b *
+// kPlaneStride + s] = bit b of the 32 keys of slot s, alive_s[s] = which of them exist.  Lane s (+32g) owns slot s as 32
+// registers; the select walks the bits from the top with one popc + one warp reduction per bit (not per key), for the ranks
+// (n-1)/2 and n/2 at once (independent chains that pipeline).  n <= 1024 * G.
+template <int G>
+__device__ __forceinline__ void warp_median_planes(const unsigned* __restrict__ planes, const unsigned* __restrict__ alive_s, int n,
+                                                   unsigned& lo, unsigned& hi) {
+  const int lane = threadIdx.x & 31;
+  const int nslots = (n + 31) >> 5;
+  unsigned P[G][32], a1[G], a2[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int sidx = lane + 32 * g;
+    const bool ok = sidx < nslots;
+    a1[g] = a2[g] = ok ? alive_s[sidx] : 0u;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) P[g][b] = ok ? planes[b * kPlaneStride + sidx] : 0u;
+  }
+  int r1 = (n - 1) >> 1, r2 = n >> 1;
+  unsigned p1 = 0, p2 = 0;
+#pragma unroll
+  for (int b = 31; b >= 0; --b) {
+    unsigned z1 = 0, z2 = 0;
+#pragma unroll
+    for (int g = 0; g < G; ++g) { z1 += __popc(a1[g] & ~P[g][b]); z2 += __popc(a2[g] & ~P[g][b]); }
+    // one warp reduction per bit for both ranks: the two counts (<= 2048 each) travel in the halves of one word
+    const unsigned zz = __reduce_add_sync(0xffffffffu, z1 | (z2 << 16));
+    const int zeros1 = (int)(zz & 0xFFFFu), zeros2 = (int)(zz >> 16);
+    const bool t1 = r1 >= zeros1, t2 = r2 >= zeros2;           // warp-uniform
+    if (t1) { r1 -= zeros1; p1 |= 1u << b; }
+    if (t2) { r2 -= zeros2; p2 |= 1u << b; }
+#pragma unroll
+    for (int g = 0; g < G; ++g) { a1[g] &= t1 ? P[g][b] : ~P[g][b]; a2[g] &= t2 ? P[g][b] : ~P[g][b]; }
+  }
+  lo = p1;
+  hi = p2;
 }
 
 // numpy.median over n keys per channel (mean of the two middle values for even n, :241): block radix select of rank
@@ -935,7 +991,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
 #pragma unroll
       for (int s = 0; s < 9; ++s) k[s] = sortable(vals[s]);
     };
-    if (n_in <= kMedianCap) {
+    if (n_in <= kMedianSmall) {
       for (int j = tid; j < n_in; j += NT) {
         unsigned k[9];
         row_keys(j, k);
@@ -943,12 +999,41 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
         for (int s = 0; s < 9; ++s) sh.mkeys[s][j] = k[s];
       }
       __syncthreads();
-      // one warp per channel, no atomics and no block barriers (a bitonic sort of the nine rows by the whole CTA was
-      // measured 3-4x slower, a histogram select with shared-memory atomics 2x slower)
+      // one warp per channel: ballots transpose the keys into bit planes, then a bit-sliced rank select
       for (int c = warp; c < nch; c += NT / 32) {
         unsigned lo, hi;
-        if (n_in <= 1024) warp_median<1>(sh.mkeys[c], n_in, lo, hi);
-        else warp_median<2>(sh.mkeys[c], n_in, lo, hi);
+        warp_median<1>(sh.mkeys[c], n_in, lo, hi);
+        if (lane == 0) { sh.prefix[c] = lo; sh.nextkey[c] = hi; }
+      }
+      __syncthreads();
+    } else if (n_in <= kMedianCap) {
+      // every thread loads the row of one inlier; each warp turns the 32 keys of a channel into 32 bit-plane words with a
+      // five-step shuffle transpose (no per-key work in the select below)
+      const int nslots = (n_in + 31) >> 5;
+      for (int j0 = 0; j0 < nslots * 32; j0 += NT) {
+        const int j = j0 + tid, sl = j >> 5;                  // sl is warp-uniform
+        if (sl < nslots) {
+          unsigned k[9];
+          if (j < n_in) row_keys(j, k);
+          else {
+#pragma unroll
+            for (int c = 0; c < 9; ++c) k[c] = 0u;
+          }
+          const unsigned av = __ballot_sync(0xffffffffu, j < n_in);
+          if (lane == 0) sh.malive[sl] = av;
+#pragma unroll
+          for (int c = 0; c < 9; ++c)
+            if (c < nch) sh.planes[c][lane * kPlaneStride + sl] = warp_transpose32(k[c], lane);
+        }
+      }
+      __syncthreads();
+      // one warp per channel, no atomics and no block barriers (measured per step, sets of 257-512 / 513-1024 / 1025-2048
+      // points: 11k / 15k / 23k cycles; ballot transposition by the channel's own warp 18k / 31k / 55k; a histogram select
+      // with shared-memory atomics 2x, a CTA-wide bitonic sort 3-4x slower than that)
+      for (int c = warp; c < nch; c += NT / 32) {
+        unsigned lo, hi;
+        if (n_in <= 1024) warp_median_planes<1>(sh.planes[c], sh.malive, n_in, lo, hi);
+        else warp_median_planes<2>(sh.planes[c], sh.malive, n_in, lo, hi);
         if (lane == 0) { sh.prefix[c] = lo; sh.nextkey[c] = hi; }
       }
       __syncthreads();
