@@ -127,6 +127,12 @@ int lrg_rooms_upload(LrgEngine* e, int n_rooms, const int64_t* room_offsets, con
  * curvature).  A room may hold at most 1,048,575 raw points. */
 int lrg_rooms_upload_raw(LrgEngine* e, int n_rooms, const int64_t* raw_offsets, const float* raw_points, int n_cols,
                          float resolution);
+/* Same with the raw points already in device memory (caller-owned, read only; raw_offsets is host memory). */
+int lrg_rooms_upload_raw_device(LrgEngine* e, int n_rooms, const int64_t* raw_offsets, const float* d_raw_points, int n_cols,
+                                float resolution);
+/* Device time (ms, CUDA events on the engine stream) of the last lrg_rooms_upload_raw / _device call: host-to-device copy (host
+ * variant), feature preparation and packing, including the one host round trip that sizes the equalised rooms. */
+int lrg_last_prepare_ms(LrgEngine* e, float* ms);
 /* After an upload: (n_rooms+1) prefix sums of the equalised room sizes. */
 int lrg_rooms_equalized_offsets(LrgEngine* e, int64_t* eq_offsets);
 /* After lrg_rooms_upload_raw: the prepared features (sum Neq, F), the seed order, equalized_idx (sum Neq: raw index of every

@@ -133,7 +133,7 @@ struct LrgEngine {
   bool last_persistent = false;
   unsigned long long* d_tile_dbg = nullptr;   // [32] tile-stage cycle counters (diagnostics, LRG_TILE_TIMING=1)
   // profile of the last segment call
-  float grow_ms = 0, fill_ms = 0, forward_ms = 0;
+  float grow_ms = 0, fill_ms = 0, forward_ms = 0, prep_ms = 0;
   float kernel_ms[4] = {0, 0, 0, 0};
   long long iterations = 0, launches = 0;
 };
@@ -627,7 +627,25 @@ int lrg_rooms_upload(LrgEngine* e, int n_rooms, const int64_t* room_offsets, con
   return LRG_OK;
 }
 
+static int upload_raw_impl(LrgEngine* e, int n_rooms, const int64_t* raw_offsets, const float* raw_points, int n_cols, float resolution,
+                           bool device_src);
+
 int lrg_rooms_upload_raw(LrgEngine* e, int n_rooms, const int64_t* raw_offsets, const float* raw_points, int n_cols, float resolution) {
+  return upload_raw_impl(e, n_rooms, raw_offsets, raw_points, n_cols, resolution, false);
+}
+
+int lrg_rooms_upload_raw_device(LrgEngine* e, int n_rooms, const int64_t* raw_offsets, const float* d_raw_points, int n_cols, float resolution) {
+  return upload_raw_impl(e, n_rooms, raw_offsets, d_raw_points, n_cols, resolution, true);
+}
+
+int lrg_last_prepare_ms(LrgEngine* e, float* ms) {
+  LRG_REQUIRE(e != nullptr && ms != nullptr, "NULL argument");
+  *ms = e->prep_ms;
+  return LRG_OK;
+}
+
+static int upload_raw_impl(LrgEngine* e, int n_rooms, const int64_t* raw_offsets, const float* raw_points, int n_cols, float resolution,
+                           bool device_src) {
   LRG_REQUIRE(e != nullptr, "engine is NULL");
   LRG_REQUIRE(n_rooms >= 0 && raw_offsets != nullptr && raw_offsets[0] == 0, "bad room table");
   LRG_REQUIRE(resolution > 0.f, "resolution must be > 0");
@@ -656,19 +674,23 @@ int lrg_rooms_upload_raw(LrgEngine* e, int n_rooms, const int64_t* raw_offsets, 
   const size_t TR = (size_t)total_raw, TS = (size_t)sort_off[n_rooms];
   int rc = LRG_OK;
   auto A = [&](int r) { if (rc == LRG_OK) rc = r; };
-  A(pool_alloc(e, &d_raw, TR * n_cols)); A(pool_alloc(e, &d_raw_off, (size_t)n_rooms + 1)); A(pool_alloc(e, &d_sort_off, (size_t)n_rooms + 1));
+  if (!device_src) A(pool_alloc(e, &d_raw, TR * n_cols));
+  A(pool_alloc(e, &d_raw_off, (size_t)n_rooms + 1)); A(pool_alloc(e, &d_sort_off, (size_t)n_rooms + 1));
   A(pool_alloc(e, &d_eq_off, (size_t)n_rooms + 1)); A(pool_alloc(e, &d_keys, TS)); A(pool_alloc(e, &d_keys2, TS)); A(pool_alloc(e, &d_vmin, (size_t)std::max(n_rooms, 1)));
   A(pool_alloc(e, &d_neq, (size_t)std::max(n_rooms, 1))); A(pool_alloc(e, &d_err, 1)); A(pool_alloc(e, &d_uvox, TR)); A(pool_alloc(e, &d_ustart, TR));
   A(pool_alloc(e, &d_equ, TR)); A(pool_alloc(e, &d_rank, TR)); A(pool_alloc(e, &d_sums, TR * 10));
   if (rc != LRG_OK) { cleanup(); pool_free(e, d_raw_off); return rc; }
   std::vector<long long> h_raw_off(raw_offsets, raw_offsets + n_rooms + 1);
-  cudaMemcpyAsync(d_raw, raw_points, sizeof(float) * TR * n_cols, cudaMemcpyHostToDevice, st);
+  cudaEvent_t pev0 = nullptr, pev1 = nullptr;      // device time of the preparation (includes the host round trip for the room sizes)
+  cudaEventCreate(&pev0); cudaEventCreate(&pev1);
+  cudaEventRecord(pev0, st);
+  if (!device_src) cudaMemcpyAsync(d_raw, raw_points, sizeof(float) * TR * n_cols, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(d_raw_off, h_raw_off.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(d_sort_off, sort_off.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice, st);
   cudaMemsetAsync(d_err, 0, sizeof(int), st);
   FeatPrepArgs fp{};
   fp.n_rooms = n_rooms; fp.C = n_cols; fp.F = e->F; fp.res = resolution;
-  fp.raw_off = d_raw_off; fp.raw = d_raw; fp.sort_off = d_sort_off; fp.keys = d_keys; fp.keys2 = d_keys2; fp.raw_vmin = d_vmin;
+  fp.raw_off = d_raw_off; fp.raw = device_src ? raw_points : d_raw; fp.sort_off = d_sort_off; fp.keys = d_keys; fp.keys2 = d_keys2; fp.raw_vmin = d_vmin;
   fp.n_eq = d_neq; fp.err = d_err; fp.uniq_vox = d_uvox; fp.uniq_start = d_ustart; fp.eq_of_uniq = d_equ; fp.sums = d_sums; fp.raw_rank = d_rank;
   rc = launch_featprep_phase1(fp, st);
   std::vector<int> h_neq(std::max(n_rooms, 1), 0);
@@ -683,7 +705,7 @@ int lrg_rooms_upload_raw(LrgEngine* e, int n_rooms, const int64_t* raw_offsets, 
     set_error("room %d spans more than 1022 voxels along an axis at resolution %g (state words hold 10 bits per axis)", bad_room - 1, (double)resolution);
     rc = LRG_E_INVALID;
   }
-  if (rc != LRG_OK) { cleanup(); pool_free(e, d_raw_off); return rc; }
+  if (rc != LRG_OK) { cleanup(); pool_free(e, d_raw_off); cudaEventDestroy(pev0); cudaEventDestroy(pev1); return rc; }
   std::vector<int64_t> eq_off((size_t)n_rooms + 1, 0);
   for (int r = 0; r < n_rooms; ++r) eq_off[r + 1] = eq_off[r] + h_neq[r];
   rc = alloc_rooms(e, n_rooms, eq_off.data(), resolution);
@@ -699,10 +721,13 @@ int lrg_rooms_upload_raw(LrgEngine* e, int n_rooms, const int64_t* raw_offsets, 
     fp.unequalized_idx = e->d_unequalized_idx;
     rc = launch_featprep_phase2(fp, st);
     if (rc == LRG_OK) rc = pack_rooms(e, e->d_feat);
+    cudaEventRecord(pev1, st);
     cudaError_t ce = cudaStreamSynchronize(st);
+    if (ce == cudaSuccess) cudaEventElapsedTime(&e->prep_ms, pev0, pev1);
     if (rc == LRG_OK && ce != cudaSuccess) { set_error("feature preparation -> %s", cudaGetErrorString(ce)); rc = LRG_E_CUDA; }
   }
   cleanup();
+  cudaEventDestroy(pev0); cudaEventDestroy(pev1);
   if (rc != LRG_OK) { pool_free(e, d_raw_off); return rc; }
   e->raw_mode = true; e->total_raw = total_raw; e->h_raw_off = h_raw_off; e->d_raw_off = d_raw_off;
   return LRG_OK;

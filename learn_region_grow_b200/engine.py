@@ -165,10 +165,16 @@ class Engine:
                if raw_rooms else np.zeros((0, ncols), np.float32))
         return self.upload_raw_concatenated(raw_off, raw, resolution)
 
-    def upload_raw_concatenated(self, raw_offsets, raw_points, resolution=0.1):
+    def upload_raw_concatenated(self, raw_offsets, raw_points, resolution=0.1, n_cols=None):
+        """raw_points: (sum Nr, C) float32 host array, or a device pointer / torch CUDA tensor of that layout (then ``n_cols``
+        is taken from the tensor or must be given): the raw points are read where they are."""
         n_rooms = len(raw_offsets) - 1
-        _lib.check(self.lib.lrg_rooms_upload_raw(self._h, n_rooms, _lib.ptr(raw_offsets), _lib.ptr(raw_points),
-                                                 int(raw_points.shape[1]), C.c_float(resolution)))
+        on_device = isinstance(raw_points, int) or (hasattr(raw_points, 'is_cuda') and raw_points.is_cuda)
+        if n_cols is None:
+            n_cols = int(raw_points.shape[1])
+        fn = self.lib.lrg_rooms_upload_raw_device if on_device else self.lib.lrg_rooms_upload_raw
+        _lib.check(fn(self._h, n_rooms, _lib.ptr(np.ascontiguousarray(raw_offsets, np.int64)), _lib.ptr(raw_points), int(n_cols),
+                      C.c_float(resolution)))
         eq = np.zeros(n_rooms + 1, dtype=np.int64)
         _lib.check(self.lib.lrg_rooms_equalized_offsets(self._h, _lib.ptr(eq)))
         self._room_offsets = eq
@@ -183,6 +189,12 @@ class Engine:
         _lib.check(self.lib.lrg_rooms_features_download(self._h, _lib.ptr(out['points']), _lib.ptr(out['order']),
                                                         _lib.ptr(out['equalized_idx']), _lib.ptr(out['unequalized_idx'])))
         return out
+
+    def prepare_ms(self):
+        """Device time of the last raw upload (copy + feature preparation + packing), CUDA events on the engine stream."""
+        ms = C.c_float(0)
+        _lib.check(self.lib.lrg_last_prepare_ms(self._h, C.byref(ms)))
+        return ms.value
 
     def raw_labels(self, filled=True):
         """cluster_label[unequalized_idx] per room (test_region_grow.py:366)."""
