@@ -82,6 +82,43 @@ def generate_room(seed, n_raw=20000, n_boxes=None, dims=None, max_dim=12.0):
     return room.astype(np.float32)
 
 
+def generate_outdoor_scene(seed, n_raw=300000, extent=100.0, n_boxes=None):
+    """Semantic-KITTI-shaped stand-in: an extent x extent metre ground plane with vehicle- and
+    pole-sized boxes on it, (N,8) float32, N ~= n_raw; meant to be segmented at resolution 0.3
+    (/root/reference/stage_semantic_kitti.py aligns 20 scans and voxel-downsamples them at 0.1 m)."""
+    rng = np.random.RandomState(seed)
+    if n_boxes is None:
+        n_boxes = int(rng.randint(150, 301))
+    e = float(extent)
+    objects = [[((0, 0, 0), (e, 0, 0), (0, e, 0))]]
+    classes = [1]
+    for _ in range(n_boxes):
+        kind = rng.randint(3)
+        sx, sy, sz = [(4.2, 1.8, 1.5), (0.4, 0.4, 6.0), (8.0, 6.0, 4.0)][kind] * rng.uniform(0.7, 1.3, 3)
+        x0, y0 = rng.uniform(0.5, e - sx - 0.5), rng.uniform(0.5, e - sy - 0.5)
+        objects.append([
+            ((x0, y0, sz), (sx, 0, 0), (0, sy, 0)),
+            ((x0, y0, 0), (sx, 0, 0), (0, 0, sz)), ((x0, y0 + sy, 0), (sx, 0, 0), (0, 0, sz)),
+            ((x0, y0, 0), (0, sy, 0), (0, 0, sz)), ((x0 + sx, y0, 0), (0, sy, 0), (0, 0, sz)),
+        ])
+        classes.append(2 + kind)
+    areas = [[np.linalg.norm(np.cross(u, v)) for (_, u, v) in faces] for faces in objects]
+    total = sum(sum(a) for a in areas)
+    out = []
+    for oid, (faces, fa) in enumerate(zip(objects, areas)):
+        parts = []
+        for (o, u, v), a in zip(faces, fa):
+            n = max(1, int(round(n_raw * a / total)))
+            parts.append(_surface(rng, n, np.array(o, float), np.array(u, float), np.array(v, float), oid + 1, classes[oid]))
+        P = np.vstack(parts)
+        _colorize(rng, P)
+        P[:, 6] = oid + 1
+        P[:, 7] = classes[oid]
+        out.append(P)
+    scene = np.vstack(out)
+    return scene[rng.permutation(len(scene))].astype(np.float32)
+
+
 def generate_area(n_rooms, seed_base=1000, n_raw=20000, log_uniform=None):
     """List of rooms; ``log_uniform=(lo, hi)`` draws the raw size per room (ScanNet-shaped)."""
     rooms = []
