@@ -260,6 +260,7 @@ constexpr int kMedianCap = 2048;   // inlier sets up to this size have their 9 m
 constexpr int kMedianCapSlots = kMedianCap / 32;
 constexpr int kMedianSmall = 256;  // up to this size the channel's own warp transposes its keys by ballots (cheaper below ~256)
 constexpr int kListCap = 1024;     // leading entries of the inlier / neighbour lists mirrored in shared memory
+constexpr int kIncCap = 2048;      // regions up to this size get their inlier list updated from the previous one (no room scan)
 
 struct StepShared {
   SlotState S;
@@ -510,6 +511,15 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     // padding rows duplicate a distinct row (:239-240,251-252): same input, same logits, own uniform draw
     src_[k] = on ? __ldcg(da.tilesrc[is_add ? 1 : 0] + (size_t)slot * kMaxTilePts + r) : 0;
     p_[k] = on ? __ldcg(da.tileidx[is_add ? 1 : 0] + (size_t)slot * kMaxTilePts + r) : -1;
+  }
+  // ... and so does the head of the slot's inlier list (four consecutive entries per thread): when a forward is pending and
+  // the region is small, the new list is derived from it instead of a scan over the whole room
+  static_assert(NT >= kMaxTilePts && NT * 4 >= kIncCap, "the list update assumes one neighbour row and four list entries per thread");
+  int li_[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int j = tid * 4 + q;
+    li_[q] = j < da.maxN ? __ldcg(da.listI + (size_t)slot * da.maxN + j) : 0;
   }
   SlotState* gS = da.slots + slot;
   for (int i = tid; i < (int)(sizeof(SlotState) / 4); i += NT)
@@ -840,12 +850,90 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
 
     // inlier list + bounding box of the updated region (:292-293); also what stop_growing marks when the region ends
     int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
-    const int n_in = scan_words<NT>(pw, N, [](unsigned w) { return (w & PW_CUR) != 0; },
-                                    [&](unsigned w) {
-                                      const int x = pw_x(w), y = pw_y(w), z = pw_z(w);
-                                      mn[0] = min(mn[0], x); mn[1] = min(mn[1], y); mn[2] = min(mn[2], z);
-                                      mx[0] = max(mx[0], x); mx[1] = max(mx[1], y); mx[2] = max(mx[2], z);
-                                    }, listI, sh.listI_s, kListCap, sh.scan);
+    auto grow_box = [&](unsigned w) {
+      const int x = pw_x(w), y = pw_y(w), z = pw_z(w);
+      mn[0] = min(mn[0], x); mn[1] = min(mn[1], y); mn[2] = min(mn[2], z);
+      mx[0] = max(mx[0], x); mx[1] = max(mx[1], y); mx[2] = max(mx[2], z);
+    };
+    int n_in;
+    const int n_old = S.n_in;                                 // length of listI = the region before this step's masks
+    if (n_odd == 0 && n_old <= kIncCap) {
+      // Small region, every selected row kept its voxel: the new list is (old list minus the removed points) merged with the
+      // added neighbour rows -- both ascending and disjoint -- instead of a scan over the room's N state words.
+      int* keepI = reinterpret_cast<int*>(sh.odd);            // [kIncCap]      (the re-rounding table is empty on this path)
+      int* addA = keepI + kIncCap;                            // [kMaxTilePts]
+      int* addflag = addA + kMaxTilePts;                      // [kMaxTilePts]
+      static_assert(sizeof(sh.odd) >= sizeof(int) * (kIncCap + 2 * kMaxTilePts), "scratch of the list update");
+      for (int r = tid; r < kMaxTilePts; r += NT) addflag[r] = 0;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < VT; ++k)                            // a padding row that sampled True adds the row it duplicates
+        if ((tid + k * NT) >= kMaxTilePts && m_[k]) addflag[src_[k]] = 1;
+      // kept inliers: the old list filtered by the CURRENT flag the removals just cleared (ordered compaction)
+      unsigned kw[4], kf = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = tid * 4 + q;
+        kw[q] = j < n_old ? pw[li_[q]] : 0u;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (kw[q] & PW_CUR) { kf |= 1u << q; grow_box(kw[q]); }
+      const int kc = __popc(kf);
+      const int kincl = warp_incl_scan(kc, lane);
+      if (lane == 31) sh.scan[warp] = kincl;
+      __syncthreads();                                        // (also publishes addflag)
+      scan_warp_totals<NT>(sh.scan, warp, lane);
+      __syncthreads();
+      const int nK = sh.scan[32];
+      {
+        int o = sh.scan[warp] + kincl - kc;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if ((kf >> q) & 1u) keepI[o++] = li_[q];
+      }
+      __syncthreads();
+      // added points: the distinct neighbour rows (ascending in point index) whose flag is set
+      const int nsetJ = min(S.n_nb, da.Nj);
+      int arow = -1;                                          // this thread's neighbour row (one per thread)
+      unsigned aw = 0;
+      int ap = 0;
+#pragma unroll
+      for (int k = 0; k < VT; ++k) {
+        const int vt = tid + k * NT;
+        if (vt >= kMaxTilePts) { arow = vt - kMaxTilePts; aw = w_[k]; ap = p_[k]; }
+      }
+      const bool af = arow >= 0 && arow < nsetJ && addflag[arow] != 0;
+      if (af) grow_box(aw);
+      const int aincl = warp_incl_scan(af ? 1 : 0, lane);
+      if (lane == 31) sh.scan[warp] = aincl;
+      __syncthreads();
+      scan_warp_totals<NT>(sh.scan, warp, lane);
+      __syncthreads();
+      const int nA = sh.scan[32];
+      if (af) addA[sh.scan[warp] + aincl - 1] = ap;
+      __syncthreads();
+      // merge by rank: position = own rank + number of smaller elements of the other list
+      auto lower_bound = [](const int* a, int n, int v) {
+        int lo = 0, hi = n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
+        return lo;
+      };
+      for (int j = tid; j < nK; j += NT) {
+        const int v = keepI[j], pos = j + lower_bound(addA, nA, v);
+        listI[pos] = v;
+        if (pos < kListCap) sh.listI_s[pos] = v;
+      }
+      for (int t = tid; t < nA; t += NT) {
+        const int v = addA[t], pos = t + lower_bound(keepI, nK, v);
+        listI[pos] = v;
+        if (pos < kListCap) sh.listI_s[pos] = v;
+      }
+      n_in = nK + nA;
+      __syncthreads();
+    } else {
+      n_in = scan_words<NT>(pw, N, [](unsigned w) { return (w & PW_CUR) != 0; }, grow_box, listI, sh.listI_s, kListCap, sh.scan);
+    }
     int reason = STOP_NONE;
     if (!updated) {
       reason = STOP_NOEXPAND;                                // :304-306 (removals alone do not count)
