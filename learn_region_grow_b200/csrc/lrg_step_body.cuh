@@ -499,6 +499,9 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       tstamp = now;
     }
   };
+  auto mark = [&](int idx) {      // diagnostics: cycles since the last stamp, without restarting the interval
+    if (da.dbg != nullptr && tid == 0) atomicAdd(da.dbg + idx, (unsigned long long)(clock64() - tstamp));
+  };
   // metadata of the pending step's tile rows: addressed by the slot alone, so these loads go out together with the slot
   // state (one round trip); they are only meaningful -- and only used -- when a forward is pending
   int p_[VT], src_[VT];
@@ -559,6 +562,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
 
   // next unvisited seed in curvature order from position `cursor` (:183-188); -1 when the room is exhausted
   auto find_seed = [&](int cursor) -> int {
+    // (four NT-wide chunks per round with all eight loads in flight were measured slower: the seed is usually in the first chunk)
     const int* order = da.order + base;
     for (int start = cursor; start < N; start += NT) {
       const int pos = start + tid;
@@ -781,8 +785,20 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
         w_[k] = pw[p_[k]];
       }
     }
+    // the uniform draws depend on nothing that was loaded: their ~80 integer instructions per row run under the loads' latency
+    float u_[VT];
+#pragma unroll
+    for (int k = 0; k < VT; ++k) {
+      const int vt = tid + k * NT;
+      const bool is_add = vt >= kMaxTilePts;
+      const unsigned draw = philox_draw(da.seed, room_rng, step_rng, rng_lane + (is_add ? kStreamAddUniform : kStreamRemoveUniform),
+                                        is_add ? vt - kMaxTilePts : vt);
+      u_[k] = (float)(draw >> 8) * (1.0f / 16777216.0f);
+    }
     bool m_[VT], normal_[VT];
     int upd = 0;
+    if (da.dbg != nullptr && tid == 0 && __float_as_uint(lg_[0].x) + w_[0] == 0x12345u) mark(14);   // (waits for thread 0's loads)
+    mark(10);
 #pragma unroll
     for (int k = 0; k < VT; ++k) {
       const int vt = tid + k * NT;
@@ -792,9 +808,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       bool m = false;
       if (p >= 0) {
         const float conf = confidence(lg_[k].x, lg_[k].y);
-        const unsigned draw = philox_draw(da.seed, room_rng, step_rng, rng_lane + (is_add ? kStreamAddUniform : kStreamRemoveUniform), r);
-        const float u = (float)(draw >> 8) * (1.0f / 16777216.0f);
-        m = u < conf;                                          // :266-267
+        m = u_[k] < conf;                                      // :266-267
       }
       const unsigned bal = __ballot_sync(0xffffffffu, m);
       if (tr != nullptr && lane == 0) {
@@ -819,7 +833,9 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       if (m && normal && is_add) { pw[p] = w_[k] | PW_CUR; upd = 1; }      // (a neighbour row is never CURRENT before this)
       m_[k] = m; normal_[k] = normal;
     }
+    mark(11);
     __syncthreads();
+    mark(12);
     const int n_odd = sh.n_odd;
     if (n_odd > 0) {
       for (int i = tid; i < N; i += NT) {
@@ -844,6 +860,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
         if (hit) pw[i] = w & ~PW_CUR;
       }
     }
+    mark(13);
     __syncthreads();
     if (tid == 0) { S.steps += 1; S.total_steps += 1; }     // :288
     stamp(1);

@@ -98,3 +98,34 @@ def test_feature_ablations(F):
     labels, stats = e.segment_raw_rooms([raw], resolution=0.1, seed=0)
     assert labels[0].min() >= 1
     e.close()
+
+
+def test_raw_points_resident_on_the_device(engine):
+    """lrg_rooms_upload_raw_device: the raw rows are read where they are (a torch CUDA tensor here, plumbing only); same
+    features, same labels as the host-buffer call; lrg_last_prepare_ms reports the preparation's device time."""
+    import torch
+    from learn_region_grow_b200 import rooms
+    raws = [rooms.generate_room(1400 + i, n_raw=4000 + 2500 * i, n_boxes=4) for i in range(3)]
+    raw_off = np.zeros(len(raws) + 1, np.int64)
+    np.cumsum([len(r) for r in raws], out=raw_off[1:])
+    cat = np.ascontiguousarray(np.concatenate(raws), np.float32)
+    eq_h = engine.upload_raw_concatenated(raw_off, cat, 0.1)
+    f_h = engine.prepared_features()
+    st_h = engine.segment_resident(resolution=0.1, seed=4)
+    lab_h = engine.raw_labels()
+    d = torch.from_numpy(cat).cuda()
+    eq_d = engine.upload_raw_concatenated(raw_off, d, 0.1)
+    assert 0.0 < engine.prepare_ms() < 1000.0
+    f_d = engine.prepared_features()
+    st_d = engine.segment_resident(resolution=0.1, seed=4)
+    lab_d = engine.raw_labels()
+    assert eq_h.tolist() == eq_d.tolist()
+    for k in ('points', 'order', 'equalized_idx', 'unequalized_idx'):
+        np.testing.assert_array_equal(f_h[k], f_d[k])
+    for a, b in zip(lab_h, lab_d):
+        np.testing.assert_array_equal(a, b)
+    assert st_h['grow_steps'].tolist() == st_d['grow_steps'].tolist()
+    assert torch.equal(d.cpu(), torch.from_numpy(cat))                                   # the caller's buffer is read only
+    # a raw device pointer with an explicit column count is accepted too
+    engine.upload_raw_concatenated(raw_off, int(d.data_ptr()), 0.1, n_cols=cat.shape[1])
+    np.testing.assert_array_equal(engine.prepared_features()['points'], f_h['points'])

@@ -49,6 +49,8 @@ def main():
         ns = max(out[47], 1)
         print('  step stages        (cycles/step, thread 0):', ', '.join('%s %d' % (n, out[32 + i] // ns) for i, n in enumerate(names_s)),
               '| total', sum(out[32 + i] for i in range(10)) // ns)
+        print('  apply, cumulative cycles (thread 0): loads returned %d, masks + add stores %d, after barrier %d, removals stored %d' %
+              tuple(out[32 + i] // ns for i in (10, 11, 12, 13)))
         bn = ['<=64', '<=256', '<=512', '<=1024', '<=2048', '>2048']
         print('  median by inlier-set size: ' + ', '.join('%s: %d steps x %d cyc' % (bn[b], out[49 + 2 * b], out[48 + 2 * b] // max(out[49 + 2 * b], 1)) for b in range(6)))
         print('  head tile stages   (cycles/tile, thread 0):', ', '.join('%s %d' % (n, out[16 + i] // nh) for i, n in enumerate(names_h)),
