@@ -87,7 +87,8 @@ size_t forward_smem_head(const NetDesc& net);
 int forward_configure(const NetDesc& net);
 
 // ---------------------------------------------------------------------------------------------- Philox4x32-10
-// Same generator as oracle/philox.py; draw = word 0 of philox(key=seed, counter=(element, stream, step, room)).
+// Same generator as oracle/philox.py; draw = word 0 of philox(key=seed, counter=(element, stream, step, room)) with
+// stream = (seed point of the region << 8) | (8 * restart lane + kStream*), step = step within the region.
 enum {
   kStreamInlierKey = 0, kStreamNeighborKey = 1, kStreamAddUniform = 2, kStreamRemoveUniform = 3,
   kStreamInlierPad = 4, kStreamNeighborPad = 5

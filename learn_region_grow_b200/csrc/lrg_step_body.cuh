@@ -535,7 +535,10 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
   const int L = da.lanes > 1 ? da.lanes : 1;
   const int lane_id = L > 1 ? slot % L : 0;
   LaneGroup* const grp = L > 1 ? da.groups + slot / L : nullptr;
-  const unsigned rng_lane = 8u * (unsigned)lane_id;        // lane l draws from the Philox streams 8l + {0..5}
+  // Philox coordinates of a draw: (room, seed point of the region, step within the region, stream, element) -- keyed by the
+  // region, not by the room's running step count, so that a region's draws do not depend on what was grown before it;
+  // restart lane l uses streams 8l + {0..5}
+  const unsigned lane_stream = 8u * (unsigned)lane_id;
   if (L > 1 && S.parked) return;
 
   int* listI = da.listI + (size_t)slot * da.maxN;
@@ -768,7 +771,8 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
   // ------------------------------------------------------------------ apply the pending step (:262-306)
   if (S.active) {
     const int room_rng = da.room_id_base + S.room;
-    const unsigned step_rng = (unsigned)S.total_steps;
+    const unsigned step_rng = (unsigned)S.steps;
+    const unsigned rng_lane = ((unsigned)S.seed << 8) | lane_stream;
     LrgStepTrace* tr = nullptr;
     if (da.trace != nullptr && S.total_steps < da.trace_capacity)
       tr = da.trace + ((size_t)S.room * L + lane_id) * da.trace_capacity + S.total_steps;
@@ -1083,7 +1087,8 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     // ---------------------------------------------------------------- tiles for the next forward (:237-254)
     const int n_in = S.n_in, n_nb = S.n_nb;
     const int room_rng = da.room_id_base + S.room;
-    const unsigned step_rng = (unsigned)S.total_steps;
+    const unsigned step_rng = (unsigned)S.steps;
+    const unsigned rng_lane = ((unsigned)S.seed << 8) | lane_stream;
     // median of every centred channel over ALL current points (:241): channels 0,1 and 6..F-1
     const int nch = 2 + (da.F > 6 ? da.F - 6 : 0);
     auto row_keys = [&](int j, unsigned (&k)[9]) {

@@ -21,7 +21,7 @@ class NumpyLegacyRng:
     def __init__(self, seed=0, state=None):
         self.rs = state if state is not None else np.random.RandomState(seed)
 
-    def begin_step(self, room, step, lane=0):
+    def begin_step(self, room, step, lane=0, seed_point=0):
         pass
 
     def sample(self, count, k, which):
@@ -42,26 +42,32 @@ class PhiloxRng:
         self.room = 0
         self.step = 0
         self.lane = 0
+        self.seed_point = 0
 
-    def begin_step(self, room, step, lane=0):
-        # restart lane l (test_random_restart.py) draws from streams 8*l + {0..5}: lanes run side by side on the device
-        self.room, self.step, self.lane = int(room), int(step), int(lane)
+    def _stream(self, stream):
+        return (self.seed_point << 8) | (stream + 8 * self.lane)
+
+    def begin_step(self, room, step, lane=0, seed_point=0):
+        # Coordinates of a draw: (room, seed point of the region, step within the region, stream, element).  Keyed by the
+        # region rather than by the room's running step count so that regions of a room can be grown out of order / side by
+        # side; restart lane l (test_random_restart.py) draws from streams 8*l + {0..5}.
+        self.room, self.step, self.lane, self.seed_point = int(room), int(step), int(lane), int(seed_point)
 
     def sample(self, count, k, which):
         key_stream = philox.STREAM_INLIER_KEY if which == 'inlier' else philox.STREAM_NEIGHBOR_KEY
         pad_stream = philox.STREAM_INLIER_PAD if which == 'inlier' else philox.STREAM_NEIGHBOR_PAD
         if count >= k:
             # k smallest (key, index) pairs, emitted in ascending index order
-            keys = philox.draw_u32(self.seed, self.room, self.step, key_stream + 8 * self.lane, count)
+            keys = philox.draw_u32(self.seed, self.room, self.step, self._stream(key_stream), count)
             chosen = np.lexsort((np.arange(count), keys))[:k]
             return np.sort(chosen)
-        r = philox.draw_u32(self.seed, self.room, self.step, pad_stream + 8 * self.lane, k - count).astype(np.uint64)
+        r = philox.draw_u32(self.seed, self.room, self.step, self._stream(pad_stream), k - count).astype(np.uint64)
         pad = (r * np.uint64(count)) >> np.uint64(32)          # multiply-high range reduction
         return np.concatenate([np.arange(count), pad.astype(np.int64)])
 
     def uniform(self, k, which):
         stream = philox.STREAM_ADD_UNIFORM if which == 'add' else philox.STREAM_REMOVE_UNIFORM
-        return philox.u32_to_unit_float(philox.draw_u32(self.seed, self.room, self.step, stream + 8 * self.lane, k))
+        return philox.u32_to_unit_float(philox.draw_u32(self.seed, self.room, self.step, self._stream(stream), k))
 
 
 # ----------------------------------------------------------------------------- confidence
@@ -104,7 +110,7 @@ class RoomGrower:
         self.trace = None          # optional list of per-step dicts
 
     def _begin_rng_step(self):
-        self.rng.begin_step(self.room_id, self.total_steps)
+        self.rng.begin_step(self.room_id, self.steps, 0, self.seed_id)
 
     # -- region lifecycle ---------------------------------------------------------------------------
     def begin_region(self, seed_id):
@@ -270,7 +276,7 @@ class RestartRoomGrower(RoomGrower):
         self.lane_regions = []      # (seed, lane, size, reason) of every restart
 
     def _begin_rng_step(self):
-        self.rng.begin_step(self.room_id, self.lane_steps[self.lane], self.lane)
+        self.rng.begin_step(self.room_id, self.steps, self.lane, self.seed_id)
 
     def stop_growing(self, reason):                                               # test_random_restart.py:170-197
         self.restart_score.append(int(np.sum(self.currentMask)))                  # :174

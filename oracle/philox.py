@@ -3,7 +3,8 @@
 
 The reference consumes one global MT19937 stream (test_region_grow.py:21,238,250,266-267); that cannot be
 sharded over rooms/GPUs, so the engine's throughput mode defines its own stream: every draw is
-``philox(key=seed, counter=(element, stream, step, room))[0]`` -- a pure function of its coordinates.
+``philox(key=seed, counter=(element, (seed point << 8) | stream, step within the region, room))[0]`` -- a pure function of
+its coordinates (oracle/lrg_driver.py PhiloxRng).
 """
 import numpy as np
 

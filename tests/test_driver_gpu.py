@@ -54,7 +54,7 @@ def _replay(points, order, weights, trace, n_steps, seed, room_id=0):
             # oracle's own masks, to bound the disagreement
             add_conf, rmv_conf = lrg_driver.confidence(add[0]), lrg_driver.confidence(rmv[0])
             rng = lrg_driver.PhiloxRng(seed)
-            rng.begin_step(room_id, g.total_steps)
+            rng.begin_step(room_id, g.steps, 0, g.seed_id)
             u_add, u_rmv = rng.uniform(512, 'add'), rng.uniform(512, 'remove')
             for dev, conf, u in ((dev_add, add_conf, u_add), (dev_rmv, rmv_conf, u_rmv)):
                 differ = dev != (u < conf)

@@ -52,7 +52,7 @@ def _replay(points, order, weights, traces, seed, R):
                 dev_add, dev_rmv = unpack_mask(rec['add_mask']), unpack_mask(rec['remove_mask'])
                 add_conf, rmv_conf = lrg_driver.confidence(add[0]), lrg_driver.confidence(rmv[0])
                 rng = lrg_driver.PhiloxRng(seed)
-                rng.begin_step(0, g.lane_steps[lane], lane)
+                rng.begin_step(0, g.steps, lane, g.seed_id)
                 u_add, u_rmv = rng.uniform(512, 'add'), rng.uniform(512, 'remove')
                 for dev, conf, u in ((dev_add, add_conf, u_add), (dev_rmv, rmv_conf, u_rmv)):
                     differ = dev != (u < conf)
