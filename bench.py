@@ -216,6 +216,7 @@ def main():
     ap.add_argument('--ref-sample-steps', type=int, default=120)
     ap.add_argument('--cpu-baseline-steps', type=int, default=150)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the statistics / random-restart measurements')
     ap.add_argument('--slots', type=int, default=0)
     ap.add_argument('--lockstep-timing', action='store_true', help='also time the lock-step loop kernel by kernel')
     args = ap.parse_args()
@@ -383,6 +384,26 @@ def main():
                'd2h_bytes_per_step': int(total_raw * 4 + args.rooms * 32), 'ms_per_step': [round(x, 2) for x in raw_ms],
                'grow_steps_per_pass': int(st_raw['grow_steps'].sum()),
                'scope': 'raw points (x y z r g b) in pinned host memory -> device feature preparation (test_region_grow.py:119-173) -> grow -> fill -> per-raw-point labels on the host'}
+    # ---- the rows either side of the path, once each on the raw rooms just uploaded (not part of `value` / `e2e`):
+    # segmentation statistics (test_region_grow.py:319-349) and the random-restart driver (test_random_restart.py)
+    extras = {}
+    if not args.no_extras:
+        obj_raw = [raw_points[raw_off[i]:raw_off[i + 1], 6].astype(np.int32) for i in range(args.rooms)]
+        eng.room_metrics(obj_raw, raw=True)
+        t0 = time.perf_counter()
+        mt = eng.room_metrics(obj_raw, raw=True)
+        extras['statistics'] = {'ms_per_call': 1e3 * (time.perf_counter() - t0), 'rooms': args.rooms,
+                                'mean': {k: float(np.nanmean(mt[k])) for k in ('nmi', 'ami', 'ars', 'prc', 'rcl', 'iou')},
+                                'scope': 'obj_id of the raw points in, NMI/AMI/ARS/PRC/RCL/IOU per room out (contingency tables and expected mutual information on the device)'}
+        eng.segment_resident(num_restarts=10, **params)
+        st_rr = eng.segment_resident(num_restarts=10, **params)
+        pr_rr = eng.profile()
+        mt_rr = eng.room_metrics(obj_raw, raw=True)
+        extras['random_restart'] = {'num_restarts': 10, 'grow_ms_per_pass': pr_rr['grow_ms'], 'grow_steps_per_pass': int(st_rr['grow_steps'].sum()),
+                                    'grow_steps_per_sec': float(st_rr['grow_steps'].sum()) / (pr_rr['grow_ms'] * 1e-3),
+                                    'points_per_sec': total_raw / ((pr_rr['grow_ms'] + pr_rr['fill_ms']) * 1e-3), 'per_gpu': True,
+                                    'mean': {k: float(np.nanmean(mt_rr[k])) for k in ('nmi', 'ami', 'ars', 'prc', 'rcl', 'iou')},
+                                    'scope': 'test_random_restart.py: 10 restarts per seed as parallel lanes, largest region kept'}
     clocks = sampler.stop()          # nvidia-smi keeps sampling through the timed regions
     if dist is not None:
         t = torch.tensor([e2e_s], device='cuda', dtype=torch.float64)
@@ -423,7 +444,7 @@ def main():
             'e2e_features': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                              'ms_per_step': [round(x, 2) for x in e2e_ms],
                              'scope': '13-D features + seed order prepared on the host beforehand (pinned) -> grow -> fill -> labels per equalised point on the host'},
-            'roofline': roofline, 'cpu_baseline': cpu_baseline,
+            'roofline': roofline, 'cpu_baseline': cpu_baseline, 'extras': extras,
             'flops_per_grow_step': FLOPS_PER_STEP,
         }
         print(json.dumps(line))
