@@ -1,13 +1,11 @@
-"""Synthetic S3DIS-shaped rooms and the host-side feature preparation that feeds the grow engine.
+"""Synthetic S3DIS- / ScanNet- / Semantic-KITTI-shaped inputs for tests, probes and the benchmark (no network: there are no
+datasets here).  Nothing in this file is on the product path: the engine takes raw rows and prepares the features on the device
+(csrc/lrg_featprep.cu); the host restatement of that preparation used by the tests lives in oracle/feature_prep.py.
 
 * ``generate_room`` follows the reference's own synthetic generator (/root/reference/tools/generate_synthetic_rooms.py:35-99:
   six noisy planes, per-surface mean colour + gaussian colour jitter clipped to [-0.5, 0.5]) and adds axis-aligned
   box "furniture" so that a room yields tens of regions like the S3DIS logs.  Layout is the H5 layout
   of the reference datasets: (N, 8) float32 = x y z r g b obj_id cls_id (README.md:47-50).
-* ``prepare_features`` is a vectorised restatement of /root/reference/test_region_grow.py:119-173 (equalise to one
-  point per voxel, room-normalised coordinates, 27-cell covariance -> normal + curvature).  It runs on the host in
-  this round (SURVEY.md 8f-1 marks the device version as the next row); the literal loop lives in
-  oracle/feature_prep.py and the two are compared in tests/test_rooms.py.
 """
 import numpy as np
 
@@ -129,64 +127,3 @@ def generate_area(n_rooms, seed_base=1000, n_raw=20000, log_uniform=None):
             n = int(np.exp(rs.uniform(np.log(log_uniform[0]), np.log(log_uniform[1]))))
         rooms.append(generate_room(seed_base + r, n_raw=n))
     return rooms
-
-
-# ----------------------------------------------------------------------------- feature preparation (host)
-def _pack(vox):
-    lo = vox.min(axis=0)
-    span = (vox.max(axis=0) - lo + 3).astype(np.int64)      # +3: room for the -1/+1 neighbour offsets
-    v = vox.astype(np.int64) - lo + 1
-    return (v[:, 0] * span[1] + v[:, 1]) * span[2] + v[:, 2], span
-
-
-def prepare_features(unequalized_points, resolution=0.1):
-    """test_region_grow.py:119-173 -> dict(points (Neq,13) f32, equalized_idx, unequalized_idx, curvatures f64, order)."""
-    raw = np.asarray(unequalized_points)
-    xyz_raw = raw[:, :3].astype(np.float32)
-    vox = np.round(xyz_raw / resolution).astype(np.int64)                       # :126
-    key, span = _pack(vox)
-    uniq, first, inverse = np.unique(key, return_index=True, return_inverse=True)
-    appearance = np.argsort(first, kind='stable')                               # voxels in first-seen order (:127-129)
-    rank = np.empty_like(appearance)
-    rank[appearance] = np.arange(len(appearance))
-    equalized_idx = first[appearance]
-    unequalized_idx = rank[inverse]                                             # :130
-    points = raw[equalized_idx]
-    xyz = points[:, :3]
-    rgb = points[:, 3:6]
-    room_coordinates = (xyz - xyz.min(axis=0)) / (xyz.max(axis=0) - xyz.min(axis=0))   # :139
-
-    # per-voxel sums of p and of the float32 outer products (:151-155), then 27-cell gather (:146-150)
-    nvox = len(uniq)
-    outer = (xyz_raw[:, :, None] * xyz_raw[:, None, :]).astype(np.float64).reshape(-1, 9)
-    sumA = np.zeros((nvox, 9))
-    sumB = np.zeros((nvox, 3))
-    cnt = np.bincount(inverse, minlength=nvox).astype(np.float64)
-    for c in range(9):
-        sumA[:, c] = np.bincount(inverse, weights=outer[:, c], minlength=nvox)
-    for c in range(3):
-        sumB[:, c] = np.bincount(inverse, weights=xyz_raw[:, c].astype(np.float64), minlength=nvox)
-    ekey = key[equalized_idx]
-    accA = np.zeros((len(ekey), 9))
-    accB = np.zeros((len(ekey), 3))
-    accN = np.zeros(len(ekey))
-    for dx in (-1, 0, 1):
-        for dy in (-1, 0, 1):
-            for dz in (-1, 0, 1):
-                q = ekey + (dx * span[1] + dy) * span[2] + dz
-                pos = np.searchsorted(uniq, q)
-                pos[pos >= nvox] = nvox - 1
-                hit = uniq[pos] == q
-                accA[hit] += sumA[pos[hit]]
-                accB[hit] += sumB[pos[hit]]
-                accN[hit] += cnt[pos[hit]]
-    cov = accA.reshape(-1, 3, 3) / accN[:, None, None] - (accB[:, :, None] * accB[:, None, :]) / (accN ** 2)[:, None, None]
-    U, S, V = np.linalg.svd(cov)                                                # :157-158
-    normals = np.fabs(V[:, 2, :])
-    curvatures = np.fabs(S[:, 2] / (S[:, 0] + S[:, 1] + S[:, 2]))               # :159-161
-    curvatures = curvatures / curvatures.max()                                  # :162-163
-    feats = np.hstack((xyz, room_coordinates, rgb, normals, curvatures.reshape(-1, 1))).astype(np.float32)   # :172
-    return dict(points=feats, equalized_idx=equalized_idx, unequalized_idx=unequalized_idx,
-                curvatures=curvatures, order=np.argsort(curvatures),            # :183
-                obj_id=raw[equalized_idx, 6].astype(int) if raw.shape[1] > 6 else None,
-                cls_id=raw[equalized_idx, 7].astype(int) if raw.shape[1] > 7 else None)

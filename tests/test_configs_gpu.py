@@ -6,6 +6,8 @@ and the statistics against the scikit-learn oracle on the engine's own labels.""
 import numpy as np
 import pytest
 
+from oracle import feature_prep
+
 pytestmark = pytest.mark.gpu
 
 
@@ -28,7 +30,7 @@ def _check_rooms(engine, raws, resolution, seed):
     obj = [r[:, 6].astype(np.int32) for r in raws]
     m = engine.room_metrics(obj, raw=True)
     for i, raw in enumerate(raws):
-        host = rooms.prepare_features(raw, resolution)
+        host = feature_prep.prepare_features(raw, resolution)
         e0, e1 = eq_off[i], eq_off[i + 1]
         assert e1 - e0 == len(host['points']) == stats['n_points'][i]
         np.testing.assert_array_equal(f['equalized_idx'][e0:e1], host['equalized_idx'])

@@ -7,6 +7,8 @@ import sys
 import numpy as np
 import pytest
 
+from oracle import feature_prep
+
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -250,7 +252,7 @@ def test_metrics_oracle_reproduces_the_reference_log(seed):
     from learn_region_grow_b200 import rooms
     z = np.load(os.path.join(REPO, 'tests', 'golden', 'driver_trace_%d.npz' % seed), allow_pickle=True)
     room = z['room']
-    f = rooms.prepare_features(room, 0.1)
+    f = feature_prep.prepare_features(room, 0.1)
     obj_id = room[f['equalized_idx'], 6].astype(int)
     assert len(obj_id) == len(z['cluster_label'])
     m = om.room_statistics(obj_id, z['cluster_label'])

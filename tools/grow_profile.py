@@ -17,10 +17,10 @@ def main():
     args = ap.parse_args()
     import bench
     from learn_region_grow_b200.engine import Engine
-    offsets, points, order, raw = bench.make_workload(args.rooms, 1000)
+    raw_off, raw = bench.make_workload(args.rooms, 1000)
     eng = Engine(1, 1, 512, 512, 13, 0)
     eng.load_weights(bench.load_weights())
-    eng.upload_concatenated(offsets, points, order, 0.1)
+    eng.upload_raw_concatenated(raw_off, raw, 0.1)
     for _ in range(args.repeat):
         stats = eng.segment_resident(resolution=0.1, seed=0, max_slots=args.slots, flags=args.flags)
         pr = eng.profile()

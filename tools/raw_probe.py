@@ -5,9 +5,7 @@ import numpy as np
 import bench
 from learn_region_grow_b200 import _lib
 from learn_region_grow_b200.engine import Engine
-offsets, points, order, raw_counts = bench.make_workload(68, 1000)
-raw = bench.RAW_ROOMS[(68, 1000)]
-raw_off = np.zeros(69, np.int64); np.cumsum(raw_counts, out=raw_off[1:])
+raw_off, raw = bench.make_workload(68, 1000)
 eng = Engine(1, 1, 512, 512, 13, 0); eng.load_weights(bench.load_weights())
 h_raw = bench.pinned_array(_lib, raw.shape, np.float32); h_raw[...] = raw
 for it in range(4):

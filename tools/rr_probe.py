@@ -7,9 +7,7 @@ import bench
 from learn_region_grow_b200.engine import Engine
 
 rooms = int(sys.argv[1]) if len(sys.argv) > 1 else 68
-offsets, points, order, raw_counts = bench.make_workload(rooms, 1000)
-raw = bench.RAW_ROOMS[(rooms, 1000)]
-raw_off = np.zeros(rooms + 1, np.int64); np.cumsum(raw_counts, out=raw_off[1:])
+raw_off, raw = bench.make_workload(rooms, 1000)
 eng = Engine(1, 1, 512, 512, 13, 0); eng.load_weights(bench.load_weights())
 eng.upload_raw_concatenated(raw_off, raw, 0.1)
 obj_raw = [raw[raw_off[i]:raw_off[i + 1], 6].astype(np.int32) for i in range(rooms)]
