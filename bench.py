@@ -328,6 +328,15 @@ def main():
         'note': 'algorithmic = 271.7 MFLOP per grow step (512+512 rows, factored heads); the kernel evaluates only distinct rows '
                 '(padding duplicates reuse logits) as 3xTF32 on tcgen05; the run is latency-bound by the longest room',
     }
+    # the driver phases' side of the roofline: algorithmic bytes per grow step = one pass over the room's state
+    # (14 B per point) + the gathered tiles and logits (62,464 B) + the fp32 weights amortised over the rooms stepped together;
+    # (the 36 B per inlier of the median are left out: the mean inlier count is not tracked)
+    n_eq_mean = float(offsets[-1]) / max(args.rooms, 1)
+    bytes_step = 14.0 * n_eq_mean + 62464.0 + 3164176.0 / max(args.rooms, 1)
+    hbm_peak = peaks.get('hbm_gbs')
+    roofline['hbm_side'] = {'algorithmic_bytes_per_grow_step': bytes_step, 'achieved_gbs': grow_steps * bytes_step / (grow_ms * 1e-3) / 1e9,
+                            'peak_gbs': hbm_peak, 'frac': (grow_steps * bytes_step / (grow_ms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
+                            'note': 'neither roofline binds: the pass is the longest room\'s chain of sequential steps (DESIGN.md section 6)'}
     if pr['persistent']:
         items, busy = pr['items'], pr['busy_ms']
         executed = 3.0 * (items['branch'] * BRANCH_TILE_FLOPS + items['head'] * HEAD_TILE_FLOPS)
