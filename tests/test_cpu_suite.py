@@ -260,3 +260,33 @@ def test_metrics_oracle_reproduces_the_reference_log(seed):
     logged = dict(zip(('nmi', 'ami', 'ars', 'prc', 'rcl', 'iou'), [float(x) for x in re.findall(r': (\d\.\d\d)', line)]))
     for k, v in logged.items():
         assert abs(m[k] - v) <= 0.005 + 1e-9, (k, m[k], v)
+
+
+def test_abi_struct_layouts_match_the_header(tmp_path):
+    """The ctypes / numpy mirrors of the structs that cross the C ABI have the layout gcc gives include/lrg_b200.h."""
+    import ctypes
+    import subprocess
+    from learn_region_grow_b200 import _lib
+    src = tmp_path / 'layout.c'
+    src.write_text('''
+#include <stdio.h>
+#include <stddef.h>
+#include "lrg_b200.h"
+int main(void) {
+  printf("LrgGrowParams %zu %zu %zu %zu\\n", sizeof(LrgGrowParams), offsetof(LrgGrowParams, seed), offsetof(LrgGrowParams, flags), offsetof(LrgGrowParams, num_restarts));
+  printf("LrgRoomStats %zu %zu\\n", sizeof(LrgRoomStats), offsetof(LrgRoomStats, stop_other));
+  printf("LrgStepTrace %zu %zu %zu\\n", sizeof(LrgStepTrace), offsetof(LrgStepTrace, center), offsetof(LrgStepTrace, neighbor_idx_crc));
+  printf("LrgRoomMetrics %zu %zu %zu\\n", sizeof(LrgRoomMetrics), offsetof(LrgRoomMetrics, iou), offsetof(LrgRoomMetrics, gt_match));
+  return 0;
+}
+''')
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-I', os.path.join(REPO, 'include'), str(src), '-o', str(exe)], check=True)
+    out = dict((l.split()[0], [int(x) for x in l.split()[1:]]) for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    G = _lib.GrowParams
+    assert out['LrgGrowParams'] == [ctypes.sizeof(G), G.seed.offset, G.flags.offset, G.num_restarts.offset]
+    assert out['LrgRoomStats'] == [_lib.ROOM_STATS_DTYPE.itemsize, _lib.ROOM_STATS_DTYPE.fields['stop_other'][1]]
+    T = _lib.STEP_TRACE_DTYPE
+    assert out['LrgStepTrace'] == [T.itemsize, T.fields['center'][1], T.fields['neighbor_idx_crc'][1]]
+    M = _lib.ROOM_METRICS_DTYPE
+    assert out['LrgRoomMetrics'] == [M.itemsize, M.fields['iou'][1], M.fields['gt_match'][1]]
