@@ -667,8 +667,10 @@ static int upload_raw_impl(LrgEngine* e, int n_rooms, const int64_t* raw_offsets
   float* d_raw = nullptr; long long *d_raw_off = nullptr, *d_sort_off = nullptr, *d_eq_off = nullptr;
   unsigned long long *d_keys = nullptr, *d_keys2 = nullptr; int4* d_vmin = nullptr; int *d_neq = nullptr, *d_err = nullptr;
   unsigned* d_uvox = nullptr; int *d_ustart = nullptr, *d_equ = nullptr, *d_rank = nullptr; double *d_sums = nullptr, *d_curv = nullptr;
+  float* d_extent = nullptr; unsigned long long* d_cmax = nullptr; int* d_has_nan = nullptr;
   auto cleanup = [&]() {
     pool_free(e, d_raw); pool_free(e, d_sort_off); pool_free(e, d_eq_off); pool_free(e, d_keys); pool_free(e, d_keys2); pool_free(e, d_vmin); pool_free(e, d_neq);
+    pool_free(e, d_extent); pool_free(e, d_cmax); pool_free(e, d_has_nan);
     pool_free(e, d_err); pool_free(e, d_uvox); pool_free(e, d_ustart); pool_free(e, d_equ); pool_free(e, d_rank); pool_free(e, d_sums); pool_free(e, d_curv);
   };
   const size_t TR = (size_t)total_raw, TS = (size_t)sort_off[n_rooms];
@@ -679,6 +681,8 @@ static int upload_raw_impl(LrgEngine* e, int n_rooms, const int64_t* raw_offsets
   A(pool_alloc(e, &d_eq_off, (size_t)n_rooms + 1)); A(pool_alloc(e, &d_keys, TS)); A(pool_alloc(e, &d_keys2, TS)); A(pool_alloc(e, &d_vmin, (size_t)std::max(n_rooms, 1)));
   A(pool_alloc(e, &d_neq, (size_t)std::max(n_rooms, 1))); A(pool_alloc(e, &d_err, 1)); A(pool_alloc(e, &d_uvox, TR)); A(pool_alloc(e, &d_ustart, TR));
   A(pool_alloc(e, &d_equ, TR)); A(pool_alloc(e, &d_rank, TR)); A(pool_alloc(e, &d_sums, TR * 10));
+  A(pool_alloc(e, &d_extent, (size_t)std::max(n_rooms, 1) * 6)); A(pool_alloc(e, &d_cmax, (size_t)std::max(n_rooms, 1)));
+  A(pool_alloc(e, &d_has_nan, (size_t)std::max(n_rooms, 1)));
   if (rc != LRG_OK) { cleanup(); pool_free(e, d_raw_off); return rc; }
   std::vector<long long> h_raw_off(raw_offsets, raw_offsets + n_rooms + 1);
   cudaEvent_t pev0 = nullptr, pev1 = nullptr;      // device time of the preparation (includes the host round trip for the room sizes)
@@ -719,6 +723,7 @@ static int upload_raw_impl(LrgEngine* e, int n_rooms, const int64_t* raw_offsets
     cudaMemcpyAsync(d_eq_off, h_eq.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice, st);
     fp.eq_off = d_eq_off; fp.feat = e->d_feat; fp.curv = d_curv; fp.order = e->d_order; fp.equalized_idx = e->d_equalized_idx;
     fp.unequalized_idx = e->d_unequalized_idx;
+    fp.extent = d_extent; fp.cmax = d_cmax; fp.has_nan = d_has_nan;
     rc = launch_featprep_phase2(fp, st);
     if (rc == LRG_OK) rc = pack_rooms(e, e->d_feat);
     cudaEventRecord(pev1, st);

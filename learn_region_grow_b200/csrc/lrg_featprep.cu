@@ -204,47 +204,55 @@ __device__ void eig3(double A[3][3], double w[3], double V[3][3]) {
 
 __device__ __forceinline__ unsigned long long dmax_bits(double v) { return (unsigned long long)__double_as_longlong(v); }
 
+// Extent of every room's equalised points (:139) and reset of the per-room curvature maximum.
+__global__ void __launch_bounds__(kFpThreads) fp_extent_kernel(const __grid_constant__ FeatPrepArgs a) {
+  __shared__ float s_wlo[32][3], s_whi[32][3];
+  const int room = blockIdx.x, tid = threadIdx.x;
+  const long long rbase = a.raw_off[room], ebase = a.eq_off[room];
+  const int n_eq = (int)(a.eq_off[room + 1] - ebase);
+  const unsigned long long* keys2 = a.keys2 + a.sort_off[room];
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int j = tid; j < n_eq; j += kFpThreads) {
+    const float* p = a.raw + (rbase + (long long)(keys2[j] >> 20)) * a.C;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { lo[c] = fminf(lo[c], p[c]); hi[c] = fmaxf(hi[c], p[c]); }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], d));
+      hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], d));
+    }
+  if ((tid & 31) == 0)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { s_wlo[tid >> 5][c] = lo[c]; s_whi[tid >> 5][c] = hi[c]; }
+  __syncthreads();
+  if (tid < 3) {
+    float l = INFINITY, h = -INFINITY;
+    for (int w = 0; w < kFpThreads / 32; ++w) { l = fminf(l, s_wlo[w][tid]); h = fmaxf(h, s_whi[w][tid]); }
+    a.extent[room * 6 + tid] = l;
+    a.extent[room * 6 + 3 + tid] = h;
+  }
+  if (tid == 0) { a.cmax[room] = 0ull; a.has_nan[room] = 0; }
+}
+
+// Per equalised point: covariance of the raw points in the 27 surrounding voxels, eigen-solve, feature row.  grid = (chunks,
+// rooms): the points of a room are independent of each other up to the curvature maximum (one atomicMax per CTA).
 __global__ void __launch_bounds__(kFpThreads) fp_features_kernel(const __grid_constant__ FeatPrepArgs a) {
-  __shared__ float s_lo[3], s_hi[3];
   __shared__ unsigned long long s_cmax;
   __shared__ int s_nan;
-  const int room = blockIdx.x, tid = threadIdx.x;
+  const int room = blockIdx.y, tid = threadIdx.x;
   const long long rbase = a.raw_off[room], ebase = a.eq_off[room];
   const int n_eq = (int)(a.eq_off[room + 1] - ebase);
   const unsigned long long* keys2 = a.keys2 + a.sort_off[room];
   const unsigned* uv = a.uniq_vox + rbase;
   if (tid == 0) { s_cmax = 0ull; s_nan = 0; }
-  // extent of the equalised points (:139): warp reductions merged through shared arrays
-  __shared__ float s_wlo[32][3], s_whi[32][3];
-  {
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int j = tid; j < n_eq; j += kFpThreads) {
-      const float* p = a.raw + (rbase + (long long)(keys2[j] >> 20)) * a.C;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { lo[c] = fminf(lo[c], p[c]); hi[c] = fmaxf(hi[c], p[c]); }
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], d));
-        hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], d));
-      }
-    if ((tid & 31) == 0)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { s_wlo[tid >> 5][c] = lo[c]; s_whi[tid >> 5][c] = hi[c]; }
-  }
   __syncthreads();
-  if (tid < 3) {
-    float lo = INFINITY, hi = -INFINITY;
-    for (int w = 0; w < kFpThreads / 32; ++w) { lo = fminf(lo, s_wlo[w][tid]); hi = fmaxf(hi, s_whi[w][tid]); }
-    s_lo[tid] = lo; s_hi[tid] = hi;
-  }
-  __syncthreads();
-  const float lo0 = s_lo[0], lo1 = s_lo[1], lo2 = s_lo[2];
-  const float ex0 = __fsub_rn(s_hi[0], lo0), ex1 = __fsub_rn(s_hi[1], lo1), ex2 = __fsub_rn(s_hi[2], lo2);
+  const float lo0 = a.extent[room * 6 + 0], lo1 = a.extent[room * 6 + 1], lo2 = a.extent[room * 6 + 2];
+  const float ex0 = __fsub_rn(a.extent[room * 6 + 3], lo0), ex1 = __fsub_rn(a.extent[room * 6 + 4], lo1), ex2 = __fsub_rn(a.extent[room * 6 + 5], lo2);
 
-  for (int j = tid; j < n_eq; j += kFpThreads) {
+  for (int j = blockIdx.x * kFpThreads + tid; j < n_eq; j += gridDim.x * kFpThreads) {
     const int u = (int)(keys2[j] & kIdxMask);
     const float* p = a.raw + (rbase + (long long)(keys2[j] >> 20)) * a.C;
     // neighbourhood sums over the 27 surrounding voxels in itertools.product order (:146-155)
@@ -291,8 +299,19 @@ __global__ void __launch_bounds__(kFpThreads) fp_features_kernel(const __grid_co
     a.equalized_idx[ebase + j] = (int)(keys2[j] >> 20);
   }
   __syncthreads();
-  // curvature normalised by the room maximum (:162-163); a NaN anywhere makes the maximum -- and everything -- NaN in numpy
-  const double cmax = s_nan ? __longlong_as_double(0x7FF8000000000000ll) : __longlong_as_double((long long)s_cmax);
+  if (tid == 0) {
+    if (s_nan) a.has_nan[room] = 1;
+    if (s_cmax) atomicMax(a.cmax + room, s_cmax);
+  }
+}
+
+// Per room: curvature / max (:162-163), seed order = argsort(curvatures) (:183), unequalized_idx (:130).
+__global__ void __launch_bounds__(kFpThreads) fp_order_kernel(const __grid_constant__ FeatPrepArgs a) {
+  const int room = blockIdx.x, tid = threadIdx.x;
+  const long long rbase = a.raw_off[room], ebase = a.eq_off[room];
+  const int n_eq = (int)(a.eq_off[room + 1] - ebase);
+  // a NaN anywhere makes the maximum -- and everything -- NaN in numpy
+  const double cmax = a.has_nan[room] ? __longlong_as_double(0x7FF8000000000000ll) : __longlong_as_double((long long)a.cmax[room]);
   unsigned long long* okeys = a.keys + a.sort_off[room];      // the voxel sort keys are dead by now: reuse for the seed order
   const int P = (int)(a.sort_off[room + 1] - a.sort_off[room]);
   int Pe = 2;
@@ -350,7 +369,9 @@ int launch_featprep_phase1(const FeatPrepArgs& a, cudaStream_t stream) {
 
 int launch_featprep_phase2(const FeatPrepArgs& a, cudaStream_t stream) {
   if (a.n_rooms <= 0) return LRG_OK;
-  fp_features_kernel<<<a.n_rooms, kFpThreads, 0, stream>>>(a);
+  fp_extent_kernel<<<a.n_rooms, kFpThreads, 0, stream>>>(a);
+  fp_features_kernel<<<dim3(8, a.n_rooms), kFpThreads, 0, stream>>>(a);
+  fp_order_kernel<<<a.n_rooms, kFpThreads, 0, stream>>>(a);
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;
 }

@@ -30,6 +30,9 @@ struct FeatPrepArgs {
   int* order;                     // (sum Neq) seed order
   int* equalized_idx;             // (sum Neq) raw index of every equalised point (room-local)
   int* unequalized_idx;           // (sum Nr) equalised index of every raw point (room-local)
+  float* extent;                  // (R, 6) min / max xyz of the equalised points
+  unsigned long long* cmax;       // (R) bit pattern of the room's largest curvature
+  int* has_nan;                   // (R) a curvature of the room is NaN
 };
 
 int launch_featprep_phase1(const FeatPrepArgs& a, cudaStream_t stream);
