@@ -84,6 +84,11 @@ typedef struct LrgGrowParams {
   int num_restarts;            /* 0/1: test_region_grow.py.  N > 1: test_random_restart.py with NUM_RESTARTS = N (:24) and
                                   'np' scoring (:40,174): every seed is grown N times from the same visited state, the N
                                   restarts side by side on the device, and the largest result is kept (max 16) */
+  int beam_width;              /* > 0: test_beam_search.py with BEAM_WIDTH (:24) = beam_width, SEARCH_WIDTH (:25) = search_width */
+  int search_width;            /* and 'np' scoring (:41,266): per seed a queue of at most beam_width candidate masks, each expanded
+                                  search_width times per round by one sampled grow step, the beam_width largest updated masks
+                                  kept (:273); the beam_width * search_width expansions of a round run side by side on the
+                                  device (product max 16).  Excludes num_restarts > 1. */
 } LrgGrowParams;
 
 enum {

@@ -16,7 +16,8 @@ class LrgError(RuntimeError):
 class GrowParams(C.Structure):
     _fields_ = [('resolution', C.c_float), ('cluster_threshold', C.c_int), ('seed', C.c_uint64),
                 ('max_slots', C.c_int), ('max_steps_per_region', C.c_int), ('room_id_base', C.c_int),
-                ('trace_capacity', C.c_int), ('flags', C.c_int), ('num_restarts', C.c_int)]
+                ('trace_capacity', C.c_int), ('flags', C.c_int), ('num_restarts', C.c_int), ('beam_width', C.c_int),
+                ('search_width', C.c_int)]
 
 
 class RoomStats(C.Structure):

@@ -30,11 +30,25 @@ struct SlotState {
 // Random-restart driver (test_random_restart.py): the NUM_RESTARTS restarts of a seed are `lanes` consecutive slots (a
 // group) that grow side by side from the same visited state, each on its own copy of the room's state words.  What the
 // reference keeps per room lives here, owned by whichever lane commits a seed (the last one to finish it).
+//
+// Beam-search driver (test_beam_search.py): a group is BEAM_WIDTH x SEARCH_WIDTH lanes; lane q * SEARCH_WIDTH + s expands
+// candidate q of the seed's queue Q for the s-th time.  A ROUND = every candidate expanded SEARCH_WIDTH times (one grow step
+// per lane); the lane that reports last builds the next Q (the BEAM_WIDTH largest updated masks, stable) as index lists in
+// the group's parent buffers, runs the stuck logic on Q[0] and starts the next round or commits Q[0] / the previous Q[0].
 constexpr int kMaxLanes = 16;
 struct LaneGroup {
-  int done;                // lanes that have finished the current seed
-  int score[kMaxLanes];    // 'np' score of every lane: points in its final region (test_random_restart.py:174)
+  int done;                // lanes that have finished the current seed (beam search: reported this round)
+  int score[kMaxLanes];    // 'np' score of every lane: points in its final region (test_random_restart.py:174); beam search:
+                           // size of the expanded mask, -1 if the expansion added nothing (test_beam_search.py:262-267)
   int room, cursor, cluster_id, regions, visited;
+  // beam search only
+  int expect;              // lanes that report this round = candidates in Q x SEARCH_WIDTH
+  int nQ;                  // candidates in Q (0: no seed in flight)
+  int round;               // rounds completed for this seed = the Philox step coordinate of the round's expansions
+  int stuck, seed;         // test_beam_search.py:161,180-186
+  int seqMin[3], seqMax[3];
+  int par_n[kMaxLanes];    // candidate q of Q: points, bounding box (its index list lives in DriverArgs::parI)
+  int par_min[kMaxLanes][3], par_max[kMaxLanes][3];
 };
 
 struct DriverArgs {
@@ -77,6 +91,9 @@ struct DriverArgs {
   LaneGroup* groups;            // (n_slots / lanes)
   long long pw_lane_stride;
   int* lane_steps;              // (n_rooms, lanes) out: grow steps every lane took in the room (trace lengths)
+  // beam search (beam_width > 0): lanes = beam_width * search_width
+  int beam_width, search_width;
+  int* parI;                    // (n_slots / lanes, beam_width, maxN) ascending index lists of the candidates in Q
 };
 
 struct FillArgs {

@@ -118,6 +118,7 @@ struct LrgEngine {
   // random restarts: per-lane copies of the state words, group records, per-lane step counts of the last run
   unsigned* d_pw_lanes = nullptr;
   LaneGroup* d_groups = nullptr;
+  int* d_parI = nullptr;        // beam search: index lists of the candidates in every group's queue
   int* d_lane_steps = nullptr;
   int last_lanes = 1;
   // persistent grow kernel: work queue, per-slot stage counters, busy-time counters
@@ -226,8 +227,8 @@ static void free_rooms(LrgEngine* e) {
   pool_free(e, e->d_room_off); pool_free(e, e->d_pts); pool_free(e, e->d_pw); pool_free(e, e->d_pw_off); pool_free(e, e->d_room_vmin); pool_free(e, e->d_label);
   pool_free(e, e->d_label_filled); pool_free(e, e->d_order); pool_free(e, e->d_lab_list); pool_free(e, e->d_unl_list);
   pool_free(e, e->d_n_lab); pool_free(e, e->d_n_unl); pool_free(e, e->d_stats);
-  pool_free(e, e->d_pw_lanes); pool_free(e, e->d_groups); pool_free(e, e->d_lane_steps);
-  e->d_pw_lanes = nullptr; e->d_groups = nullptr; e->d_lane_steps = nullptr;
+  pool_free(e, e->d_pw_lanes); pool_free(e, e->d_groups); pool_free(e, e->d_lane_steps); pool_free(e, e->d_parI);
+  e->d_pw_lanes = nullptr; e->d_groups = nullptr; e->d_lane_steps = nullptr; e->d_parI = nullptr;
   pool_free(e, e->d_raw_off); pool_free(e, e->d_equalized_idx); pool_free(e, e->d_unequalized_idx); pool_free(e, e->d_feat);
   e->d_raw_off = nullptr; e->d_equalized_idx = e->d_unequalized_idx = nullptr; e->d_feat = nullptr; e->raw_mode = false; e->total_raw = 0;
   e->d_room_off = nullptr; e->d_pts = nullptr; e->d_pw = nullptr; e->d_pw_off = nullptr; e->d_room_vmin = nullptr; e->d_label = nullptr;
@@ -780,19 +781,30 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   const int n_rooms = e->n_rooms;
   const size_t T = (size_t)e->total_pts;
   // random restarts (test_random_restart.py): `lanes` consecutive slots grow the restarts of one seed side by side
-  const int lanes = params->num_restarts > 1 ? params->num_restarts : 1;
+  // beam search (test_beam_search.py): the beam_width x search_width expansions of a round are the lanes of a group
+  const bool beam = params->beam_width > 0 || params->search_width > 0;
+  if (beam) {
+    LRG_REQUIRE(params->beam_width > 0 && params->search_width > 0, "beam_width %d and search_width %d must both be positive",
+                params->beam_width, params->search_width);
+    LRG_REQUIRE(params->num_restarts <= 1, "beam search and random restarts (num_restarts %d) exclude each other", params->num_restarts);
+    LRG_REQUIRE((long long)params->beam_width * params->search_width <= kMaxLanes, "beam_width %d x search_width %d exceeds the limit of %d lanes",
+                params->beam_width, params->search_width, kMaxLanes);
+  }
+  const int lanes = beam ? params->beam_width * params->search_width : params->num_restarts > 1 ? params->num_restarts : 1;
+  const bool grouped = lanes > 1 || beam;     // slots form groups with a LaneGroup record (a 1 x 1 beam is a group of one lane)
   LRG_REQUIRE(lanes <= kMaxLanes, "num_restarts %d exceeds the limit of %d", lanes, kMaxLanes);
-  int n_slots = params->max_slots > 0 ? params->max_slots : (lanes > 1 ? 296 : 148);
+  int n_slots = params->max_slots > 0 ? std::max(params->max_slots, lanes) : (lanes > 1 ? 296 : 148);
   int n_groups = std::max(1, std::min(n_slots / lanes, std::max(n_rooms, 1)));
   n_slots = n_groups * lanes;
   LRG_TRY(ensure_slots(e, n_slots));
   e->last_lanes = lanes;
-  if (lanes > 1) {
-    pool_free(e, e->d_pw_lanes); pool_free(e, e->d_groups); pool_free(e, e->d_lane_steps);
-    e->d_pw_lanes = nullptr; e->d_groups = nullptr; e->d_lane_steps = nullptr;
+  if (grouped) {
+    pool_free(e, e->d_pw_lanes); pool_free(e, e->d_groups); pool_free(e, e->d_lane_steps); pool_free(e, e->d_parI);
+    e->d_pw_lanes = nullptr; e->d_groups = nullptr; e->d_lane_steps = nullptr; e->d_parI = nullptr;
     LRG_TRY(pool_alloc(e, &e->d_pw_lanes, (size_t)std::max<long long>(e->total_words, 4) * lanes));
     LRG_TRY(pool_alloc(e, &e->d_groups, (size_t)n_groups));
     LRG_TRY(pool_alloc(e, &e->d_lane_steps, (size_t)std::max(n_rooms, 1) * lanes));
+    if (beam) LRG_TRY(pool_alloc(e, &e->d_parI, (size_t)n_groups * params->beam_width * std::max(e->slots_maxN, 1)));
   }
   cudaStream_t st = e->stream;
   cudaEvent_t ev0, ev1, ev2;
@@ -807,7 +819,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   LRG_CUDA(cudaEventRecord(ev0, st));
   // reset per-run state (inside the timed region: it is part of one pass over the rooms)
   unsigned* d_words = e->d_pw;
-  if (lanes > 1) {
+  if (grouped) {
     d_words = e->d_pw_lanes;
     if (e->total_words > 0) LRG_CUDA(cudaMemcpyAsync(d_words, e->d_pw, sizeof(unsigned) * (size_t)e->total_words, cudaMemcpyDeviceToDevice, st));
     std::vector<LaneGroup> ginit(n_groups);
@@ -824,7 +836,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   std::vector<SlotState> init(n_slots);
   memset(init.data(), 0, sizeof(SlotState) * n_slots);
   for (auto& s : init) s.room = -1;
-  if (lanes > 1)
+  if (grouped)
     for (int s = 0; s < n_slots; ++s) init[s].parked = (s % lanes) != 0;      // lane 0 of every group takes the first room
   LRG_CUDA(cudaMemcpyAsync(e->d_slots, init.data(), sizeof(SlotState) * n_slots, cudaMemcpyHostToDevice, st));
   if (params->trace_capacity > 0) {
@@ -848,7 +860,8 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   da.next_room = e->d_counters; da.finished_slots = e->d_counters + 1; da.done_flag = e->d_done;
   da.dbg = e->d_tile_dbg ? e->d_tile_dbg + 32 : nullptr;
   da.stats = e->d_stats; da.trace = e->trace_capacity > 0 ? e->d_trace : nullptr; da.trace_capacity = e->trace_capacity;
-  da.lanes = lanes; da.groups = e->d_groups; da.pw_lane_stride = e->total_words; da.lane_steps = lanes > 1 ? e->d_lane_steps : nullptr;
+  da.lanes = lanes; da.groups = e->d_groups; da.pw_lane_stride = e->total_words; da.lane_steps = grouped ? e->d_lane_steps : nullptr;
+  da.beam_width = beam ? params->beam_width : 0; da.search_width = beam ? params->search_width : 0; da.parI = beam ? e->d_parI : nullptr;
 
   ForwardArgs fa{};
   fa.x[0] = e->d_tile[0]; fa.x[1] = e->d_tile[1]; fa.x_stride = 16;

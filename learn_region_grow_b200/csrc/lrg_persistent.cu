@@ -170,10 +170,11 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
           }
         }
         if (sh.wake && !sh.all_done) {
-          // random restarts: this step committed a seed and started every lane of its group on the next one
+          // random restarts: this step committed a seed and started every lane of its group on the next one; beam search:
+          // it closed a round and handed the candidates of the next one to these lanes
           const int L = ga.da.lanes, first_slot = slot - slot % L;
           for (int l = 0; l < L; ++l)
-            if (first_slot + l != slot) next[n_next++] = make_item(ITEM_STEP, first_slot + l, 0, 0);
+            if ((sh.wake >> l) & 1u) next[n_next++] = make_item(ITEM_STEP, first_slot + l, 0, 0);
         }
       }
     } else if (type == ITEM_BRANCH) {

@@ -273,7 +273,7 @@ struct StepShared {
   int red[32 * 6];
   int flag;
   int all_done;                 // set when this call retired the last slot of the run
-  int wake;                     // random restarts: this call handed a fresh seed to the other lanes of its group (they need a STEP)
+  unsigned wake;                // random restarts / beam search: lanes of this group (bit l) this call handed work to (they need a STEP)
   LaneGroup G;                  // random restarts: the group's room-level state while this CTA owns it
   unsigned nextkey[16];         // median: smallest key above the lower median, per channel
   int listI_s[kListCap], listJ_s[kListCap];
@@ -534,12 +534,24 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
   // random restarts (test_random_restart.py): slot = group * L + lane; a parked lane waits for the other restarts of its seed
   const int L = da.lanes > 1 ? da.lanes : 1;
   const int lane_id = L > 1 ? slot % L : 0;
-  LaneGroup* const grp = L > 1 ? da.groups + slot / L : nullptr;
+  LaneGroup* const grp = (L > 1 || da.beam_width > 0) ? da.groups + slot / L : nullptr;
   // Philox coordinates of a draw: (room, seed point of the region, step within the region, stream, element) -- keyed by the
   // region, not by the room's running step count, so that a region's draws do not depend on what was grown before it;
   // restart lane l uses streams 8l + {0..5}
   const unsigned lane_stream = 8u * (unsigned)lane_id;
-  if (L > 1 && S.parked) return;
+  // beam search (test_beam_search.py): lane q * SW + s expands candidate q of the seed's queue for the s-th time
+  const bool beam = da.beam_width > 0;
+  const int BW = da.beam_width, SW = da.search_width;
+  if ((L > 1 || beam) && S.parked && !(beam && S.begin)) return;
+  if (beam && S.begin) {
+    // handed a candidate by the lane that closed the previous round: everything it wrote precedes the flag, so read the
+    // state again behind an acquire fence (the lock-step loop may have loaded a torn record)
+    __threadfence();
+    __syncthreads();
+    for (int i = tid; i < (int)(sizeof(SlotState) / 4); i += NT)
+      reinterpret_cast<int*>(&sh.S)[i] = __ldcg(reinterpret_cast<const int*>(gS) + i);
+    __syncthreads();
+  }
 
   int* listI = da.listI + (size_t)slot * da.maxN;
   int* listJ = da.listJ + (size_t)slot * da.maxN;
@@ -646,43 +658,11 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     __syncthreads();
     return true;
   };
-  // Owner of the group: next seed of the room, else the next room, else retire every lane.  Returns false when retired.
-  auto advance_group = [&]() -> bool {
+  // Owner of the group: the room is exhausted (or this is the first call) -- publish its stats and fetch the next room from
+  // the queue; with none left retire every lane.  Returns false when retired.
+  auto group_next_room = [&]() -> bool {
     LaneGroup& G = sh.G;
-    while (true) {
-      int found = -1;
-      if (G.room >= 0) found = find_seed(G.cursor);
-      if (found >= 0) {
-        const int seed = da.order[base + found];
-        const unsigned w = pw[seed];
-        if (tid == 0) {
-          G.cursor = found + 1;
-          const int vx = pw_x(w), vy = pw_y(w), vz = pw_z(w);
-          // order: the commit's word / label stores (all threads, before the barrier) and the seed's flags and list heads
-          // become visible before any lane can observe its `begin` flag
-          __threadfence();
-          for (int l = 0; l < L; ++l) {
-            (da.pw + (long long)l * da.pw_lane_stride + da.pw_off[G.room])[seed] = w | PW_CUR;
-            (da.listI + (size_t)(slot - lane_id + l) * da.maxN)[0] = seed;
-          }
-          __threadfence();
-          for (int l = 0; l < L; ++l) {
-            SlotState* o = l == lane_id ? &S : da.slots + (slot - lane_id + l);
-            o->active = 0; o->finished = 0; o->room = G.room; o->seed = seed;
-            o->minD[0] = o->maxD[0] = o->seqMin[0] = o->seqMax[0] = vx;
-            o->minD[1] = o->maxD[1] = o->seqMin[1] = o->seqMax[1] = vy;
-            o->minD[2] = o->maxD[2] = o->seqMin[2] = o->seqMax[2] = vz;
-            o->stuck = 0; o->steps = 0; o->n_in = 1; o->n_nb = 0;
-            o->parked = 0;
-            *reinterpret_cast<volatile int*>(&o->begin) = l == lane_id ? 0 : 1;
-          }
-          sh.listI_s[0] = seed;
-          sh.wake = 1;
-          *grp = G;
-        }
-        __syncthreads();
-        return true;
-      }
+    {
       // room exhausted (or first call): publish its stats and fetch the next room from the queue
       if (tid == 0) {
         if (G.room >= 0) {
@@ -724,7 +704,240 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
         return false;
       }
       bind_room();
+      return true;
     }
+  };
+  // Owner of the group: next seed of the room, else the next room, else retire every lane.  Returns false when retired.
+  auto advance_group = [&]() -> bool {
+    LaneGroup& G = sh.G;
+    while (true) {
+      int found = -1;
+      if (G.room >= 0) found = find_seed(G.cursor);
+      if (found >= 0) {
+        const int seed = da.order[base + found];
+        const unsigned w = pw[seed];
+        if (tid == 0) {
+          G.cursor = found + 1;
+          const int vx = pw_x(w), vy = pw_y(w), vz = pw_z(w);
+          // order: the commit's word / label stores (all threads, before the barrier) and the seed's flags and list heads
+          // become visible before any lane can observe its `begin` flag
+          __threadfence();
+          for (int l = 0; l < L; ++l) {
+            (da.pw + (long long)l * da.pw_lane_stride + da.pw_off[G.room])[seed] = w | PW_CUR;
+            (da.listI + (size_t)(slot - lane_id + l) * da.maxN)[0] = seed;
+          }
+          __threadfence();
+          for (int l = 0; l < L; ++l) {
+            SlotState* o = l == lane_id ? &S : da.slots + (slot - lane_id + l);
+            o->active = 0; o->finished = 0; o->room = G.room; o->seed = seed;
+            o->minD[0] = o->maxD[0] = o->seqMin[0] = o->seqMax[0] = vx;
+            o->minD[1] = o->maxD[1] = o->seqMin[1] = o->seqMax[1] = vy;
+            o->minD[2] = o->maxD[2] = o->seqMin[2] = o->seqMax[2] = vz;
+            o->stuck = 0; o->steps = 0; o->n_in = 1; o->n_nb = 0;
+            o->parked = 0;
+            *reinterpret_cast<volatile int*>(&o->begin) = l == lane_id ? 0 : 1;
+          }
+          sh.listI_s[0] = seed;
+          sh.wake = ((1u << L) - 1u) & ~(1u << lane_id);
+          *grp = G;
+        }
+        __syncthreads();
+        return true;
+      }
+      if (!group_next_room()) return false;
+    }
+  };
+
+  // ---- beam search (test_beam_search.py:164-279) -----------------------------------------------------------------------
+  // A lane that was handed candidate q of the queue: its region is the candidate's index list (this lane's copy of the words
+  // carries no CURRENT flag between expansions), bounding box and size came with the slot state.
+  auto beam_begin = [&]() {
+    const int n = S.n_in;
+    const int* par = da.parI + ((size_t)(slot / L) * BW + lane_id / SW) * da.maxN;
+    for (int j = tid; j < n; j += NT) {
+      const int i = __ldcg(par + j);
+      pw[i] |= PW_CUR;
+      listI[j] = i;
+      if (j < kListCap) sh.listI_s[j] = i;
+    }
+    if (tid == 0) { S.begin = 0; S.parked = 0; }
+    __syncthreads();
+  };
+  // The lane's expansion is over (listI[0..n_cur) = the expanded mask): report its score -- 'np': the size of the mask if the
+  // expansion added a point (:262-267), else no candidate -- clear the CURRENT flags and park.  Returns true to the lane
+  // that reports LAST in the round, which then owns the group (sh.G).
+  auto beam_park = [&](bool candidate, int n_cur) -> bool {
+    for (int j = tid; j < n_cur; j += NT) pw[listI[j]] &= ~PW_CUR;
+    if (tid == 0) { S.active = 0; S.parked = 1; S.begin = 0; S.n_in = n_cur; }
+    __syncthreads();
+    for (int i = tid; i < (int)(sizeof(SlotState) / 4); i += NT)
+      reinterpret_cast<int*>(gS)[i] = reinterpret_cast<const int*>(&sh.S)[i];
+    __syncthreads();
+    if (tid == 0) {
+      *reinterpret_cast<volatile int*>(&grp->score[lane_id]) = candidate ? n_cur : -1;
+      __threadfence();
+      const int expect = __ldcg(&grp->expect);
+      const int done = atomicAdd(&grp->done, 1) + 1;
+      sh.flag = done == expect ? 1 : 0;
+      if (done == expect) {
+        __threadfence();
+        for (int i = 0; i < (int)(sizeof(LaneGroup) / 4); ++i)
+          reinterpret_cast<int*>(&sh.G)[i] = __ldcg(reinterpret_cast<const int*>(grp) + i);
+      }
+    }
+    __syncthreads();
+    const bool last = sh.flag != 0;
+    __syncthreads();
+    return last;
+  };
+  // Owner of the group (sh.G): close the round that just ended (if any), commit the seed's region when the search is over,
+  // find the next seed / room, and start the next round.  Returns 0 when the group has retired, 1 when this lane expands a
+  // candidate of the new round (its region is set up), 2 when it is not part of the new round (parked, state written back).
+  auto beam_commit = [&]() -> int {
+    LaneGroup& G = sh.G;
+    const int slot0 = slot - lane_id;
+    int* const par0 = da.parI + (size_t)(slot / L) * BW * da.maxN;
+    if (G.nQ > 0) {
+      // next Q = the BEAM_WIDTH best of newQ, stable (:273); newQ is in (candidate, search) order = lane order
+      if (tid == 0) {
+        unsigned used = 0;
+        int nc = 0;
+        for (int q = 0; q < BW; ++q) {
+          int best = -1;
+          for (int l = 0; l < G.expect; ++l)
+            if (!((used >> l) & 1u) && G.score[l] >= 0 && (best < 0 || G.score[l] > G.score[best])) best = l;
+          if (best < 0) break;
+          used |= 1u << best;
+          sh.red[1 + nc++] = best;
+        }
+        sh.red[0] = nc;
+      }
+      __syncthreads();
+      const int nc = sh.red[0];
+      int fin = 0;                      // 0: the search goes on; else 1 + index into stops[] of why the seed's search ended
+      if (nc == 0) {
+        fin = 1 + 1;                    // no expansion added a point: Q is empty (:169), bestMask = the last Q[0] (:179)
+      } else {
+        for (int q = 0; q < nc; ++q) {
+          const int l = sh.red[1 + q], n = G.score[l];
+          const int* sl = da.listI + (size_t)(slot0 + l) * da.maxN;
+          int* dst = par0 + (size_t)q * da.maxN;
+          for (int j = tid; j < n; j += NT) __stcg(dst + j, l == lane_id ? sl[j] : __ldcg(sl + j));
+        }
+        if (tid == 0) {
+          for (int q = 0; q < nc; ++q) {
+            const int l = sh.red[1 + q];
+            const SlotState* o = da.slots + slot0 + l;
+            G.par_n[q] = G.score[l];
+            for (int a = 0; a < 3; ++a) {
+              G.par_min[q][a] = l == lane_id ? S.minD[a] : __ldcg(&o->minD[a]);
+              G.par_max[q][a] = l == lane_id ? S.maxD[a] : __ldcg(&o->maxD[a]);
+            }
+          }
+          // head of the next round (qid == 0, :178-190): bestMask = Q[0]; stuck logic on its bounding box
+          bool expanded = false;
+          for (int a = 0; a < 3; ++a) expanded |= (G.par_min[0][a] < G.seqMin[a]) || (G.par_max[0][a] > G.seqMax[a]);
+          int f = 0;
+          if (!expanded) {
+            if (G.stuck >= 1) f = 1 + 2; else G.stuck += 1;
+          } else {
+            G.stuck = 0;
+          }
+          for (int a = 0; a < 3; ++a) { G.seqMin[a] = min(G.seqMin[a], G.par_min[0][a]); G.seqMax[a] = max(G.seqMax[a], G.par_max[0][a]); }
+          G.nQ = nc;
+          G.round += 1;
+          if (f == 0 && da.max_steps > 0 && G.round >= da.max_steps) f = 1 + 3;
+          sh.flag = f;
+        }
+        __syncthreads();
+        fin = sh.flag;
+        __syncthreads();
+      }
+      if (fin != 0) {
+        // visited[bestMask] = True; label it when it is larger than the threshold (:276-279)
+        const int n_best = G.par_n[0];
+        const bool labelled = n_best > da.cluster_threshold;
+        const int cid = G.cluster_id;
+        int* label = da.label + base;
+        unsigned* pw0 = da.pw + da.pw_off[G.room];
+        for (int j = tid; j < n_best; j += NT) {
+          const int i = __ldcg(par0 + j);
+          const unsigned w = (pw[i] & PW_XYZ) | PW_VIS;
+          for (int l = 0; l < L; ++l) pw0[(long long)l * da.pw_lane_stride + i] = w;
+          if (labelled) label[i] = cid;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          if (labelled) G.cluster_id += 1;
+          G.regions += 1;
+          G.visited += n_best;
+          G.nQ = 0;
+          S.stops[fin - 1] += 1;
+        }
+        __syncthreads();
+      }
+    }
+    // next seed of the room (:143-145), else the next room: Q = [(0, seed alone)] (:154-164)
+    while (G.nQ == 0) {
+      int found = -1;
+      if (G.room >= 0) found = find_seed(G.cursor);
+      if (found >= 0) {
+        const int seed = da.order[base + found];
+        const unsigned w = pw[seed];
+        if (tid == 0) {
+          G.cursor = found + 1;
+          G.seed = seed;
+          __stcg(par0, seed);
+          G.par_n[0] = 1;
+          const int v[3] = {pw_x(w), pw_y(w), pw_z(w)};
+          for (int a = 0; a < 3; ++a) G.par_min[0][a] = G.par_max[0][a] = G.seqMin[a] = G.seqMax[a] = v[a];
+          G.stuck = 1;                  // the head of the first round finds the seed's box inside itself (:180-184)
+          G.round = 0;
+          G.nQ = 1;
+        }
+        __syncthreads();
+        break;
+      }
+      if (!group_next_room()) return 0;
+    }
+    // start the round: lane q * SW + s takes candidate q
+    const int expect = G.nQ * SW;
+    if (tid == 0) {
+      G.done = 0;
+      G.expect = expect;
+      *grp = G;
+      for (int l = 0; l < expect; ++l) {
+        const int q = l / SW;
+        SlotState* o = l == lane_id ? &S : da.slots + slot0 + l;
+        o->active = 0; o->finished = 0; o->room = G.room; o->seed = G.seed;
+        for (int a = 0; a < 3; ++a) { o->minD[a] = G.par_min[q][a]; o->maxD[a] = G.par_max[q][a]; }
+        o->steps = G.round; o->n_in = G.par_n[q]; o->n_nb = 0; o->stuck = 0;
+      }
+      if (lane_id >= expect) { S.active = 0; S.parked = 1; S.begin = 0; }
+    }
+    __syncthreads();
+    if (lane_id >= expect) {
+      // not part of the round: this lane's record must be at rest before any other lane can close the round and write to it
+      for (int i = tid; i < (int)(sizeof(SlotState) / 4); i += NT)
+        reinterpret_cast<int*>(gS)[i] = reinterpret_cast<const int*>(&sh.S)[i];
+      __syncthreads();
+    }
+    if (tid == 0) {
+      // order: the commit's word / label / list stores (all threads, before the barriers), the group record and the lanes'
+      // states become visible before any lane can observe its `begin` flag
+      __threadfence();
+      unsigned wake = 0;
+      for (int l = 0; l < expect; ++l)
+        if (l != lane_id) {
+          *reinterpret_cast<volatile int*>(&da.slots[slot0 + l].begin) = 2;
+          wake |= 1u << l;
+        }
+      sh.wake = wake;
+    }
+    __syncthreads();
+    if (lane_id >= expect) return 2;
+    beam_begin();
+    return 1;
   };
 
   // stop_growing (:210-217): visited |= current; label when the region is larger than the threshold.
@@ -753,7 +966,17 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
   };
 
   int mode = MODE_NEW_REGION;
-  if (L > 1 && !S.active) {
+  if (beam && !S.active) {
+    if (S.begin) {                      // a candidate of the new round handed over by the lane that closed the previous one
+      beam_begin();
+      mode = MODE_SCAN;
+    } else {                            // first call of the run (lane 0): take the group (no seed in flight: nQ == 0)
+      if (tid == 0)
+        for (int i = 0; i < (int)(sizeof(LaneGroup) / 4); ++i)
+          reinterpret_cast<int*>(&sh.G)[i] = __ldcg(reinterpret_cast<const int*>(grp) + i);
+      __syncthreads();
+    }
+  } else if (L > 1 && !S.active) {
     if (S.begin) {                      // a fresh seed handed over by the lane that committed the previous one
       __threadfence();                  // (acquire: the committing CTA's stores to this lane's words and list)
       __syncthreads();
@@ -977,16 +1200,18 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
             for (int w = 0; w < NT / 32; ++w) { lo = min(lo, sh.red[w * 6 + a]); hi = max(hi, sh.red[w * 6 + 3 + a]); }
             S.minD[a] = lo; S.maxD[a] = hi;
           }
-          bool expanded = false;
-          for (int a = 0; a < 3; ++a) expanded |= (S.minD[a] < S.seqMin[a]) || (S.maxD[a] > S.seqMax[a]);
           int rsn = STOP_NONE;
-          if (!expanded) {                                   // :294-299
-            if (S.stuck >= 1) rsn = STOP_STUCK; else S.stuck += 1;
-          } else {
-            S.stuck = 0;                                     // :300-301
+          if (!beam) {                                       // (beam search runs this on Q[0] at the head of a round)
+            bool expanded = false;
+            for (int a = 0; a < 3; ++a) expanded |= (S.minD[a] < S.seqMin[a]) || (S.maxD[a] > S.seqMax[a]);
+            if (!expanded) {                                 // :294-299
+              if (S.stuck >= 1) rsn = STOP_STUCK; else S.stuck += 1;
+            } else {
+              S.stuck = 0;                                   // :300-301
+            }
+            for (int a = 0; a < 3; ++a) { S.seqMin[a] = min(S.seqMin[a], S.minD[a]); S.seqMax[a] = max(S.seqMax[a], S.maxD[a]); }
+            if (rsn == STOP_NONE && da.max_steps > 0 && S.steps >= da.max_steps) rsn = STOP_MAXSTEPS;
           }
-          for (int a = 0; a < 3; ++a) { S.seqMin[a] = min(S.seqMin[a], S.minD[a]); S.seqMax[a] = max(S.seqMax[a], S.maxD[a]); }
-          if (rsn == STOP_NONE && da.max_steps > 0 && S.steps >= da.max_steps) rsn = STOP_MAXSTEPS;
           sh.flag = rsn;
         } else {
           sh.flag = STOP_EMPTY;
@@ -998,7 +1223,11 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     }
     if (tr != nullptr && tid == 0) { tr->stop_reason = reason; tr->size_after = n_in; }
     stamp(2);
-    if (reason != STOP_NONE) {
+    if (beam) {
+      // one expansion per lane and round: the mask joins newQ if it added a point (:262-267)
+      if (!beam_park(reason == STOP_NONE, n_in)) return;
+      mode = MODE_NEW_REGION;                              // this lane reported last: it closes the round
+    } else if (reason != STOP_NONE) {
       if (!stop_region(reason, n_in)) return;              // (random restarts: parked until the seed's other restarts end)
       mode = MODE_NEW_REGION;
     } else {
@@ -1009,7 +1238,12 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
   stamp(3);
   // ------------------------------------------------------------------ find the next region that needs a forward
   while (true) {
-    if (mode == MODE_NEW_REGION && L > 1) {
+    if (mode == MODE_NEW_REGION && beam) {
+      const int r = beam_commit();
+      if (r == 0) break;
+      if (r == 2) return;
+      mode = MODE_SCAN;
+    } else if (mode == MODE_NEW_REGION && L > 1) {
       if (!advance_group()) break;
       mode = MODE_SCAN;
     } else if (mode == MODE_NEW_REGION) {
@@ -1072,6 +1306,11 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       const int x = pw_x(w), y = pw_y(w), z = pw_z(w);
       return x >= lo0 && x <= hi0 && y >= lo1 && y <= hi1 && z >= lo2 && z <= hi2;
     }, [](unsigned) {}, listJ, sh.listJ_s, kListCap, sh.scan);
+    if (n_nb == 0 && beam) {                                  // empty shell: the candidate is not expanded (:206)
+      if (!beam_park(false, S.n_in)) return;
+      mode = MODE_NEW_REGION;
+      continue;
+    }
     if (n_nb == 0) {                                          // :233-235
       if (!stop_region(STOP_NONEIGHBOR, S.n_in)) return;
       mode = MODE_NEW_REGION;

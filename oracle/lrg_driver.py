@@ -320,6 +320,152 @@ class RestartRoomGrower(RoomGrower):
                 return reason
 
 
+class BeamRoomGrower(RoomGrower):
+    """One room of /root/reference/test_beam_search.py:142-285 (BEAM_WIDTH :24, SEARCH_WIDTH :25, ``scoring = 'np'`` :41).
+
+    Per seed the reference keeps a queue ``Q`` of at most BEAM_WIDTH (score, mask) candidates.  Every round each candidate
+    is expanded SEARCH_WIDTH times by one sampled grow step (:207-268); an expansion that added a point joins ``newQ`` with
+    the score ``numpy.sum(newMask)`` (:266); the next ``Q`` is the BEAM_WIDTH best of ``newQ`` (stable sort, descending,
+    :273).  At the head of every round (``qid == 0``, :179-190) ``bestMask = Q[0]`` and the stuck logic of the plain driver
+    runs on its bounding box; the search ends when it sticks twice or no expansion added anything, and ``bestMask`` becomes
+    visited / labelled (:276-279).
+
+    ('ml' scoring accumulates log-probabilities over the *padded* tile rows, :236-256; not restated -- 'np' is the default.)
+
+    The script as shipped needs Python 2 (``range(n) + list(...)``, :212,224); oracle/make_golden.py runs it unmodified with
+    a list-returning ``range`` in its globals (oracle/run_reference.py).
+
+    RNG: with ``NumpyLegacyRng`` the expansions consume the single global stream in the reference's order (candidate-major);
+    with ``PhiloxRng`` expansion (q, s) of round r draws at (room, seed point, step r, lane q*SEARCH_WIDTH + s), so that the
+    device can run the expansions of a round side by side.
+    """
+
+    def __init__(self, *args, beam_width=3, search_width=3, **kw):
+        super().__init__(*args, **kw)
+        self.B, self.W = int(beam_width), int(search_width)
+        self.lane = 0
+        self.round = 0
+        self.lane_steps = [0] * (self.B * self.W)
+        self.lane_log = []          # (seed, round, lane, updated, size) of every expansion
+
+    def _begin_rng_step(self):
+        self.rng.begin_step(self.room_id, self.round, self.lane, self.seed_id)
+
+    def expand(self, mask, lane, forced=None):
+        """One sampled grow step from ``mask`` (:191-268).  Returns None if the shell is empty, else (updated, newMask).
+        ``forced(step) -> (add_logits, rmv_logits, add_mask, rmv_mask)`` lets a parity test supply the device's masks."""
+        pv = self.point_voxels
+        self.lane = lane
+        self.currentMask = mask.copy()
+        self.minDims = pv[mask, :].min(axis=0)                                    # :176-177
+        self.maxDims = pv[mask, :].max(axis=0)
+        st = self._prepare_tiles()
+        if st is None:
+            return None
+        if forced is None:
+            add, rmv = self.forward_fn(st['inlier'], st['neighbor'])
+            add_mask = rmv_mask = None
+        else:
+            add, rmv, add_mask, rmv_mask = forced(st)
+        updated = self._apply_masks(np.asarray(add)[0], np.asarray(rmv)[0], add_mask, rmv_mask)
+        self.steps += 1                                                           # :261
+        self.total_steps += 1
+        self.lane_steps[lane] += 1
+        self.lane_log.append((self.seed_id, self.round, lane, updated, int(self.currentMask.sum())))
+        return updated, self.currentMask
+
+    def _prepare_tiles(self):
+        """prepare_step without the plain driver's stop bookkeeping (an empty shell just yields no candidate, :206)."""
+        saved = self.stop_growing
+        self.stop_growing = lambda reason: None
+        try:
+            return self.prepare_step()
+        finally:
+            self.stop_growing = saved
+
+    def _apply_masks(self, add_logits, rmv_logits, add_mask, rmv_mask):
+        """:230-260 -- sample the masks, re-voxelise the selected rows, set semantics of the update.  Returns ``updated``."""
+        st = self._step
+        add_conf = confidence(add_logits)
+        rmv_conf = confidence(rmv_logits)
+        u_add = self.rng.uniform(len(add_conf), 'add')                            # :232
+        u_rmv = self.rng.uniform(len(rmv_conf), 'remove')                         # :233
+        if add_mask is None:
+            add_mask = u_add < add_conf
+        if rmv_mask is None:
+            rmv_mask = u_rmv < rmv_conf
+        st.update(add_conf=add_conf, rmv_conf=rmv_conf, u_add=u_add, u_rmv=u_rmv,
+                  add_mask=np.asarray(add_mask, bool), rmv_mask=np.asarray(rmv_mask, bool))
+        center = st['center']
+        addPoints = st['neighbor'][0, :, :][st['add_mask']]                       # :234-237
+        addPoints[:, :2] += center[:2]
+        addVoxels = voxelize(addPoints[:, :3], self.resolution)
+        rmvPoints = st['inlier'][0, :, :][st['rmv_mask']]                         # :245-248
+        rmvPoints[:, :2] += center[:2]
+        rmvVoxels = voxelize(rmvPoints[:, :3], self.resolution)
+        in_add = _rows_in(self.point_voxels, addVoxels)                           # :251-258
+        in_rmv = _rows_in(self.point_voxels, rmvVoxels)
+        updated = bool(np.any(np.logical_and(~self.currentMask, in_add)))
+        self.currentMask = np.logical_and(np.logical_or(self.currentMask, in_add), ~in_rmv)
+        if self.trace is not None:
+            self.trace.append(dict(st, seed=self.seed_id, size_after=int(self.currentMask.sum())))
+        return updated
+
+    def grow_seed(self, seed_id, forced=None):
+        """:153-279 for one seed.  Returns the stop reason ('stuck' or 'exhausted')."""
+        pv = self.point_voxels
+        self.seed_id = int(seed_id)
+        seedMask = np.zeros(len(self.points), dtype=bool)                         # :154-155
+        seedMask[seed_id] = True
+        seqMin = pv[seed_id].copy()                                               # :156-159
+        seqMax = pv[seed_id].copy()
+        self.steps = 0
+        stuck = 0
+        bestMask = seedMask
+        Q = [(0, seedMask)]                                                       # :164
+        self.round = 0
+        reason = 'exhausted'
+        while len(Q) > 0:                                                         # :169
+            bestMask = Q[0][1]                                                    # :179
+            mn, mx = pv[bestMask, :].min(axis=0), pv[bestMask, :].max(axis=0)
+            if not np.any(mn < seqMin) and not np.any(mx > seqMax):               # :180-186
+                if stuck >= 1:
+                    reason = 'stuck'
+                    break
+                stuck += 1
+            else:
+                stuck = 0
+            seqMin = np.minimum(seqMin, mn)                                       # :187-188
+            seqMax = np.maximum(seqMax, mx)
+            newQ = []
+            for q, (score, mask) in enumerate(Q):
+                for s in range(self.W):                                           # :207
+                    lane = q * self.W + s
+                    r = self.expand(mask, lane, None if forced is None else (lambda st, lane=lane: forced(st, lane)))
+                    if r is None:
+                        break                                                     # empty shell: no expansion of this candidate (:206)
+                    updated, newMask = r
+                    if updated:                                                   # :262-267 ('np': the score is the region size)
+                        newQ.append((int(np.sum(newMask)), newMask))
+            Q = sorted(newQ, key=lambda x: x[0], reverse=True)[:self.B]           # :273
+            self.round += 1
+        self.visited[bestMask] = True                                             # :276
+        size = int(np.sum(bestMask))
+        labelled = size > self.cluster_threshold
+        if labelled:                                                              # :277-279
+            self.cluster_label[bestMask] = self.cluster_id
+            self.cluster_id += 1
+        self.regions.append((self.seed_id, self.steps, size, reason, labelled))
+        return reason
+
+    def run(self, forced=None):
+        for seed_id in np.arange(len(self.points))[self.order]:                   # :143-145
+            if self.visited[seed_id]:
+                continue
+            self.grow_seed(seed_id, forced)
+        return self.cluster_label
+
+
 def _rows_in(voxels, query):
     """Row-wise membership of (N,3) int voxels in a set of (M,3) voxels (python ``tuple in set`` at :283-286)."""
     if len(query) == 0:

@@ -124,9 +124,58 @@ def golden_restart_trace(seed, n_raw, n_boxes):
     print(log[-300:])
 
 
+def golden_beam_trace(seed, n_raw, n_boxes):
+    """4. ``beam_trace_<seed>.npz`` - the UNMODIFIED /root/reference/test_beam_search.py (BEAM_WIDTH 3, SEARCH_WIDTH 3, 'np'
+    scoring) on the room of driver_trace_<seed>.npz.  The script concatenates ``range(n) + list(...)`` (:212,224), which is
+    Python 2; it is executed as it is with a list-returning ``range`` among its module globals (run_reference.py2_range)."""
+    room = rooms.generate_room(seed, n_raw=n_raw, n_boxes=n_boxes, dims=np.array([3.0, 2.5, 2.2]))
+    scratch = '/tmp/lrg_golden_bs_%d' % seed
+    os.makedirs(os.path.join(scratch, 'data'), exist_ok=True)
+    os.makedirs(os.path.join(scratch, 'models'), exist_ok=True)
+    for ext in ('index', 'data-00000-of-00001'):
+        dst = os.path.join(scratch, 'models', 'lrgnet_model5.ckpt.' + ext)
+        if not os.path.exists(dst):
+            os.symlink(os.path.join(REF, 'models', 'lrgnet_model5.ckpt.' + ext), dst)
+    head, tail = run_reference.shim_paths(REF)
+    sys.path[:0] = head
+    sys.path.extend(tail)
+    from learn_region_grow_b200 import io_util
+    cwd = os.getcwd()
+    os.chdir(scratch)
+    try:
+        io_util.saveToH5('data/s3dis_area5.h5', [room])
+        import learn_region_grow_util as shim_util
+        shim_util.TRACE = []
+        shim_util.FORWARD_DTYPE = np.float64
+        buf = io.StringIO()
+        t0 = time.time()
+        with contextlib.redirect_stdout(buf):
+            g = run_reference.run(os.path.join(REF, 'test_beam_search.py'), ['--area', '5'],
+                                  init_globals={'range': run_reference.py2_range})
+        wall = time.time() - t0
+        trace = shim_util.TRACE
+        shim_util.TRACE = None
+        shim_util.FORWARD_DTYPE = np.float32
+    finally:
+        os.chdir(cwd)
+    log = buf.getvalue()
+    out = dict(cluster_label=np.asarray(g['cluster_label']),
+               inlier_crc=np.array([t['inlier_crc'] for t in trace], dtype=np.uint32),
+               neighbor_crc=np.array([t['neighbor_crc'] for t in trace], dtype=np.uint32),
+               log=np.array(log), reference_wall_s=np.array(wall),
+               beam_width=np.array(g['BEAM_WIDTH']), search_width=np.array(g['SEARCH_WIDTH']))
+    np.savez_compressed(os.path.join(GOLD, 'beam_trace_%d.npz' % seed), **out)
+    print('beam trace %d: steps %d wall %.1fs' % (seed, len(trace), wall))
+    print(log[-300:])
+
+
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
+    if sys.argv[1:] == ['beam']:
+        golden_beam_trace(1000, 2500, 4)
+        sys.exit(0)
     golden_weights()
     golden_trace(1000, 2500, 4)
     golden_trace(1001, 6000, 8)
     golden_restart_trace(1000, 2500, 4)
+    golden_beam_trace(1000, 2500, 4)

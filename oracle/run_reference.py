@@ -23,14 +23,20 @@ def shim_paths(ref_dir):
     return head, tail
 
 
-def run(script, argv):
+def py2_range(*a):
+    """Python 2's ``range``: a list.  test_beam_search.py:212,224 concatenate ``range(n) + list(...)``, which only Python 2
+    accepts; handing this to the script as a module global runs it unmodified."""
+    return list(range(*a))
+
+
+def run(script, argv, init_globals=None):
     head, tail = shim_paths(os.path.dirname(os.path.abspath(script)))
     old_path, old_argv = list(sys.path), list(sys.argv)
     sys.path[:0] = head
     sys.path.extend(tail)
     sys.argv = [script] + list(argv)
     try:
-        return runpy.run_path(script, run_name='__main__')
+        return runpy.run_path(script, init_globals=init_globals, run_name='__main__')
     finally:
         sys.path[:] = old_path
         sys.argv = old_argv

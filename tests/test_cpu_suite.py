@@ -273,7 +273,7 @@ def test_abi_struct_layouts_match_the_header(tmp_path):
 #include <stddef.h>
 #include "lrg_b200.h"
 int main(void) {
-  printf("LrgGrowParams %zu %zu %zu %zu\\n", sizeof(LrgGrowParams), offsetof(LrgGrowParams, seed), offsetof(LrgGrowParams, flags), offsetof(LrgGrowParams, num_restarts));
+  printf("LrgGrowParams %zu %zu %zu %zu %zu %zu\\n", sizeof(LrgGrowParams), offsetof(LrgGrowParams, seed), offsetof(LrgGrowParams, flags), offsetof(LrgGrowParams, num_restarts), offsetof(LrgGrowParams, beam_width), offsetof(LrgGrowParams, search_width));
   printf("LrgRoomStats %zu %zu\\n", sizeof(LrgRoomStats), offsetof(LrgRoomStats, stop_other));
   printf("LrgStepTrace %zu %zu %zu\\n", sizeof(LrgStepTrace), offsetof(LrgStepTrace, center), offsetof(LrgStepTrace, neighbor_idx_crc));
   printf("LrgRoomMetrics %zu %zu %zu\\n", sizeof(LrgRoomMetrics), offsetof(LrgRoomMetrics, iou), offsetof(LrgRoomMetrics, gt_match));
@@ -284,7 +284,7 @@ int main(void) {
     subprocess.run(['gcc', '-I', os.path.join(REPO, 'include'), str(src), '-o', str(exe)], check=True)
     out = dict((l.split()[0], [int(x) for x in l.split()[1:]]) for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
     G = _lib.GrowParams
-    assert out['LrgGrowParams'] == [ctypes.sizeof(G), G.seed.offset, G.flags.offset, G.num_restarts.offset]
+    assert out['LrgGrowParams'] == [ctypes.sizeof(G), G.seed.offset, G.flags.offset, G.num_restarts.offset, G.beam_width.offset, G.search_width.offset]
     assert out['LrgRoomStats'] == [_lib.ROOM_STATS_DTYPE.itemsize, _lib.ROOM_STATS_DTYPE.fields['stop_other'][1]]
     T = _lib.STEP_TRACE_DTYPE
     assert out['LrgStepTrace'] == [T.itemsize, T.fields['center'][1], T.fields['neighbor_idx_crc'][1]]

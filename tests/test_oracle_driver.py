@@ -76,3 +76,32 @@ def test_restart_driver_replays_reference_trace(golden_weights):
     for line, (seed_id, steps, size, reason, _) in zip(lines, labelled):
         tok = line.split()
         assert int(tok[6]) == steps and int(tok[7].split('/')[0]) == size and tok[-1] == reason
+
+
+def test_beam_driver_replays_reference_trace(golden_weights):
+    """oracle BeamRoomGrower vs the UNMODIFIED /root/reference/test_beam_search.py (tests/golden/beam_trace_1000.npz, run
+    with Python 2's list-returning ``range`` in the script's globals, oracle/make_golden.py): every tile fed to Session.run
+    (BEAM_WIDTH x SEARCH_WIDTH expansions per round), the final labels and the printed region lines."""
+    base = np.load(os.path.join(GOLDEN, 'driver_trace_1000.npz'))
+    g = np.load(os.path.join(GOLDEN, 'beam_trace_1000.npz'))
+    calls = []
+
+    def fwd(inlier, neighbor):
+        calls.append((_crc(inlier), _crc(neighbor)))
+        add, rmv = lrg_forward.forward(golden_weights, inlier, neighbor, dtype=np.float64)
+        return add.astype(np.float32), rmv.astype(np.float32)
+
+    grower = lrg_driver.BeamRoomGrower(base['points'], base['order'], fwd, lrg_driver.NumpyLegacyRng(0), resolution=0.1,
+                                       beam_width=int(g['beam_width']), search_width=int(g['search_width']))
+    grower.run()
+    assert len(calls) == len(g['inlier_crc'])
+    assert [c[0] for c in calls] == [int(x) for x in g['inlier_crc']]
+    assert [c[1] for c in calls] == [int(x) for x in g['neighbor_crc']]
+    np.testing.assert_array_equal(grower.fill(), g['cluster_label'])
+    # room R target T CLS: step S n/m points IOU ...   (test_beam_search.py:281)
+    lines = [l for l in str(g['log']).split('\n') if l.startswith('room ')]
+    labelled = [r for r in grower.regions if r[4]]
+    assert len(lines) == len(labelled)
+    for line, (seed_id, steps, size, reason, _) in zip(lines, labelled):
+        tok = line.split()
+        assert int(tok[6]) == steps and int(tok[7].split('/')[0]) == size
