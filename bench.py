@@ -214,7 +214,7 @@ def main():
     ap.add_argument('--ref-sample-steps', type=int, default=120)
     ap.add_argument('--cpu-baseline-steps', type=int, default=150)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-extras', action='store_true', help='skip the statistics / random-restart measurements')
+    ap.add_argument('--no-extras', action='store_true', help='skip the statistics / random-restart / beam-search measurements')
     ap.add_argument('--slots', type=int, default=0)
     ap.add_argument('--lockstep-timing', action='store_true', help='also time the lock-step loop kernel by kernel')
     args = ap.parse_args()
@@ -394,7 +394,8 @@ def main():
                'grow_steps_per_pass': int(st_raw['grow_steps'].sum()),
                'scope': 'raw points (x y z r g b) in pinned host memory -> device feature preparation (test_region_grow.py:119-173) -> grow -> fill -> per-raw-point labels on the host'}
     # ---- the rows either side of the path, once each on the raw rooms just uploaded (not part of `value` / `e2e`):
-    # segmentation statistics (test_region_grow.py:319-349) and the random-restart driver (test_random_restart.py)
+    # segmentation statistics (test_region_grow.py:319-349), the random-restart driver (test_random_restart.py) and the
+    # beam-search driver (test_beam_search.py)
     extras = {}
     if not args.no_extras:
         obj_raw = [raw_points[raw_off[i]:raw_off[i + 1], 6].astype(np.int32) for i in range(args.rooms)]
@@ -413,6 +414,15 @@ def main():
                                     'points_per_sec': total_raw / ((pr_rr['grow_ms'] + pr_rr['fill_ms']) * 1e-3), 'per_gpu': True,
                                     'mean': {k: float(np.nanmean(mt_rr[k])) for k in ('nmi', 'ami', 'ars', 'prc', 'rcl', 'iou')},
                                     'scope': 'test_random_restart.py: 10 restarts per seed as parallel lanes, largest region kept'}
+        eng.segment_resident(beam_width=3, search_width=3, **params)
+        st_bs = eng.segment_resident(beam_width=3, search_width=3, **params)
+        pr_bs = eng.profile()
+        mt_bs = eng.room_metrics(obj_raw, raw=True)
+        extras['beam_search'] = {'beam_width': 3, 'search_width': 3, 'grow_ms_per_pass': pr_bs['grow_ms'], 'grow_steps_per_pass': int(st_bs['grow_steps'].sum()),
+                                 'grow_steps_per_sec': float(st_bs['grow_steps'].sum()) / (pr_bs['grow_ms'] * 1e-3),
+                                 'points_per_sec': total_raw / ((pr_bs['grow_ms'] + pr_bs['fill_ms']) * 1e-3), 'per_gpu': True,
+                                 'mean': {k: float(np.nanmean(mt_bs[k])) for k in ('nmi', 'ami', 'ars', 'prc', 'rcl', 'iou')},
+                                 'scope': 'test_beam_search.py: 3 candidates x 3 expansions per round as parallel lanes, largest masks kept'}
     clocks = sampler.stop()          # nvidia-smi keeps sampling through the timed regions
     if dist is not None:
         t = torch.tensor([e2e_s], device='cuda', dtype=torch.float64)
