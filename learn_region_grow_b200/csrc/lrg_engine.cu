@@ -898,7 +898,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
         e->d_sync = nullptr; e->d_remaining = nullptr;
         e->sync_slots = 0;
         LRG_TRY(dev_alloc(&e->d_sync, (size_t)n_slots));
-        LRG_TRY(dev_alloc(&e->d_remaining, (size_t)n_slots));
+        LRG_TRY(dev_alloc(&e->d_remaining, (size_t)n_slots + 1));
         e->sync_slots = n_slots;
       }
       // (random restarts: only lane 0 of every group starts; it wakes the other lanes once it holds a seed)
@@ -910,7 +910,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
       LRG_CUDA(cudaMemcpyAsync(e->d_qctr, ctr, sizeof(ctr), cudaMemcpyHostToDevice, st));
       LRG_CUDA(cudaMemsetAsync(e->d_busy, 0, sizeof(unsigned long long) * 24, st));
       LRG_CUDA(cudaMemsetAsync(e->d_sync, 0, sizeof(SlotSync) * n_slots, st));
-      LRG_CUDA(cudaMemsetAsync(e->d_remaining, 0, sizeof(int) * n_slots, st));
+      LRG_CUDA(cudaMemsetAsync(e->d_remaining, 0, sizeof(int) * ((size_t)n_slots + 1), st));
       GrowArgs ga{};
       ga.da = da;
       ga.da.done_flag = nullptr;
@@ -924,7 +924,14 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
       ga.sync = e->d_sync;
       ga.busy_ns = e->d_busy;
       ga.remaining = e->d_remaining;
-      ga.hi_slots = (params->flags & LRG_FLAG_PRIORITY) && lanes == 1 ? std::max(2, n_slots / 8) : 0;
+      // reserved CTAs for the slots with the most work left (LRG_FLAG_PRIORITY; LRG_HI="slots,ctas" overrides for experiments)
+      ga.hi_slots = 0; ga.hi_ctas = 0;
+      if (lanes == 1 && !beam) {
+        int hs = (params->flags & LRG_FLAG_PRIORITY) ? 2 : 0, hc = (params->flags & LRG_FLAG_PRIORITY) ? 24 : 0;
+        if (const char* env = getenv("LRG_HI")) sscanf(env, "%d,%d", &hs, &hc);
+        const int n_ctas = e->sm_count > 0 ? e->sm_count : 148;
+        if (hs > 0 && hc > 0 && hc < n_ctas) { ga.hi_slots = std::min(hs, 8); ga.hi_ctas = hc; }
+      }
       ga.tune = getenv("LRG_TUNE") ? atoi(getenv("LRG_TUNE")) : 3;   // both measured positive (profiles/README.md)
       rc = launch_grow(ga, e->sm_count > 0 ? e->sm_count : 148, st);
       if (rc == LRG_OK) {

@@ -53,23 +53,6 @@ __device__ __forceinline__ unsigned queue_pop(const GrowQueue& q) {
   return (unsigned)v;                                // (the caller issues the acquire fence where the item needs one)
 }
 
-// Non-blocking pop of the high-priority ring: claims a ticket only if an item has been published for it (CAS, never
-// over-claims).  Called once per item a CTA retires, never in a spin loop (every CTA would hammer the same two words).
-__device__ __forceinline__ bool queue_try_pop(const GrowQueue& q, unsigned& item) {
-  while (true) {
-    const unsigned h = *reinterpret_cast<volatile unsigned*>(q.head);
-    const unsigned t = *reinterpret_cast<volatile unsigned*>(q.tail);
-    if ((int)(t - h) <= 0) return false;
-    if (atomicCAS(q.head, h, h + 1u) != h) continue;  // lost the race for this ticket: look again
-    const unsigned long long gen = (unsigned long long)(h / (q.cap_mask + 1u)) + 1ull;
-    const volatile unsigned long long* e = q.ring + (h & q.cap_mask);
-    unsigned long long v;
-    while (((v = *e) >> 32) != gen) {}               // the producer bumped tail first and is writing the entry right now
-    item = (unsigned)v;
-    return true;
-  }
-}
-
 __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_constant__ GrowArgs ga) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(16) TcStatic st;
@@ -86,26 +69,17 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
   float* const sP = reinterpret_cast<float*>(smem);
   float* const sR = sP + 1024;
 
-  // Scheduling: items of the high-priority slots go to ring 0 and a WAKE token goes to ring 1 with them; a CTA blocks on
-  // ring 1 only, and before running what it popped there it drains ring 0.  Under load every retiring CTA therefore serves
-  // the high-priority ring first; when idle, the token wakes a CTA that finds the item.
-  unsigned deferred = 0;                              // the ring-1 item to run once ring 0 is empty (0 = none)
+  // Scheduling (optional, hi_ctas > 0): the run ends with the rooms that have the most work left, so the few slots with the
+  // most unvisited points are served by RESERVED CTAs -- CTAs below hi_ctas pop ring 0 only, the others ring 1 only; a
+  // producer sends a high-priority slot's items to ring 0 only when that many reserved CTAs are waiting there right now
+  // (all or nothing, so the FIFO argument for the head tiles holds within a ring), else to ring 1 like everybody else's.
+  const int my_ring = (ga.hi_ctas > 0 && (int)blockIdx.x < ga.hi_ctas) ? 0 : 1;
   unsigned chained = 0;                               // item this CTA hands to itself (the STEP that follows the last head tile)
   while (true) {
     if (tid == 0) {
       unsigned it = chained;
       chained = 0;
-      if (it == 0) {
-        if (ga.hi_slots <= 0) it = queue_pop(ga.q[1]);    // priorities off: one FIFO
-        else if (!queue_try_pop(ga.q[0], it)) {
-          if (deferred != 0) { it = deferred; deferred = 0; }
-          else {
-            it = queue_pop(ga.q[1]);
-            unsigned hi_item = 0;
-            if (queue_try_pop(ga.q[0], hi_item)) { deferred = it; it = hi_item; }
-          }
-        }
-      }
+      if (it == 0) it = queue_pop(ga.q[my_ring]);
       // acquire: the driver step reads state other CTAs wrote with plain stores (drop stale L1 lines); the tensor tiles and
       // the projection read everything produced in this launch with ld.global.cg and need no fence
       if ((it & 7u) == ITEM_STEP) __threadfence();
@@ -115,7 +89,6 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
     const unsigned item = s_item;
     const int type = (int)(item & 7u), slot = (int)((item >> 3) & 0x1FFFu), a = (int)((item >> 16) & 15u), t = (int)((item >> 20) & 15u);
     if (type == ITEM_EXIT) break;
-    if (type == ITEM_WAKE) { __syncthreads(); continue; }
     const unsigned long long t0 = (tid == 0) ? global_ns() : 0ull;
     SlotSync* sy = ga.sync + slot;
     if (tid == 0 && ga.busy_ns != nullptr) {
@@ -132,22 +105,33 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
         if (sh.S.finished) *reinterpret_cast<volatile int*>(ga.remaining + slot) = 0;
         if (sh.all_done) {
           // the last slot has retired: nothing is in flight any more, release every CTA
-          for (unsigned left = gridDim.x; left > 0;) {
-            const int n = left > 16u ? 16 : (int)left;
-            for (int i = 0; i < n; ++i) next[i] = make_item(ITEM_EXIT, 0, 0, 0);
-            __threadfence();
-            queue_push(ga.q[1], next, n);
-            left -= (unsigned)n;
-          }
+          for (int ring = 0; ring < 2; ++ring)
+            for (unsigned left = ring == 0 ? (unsigned)ga.hi_ctas : gridDim.x - (unsigned)ga.hi_ctas; left > 0;) {
+              const int n = left > 16u ? 16 : (int)left;
+              for (int i = 0; i < n; ++i) next[i] = make_item(ITEM_EXIT, 0, 0, 0);
+              __threadfence();
+              queue_push(ga.q[ring], next, n);
+              left -= (unsigned)n;
+            }
         } else if (sh.S.active && !sh.S.finished) {
-          // scheduling (optional): the run ends with the rooms that have the most work left; rank this slot by unvisited points
+          // scheduling (optional): rank this slot by the unvisited points of its room; the bar for the high-priority queue
+          // (the hi_slots-th largest count over all slots) is refreshed by every 64th step of a slot
           sy->prio = 1;
-          if (ga.hi_slots > 0) {
+          if (ga.hi_ctas > 0) {
             const int mine = (int)(ga.da.room_off[sh.S.room + 1] - ga.da.room_off[sh.S.room]) - sh.S.visited;
             *reinterpret_cast<volatile int*>(ga.remaining + slot) = mine;
-            int ahead = 0;
-            for (int i = 0; i < ga.da.n_slots; ++i) ahead += (*reinterpret_cast<volatile int*>(ga.remaining + i) > mine) ? 1 : 0;
-            if (ahead < ga.hi_slots) sy->prio = 0;
+            volatile int* bar = ga.remaining + ga.da.n_slots;
+            if ((sh.S.total_steps & 63) == 0) {
+              int top[8];
+              for (int k = 0; k < ga.hi_slots; ++k) top[k] = 0;
+              for (int i = 0; i < ga.da.n_slots; ++i) {
+                int v = *reinterpret_cast<volatile int*>(ga.remaining + i);
+                for (int k = 0; k < ga.hi_slots; ++k)
+                  if (v > top[k]) { const int t2 = top[k]; top[k] = v; v = t2; }
+              }
+              *bar = top[ga.hi_slots - 1];
+            }
+            if (mine >= *bar) sy->prio = 0;
           }
           // only rows that carry distinct points are evaluated (the rest are padding duplicates of them)
           const int tilesI = (min(sh.S.n_in, ga.fa.n_pts[0]) + 127) / 128, tilesJ = (min(sh.S.n_nb, ga.fa.n_pts[1]) + 127) / 128;
@@ -226,11 +210,12 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
         // release: a STEP publishes the counters it just wrote; the tile / projection finishers already fenced before the
         // atomic that made them last (the push is control-dependent on that atomic's result)
         if (type == ITEM_STEP) __threadfence();
-        if (ga.hi_slots > 0 && (*reinterpret_cast<volatile int*>(&sy->prio) & 1) == 0) {
-          queue_push(ga.q[0], next + first, n_next - first);
-          for (int i = first; i < n_next; ++i) next[i] = make_item(ITEM_WAKE, 0, 0, 0);
+        int ring = 1;
+        if (ga.hi_ctas > 0 && (*reinterpret_cast<volatile int*>(&sy->prio) & 1) == 0) {
+          const int waiting = (int)(*reinterpret_cast<volatile unsigned*>(ga.q[0].head) - *reinterpret_cast<volatile unsigned*>(ga.q[0].tail));
+          if (waiting >= n_next - first) ring = 0;
         }
-        queue_push(ga.q[1], next + first, n_next - first);
+        queue_push(ga.q[ring], next + first, n_next - first);
       }
       if (ga.busy_ns != nullptr) {
         atomicAdd(ga.busy_ns + type, global_ns() - t0);

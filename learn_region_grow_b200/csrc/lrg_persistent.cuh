@@ -6,7 +6,7 @@
 namespace lrg {
 
 constexpr int kGrowThreads = 512;
-enum { ITEM_STEP = 1, ITEM_BRANCH = 2, ITEM_GPROJ = 3, ITEM_HEAD = 4, ITEM_WAKE = 6, ITEM_EXIT = 7 };
+enum { ITEM_STEP = 1, ITEM_BRANCH = 2, ITEM_GPROJ = 3, ITEM_HEAD = 4, ITEM_EXIT = 7 };
 
 // type: bits [0,3); slot: bits [3,16); a (branch / head index): bits [16,20); t (tile / column block): bits [20,24)
 __host__ __device__ inline unsigned make_item(int type, int slot, int a, int t) {
@@ -27,9 +27,11 @@ struct GrowArgs {
   DriverArgs da;
   ForwardArgs fa;
   TcNet net;
-  GrowQueue q[2];               // [0] high priority (the slots with the most unvisited points left: the run ends with them), [1] normal
-  int* remaining;               // (n_slots) unvisited points of the slot's room, refreshed by every STEP
+  GrowQueue q[2];               // [0] served by the reserved CTAs (items of the slots with the most unvisited points left), [1] everybody else
+  int* remaining;               // (n_slots + 1) unvisited points of the slot's room, refreshed by every STEP; [n_slots] = the
+                                // count a slot needs to be served from the high-priority queue (refreshed every 64 steps of a slot)
   int hi_slots;                 // how many slots are served from the high-priority queue
+  int hi_ctas;                  // CTAs reserved for the high-priority queue (blockIdx < hi_ctas pop ring 0 only, the rest ring 1 only)
   int tune;                     // bit 0: split branch tiles over CTAs when the backlog is short; bit 1: publish head tiles with the projection blocks
   SlotSync* sync;               // (n_slots)
   unsigned long long* busy_ns;  // [24]: [type] = summed handler time in ns, [8 + type] = items handled, [16 + type] = summed queue delay; may be NULL
