@@ -888,10 +888,10 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
         cudaFree(e->d_qring);
         e->d_qring = nullptr;
         e->q_capacity = 0;
-        LRG_TRY(dev_alloc(&e->d_qring, (size_t)2 * cap));     // two rings: high priority, normal
+        LRG_TRY(dev_alloc(&e->d_qring, (size_t)3 * cap));     // three rings: reserved CTAs, everybody, projection requests
         e->q_capacity = cap;
       }
-      if (e->d_qctr == nullptr) LRG_TRY(dev_alloc(&e->d_qctr, 4));
+      if (e->d_qctr == nullptr) LRG_TRY(dev_alloc(&e->d_qctr, 8));
       if (e->d_busy == nullptr) LRG_TRY(dev_alloc(&e->d_busy, 24));
       if (n_slots > e->sync_slots) {
         cudaFree(e->d_sync); cudaFree(e->d_remaining);
@@ -904,8 +904,8 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
       // (random restarts: only lane 0 of every group starts; it wakes the other lanes once it holds a seed)
       std::vector<unsigned long long> first(n_groups);
       for (int g = 0; g < n_groups; ++g) first[g] = (1ull << 32) | make_item(ITEM_STEP, g * lanes, 0, 0);
-      const unsigned ctr[4] = {0u, 0u, 0u, (unsigned)n_groups};
-      LRG_CUDA(cudaMemsetAsync(e->d_qring, 0, sizeof(unsigned long long) * 2 * e->q_capacity, st));
+      const unsigned ctr[8] = {0u, 0u, 0u, (unsigned)n_groups, 0u, 0u, 0u, 0u};
+      LRG_CUDA(cudaMemsetAsync(e->d_qring, 0, sizeof(unsigned long long) * 3 * e->q_capacity, st));
       LRG_CUDA(cudaMemcpyAsync(e->d_qring + e->q_capacity, first.data(), sizeof(unsigned long long) * n_groups, cudaMemcpyHostToDevice, st));
       LRG_CUDA(cudaMemcpyAsync(e->d_qctr, ctr, sizeof(ctr), cudaMemcpyHostToDevice, st));
       LRG_CUDA(cudaMemsetAsync(e->d_busy, 0, sizeof(unsigned long long) * 24, st));
@@ -932,6 +932,11 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
         const int n_ctas = e->sm_count > 0 ? e->sm_count : 148;
         if (hs > 0 && hc > 0 && hc < n_ctas) { ga.hi_slots = std::min(hs, 8); ga.hi_ctas = hc; }
       }
+      // pooled-projection servers: 16 of the CTAs keep W0[:1024] of both heads in shared memory (LRG_GSERVERS=0 turns them off)
+      const int n_ctas_total = e->sm_count > 0 ? e->sm_count : 148;
+      ga.n_servers = (getenv("LRG_GSERVERS") ? atoi(getenv("LRG_GSERVERS")) != 0 : true) && n_ctas_total >= 4 * kProjServers ? kProjServers : 0;
+      ga.greq_ring = e->d_qring + (size_t)2 * e->q_capacity; ga.greq_mask = e->q_capacity - 1; ga.greq_tail = e->d_qctr + 4;
+      if (ga.hi_ctas + ga.n_servers >= n_ctas_total) { ga.hi_ctas = 0; ga.hi_slots = 0; }
       ga.tune = getenv("LRG_TUNE") ? atoi(getenv("LRG_TUNE")) : 3;   // both measured positive (profiles/README.md)
       rc = launch_grow(ga, e->sm_count > 0 ? e->sm_count : 148, st);
       if (rc == LRG_OK) {

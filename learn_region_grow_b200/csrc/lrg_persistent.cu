@@ -53,12 +53,85 @@ __device__ __forceinline__ unsigned queue_pop(const GrowQueue& q) {
   return (unsigned)v;                                // (the caller issues the acquire fence where the item needs one)
 }
 
+// Pooled-projection server: gproj[slot][h][c0 + c] = bias0_h[c0 + c] + sum_k pooled[slot][k] * W0g_h[k][c0 + c] for the 32
+// columns of this CTA, the weights resident in shared memory (128 KB) instead of being streamed from L2 by every grow step
+// (256 KB per 64-column block item).  Four request groups of 128 threads work on different requests at once (group g takes
+// the tickets = g mod 4 of the broadcast ring); summation order = tc_gproj_block's (32 K-groups of 32 rows, each a
+// sequential fmaf chain from 0, combined in order on top of the bias), so both paths give the same bits.
+__device__ void proj_server(const GrowArgs& ga, unsigned char* smem) {
+  const int tid = threadIdx.x, grp = tid >> 7, t = tid & 127, c = t & 31, kq = t >> 5;
+  const int h = (int)blockIdx.x / 8, c0 = ((int)blockIdx.x % 8) * 32;
+  float* const sW = reinterpret_cast<float*>(smem);                 // [1024][32]
+  float* const sP = sW + 1024 * 32 + grp * 2048;                    // [1024] pooled row of this group's request
+  float* const sR = sP + 1024;                                      // [32][32] K-group partial sums
+  {
+    const float4* W = reinterpret_cast<const float4*>(ga.net.W0g[h] + c0);
+    for (int i = tid; i < 1024 * 8; i += kGrowThreads) {
+      const int k = i >> 3, q = i & 7;
+      reinterpret_cast<float4*>(sW)[i] = __ldg(W + (size_t)k * 64 + q);
+    }
+  }
+  const float bias = __ldg(ga.net.head_bias0[h] + c0 + c);
+  __syncthreads();
+  for (unsigned ticket = (unsigned)grp;; ticket += 4u) {
+    const unsigned long long gen = (unsigned long long)(ticket / (ga.greq_mask + 1u)) + 1ull;
+    const volatile unsigned long long* e = ga.greq_ring + (ticket & ga.greq_mask);
+    unsigned long long v = *e;
+    if ((v >> 32) != gen) {
+      const long long t0 = clock64();
+      while (((v = *e) >> 32) != gen) {
+        __nanosleep(20);
+        if (clock64() - t0 > 60000000000ll) asm volatile("trap;");
+      }
+    }
+    const unsigned slot = (unsigned)v;
+    if (slot == kProjExit) break;
+    // (every thread polled the entry itself: no broadcast through shared memory, no barrier before the loads)
+    const float4* prow = reinterpret_cast<const float4*>(ga.fa.pooled + (size_t)slot * 1024);
+    reinterpret_cast<float4*>(sP)[t] = __ldcg(prow + t);
+    reinterpret_cast<float4*>(sP)[t + 128] = __ldcg(prow + t + 128);
+    asm volatile("bar.sync %0, 128;" ::"r"(grp + 1));
+    {
+      // eight K-groups per thread as eight independent fmaf chains (each chain sequential in k like tc_gproj_block)
+      float acc[8];
+#pragma unroll
+      for (int g8 = 0; g8 < 8; ++g8) acc[g8] = 0.f;
+      const float* w = sW + (kq * 8 * 32) * 32 + c;
+      const float* p = sP + kq * 8 * 32;
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+#pragma unroll
+        for (int g8 = 0; g8 < 8; ++g8) acc[g8] = fmaf(p[g8 * 32 + i], w[(g8 * 32 + i) * 32], acc[g8]);
+      }
+#pragma unroll
+      for (int g8 = 0; g8 < 8; ++g8) sR[(kq * 8 + g8) * 32 + c] = acc[g8];
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(grp + 1));
+    if (t < 32) {
+      float s2 = bias;
+#pragma unroll
+      for (int g2 = 0; g2 < 32; ++g2) s2 += sR[g2 * 32 + t];
+      ga.fa.gproj[((size_t)slot * 2 + h) * 256 + c0 + t] = s2;
+      __syncwarp();
+      if (t == 0) {
+        __threadfence();
+        atomicSub(&ga.sync[slot].gproj_left, 1);
+      }
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(grp + 1));     // sP / sR are reused by the group's next request
+  }
+}
+
 __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_constant__ GrowArgs ga) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(16) TcStatic st;
   __shared__ uint32_t tmem_base;
   __shared__ unsigned s_item;
   const int tid = threadIdx.x, warp = tid >> 5;
+  if ((int)blockIdx.x < ga.n_servers) {               // (no tensor memory, no work items: requests only)
+    proj_server(ga, smem);
+    return;
+  }
   if (warp == 4) tmem_alloc(smem_u32(&tmem_base), kTmemCols);
   tcgen05_fence_before();
   __syncthreads();
@@ -73,7 +146,7 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
   // most unvisited points are served by RESERVED CTAs -- CTAs below hi_ctas pop ring 0 only, the others ring 1 only; a
   // producer sends a high-priority slot's items to ring 0 only when that many reserved CTAs are waiting there right now
   // (all or nothing, so the FIFO argument for the head tiles holds within a ring), else to ring 1 like everybody else's.
-  const int my_ring = (ga.hi_ctas > 0 && (int)blockIdx.x < ga.hi_ctas) ? 0 : 1;
+  const int my_ring = (ga.hi_ctas > 0 && (int)blockIdx.x - ga.n_servers < ga.hi_ctas) ? 0 : 1;
   unsigned chained = 0;                               // item this CTA hands to itself (the STEP that follows the last head tile)
   while (true) {
     if (tid == 0) {
@@ -105,8 +178,17 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
         if (sh.S.finished) *reinterpret_cast<volatile int*>(ga.remaining + slot) = 0;
         if (sh.all_done) {
           // the last slot has retired: nothing is in flight any more, release every CTA
+          if (ga.n_servers > 0) {                          // one closing request per request group of the servers
+            __threadfence();
+            const unsigned t4 = atomicAdd(ga.greq_tail, 4u);
+            for (unsigned i = 0; i < 4u; ++i) {
+              const unsigned idx = t4 + i;
+              *reinterpret_cast<volatile unsigned long long*>(ga.greq_ring + (idx & ga.greq_mask)) =
+                  (((unsigned long long)(idx / (ga.greq_mask + 1u)) + 1ull) << 32) | kProjExit;
+            }
+          }
           for (int ring = 0; ring < 2; ++ring)
-            for (unsigned left = ring == 0 ? (unsigned)ga.hi_ctas : gridDim.x - (unsigned)ga.hi_ctas; left > 0;) {
+            for (unsigned left = ring == 0 ? (unsigned)ga.hi_ctas : gridDim.x - (unsigned)(ga.hi_ctas + ga.n_servers); left > 0;) {
               const int n = left > 16u ? 16 : (int)left;
               for (int i = 0; i < n; ++i) next[i] = make_item(ITEM_EXIT, 0, 0, 0);
               __threadfence();
@@ -144,7 +226,7 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
           const int lg = !(ga.tune & 1) ? 0 : idle >= 8 * (tilesI + tilesJ) ? 2 : idle >= 4 * (tilesI + tilesJ) ? 1 : 0;
           const int parts = 1 << lg;
           sy->branch_left = (tilesI + tilesJ) * parts;
-          sy->gproj_left = 8;
+          sy->gproj_left = ga.n_servers > 0 ? ga.n_servers : 8;
           sy->head_left = tilesI + tilesJ;
           sy->tiles[0] = tilesI;
           sy->tiles[1] = tilesJ;
@@ -172,9 +254,20 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
           // the pooled row is complete: publish the projection blocks and, behind them in the FIFO, the head tiles -- a CTA
           // that pops a head tile knows every projection block of its slot is already running (or done), so the head's
           // wait on gproj_left cannot deadlock, and its prologue overlaps the projection
-          for (int h = 0; h < 2; ++h)
-            for (int cb = 0; cb < 4; ++cb) next[n_next++] = make_item(ITEM_GPROJ, slot, h, cb);
-          if (ga.tune & 2) {
+          if (ga.n_servers > 0) {
+            // one request to the projection servers (they hold the weights in shared memory); the fence above ordered the
+            // pooled row before it.  The head tiles go out right away: prologue and first MMAs overlap the servers, the tiles
+            // spin on gproj_left (servers never wait on a work item, so this cannot deadlock).  (Letting the server that
+            // answers last publish them instead -- no spinning CTAs -- was measured slower in every regime: 342 vs 297 ms
+            // plain, 1350 vs 1180 ms with 10 restarts.)
+            const unsigned idx = atomicAdd(ga.greq_tail, 1u);
+            *reinterpret_cast<volatile unsigned long long*>(ga.greq_ring + (idx & ga.greq_mask)) =
+                (((unsigned long long)(idx / (ga.greq_mask + 1u)) + 1ull) << 32) | (unsigned)slot;
+          } else {
+            for (int h = 0; h < 2; ++h)
+              for (int cb = 0; cb < 4; ++cb) next[n_next++] = make_item(ITEM_GPROJ, slot, h, cb);
+          }
+          if ((ga.tune & 2) || ga.n_servers > 0) {
             const int tilesI = __ldcg(&sy->tiles[0]), tilesJ = __ldcg(&sy->tiles[1]);
             for (int i = 0; i < tilesI; ++i) next[n_next++] = make_item(ITEM_HEAD, slot, 0, i);
             for (int i = 0; i < tilesJ; ++i) next[n_next++] = make_item(ITEM_HEAD, slot, 1, i);

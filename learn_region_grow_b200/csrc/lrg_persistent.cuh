@@ -13,6 +13,8 @@ __host__ __device__ inline unsigned make_item(int type, int slot, int a, int t) 
   return (unsigned)type | ((unsigned)slot << 3) | ((unsigned)a << 16) | ((unsigned)t << 20);
 }
 constexpr int kMaxGrowSlots = 8192;
+constexpr int kProjServers = 16;         // 2 heads x 8 slices of 32 columns
+constexpr unsigned kProjExit = 0x1FFFu;  // request that ends a server's request group
 
 struct GrowQueue {
   unsigned long long* ring;     // capacity entries, zero-initialised; entry = (generation << 32) | item
@@ -33,6 +35,12 @@ struct GrowArgs {
   int hi_slots;                 // how many slots are served from the high-priority queue
   int hi_ctas;                  // CTAs reserved for the high-priority queue (blockIdx < hi_ctas pop ring 0 only, the rest ring 1 only)
   int tune;                     // bit 0: split branch tiles over CTAs when the backlog is short; bit 1: publish head tiles with the projection blocks
+  // pooled-projection servers (n_servers = 16 or 0): the first n_servers CTAs keep one 32-column slice of a head's pooled
+  // weights W0[:1024] in shared memory for the whole run and answer one request per (slot, grow step)
+  int n_servers;
+  unsigned long long* greq_ring;  // broadcast ring: every server reads every entry; entry = (generation << 32) | slot
+  unsigned greq_mask;             // capacity - 1
+  unsigned* greq_tail;
   SlotSync* sync;               // (n_slots)
   unsigned long long* busy_ns;  // [24]: [type] = summed handler time in ns, [8 + type] = items handled, [16 + type] = summed queue delay; may be NULL
 };

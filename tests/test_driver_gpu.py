@@ -192,3 +192,24 @@ def test_room_span_limit(engine):
     pts[:, 0] = [0.0, 50.0, 100.0, 102.0]          # 1020 voxels: fine
     labels, stats = engine.segment_rooms([pts], [np.arange(4)], resolution=0.1, seed=0)
     assert stats['n_points'][0] == 4 and labels[0].shape == (4,)
+
+
+def test_projection_servers_give_identical_labels(engine, monkeypatch):
+    """The pooled projection answered by the server CTAs (weights resident in shared memory, the default of the persistent
+    kernel) and by work items that stream the weights from L2 (LRG_GSERVERS=0) sum in the same order: identical labels."""
+    from learn_region_grow_b200 import rooms as R
+    feats = [feature_prep.prepare_features(R.generate_room(1200 + i, n_raw=5000 + 2500 * i, n_boxes=6)) for i in range(4)]
+    pts, orders = [f['points'] for f in feats], [f['order'] for f in feats]
+    monkeypatch.setenv('LRG_GSERVERS', '0')
+    ref, st0 = engine.segment_rooms(pts, orders, resolution=0.1, seed=11)
+    assert engine.profile()['persistent'] and engine.profile()['items']['gproj'] == 8 * st0['grow_steps'].sum()
+    monkeypatch.setenv('LRG_GSERVERS', '1')
+    for kw in ({}, dict(num_restarts=3), dict(beam_width=2, search_width=2)):
+        monkeypatch.setenv('LRG_GSERVERS', '0')
+        a, sa = engine.segment_rooms(pts, orders, resolution=0.1, seed=11, **kw)
+        monkeypatch.setenv('LRG_GSERVERS', '1')
+        b, sb = engine.segment_rooms(pts, orders, resolution=0.1, seed=11, **kw)
+        assert engine.profile()['persistent'] and engine.profile()['items']['gproj'] == 0
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+        assert sa['grow_steps'].tolist() == sb['grow_steps'].tolist()
