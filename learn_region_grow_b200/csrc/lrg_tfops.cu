@@ -10,8 +10,8 @@ namespace lrg {
 // ------------------------------------------------------------------------------------- farthest point sampling
 // Reference: farthestpointsamplingKernel (tf_sampling_g.cu:105-170), <<<32,512>>>, min-distances in a global
 // (32,n) workspace, 512-wide shared-memory tree argmax with 9 barriers per round.
-// Here: one CTA per cloud, points and running min-distances in registers (PPT per thread), argmax by 64-bit
-// shuffle reduction + one barrier per round.  The reference's tie rule -- smallest (k mod 512), then smallest k --
+// Here: one CTA per cloud, points and running min-distances in registers (PPT per thread), argmax by redux.sync
+// reductions (fps_block_argmax) + one barrier per round.  The reference's tie rule -- smallest (k mod 512), then smallest k --
 // is encoded in the low word of the key.
 constexpr int kFpsThreads = 512;
 
@@ -20,15 +20,36 @@ __device__ __forceinline__ unsigned long long fps_key(float d, int k) {
   return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(0x7FFFFFFFu - tie);
 }
 
-template <int PPT>
-__global__ void __launch_bounds__(kFpsThreads) lrg_fps_kernel(int n, int m, const float* __restrict__ dataset, int* __restrict__ idxs) {
-  __shared__ unsigned long long sred[2][kFpsThreads / 32];
+// CTA-wide argmax of the 64-bit keys (distance bits ‖ tie word) as two 32-bit maxima per stage -- redux.sync on the
+// distance bits (non-negative floats order like unsigned integers), then on the tie words of the lanes that hold the maximum
+// -- instead of a 64-bit shuffle butterfly: 2 + 2 warp reductions and one barrier per round.  Returns the winning index.
+template <int NT>
+__device__ __forceinline__ int fps_block_argmax(float best, int besti, uint2 (*sred)[NT / 32], int j, int lane, int warp) {
+  // a thread without points keeps (-1, 0) like the reference; it must lose against every real candidate: key 0
+  const unsigned long long key = best < 0.f ? 0ull : fps_key(best, besti);
+  const unsigned d = (unsigned)(key >> 32), t = (unsigned)key;
+  const unsigned dmax = __reduce_max_sync(0xffffffffu, d);
+  const unsigned tmax = __reduce_max_sync(0xffffffffu, d == dmax ? t : 0u);
+  if (lane == 0) sred[j & 1][warp] = make_uint2(dmax, tmax);
+  __syncthreads();
+  const uint2 w = lane < NT / 32 ? sred[j & 1][lane] : make_uint2(0u, 0u);
+  const unsigned d2 = __reduce_max_sync(0xffffffffu, w.x);
+  const unsigned t2 = __reduce_max_sync(0xffffffffu, w.x == d2 ? w.y : 0u);
+  if (d2 == 0u && t2 == 0u) return 0;
+  const unsigned tie = 0x7FFFFFFFu - t2;
+  return (int)(((tie & 0x3FFFFFu) << 9) | (tie >> 22));
+}
+
+// NT threads x PPT points per thread >= n.
+template <int NT, int PPT>      // NT in {128, 256, 512}
+__global__ void __launch_bounds__(NT) lrg_fps_kernel(int n, int m, const float* __restrict__ dataset, int* __restrict__ idxs) {
+  __shared__ uint2 sred[2][NT / 32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* pts = dataset + (size_t)b * n * 3;
   float px[PPT], py[PPT], pz[PPT], td[PPT];
 #pragma unroll
   for (int q = 0; q < PPT; ++q) {
-    const int k = tid + q * kFpsThreads;
+    const int k = tid + q * NT;
     px[q] = py[q] = pz[q] = 0.f;
     if (k < n) { px[q] = pts[k * 3 + 0]; py[q] = pts[k * 3 + 1]; pz[q] = pts[k * 3 + 2]; }
     td[q] = 1e38f;
@@ -39,35 +60,23 @@ __global__ void __launch_bounds__(kFpsThreads) lrg_fps_kernel(int n, int m, cons
     const float x1 = pts[old * 3 + 0], y1 = pts[old * 3 + 1], z1 = pts[old * 3 + 2];
     float best = -1.f;
     int besti = 0;
+    // a thread's own points are visited in the order of the tie rule -- (k mod 512, k) ascending -- so that the first of
+    // equal distances is the one the reference keeps: with NT < 512 that is q = r, r + 512/NT, ... for r = 0 .. 512/NT - 1
+    constexpr int R = 512 / NT;
 #pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-      const int k = tid + q * kFpsThreads;
-      if (k < n) {
-        const float x2 = px[q], y2 = py[q], z2 = pz[q];
-        const float d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1);
-        const float d2 = min(d, td[q]);
-        td[q] = d2;
-        if (d2 > best) { best = d2; besti = k; }
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int q = r; q < PPT; q += R) {
+        const int k = tid + q * NT;
+        if (k < n) {
+          const float x2 = px[q], y2 = py[q], z2 = pz[q];
+          const float d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1);
+          const float d2 = min(d, td[q]);
+          td[q] = d2;
+          if (d2 > best) { best = d2; besti = k; }
+        }
       }
-    }
-    // a thread without points keeps (-1, 0) like the reference; -1 has the largest bit pattern, so map it to key 0
-    unsigned long long key = best < 0.f ? 0ull : fps_key(best, besti);
-#pragma unroll
-    for (int dlt = 16; dlt > 0; dlt >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, dlt);
-      key = o > key ? o : key;
-    }
-    if (lane == 0) sred[j & 1][warp] = key;
-    __syncthreads();
-    unsigned long long k2 = lane < kFpsThreads / 32 ? sred[j & 1][lane] : 0ull;
-#pragma unroll
-    for (int dlt = 8; dlt > 0; dlt >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(0xffffffffu, k2, dlt);
-      k2 = o > k2 ? o : k2;
-    }
-    k2 = __shfl_sync(0xffffffffu, k2, 0);
-    const unsigned tie = 0x7FFFFFFFu - (unsigned)(k2 & 0xFFFFFFFFull);
-    old = k2 == 0ull ? 0 : (int)(((tie & 0x3FFFFFu) << 9) | (tie >> 22));
+    old = fps_block_argmax<NT>(best, besti, sred, j, lane, warp);
     if (tid == 0) idxs[(size_t)b * m + j] = old;
   }
 }
@@ -75,7 +84,7 @@ __global__ void __launch_bounds__(kFpsThreads) lrg_fps_kernel(int n, int m, cons
 // Large clouds: min-distances in the caller's workspace (same layout as the reference: one row per CTA).
 __global__ void __launch_bounds__(kFpsThreads) lrg_fps_big_kernel(int b_total, int n, int m, const float* __restrict__ dataset,
                                                                 float* __restrict__ temp, int* __restrict__ idxs) {
-  __shared__ unsigned long long sred[2][kFpsThreads / 32];
+  __shared__ uint2 sred[2][kFpsThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int b = blockIdx.x; b < b_total; b += gridDim.x) {
     const float* pts = dataset + (size_t)b * n * 3;
@@ -95,26 +104,114 @@ __global__ void __launch_bounds__(kFpsThreads) lrg_fps_big_kernel(int b_total, i
         td[k] = d2;
         if (d2 > best) { best = d2; besti = k; }
       }
-      unsigned long long key = best < 0.f ? 0ull : fps_key(best, besti);
-#pragma unroll
-      for (int dlt = 16; dlt > 0; dlt >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, dlt);
-        key = o > key ? o : key;
-      }
-      if (lane == 0) sred[j & 1][warp] = key;
-      __syncthreads();
-      unsigned long long k2 = lane < kFpsThreads / 32 ? sred[j & 1][lane] : 0ull;
-#pragma unroll
-      for (int dlt = 8; dlt > 0; dlt >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, k2, dlt);
-        k2 = o > k2 ? o : k2;
-      }
-      k2 = __shfl_sync(0xffffffffu, k2, 0);
-      const unsigned tie = 0x7FFFFFFFu - (unsigned)(k2 & 0xFFFFFFFFull);
-      old = k2 == 0ull ? 0 : (int)(((tie & 0x3FFFFFu) << 9) | (tie >> 22));
+      old = fps_block_argmax<kFpsThreads>(best, besti, sred, j, lane, warp);
       if (tid == 0) idxs[(size_t)b * m + j] = old;
     }
     __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------- prob_sample
+// Reference: cumsumKernel + binarysearchKernel (tf_sampling_g.cu:7-104): an inclusive float32 cumulative sum of every row of
+// probabilities, then for every query r in [0,1) the first category whose cumulative sum reaches r * total.  The indices
+// depend on how the cumulative sums round, so the sums are formed in the reference's association:
+//   * chunks of 8192 categories; a chunk = groups of four with the in-group prefixes v1, v1+v2, (v1+v2)+v3, (v3+v4)+(v1+v2)
+//     (a trailing short group: plain running sums);
+//   * the inclusive prefix P(x) of the first x group totals follows the reference's in-place sweep: with x = 2^b1 + 2^b2 + ...
+//     (b1 > b2 > ...) it is ((S(0, 2^b1) + S(2^b1, 2^b1 + 2^b2)) + ...) where S(a, a + 2^b) is the balanced pairwise sum of
+//     that aligned block -- so one up-sweep leaves every block sum a prefix needs in place (the blocks a prefix uses start
+//     at even multiples of their size and are never overwritten by a higher level), and each thread assembles its prefix
+//     from at most 11 of them instead of a second (down-)sweep with a barrier per level;
+//   * element = (in-group prefix + P(groups before it)) + carry, the carry updated across chunks by the reference's
+//     compensated sum (tf_sampling_g.cu:96-99).
+// One CTA per row; the reference runs 32 CTAs x 512 threads over all rows.
+constexpr int kProbThreads = 1024, kProbChunk = 8192;
+
+__device__ __forceinline__ float prob_prefix(const float* T, int x) {      // inclusive prefix of the first x (>= 1) group totals
+  float P = 0.f;
+  int pos = 0;
+  bool first = true;
+  for (int b = 31 - __clz(x); b >= 0; --b)
+    if ((x >> b) & 1) {
+      const float S = T[pos + (1 << b) - 1];
+      P = first ? S : __fadd_rn(S, P);
+      first = false;
+      pos += 1 << b;
+    }
+  return P;
+}
+
+__global__ void __launch_bounds__(kProbThreads) lrg_prob_cumsum_kernel(int n, const float* __restrict__ inp, float* __restrict__ out) {
+  __shared__ float G[kProbChunk];            // in-group inclusive prefixes
+  __shared__ float T[kProbChunk / 4];        // group totals -> pairwise block sums
+  const int tid = threadIdx.x;
+  const float* row = inp + (size_t)blockIdx.x * n;
+  float* orow = out + (size_t)blockIdx.x * n;
+  float carry = 0.f, comp = 0.f;
+  for (int j = 0; j < n; j += kProbChunk) {
+    const int len = min(n - j, kProbChunk), groups = (len + 3) >> 2;
+    for (int g = tid; g < groups; g += kProbThreads) {
+      const int k = g * 4;
+      float a, b2, c, d;
+      if (k + 3 < len) {
+        const float v1 = row[j + k], v2 = row[j + k + 1], v3 = row[j + k + 2], v4 = row[j + k + 3];
+        a = v1;
+        b2 = __fadd_rn(v2, v1);
+        c = __fadd_rn(v3, b2);
+        d = __fadd_rn(__fadd_rn(v4, v3), b2);
+      } else {
+        float v = 0.f;
+        float t[4];
+        for (int q = 0; q < 4; ++q) {
+          if (k + q < len) v = __fadd_rn(v, row[j + k + q]);
+          t[q] = v;
+        }
+        a = t[0]; b2 = t[1]; c = t[2]; d = t[3];
+      }
+      G[k] = a; G[k + 1] = b2; G[k + 2] = c; G[k + 3] = d;
+      T[g] = d;
+    }
+    for (int u = 0; (2 << u) <= groups; ++u) {       // up-sweep: T[(k+1) * 2^(u+1) - 1] = balanced sum of that aligned block
+      __syncthreads();
+      for (int k = tid; k < (groups >> (u + 1)); k += kProbThreads) {
+        const int hi = (((k << 1) + 2) << u) - 1, lo = (((k << 1) + 1) << u) - 1;
+        T[hi] = __fadd_rn(T[hi], T[lo]);
+      }
+    }
+    __syncthreads();
+    for (int g = tid; g < groups; g += kProbThreads) {
+      const int k = g * 4;
+      const float before = g > 0 ? prob_prefix(T, g) : 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (k + q < len) {
+          const float v = g > 0 ? __fadd_rn(G[k + q], before) : G[k + q];
+          orow[j + k + q] = __fadd_rn(v, carry);
+        }
+    }
+    // carry across chunks, compensated like the reference (every thread keeps its own copy)
+    const float t = __fadd_rn(prob_prefix(T, groups), comp);
+    const float r2 = __fadd_rn(carry, t);
+    comp = __fsub_rn(t, __fsub_rn(r2, carry));
+    carry = r2;
+    __syncthreads();
+  }
+}
+
+// result = n-1 walked down by descending powers of two while the cumulative sum k places below still reaches the query
+// (tf_sampling_g.cu:91-103) -- the first category whose cumulative sum is >= r * total when the sums are monotone.
+__global__ void lrg_prob_search_kernel(int b, int n, int m, const float* __restrict__ cum, const float* __restrict__ query, int* __restrict__ result) {
+  int base = 1;
+  while (base < n) base <<= 1;
+  const long long total = (long long)b * m;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / m;
+    const float* c = cum + i * n;
+    const float q = __fmul_rn(query[t], c[n - 1]);
+    int r = n - 1;
+    for (int k = base; k >= 1; k >>= 1)
+      if (r >= k && c[r - k] >= q) r -= k;
+    result[t] = r;
   }
 }
 
@@ -334,11 +431,12 @@ int lrg_farthest_point_sampling(int b, int n, int m, const float* d_inp, float* 
   if (b == 0 || m == 0) return LRG_OK;
   LRG_REQUIRE(d_inp && d_out, "NULL tensor pointer");
   cudaStream_t st = (cudaStream_t)s;
-  if (n <= kFpsThreads * 1) lrg_fps_kernel<1><<<b, kFpsThreads, 0, st>>>(n, m, d_inp, d_out);
-  else if (n <= kFpsThreads * 2) lrg_fps_kernel<2><<<b, kFpsThreads, 0, st>>>(n, m, d_inp, d_out);
-  else if (n <= kFpsThreads * 4) lrg_fps_kernel<4><<<b, kFpsThreads, 0, st>>>(n, m, d_inp, d_out);
-  else if (n <= kFpsThreads * 8) lrg_fps_kernel<8><<<b, kFpsThreads, 0, st>>>(n, m, d_inp, d_out);
-  else if (n <= kFpsThreads * 16) lrg_fps_kernel<16><<<b, kFpsThreads, 0, st>>>(n, m, d_inp, d_out);
+  // (fewer, fatter threads were measured slower: 1024 points as 128 threads x 8 take 466 us for 1024 samples, 512 x 2 take 265 us)
+  if (n <= 512 * 1) lrg_fps_kernel<512, 1><<<b, 512, 0, st>>>(n, m, d_inp, d_out);
+  else if (n <= 512 * 2) lrg_fps_kernel<512, 2><<<b, 512, 0, st>>>(n, m, d_inp, d_out);
+  else if (n <= 512 * 4) lrg_fps_kernel<512, 4><<<b, 512, 0, st>>>(n, m, d_inp, d_out);
+  else if (n <= 512 * 8) lrg_fps_kernel<512, 8><<<b, 512, 0, st>>>(n, m, d_inp, d_out);
+  else if (n <= 512 * 16) lrg_fps_kernel<512, 16><<<b, 512, 0, st>>>(n, m, d_inp, d_out);
   else {
     LRG_REQUIRE(d_temp != nullptr, "FarthestPointSample with n=%d > %d needs the (32,n) temp workspace", n, kFpsThreads * 16);
     lrg_fps_big_kernel<<<b < 32 ? b : 32, kFpsThreads, 0, st>>>(b, n, m, d_inp, d_temp, d_out);
@@ -364,9 +462,14 @@ int lrg_scatter_add_point(int b, int n, int m, const float* d_out_g, const int* 
 }
 
 int lrg_prob_sample(int b, int n, int m, const float* d_inp_p, const float* d_inp_r, float* d_temp, int* d_out, lrg_stream_t s) {
-  (void)b; (void)n; (void)m; (void)d_inp_p; (void)d_inp_r; (void)d_temp; (void)d_out; (void)s;
-  set_error("ProbSample is not implemented in this build (SURVEY.md 8 a23: unused by every shipped model)");
-  return LRG_E_STATE;
+  LRG_REQUIRE(b >= 0 && n > 0 && m >= 0, "ProbSample: bad shape (b %d, n %d, m %d)", b, n, m);
+  if (b == 0) return LRG_OK;
+  LRG_REQUIRE(d_inp_p != nullptr && d_temp != nullptr && (d_out != nullptr || m == 0) && (d_inp_r != nullptr || m == 0), "ProbSample: NULL argument (temp is a (b,n) workspace)");
+  cudaStream_t st = (cudaStream_t)s;
+  lrg_prob_cumsum_kernel<<<b, kProbThreads, 0, st>>>(n, d_inp_p, d_temp);
+  if (m > 0) lrg_prob_search_kernel<<<grid_for((long long)b * m, 256), 256, 0, st>>>(b, n, m, d_temp, d_inp_r, d_out);
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
 }
 
 int lrg_query_ball_point(int b, int n, int m, float radius, int nsample, const float* d_xyz1, const float* d_xyz2, int* d_idx,

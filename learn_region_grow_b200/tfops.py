@@ -136,8 +136,20 @@ def gather_point_grad(inp, idx, out_g):
 
 
 def prob_sample(inp, inpr):
-    """tf_sampling.py:13-21 (unused by every shipped model; not implemented in this build)."""
-    _lib.check(_lib.lib().lrg_prob_sample(0, 0, 0, None, None, None, None, None))
+    """tf_sampling.py:13-21: inp (B, ncategory) float32 probabilities (any positive scale), inpr (B, npoints) float32 uniforms in
+    [0,1) -> (B, npoints) int32: for every uniform the first category whose float32 cumulative sum reaches uniform * total
+    (cumulative sums in the reference's association, so the indices agree with its kernel)."""
+    _require(len(_shape(inp)) == 2, 'ProbSample expects (batch_size,num_choices) inp shape')                  # tf_sampling.cpp:76
+    b, n = _shape(inp)
+    _require(len(_shape(inpr)) == 2 and _shape(inpr)[0] == b, 'ProbSample expects (batch_size,num_points) inpr shape')   # :79
+    _require(n > 0, 'ProbSample expects at least one choice')
+    m = _shape(inpr)[1]
+    c = _Call(inp, inpr)
+    d_p, d_r = c.inp(inp, np.float32), c.inp(inpr, np.float32)
+    d_tmp = c.out((b, n), np.float32)
+    d_out = c.out((b, m), np.int32)
+    _lib.check(_lib.lib().lrg_prob_sample(b, n, m, d_p, d_r, d_tmp, d_out, c.stream()))
+    return c.finish()[1]
 
 
 # ----------------------------------------------------------------------------- tf_grouping.py

@@ -119,6 +119,85 @@ def three_interpolate_grad(points, idx, weight, grad_out):
     return g
 
 
+def prob_cumsum(inp):
+    """The float32 cumulative sums of /root/reference/tf_ops/sampling/tf_sampling_g.cu:7-89 (cumsumKernel), restated per
+    row in numpy float32 scalars with the kernel's association: chunks of 8192 (BlockSize*4, :8,14); inside a chunk groups of
+    four with the prefixes v1, v1+v2, (v1+v2)+v3, (v3+v4)+(v1+v2) (:20-33; a short last group: running sums :35-43); an
+    in-place up-sweep / down-sweep over the group totals (:46-67); element = (group prefix + totals before the group) +
+    running sum (:69-81); compensated running sum across chunks (:82-85)."""
+    inp = _f(inp)
+    f = np.float32
+    b, n = inp.shape
+    out = np.zeros((b, n), np.float32)
+    for i in range(b):
+        running, running2 = f(0), f(0)
+        for j in range(0, n, 8192):
+            ln = min(n - j, 8192)
+            n2 = (ln + 3) // 4
+            buf4 = np.zeros(n2 * 4, np.float32)
+            tot = np.zeros(n2, np.float32)
+            for g in range(n2):
+                k = 4 * g
+                if k + 3 < ln:
+                    v1, v2, v3, v4 = (f(x) for x in inp[i, j + k:j + k + 4])
+                    v2 = f(v2 + v1)
+                    v4 = f(v4 + v3)
+                    v3 = f(v3 + v2)
+                    v4 = f(v4 + v2)
+                    buf4[k:k + 4] = (v1, v2, v3, v4)
+                    tot[g] = v4
+                else:
+                    v = f(0)
+                    for k2 in range(k, ln):
+                        v = f(v + inp[i, j + k2])
+                        buf4[k2] = v
+                    buf4[ln:n2 * 4] = v
+                    tot[g] = v
+            u = 0
+            while (2 << u) <= n2:                                   # up-sweep (:46-55)
+                for k in range(n2 >> (u + 1)):
+                    i1, i2 = (((k << 1) + 2) << u) - 1, (((k << 1) + 1) << u) - 1
+                    tot[i1] = f(tot[i1] + tot[i2])
+                u += 1
+            u -= 1
+            while u >= 0:                                           # down-sweep (:56-66)
+                for k in range((n2 - (1 << u)) >> (u + 1)):
+                    i1, i2 = (((k << 1) + 3) << u) - 1, (((k << 1) + 2) << u) - 1
+                    tot[i1] = f(tot[i1] + tot[i2])
+                u -= 1
+            for g in range(1, n2):                                  # :68-76
+                buf4[4 * g:4 * g + 4] = (buf4[4 * g:4 * g + 4] + tot[g - 1]).astype(np.float32)
+            out[i, j:j + ln] = (buf4[:ln] + running).astype(np.float32)      # :78-80
+            t = f(tot[n2 - 1] + running2)                           # :82-85
+            r2 = f(running + t)
+            running2 = f(t - f(r2 - running))
+            running = r2
+    return out
+
+
+def prob_sample(inp, inpr):
+    """tf_sampling.py:13-21 -> probsampleLauncher (tf_sampling_g.cu:198-201): cumsumKernel, then binarysearchKernel (:91-104)."""
+    inp, inpr = _f(inp), _f(inpr)
+    b, n = inp.shape
+    m = inpr.shape[1]
+    cum = prob_cumsum(inp)
+    base = 1
+    while base < n:
+        base <<= 1
+    out = np.zeros((b, m), np.int32)
+    for i in range(b):
+        for j in range(m):
+            q = np.float32(inpr[i, j] * cum[i, n - 1])
+            r = n - 1
+            k = base
+            while k >= 1:
+                if r >= k and cum[i, r - k] >= q:
+                    r -= k
+                k >>= 1
+            out[i, j] = r
+    return out
+
+
 # ----------------------------------------------------------------------------- the reference's own kernels (GPU box)
 class ReferenceKernels:
     """The unmodified reference launchers from oracle/_ref (device pointers in, legacy default stream)."""
@@ -131,13 +210,15 @@ class ReferenceKernels:
         self.query_ball = self.grouping._Z22queryBallPointLauncheriiifiPKfS0_PiS1_
         self.group = self.grouping._Z18groupPointLauncheriiiiiPKfPKiPf
         self.selection_sort = self.grouping._Z21selectionSortLauncheriiiiPKfPiPf
-        for fn in (self.fps, self.gather, self.query_ball, self.group, self.selection_sort):
+        self.prob_sample = self.sampling._Z18probsampleLauncheriiiPKfS0_PfPi
+        for fn in (self.fps, self.gather, self.query_ball, self.group, self.selection_sort, self.prob_sample):
             fn.restype = None
         self.fps.argtypes = [C.c_int] * 3 + [C.c_void_p] * 3
         self.gather.argtypes = [C.c_int] * 3 + [C.c_void_p] * 3
         self.query_ball.argtypes = [C.c_int] * 3 + [C.c_float, C.c_int] + [C.c_void_p] * 4
         self.group.argtypes = [C.c_int] * 5 + [C.c_void_p] * 3
         self.selection_sort.argtypes = [C.c_int] * 4 + [C.c_void_p] * 3
+        self.prob_sample.argtypes = [C.c_int] * 3 + [C.c_void_p] * 4
 
     @staticmethod
     def available():

@@ -133,6 +133,31 @@ def test_oracle_tfops_known_answer():
     assert np.all(bi[:, :, 0] <= np.arange(30)) and cnt.max() <= 8 and cnt.min() >= 1
 
 
+def test_oracle_prob_sample_properties():
+    """oracle.tfops.prob_sample (restatement of cumsumKernel + binarysearchKernel, tf_sampling_g.cu:7-104): the float32
+    cumulative sums are monotone and within float32 rounding of the exact sums; an index is the first category whose
+    cumulative sum reaches uniform * total; one-hot rows return the hot category; multi-chunk rows (> 8192) carry over."""
+    from oracle import tfops
+    rng = np.random.RandomState(3)
+    for n in (1, 5, 64, 1000, 8193, 20000):
+        p = rng.rand(2, n).astype(np.float32)
+        c = tfops.prob_cumsum(p)
+        exact = np.cumsum(p.astype(np.float64), axis=1)
+        assert np.all(np.diff(c, axis=1) >= 0) and np.abs(c - exact).max() <= 1e-6 * exact.max()
+    p = rng.rand(3, 777).astype(np.float32)
+    r = rng.rand(3, 200).astype(np.float32)
+    idx = tfops.prob_sample(p, r)
+    c = tfops.prob_cumsum(p)
+    assert idx.dtype == np.int32 and idx.shape == (3, 200)
+    for i in range(3):
+        np.testing.assert_array_equal(idx[i], np.searchsorted(c[i], (r[i] * c[i, -1]).astype(np.float32), side='left'))
+    hot = np.zeros((1, 100), np.float32)
+    hot[0, 37] = 2.5
+    assert set(tfops.prob_sample(hot, r[:1])[0].tolist()) == {37}
+    freq = np.bincount(tfops.prob_sample(np.array([[1, 3]], np.float32), rng.rand(1, 4000).astype(np.float32))[0], minlength=2) / 4000.0
+    assert abs(freq[1] - 0.75) < 0.03
+
+
 def test_numpy_row_sum_order_assumption():
     """The fill kernel restates numpy's float32 row sum (pairwise: 8 accumulators then a sequential tail)."""
     rng = np.random.RandomState(0)

@@ -90,6 +90,34 @@ def test_three_nn_and_interpolate(b, n, m, c):
     np.testing.assert_allclose(T.three_interpolate_grad(pts, idx, w, go), O.three_interpolate_grad(pts, idx, w, go), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize('b,n,m', [(1, 1, 5), (2, 3, 16), (3, 64, 100), (2, 1000, 513), (2, 8192, 300), (1, 8193, 300), (2, 20001, 1000)])
+def test_prob_sample(b, n, m):
+    """prob_sample: index-exact against the restated cumsum / binary search and, where oracle/_ref is built, against the
+    reference's own probsampleLauncher on the same device buffers (the float32 cumulative sums bit for bit)."""
+    import torch
+    from learn_region_grow_b200 import tfops as T, _lib
+    rng = np.random.RandomState(100 + n)
+    p = (rng.rand(b, n) * rng.choice([1e-3, 1.0, 50.0], size=(b, n))).astype(np.float32)
+    r = rng.rand(b, m).astype(np.float32)
+    r[:, 0] = 0.0
+    got = T.prob_sample(p, r)
+    assert got.dtype == np.int32 and got.shape == (b, m)
+    np.testing.assert_array_equal(got, O.prob_sample(p, r))
+    tp, tr = torch.from_numpy(p).cuda(), torch.from_numpy(r).cuda()
+    tmp, out = torch.zeros(b, n, device='cuda'), torch.zeros(b, m, dtype=torch.int32, device='cuda')
+    _lib.check(_lib.lib().lrg_prob_sample(b, n, m, C.c_void_p(tp.data_ptr()), C.c_void_p(tr.data_ptr()), C.c_void_p(tmp.data_ptr()),
+                                          C.c_void_p(out.data_ptr()), None))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(tmp.cpu().numpy(), O.prob_cumsum(p))          # the cumulative sums themselves, bit for bit
+    assert torch.equal(T.prob_sample(tp, tr), out)
+    if O.ReferenceKernels.available():
+        R = O.ReferenceKernels()
+        tmp2, out2 = torch.zeros(b, n, device='cuda'), torch.zeros(b, m, dtype=torch.int32, device='cuda')
+        R.prob_sample(b, n, m, C.c_void_p(tp.data_ptr()), C.c_void_p(tr.data_ptr()), C.c_void_p(tmp2.data_ptr()), C.c_void_p(out2.data_ptr()))
+        torch.cuda.synchronize()
+        assert torch.equal(tmp2, tmp) and torch.equal(out2, out)
+
+
 def test_op_argument_errors():
     from learn_region_grow_b200 import tfops as T
     x = _clouds(1, 16, 0)
@@ -99,6 +127,8 @@ def test_op_argument_errors():
         T.query_ball_point(0.1, 0, x, x)
     with pytest.raises(ValueError, match='FarthestPointSample expects'):
         T.farthest_point_sample(4, x[..., :2])
+    with pytest.raises(ValueError, match='ProbSample expects'):
+        T.prob_sample(np.zeros((2, 4), np.float32), np.zeros((3, 5), np.float32))
     with pytest.raises(ValueError, match='positive k'):
         T.select_top_k(0, np.zeros((1, 2, 3), np.float32))
 
