@@ -79,6 +79,17 @@ def test_tfops_beside_reference_kernels():
             assert torch.equal(g_new, g_ref)
             lines.append('%-22s %5d %5d %5d %4d | %10.1f %10.1f %7.2f | %9.2f' % ('group_point', B, n, m, c, t_new, t_ref, t_ref / t_new,
                                                                                    B * m * NSAMPLE * (4 + 8 * c) / t_new / 1e3))
+        for (n, m) in [(1024, 1024), (20000, 4096)]:                      # prob_sample: n categories, m draws per row
+            pr = torch.from_numpy(rng.rand(B, n).astype(np.float32)).cuda()
+            un = torch.from_numpy(rng.rand(B, m).astype(np.float32)).cuda()
+            tmp_new, tmp_ref = torch.zeros(B, n, device='cuda'), torch.zeros(B, n, device='cuda')
+            s_new = torch.zeros(B, m, dtype=torch.int32, device='cuda')
+            s_ref = torch.zeros_like(s_new)
+            t_new = _time(torch, lambda: _lib.check(L.lrg_prob_sample(B, n, m, p(pr), p(un), p(tmp_new), p(s_new), None)))
+            t_ref = _time(torch, lambda: R.prob_sample(B, n, m, p(pr), p(un), p(tmp_ref), p(s_ref)))
+            assert torch.equal(tmp_new, tmp_ref) and torch.equal(s_new, s_ref)
+            lines.append('%-22s %5d %5d %5d %4s | %10.1f %10.1f %7.2f | %9.2f' % ('prob_sample', B, n, m, '-', t_new, t_ref, t_ref / t_new,
+                                                                                   B * (n * 8 + m * 8) / t_new / 1e3))
         # feature propagation: three_nn(xyz1 (n), xyz2 (m)) + three_interpolate -- CPU ops in the reference
         for (n, m, c) in [(64, 16, 512), (256, 64, 256), (1024, 256, 256), (1024, 1024, 128)]:
             x1 = rng.rand(B, n, 3).astype(np.float32)
