@@ -200,17 +200,10 @@ __device__ __forceinline__ int pw_z(unsigned w) { return (int)((w >> 20) & 1023u
 // (Plain loads on purpose: the words are rewritten by this CTA between scans and by other CTAs between steps; the
 // CTA barrier orders the former, the acquire fence at the start of a work item drops stale L1 lines for the latter.)
 constexpr int kScanU = 8;
-// Barrier over a group of warps of the CTA: bar 0 = the whole CTA, else a named barrier with `count` participating threads.
-__device__ __forceinline__ void part_sync(int bar, int count) {
-  if (bar == 0) __syncthreads();
-  else asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(count) : "memory");
-}
-// NT = participating threads (the CTA, or the warps from warp0 on, synchronising on named barrier `bar`).
 template <int NT, class Pred, class Visit>
-__device__ int scan_words(const unsigned* pw, int N, Pred pred, Visit visit, int* out, int* out_s, int cap_s, int* s_scan,
-                          int warp0 = 0, int bar = 0) {
+__device__ int scan_words(const unsigned* pw, int N, Pred pred, Visit visit, int* out, int* out_s, int cap_s, int* s_scan) {
   constexpr int U = kScanU;
-  const int tid = threadIdx.x - warp0 * 32, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n4 = (N + 3) >> 2;
   int running = 0;
   for (int c4 = 0; c4 < n4; c4 += NT * U) {
@@ -238,9 +231,9 @@ __device__ int scan_words(const unsigned* pw, int N, Pred pred, Visit visit, int
       wtotal += __shfl_sync(0xffffffffu, incl, 31);
     }
     if (lane == 0) s_scan[warp] = wtotal;
-    part_sync(bar, NT);
+    __syncthreads();
     scan_warp_totals<NT>(s_scan, warp, lane);
-    part_sync(bar, NT);
+    __syncthreads();
     const int wbase = running + s_scan[warp];
     if (flags) {
 #pragma unroll
@@ -257,7 +250,7 @@ __device__ int scan_words(const unsigned* pw, int N, Pred pred, Visit visit, int
       }
     }
     running += s_scan[32];
-    part_sync(bar, NT);
+    __syncthreads();
   }
   return running;
 }
@@ -279,7 +272,6 @@ struct StepShared {
   int n_odd;
   int red[32 * 6];
   int flag;
-  int nnb;                      // neighbour count handed from the scanning warps to the rest of the CTA
   int all_done;                 // set when this call retired the last slot of the run
   unsigned wake;                // random restarts / beam search: lanes of this group (bit l) this call handed work to (they need a STEP)
   LaneGroup G;                  // random restarts: the group's room-level state while this CTA owns it
@@ -1244,75 +1236,6 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
   }
 
   stamp(3);
-  // median of every centred channel over ALL current points (:241): channels 0,1 and 6..F-1
-  const int nch = 2 + (da.F > 6 ? da.F - 6 : 0);
-  auto row_keys = [&](int j, unsigned (&k)[9]) {
-    const float* row = pts + (size_t)(j < kListCap ? sh.listI_s[j] : listI[j]) * 16;
-    const float4 a = *reinterpret_cast<const float4*>(row);
-    const float4 b = *reinterpret_cast<const float4*>(row + 4);
-    const float4 c = *reinterpret_cast<const float4*>(row + 8);
-    const float4 d = *reinterpret_cast<const float4*>(row + 12);
-    const float vals[9] = {a.x, a.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x};
-#pragma unroll
-    for (int s = 0; s < 9; ++s) k[s] = sortable(vals[s]);
-  };
-  // Median keys of a region of up to kMedianCap points (sh.prefix / sh.nextkey per channel) by the `nthr` threads that call
-  // this together (t = index among them, whole warps, synchronising on barrier `bar`): one warp per channel.
-  auto median_upto_cap = [&](int n_in, int t, int nthr, int bar) {
-    const int wl = t >> 5, nw = nthr >> 5;
-    if (n_in <= kMedianSmall) {
-      for (int j = t; j < n_in; j += nthr) {
-        unsigned k[9];
-        row_keys(j, k);
-#pragma unroll
-        for (int s = 0; s < 9; ++s) sh.mkeys[s][j] = k[s];
-      }
-      part_sync(bar, nthr);
-      // one warp per channel: ballots transpose the keys into bit planes, then a bit-sliced rank select
-      for (int c = wl; c < nch; c += nw) {
-        unsigned lo, hi;
-        warp_median<1>(sh.mkeys[c], n_in, lo, hi);
-        if (lane == 0) { sh.prefix[c] = lo; sh.nextkey[c] = hi; }
-      }
-      part_sync(bar, nthr);
-    } else {
-      // every thread loads the row of one inlier; each warp turns the 32 keys of a channel into 32 bit-plane words with a
-      // five-step shuffle transpose (no per-key work in the select below)
-      const int nslots = (n_in + 31) >> 5;
-      for (int j0 = 0; j0 < nslots * 32; j0 += nthr) {
-        const int j = j0 + t, sl = j >> 5;                    // sl is warp-uniform
-        if (sl < nslots) {
-          unsigned k[9];
-          if (j < n_in) row_keys(j, k);
-          else {
-#pragma unroll
-            for (int c = 0; c < 9; ++c) k[c] = 0u;
-          }
-          const unsigned av = __ballot_sync(0xffffffffu, j < n_in);
-          if (lane == 0) sh.malive[sl] = av;
-#pragma unroll
-          for (int c = 0; c < 9; ++c)
-            if (c < nch) sh.planes[c][lane * kPlaneStride + sl] = warp_transpose32(k[c], lane);
-        }
-      }
-      part_sync(bar, nthr);
-      // one warp per channel, no atomics and no block barriers (measured per step, sets of 257-512 / 513-1024 / 1025-2048
-      // points: 11k / 15k / 23k cycles; ballot transposition by the channel's own warp 18k / 31k / 55k; a histogram select
-      // with shared-memory atomics 2x, a CTA-wide bitonic sort 3-4x slower than that)
-      for (int c = wl; c < nch; c += nw) {
-        unsigned lo, hi;
-        if (n_in <= 1024) warp_median_planes<1>(sh.planes[c], sh.malive, n_in, lo, hi);
-        else warp_median_planes<2>(sh.planes[c], sh.malive, n_in, lo, hi);
-        if (lane == 0) { sh.prefix[c] = lo; sh.nextkey[c] = hi; }
-      }
-      part_sync(bar, nthr);
-    }
-  };
-  // The median of the region and the scan for its neighbour shell are independent until the gather: while the region is small
-  // enough for the warp-per-channel median, warps 0-8 take the median and the other warps the scan.
-  constexpr int kMedianWarps = 9;
-  static_assert(NT / 32 > kMedianWarps, "the scan needs warps of its own");
-  bool median_done = false;
   // ------------------------------------------------------------------ find the next region that needs a forward
   while (true) {
     if (mode == MODE_NEW_REGION && beam) {
@@ -1378,25 +1301,11 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     // neighbour shell: bbox +- 1 voxel, not current, not visited (:222-229)
     const int lo0 = S.minD[0] - 1, lo1 = S.minD[1] - 1, lo2 = S.minD[2] - 1;
     const int hi0 = S.maxD[0] + 1, hi1 = S.maxD[1] + 1, hi2 = S.maxD[2] + 1;
-    auto in_shell = [&](unsigned w) {
+    const int n_nb = scan_words<NT>(pw, N, [&](unsigned w) {
       if (w & (PW_CUR | PW_VIS)) return false;
       const int x = pw_x(w), y = pw_y(w), z = pw_z(w);
       return x >= lo0 && x <= hi0 && y >= lo1 && y <= hi1 && z >= lo2 && z <= hi2;
-    };
-    int n_nb;
-    median_done = S.n_in <= kMedianCap;
-    if (median_done) {
-      if (warp < kMedianWarps) {
-        median_upto_cap(S.n_in, tid, kMedianWarps * 32, 1);
-      } else {
-        const int cnt = scan_words<NT - kMedianWarps * 32>(pw, N, in_shell, [](unsigned) {}, listJ, sh.listJ_s, kListCap, sh.scan, kMedianWarps, 2);
-        if (tid == kMedianWarps * 32) sh.nnb = cnt;
-      }
-      __syncthreads();
-      n_nb = sh.nnb;
-    } else {
-      n_nb = scan_words<NT>(pw, N, in_shell, [](unsigned) {}, listJ, sh.listJ_s, kListCap, sh.scan);
-    }
+    }, [](unsigned) {}, listJ, sh.listJ_s, kListCap, sh.scan);
     if (n_nb == 0 && beam) {                                  // empty shell: the candidate is not expanded (:206)
       if (!beam_park(false, S.n_in)) return;
       mode = MODE_NEW_REGION;
@@ -1419,7 +1328,65 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     const int room_rng = da.room_id_base + S.room;
     const unsigned step_rng = (unsigned)S.steps;
     const unsigned rng_lane = ((unsigned)S.seed << 8) | lane_stream;
-    if (!median_done) {                                       // (regions above kMedianCap points: block-wide histogram select)
+    // median of every centred channel over ALL current points (:241): channels 0,1 and 6..F-1
+    const int nch = 2 + (da.F > 6 ? da.F - 6 : 0);
+    auto row_keys = [&](int j, unsigned (&k)[9]) {
+      const float* row = pts + (size_t)(j < kListCap ? sh.listI_s[j] : listI[j]) * 16;
+      const float4 a = *reinterpret_cast<const float4*>(row);
+      const float4 b = *reinterpret_cast<const float4*>(row + 4);
+      const float4 c = *reinterpret_cast<const float4*>(row + 8);
+      const float4 d = *reinterpret_cast<const float4*>(row + 12);
+      const float vals[9] = {a.x, a.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x};
+#pragma unroll
+      for (int s = 0; s < 9; ++s) k[s] = sortable(vals[s]);
+    };
+    if (n_in <= kMedianSmall) {
+      for (int j = tid; j < n_in; j += NT) {
+        unsigned k[9];
+        row_keys(j, k);
+#pragma unroll
+        for (int s = 0; s < 9; ++s) sh.mkeys[s][j] = k[s];
+      }
+      __syncthreads();
+      // one warp per channel: ballots transpose the keys into bit planes, then a bit-sliced rank select
+      for (int c = warp; c < nch; c += NT / 32) {
+        unsigned lo, hi;
+        warp_median<1>(sh.mkeys[c], n_in, lo, hi);
+        if (lane == 0) { sh.prefix[c] = lo; sh.nextkey[c] = hi; }
+      }
+      __syncthreads();
+    } else if (n_in <= kMedianCap) {
+      // every thread loads the row of one inlier; each warp turns the 32 keys of a channel into 32 bit-plane words with a
+      // five-step shuffle transpose (no per-key work in the select below)
+      const int nslots = (n_in + 31) >> 5;
+      for (int j0 = 0; j0 < nslots * 32; j0 += NT) {
+        const int j = j0 + tid, sl = j >> 5;                  // sl is warp-uniform
+        if (sl < nslots) {
+          unsigned k[9];
+          if (j < n_in) row_keys(j, k);
+          else {
+#pragma unroll
+            for (int c = 0; c < 9; ++c) k[c] = 0u;
+          }
+          const unsigned av = __ballot_sync(0xffffffffu, j < n_in);
+          if (lane == 0) sh.malive[sl] = av;
+#pragma unroll
+          for (int c = 0; c < 9; ++c)
+            if (c < nch) sh.planes[c][lane * kPlaneStride + sl] = warp_transpose32(k[c], lane);
+        }
+      }
+      __syncthreads();
+      // one warp per channel, no atomics and no block barriers (measured per step, sets of 257-512 / 513-1024 / 1025-2048
+      // points: 11k / 15k / 23k cycles; ballot transposition by the channel's own warp 18k / 31k / 55k; a histogram select
+      // with shared-memory atomics 2x, a CTA-wide bitonic sort 3-4x slower than that)
+      for (int c = warp; c < nch; c += NT / 32) {
+        unsigned lo, hi;
+        if (n_in <= 1024) warp_median_planes<1>(sh.planes[c], sh.malive, n_in, lo, hi);
+        else warp_median_planes<2>(sh.planes[c], sh.malive, n_in, lo, hi);
+        if (lane == 0) { sh.prefix[c] = lo; sh.nextkey[c] = hi; }
+      }
+      __syncthreads();
+    } else {
       __syncthreads();
       block_median9<NT>(n_in, nch, row_keys, sh.prefix, sh.rank, sh.hist, sh.nextkey);
     }
