@@ -169,8 +169,15 @@ int lrg_last_segment_profile(LrgEngine* e, float* grow_ms, float* fill_ms, int64
  * ran as one persistent launch, and per work-item type (step, branch tile, pooled-projection block, head tile) the summed
  * handler time over all CTAs in ms and the number of items handled. */
 int lrg_last_grow_profile(LrgEngine* e, int* persistent, double busy_ms[4], int64_t items[4]);
+/* (With the projection servers -- the default -- no projection items exist: items[2] = 0 and the servers' time is not counted.) */
 /* Summed time (ms) the items of each type waited in the device queue between publication and pick-up (same order). */
 int lrg_last_grow_queue_delay(LrgEngine* e, double delay_ms[4]);
+
+/* Environment switches read by lrg_segment_resident (A/B measurements; the defaults are the measured best, profiles/README.md):
+ *   LRG_GSERVERS=0   persistent kernel without the pooled-projection server CTAs (8 projection work items per grow step instead)
+ *   LRG_TUNE=bits    bit 0: split branch tiles over idle CTAs, bit 1: publish head tiles with the projection (default 3)
+ *   LRG_HI="s,c"     reserve c CTAs for the s slots with the most unvisited points (what LRG_FLAG_PRIORITY sets to 2,24)
+ * The results do not depend on any of them (tests/test_driver_gpu.py). */
 
 /* Diagnostics: with LRG_TILE_TIMING=1 in the environment at load_weights time the tensor tiles add the SM cycles of each
  * of their stages to counters (out[0..13] branch tile stages, out[15] branch tiles; out[16..23] head tile stages,

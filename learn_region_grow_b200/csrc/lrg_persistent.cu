@@ -4,12 +4,18 @@
 // iteration, so every iteration costs the slowest room's step plus four launch boundaries, and the run lasts as many
 // iterations as the longest room has steps.  Here each room slot instead walks its own dependency chain
 //
-//     STEP(slot) -> 8 x BRANCH(slot, branch, tile) -> 8 x GPROJ(slot, head, column block) -> 8 x HEAD(slot, head, tile) -> STEP(slot) ...
+//     STEP(slot) -> BRANCH(slot, branch, tile)... -> { pooled projection, HEAD(slot, head, tile)... } -> STEP(slot) ...
 //
 // through a device-side work queue: CTAs pop items, run the same device bodies the stand-alone kernels use
 // (lrg_step_body.cuh, lrg_tc_tiles.cuh) and the CTA that retires the last item of a stage publishes the next stage.
-// Items are only published when they are runnable, so a CTA never waits on another item (no deadlock by construction);
-// rooms progress independently (a slow step of one room no longer stalls the others) and nothing is launched per step.
+// Items are only published when they are runnable, so a CTA never waits on another item -- with one exception: head tiles
+// go out together with the projection and spin on its counter after their prologue, which is safe because whoever
+// computes the projection never waits on a work item (the projection servers below; without them the 8 GPROJ items sit in
+// front of the head tiles in the same FIFO).  Rooms progress independently (a slow step of one room no longer stalls the
+// others) and nothing is launched per step.
+//
+// The pooled projection (head layer 0 applied to the pooled 1024-vector, a GEMV) is answered by 16 SERVER CTAs that keep
+// the weights in shared memory for the whole run (proj_server) instead of 8 work items that stream them from L2.
 //
 // Memory ordering: producers finish their global writes, __syncthreads(), then one thread does __threadfence() and
 // the atomic / queue store that publishes; the consumer's popping thread spins on the volatile queue entry, does
