@@ -105,3 +105,37 @@ def test_beam_driver_replays_reference_trace(golden_weights):
     for line, (seed_id, steps, size, reason, _) in zip(lines, labelled):
         tok = line.split()
         assert int(tok[6]) == steps and int(tok[7].split('/')[0]) == size
+
+
+def test_beam_driver_philox_lanes_and_forced_replay(golden_weights):
+    """The Philox form of the beam-search oracle (expansion (q, s) of round r draws at lane q * SEARCH_WIDTH + s, step r): a
+    run is deterministic, and re-driving it with the masks it sampled (the hook tests/test_beam_gpu.py feeds with the device's
+    masks) reproduces it exactly -- the replay harness itself is sound."""
+    base = np.load(os.path.join(GOLDEN, 'driver_trace_1000.npz'))
+    fwd = lambda a, b: lrg_forward.forward(golden_weights, a, b)
+    runs = []
+    for _ in range(2):
+        g = lrg_driver.BeamRoomGrower(base['points'], base['order'], fwd, lrg_driver.PhiloxRng(9), beam_width=2, search_width=2)
+        g.trace = []
+        g.run()
+        runs.append(g)
+    a, b = runs
+    assert np.array_equal(a.cluster_label, b.cluster_label) and a.lane_log == b.lane_log and a.regions == b.regions
+    assert a.total_steps == len(a.lane_log) == sum(a.lane_steps) and max(x[2] for x in a.lane_log) <= 3
+    assert all(r[3] in ('stuck', 'exhausted') for r in a.regions) and a.visited.all()
+    # lanes of one round share the parent: the candidates of a round differ only through their lane's streams
+    masks = iter(a.trace)
+
+    def forced(st, lane):
+        rec = next(masks)
+        assert rec['n_inlier'] == st['n_inlier'] and np.array_equal(rec['inlier_idx'], st['inlier_idx'])
+        add, rmv = fwd(st['inlier'], st['neighbor'])
+        return add, rmv, rec['add_mask'], rec['rmv_mask']
+
+    c = lrg_driver.BeamRoomGrower(base['points'], base['order'], fwd, lrg_driver.PhiloxRng(9), beam_width=2, search_width=2)
+    c.run(forced)
+    assert next(masks, None) is None
+    assert np.array_equal(c.cluster_label, a.cluster_label) and c.lane_log == a.lane_log
+    other = lrg_driver.BeamRoomGrower(base['points'], base['order'], fwd, lrg_driver.PhiloxRng(10), beam_width=2, search_width=2)
+    other.run()
+    assert other.lane_log != a.lane_log                                      # the seed matters
