@@ -466,6 +466,93 @@ class BeamRoomGrower(RoomGrower):
         return self.cluster_label
 
 
+class _LaneGrower(RoomGrower):
+    """One speculative lane of SpeculativeRoomGrower: a region grown on the shared (committed) ``visited`` array; stopping
+    only records the reason -- the controller commits in seed order."""
+
+    def stop_growing(self, reason):
+        self.finished = reason
+
+
+class SpeculativeRoomGrower:
+    """DESIGN STUDY for intra-room parallelism that keeps the plain driver's result (test_region_grow.py:183-306) -- not a
+    reference restatement.  ``lanes`` regions of one room grow side by side (one grow step per lane and tick), seeds handed
+    out in curvature order, regions COMMITTED strictly in that order.  A region's trajectory depends on the regions before it
+    only through ``visited`` inside the boxes it looked at (bounding box +- 1 voxel, :222-229); so when a commit makes points
+    visited that lie inside the envelope a younger lane has looked at so far, that lane starts over (or is dropped if its
+    seed itself was swallowed: in seed order it would never have been a seed); points outside the envelope are seen as
+    visited from then on, exactly as in the sequential run.  Draws are keyed by (room, seed point, step in region) (PhiloxRng),
+    so a region does not care when or on which lane it runs.  ``run()`` returns the labels, which equal RoomGrower's
+    (tests/test_oracle_driver.py); ``ticks`` is the makespan in grow steps, ``wasted`` the steps of discarded attempts."""
+
+    def __init__(self, points, order, forward_fn, seed=0, lanes=2, room_id=0, **kw):
+        self.points, self.order, self.forward_fn = points, np.asarray(order), forward_fn
+        self.seed, self.L, self.room_id, self.kw = seed, int(lanes), room_id, kw
+        self.ticks = self.wasted = self.useful = self.restarts = self.dropped = 0
+
+    def _lane(self, seed_id, visited, template):
+        g = _LaneGrower(self.points, self.order, self.forward_fn, PhiloxRng(self.seed), room_id=self.room_id, **self.kw) \
+            if template is None else template
+        g.visited = visited
+        g.finished = None
+        g.begin_region(seed_id)
+        g.envelope = (g.point_voxels[seed_id] - 1, g.point_voxels[seed_id] + 1)
+        return g
+
+    def run(self):
+        n = len(self.points)
+        visited = np.zeros(n, dtype=bool)
+        label = np.zeros(n, dtype=int)
+        cluster_id, cursor = 1, 0
+        window = []                      # lanes in seed order; window[0] commits next
+        threshold = self.kw.get('cluster_threshold', 10)
+        self.regions = []
+        while True:
+            while len(window) < self.L:                                        # hand out the next unvisited seeds (:183-188)
+                issued = {g.seed_id for g in window}
+                while cursor < n and (visited[self.order[cursor]] or self.order[cursor] in issued):
+                    cursor += 1
+                if cursor >= n:
+                    break
+                window.append(self._lane(int(self.order[cursor]), visited, None))
+                cursor += 1
+            if not window:
+                break
+            stepped = False
+            for g in window:                                                   # one grow step per running lane
+                if g.finished is not None:
+                    continue
+                st = g.prepare_step()
+                if st is not None:
+                    add, rmv = self.forward_fn(st['inlier'], st['neighbor'])
+                    g.apply_step(np.asarray(add)[0], np.asarray(rmv)[0])
+                    g.envelope = (np.minimum(g.envelope[0], g.seqMinDims - 1), np.maximum(g.envelope[1], g.seqMaxDims + 1))
+                    stepped = True
+            self.ticks += 1 if stepped else 0
+            while window and window[0].finished is not None:                   # commit in seed order (:210-217)
+                g = window.pop(0)
+                mask = g.currentMask
+                visited[mask] = True
+                size = int(mask.sum())
+                if size > threshold:
+                    label[mask] = cluster_id
+                    cluster_id += 1
+                self.regions.append((g.seed_id, g.steps, size, g.finished, size > threshold))
+                self.useful += g.steps
+                vox = g.point_voxels[mask]
+                for k, y in enumerate(list(window)):                           # younger lanes that looked at these points
+                    if np.any(np.all((vox >= y.envelope[0]) & (vox <= y.envelope[1]), axis=1)):
+                        self.wasted += y.steps
+                        if visited[y.seed_id]:
+                            window.remove(y)
+                            self.dropped += 1
+                        else:
+                            self._lane(y.seed_id, visited, y)
+                            self.restarts += 1
+        self.cluster_label = label
+        return label
+
+
 def _rows_in(voxels, query):
     """Row-wise membership of (N,3) int voxels in a set of (M,3) voxels (python ``tuple in set`` at :283-286)."""
     if len(query) == 0:
