@@ -485,9 +485,14 @@ class SpeculativeRoomGrower:
     so a region does not care when or on which lane it runs.  ``run()`` returns the labels, which equal RoomGrower's
     (tests/test_oracle_driver.py); ``ticks`` is the makespan in grow steps, ``wasted`` the steps of discarded attempts."""
 
-    def __init__(self, points, order, forward_fn, seed=0, lanes=2, room_id=0, **kw):
+    def __init__(self, points, order, forward_fn, seed=0, lanes=2, room_id=0, validate='early', **kw):
+        """``validate='early'``: a commit restarts the younger lanes it invalidates at once (needs the committer to read the
+        other lanes' envelopes).  ``validate='commit'``: nobody looks at another lane -- a region is checked only when it
+        reaches the head of the window, against the points committed since it started, and grown again there if they touch
+        its envelope (simpler on a device: the head lane reads immutable committed lists; conflicts cost more)."""
         self.points, self.order, self.forward_fn = points, np.asarray(order), forward_fn
         self.seed, self.L, self.room_id, self.kw = seed, int(lanes), room_id, kw
+        self.validate = validate
         self.ticks = self.wasted = self.useful = self.restarts = self.dropped = 0
 
     def _lane(self, seed_id, visited, template):
@@ -497,6 +502,7 @@ class SpeculativeRoomGrower:
         g.finished = None
         g.begin_region(seed_id)
         g.envelope = (g.point_voxels[seed_id] - 1, g.point_voxels[seed_id] + 1)
+        g.seen_commits = len(getattr(self, 'commit_log', []))        # commits that were already visible when the region began
         return g
 
     def run(self):
@@ -507,6 +513,7 @@ class SpeculativeRoomGrower:
         window = []                      # lanes in seed order; window[0] commits next
         threshold = self.kw.get('cluster_threshold', 10)
         self.regions = []
+        self.commit_log = []             # voxels of every committed region, in commit order
         while True:
             while len(window) < self.L:                                        # hand out the next unvisited seeds (:183-188)
                 issued = {g.seed_id for g in window}
@@ -530,7 +537,20 @@ class SpeculativeRoomGrower:
                     stepped = True
             self.ticks += 1 if stepped else 0
             while window and window[0].finished is not None:                   # commit in seed order (:210-217)
-                g = window.pop(0)
+                g = window[0]
+                if self.validate == 'commit':
+                    if visited[g.seed_id]:                                     # swallowed by a region committed meanwhile
+                        window.pop(0)
+                        self.wasted += g.steps
+                        self.dropped += 1
+                        continue
+                    hit = any(np.any(np.all((v >= g.envelope[0]) & (v <= g.envelope[1]), axis=1)) for v in self.commit_log[g.seen_commits:])
+                    if hit:                                                    # grown on a stale visited set: again, now at the head
+                        self.wasted += g.steps
+                        self.restarts += 1
+                        self._lane(g.seed_id, visited, g)
+                        break
+                window.pop(0)
                 mask = g.currentMask
                 visited[mask] = True
                 size = int(mask.sum())
@@ -540,6 +560,9 @@ class SpeculativeRoomGrower:
                 self.regions.append((g.seed_id, g.steps, size, g.finished, size > threshold))
                 self.useful += g.steps
                 vox = g.point_voxels[mask]
+                self.commit_log.append(vox)
+                if self.validate == 'commit':
+                    continue
                 for k, y in enumerate(list(window)):                           # younger lanes that looked at these points
                     if np.any(np.all((vox >= y.envelope[0]) & (vox <= y.envelope[1]), axis=1)):
                         self.wasted += y.steps

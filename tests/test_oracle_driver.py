@@ -141,16 +141,16 @@ def test_beam_driver_philox_lanes_and_forced_replay(golden_weights):
     assert other.lane_log != a.lane_log                                      # the seed matters
 
 
-@pytest.mark.parametrize('lanes', [1, 3])
-def test_speculative_lanes_keep_the_plain_result(lanes, golden_weights):
+@pytest.mark.parametrize('lanes,validate', [(1, 'early'), (3, 'early'), (3, 'commit')])
+def test_speculative_lanes_keep_the_plain_result(lanes, validate, golden_weights):
     """Design study for intra-room parallelism (oracle.lrg_driver.SpeculativeRoomGrower): regions of one room grown
     side by side, committed in seed order, a lane started over when a commit lands inside the envelope it has looked at --
-    labels and region records are exactly the plain driver's."""
+    labels and region records are exactly the plain driver's, also when a region is only validated at its own commit."""
     base = np.load(os.path.join(GOLDEN, 'driver_trace_1000.npz'))
     fwd = lambda a, b: lrg_forward.forward(golden_weights, a, b)
     ref = lrg_driver.RoomGrower(base['points'], base['order'], fwd, lrg_driver.PhiloxRng(4))
     ref.run()
-    s = lrg_driver.SpeculativeRoomGrower(base['points'], base['order'], fwd, seed=4, lanes=lanes)
+    s = lrg_driver.SpeculativeRoomGrower(base['points'], base['order'], fwd, seed=4, lanes=lanes, validate=validate)
     np.testing.assert_array_equal(s.run(), ref.cluster_label)
     assert s.regions == ref.regions and s.useful == ref.total_steps
     if lanes == 1:
