@@ -326,7 +326,9 @@ def main():
         'launches_per_pass': 1 if pr['persistent'] else None, 'avg_launch_ms': grow_ms,
         'algorithmic_flops_per_launch': grow_steps * FLOPS_PER_STEP,
         'note': 'algorithmic = 271.7 MFLOP per grow step (512+512 rows, factored heads); the kernel evaluates only distinct rows '
-                '(padding duplicates reuse logits) as 3xTF32 on tcgen05; the run is latency-bound by the longest room',
+                '(padding duplicates reuse logits) as 3xTF32 on tcgen05; the run is latency-bound by the longest room; '
+                'grid = one CTA per SM: 132 work-item CTAs + 16 pooled-projection server CTAs (weights resident in shared memory), '
+                'unless LRG_GSERVERS=0',
     }
     # the driver phases' side of the roofline: algorithmic bytes per grow step = one pass over the room's state
     # (14 B per point) + the gathered tiles and logits (62,464 B) + the fp32 weights amortised over the rooms stepped together;
