@@ -350,6 +350,18 @@ def main():
             'frac_of_tf32_peak_executed': executed / (grow_ms * 1e-3) / 1e12 / (peak_tf / 2.0) if peak_tf else None,
             'tensor_tile_busy_tflops': executed / ((busy['branch'] + busy['head']) * 1e-3 / 148.0) / 1e12 if (busy['branch'] + busy['head']) > 0 else None,
         })
+        try:
+            # the reference's own timing buckets (comp_time_analysis, test_region_grow.py:40-51,120-317), per pass: 'feature' =
+            # feature preparation (device time); 'net' = the forward (branch + projection + head handlers), 'neighbor' + 'inlier'
+            # = the driver step handler -- SM time summed over CTAs, since the phases of different rooms overlap on the device
+            net_ms = float(busy['branch'] + busy['gproj'] + busy['head'])
+            drv_ms = float(busy['step'])
+            roofline['reference_buckets'] = {
+                'feature_ms_device': float(np.mean(prep_ms_list)), 'net_sm_ms': net_ms, 'neighbor_plus_inlier_sm_ms': drv_ms,
+                'net_share_of_sm_time': net_ms / (net_ms + drv_ms) if (net_ms + drv_ms) > 0 else None,
+                'note': 'the pooled projection runs on 16 server CTAs and is not in net_sm_ms unless LRG_GSERVERS=0'}
+        except Exception:
+            pass
     if args.lockstep_timing:
         # per-kernel CUDA-event times of the lock-step loop (the A/B path; one {step, branch, gproj, head} quartet per iteration)
         eng.segment_resident(flags=_lib.FLAG_KERNEL_TIMING, **params)
