@@ -42,7 +42,7 @@ def load_peaks():
 
 def make_workload(n_rooms, seed_base, cache=True):
     """Synthetic raw rooms (x y z r g b obj_id cls_id rows): (raw_offsets (R+1) int64, raw_points (sum Nr, 8) float32)."""
-    from learn_region_grow_b200 import rooms
+    from tools import rooms
     path = '/tmp/lrg_bench_rooms_v3_%d_%d.npz' % (n_rooms, seed_base)
     if cache and os.path.exists(path):
         z = np.load(path)

@@ -3,8 +3,11 @@ oracle/_ref/ -- TEST INFRASTRUCTURE (oracle/__init__.py).  Nothing is copied int
 but travels to the GPU box with the snapshot, where tests/test_tfops_gpu.py calls the C++-mangled ``*Launcher`` symbols
 (tf_sampling_g.cu:194-211, tf_grouping_g.cu:125-141) to pin our kernels and the C restatement against them.
 
-tf_ops/3d_interpolation/tf_interpolate.cpp is NOT buildable here (it includes TensorFlow headers, :6-9); its three
-plain-C++ loops are restated in oracle/tfops_oracle.c instead.
+tf_ops/3d_interpolation/tf_interpolate.cpp includes four TensorFlow headers (:6-9) and TensorFlow is absent; it is
+compiled UNMODIFIED all the same, with g++, against the from-scratch stand-in headers of oracle/tf_stubs (op registration
+and a tiny OpKernel / Tensor surface) plus oracle/tf_stubs/harness.cpp (C ABI) -> oracle/_ref/libref_interpolate.so: the
+reference's own three_nn / three_interpolate loops and its OpKernels' shape checks then pin oracle/tfops_oracle.c
+(tests/test_cpu_suite.py) and the CUDA kernels (tests/test_tfops_gpu.py).
 """
 import os
 import subprocess
@@ -34,6 +37,11 @@ def build_ref():
             continue
         subprocess.run(['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-Xcompiler', '-fPIC', '-x', 'cu',
                         srcp, '-o', dst], check=True)
+    dst = os.path.join(OUT, 'libref_interpolate.so')
+    srcs = [os.path.join(HERE, 'tf_stubs', 'harness.cpp'), os.path.join(REF, 'tf_ops/3d_interpolation/tf_interpolate.cpp')]
+    deps = srcs + [os.path.join(HERE, 'tf_stubs', 'tensorflow', 'core', 'framework', 'op_kernel.h')]
+    if not os.path.exists(dst) or any(os.path.getmtime(dst) < os.path.getmtime(d) for d in deps):
+        subprocess.run(['g++', '-O2', '-shared', '-fPIC', '-std=c++14', '-I', os.path.join(HERE, 'tf_stubs')] + srcs + ['-o', dst], check=True)
     return OUT
 
 

@@ -25,7 +25,8 @@ REF = '/root/reference'
 GOLD = os.path.join(REPO, 'tests', 'golden')
 sys.path.insert(0, REPO)
 
-from learn_region_grow_b200 import ckpt, rooms       # noqa: E402
+from learn_region_grow_b200 import ckpt              # noqa: E402
+from tools import rooms                               # noqa: E402
 from oracle import run_reference                      # noqa: E402
 
 
@@ -169,13 +170,56 @@ def golden_beam_trace(seed, n_raw, n_boxes):
     print(log[-300:])
 
 
+def golden_forward_pin():
+    """5. ``forward_graphdef.npz`` - the forward PINNED TO THE SHIPPED GRAPH: tile pairs the oracle driver feeds the network
+    on the golden room 1000 (steps 3, 10 and 25 of the first regions that get that far -- SURVEY 8d config 1 -- plus two
+    random pairs) evaluated by interpreting /root/reference/models/lrgnet_model5.ckpt.meta op by op
+    (oracle/graphdef_forward.py) on the checkpoint's own tensors, in float64 and in float32."""
+    from oracle import graphdef_forward, lrg_driver, lrg_forward
+    with np.load(os.path.join(GOLD, 'driver_trace_1000.npz')) as z:
+        points, order = z['points'], z['order']
+    with np.load(os.path.join(GOLD, 'lrgnet_model5.npz')) as z:
+        weights = {k: z[k] for k in z.files}
+    g = lrg_driver.RoomGrower(points, order, lambda a, b: lrg_forward.forward(weights, a, b), lrg_driver.PhiloxRng(0))
+    g.trace = []
+    g.run()
+    tiles, where = [], []
+    per_region = {}
+    for t in g.trace:
+        per_region.setdefault(t['seed'], []).append(t)
+    for seed, steps in per_region.items():
+        for want in (3, 10, 25):
+            if len(steps) > want and len(tiles) < 6:
+                tiles.append((steps[want]['inlier'][0], steps[want]['neighbor'][0]))
+                where.append((seed, want, steps[want]['n_inlier'], steps[want]['n_neighbor']))
+    rng = np.random.RandomState(5)
+    for _ in range(2):
+        tiles.append((rng.randn(512, 13).astype(np.float32), rng.randn(512, 13).astype(np.float32)))
+        where.append((-1, -1, 512, 512))
+    inlier = np.stack([t[0] for t in tiles]).astype(np.float32)
+    neighbor = np.stack([t[1] for t in tiles]).astype(np.float32)
+    out = dict(inlier=inlier, neighbor=neighbor, where=np.array(where))
+    for name, dt in (('f64', np.float64), ('f32', np.float32)):
+        sg = graphdef_forward.ShippedGraphForward(os.path.join(REF, 'models', 'lrgnet_model5.ckpt'), dt)
+        add, rmv = sg.forward(inlier, neighbor)
+        out['add_' + name], out['remove_' + name] = add, rmv
+    out['ops'] = np.array(sorted('%s x %d' % kv for kv in sg.interp.ops_seen.items()))
+    out['endpoints'] = np.array([sg.inlier_pl, sg.neighbor_pl, sg.add_out, sg.remove_out])
+    np.savez_compressed(os.path.join(GOLD, 'forward_graphdef.npz'), **out)
+    print('forward pin: %d tile pairs %s; ops %s' % (len(tiles), where, list(out['ops'])))
+
+
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
     if sys.argv[1:] == ['beam']:
         golden_beam_trace(1000, 2500, 4)
+        sys.exit(0)
+    if sys.argv[1:] == ['forward']:
+        golden_forward_pin()
         sys.exit(0)
     golden_weights()
     golden_trace(1000, 2500, 4)
     golden_trace(1001, 6000, 8)
     golden_restart_trace(1000, 2500, 4)
     golden_beam_trace(1000, 2500, 4)
+    golden_forward_pin()

@@ -31,7 +31,7 @@ class _Recorder(lrg_driver.RoomGrower):
 
 
 def analyse(room_seed, weights, n_raw=None):
-    from learn_region_grow_b200 import rooms
+    from tools import rooms
     raw = rooms.generate_room(room_seed) if n_raw is None else rooms.generate_room(room_seed, n_raw=n_raw)
     f = feature_prep.prepare_features(raw)
     fwd = lambda a, b: lrg_forward.forward(weights, a, b)

@@ -224,3 +224,59 @@ class ReferenceKernels:
     def available():
         return os.path.exists(os.path.join(HERE, '_ref', 'libref_sampling.so')) and \
             os.path.exists(os.path.join(HERE, '_ref', 'libref_grouping.so'))
+
+
+class ReferenceInterpolate:
+    """The reference's own three_nn / three_interpolate(+grad): /root/reference/tf_ops/3d_interpolation/tf_interpolate.cpp
+    compiled UNMODIFIED with g++ against the stand-in TensorFlow headers of oracle/tf_stubs (oracle/build_ref.py) into
+    oracle/_ref/libref_interpolate.so.  CPU code -- runs in the build container and on the GPU box alike.  ``*_loop`` call the
+    plain functions (:60,107,131); ``run_kernel`` drives the registered OpKernel's Compute (shape checks included)."""
+
+    def __init__(self):
+        self.lib = C.CDLL(os.path.join(HERE, '_ref', 'libref_interpolate.so'))
+        self.lib.ref_run_kernel.restype = C.c_int
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(HERE, '_ref', 'libref_interpolate.so'))
+
+    def three_nn(self, xyz1, xyz2):
+        xyz1, xyz2 = _f(xyz1), _f(xyz2)
+        b, n, _ = xyz1.shape
+        dist, idx = np.zeros((b, n, 3), np.float32), np.zeros((b, n, 3), np.int32)
+        self.lib.ref_threenn_cpu(b, n, xyz2.shape[1], _p(xyz1), _p(xyz2), _p(dist), _p(idx))
+        return dist, idx
+
+    def three_interpolate(self, points, idx, weight):
+        points, idx, weight = _f(points), _i(idx), _f(weight)
+        b, m, c = points.shape
+        n = idx.shape[1]
+        out = np.zeros((b, n, c), np.float32)
+        self.lib.ref_threeinterpolate_cpu(b, m, c, n, _p(points), _p(idx), _p(weight), _p(out))
+        return out
+
+    def three_interpolate_grad(self, points, idx, weight, grad_out):
+        points, idx, weight, grad_out = _f(points), _i(idx), _f(weight), _f(grad_out)
+        b, m, c = points.shape
+        n = idx.shape[1]
+        g = np.zeros_like(points)
+        self.lib.ref_threeinterpolate_grad_cpu(b, n, c, m, _p(grad_out), _p(idx), _p(weight), _p(g))
+        return g
+
+    def run_kernel(self, name, inputs, outputs):
+        """inputs: list of float32 / int32 arrays; outputs: list of preallocated arrays.  Raises ValueError with the
+        OpKernel's InvalidArgument message (OP_REQUIRES) when a shape check fails."""
+        inputs = [np.ascontiguousarray(a) for a in inputs]
+        n_in = len(inputs)
+        ptrs = (C.c_void_p * n_in)(*[a.ctypes.data for a in inputs])
+        ranks = (C.c_int * n_in)(*[a.ndim for a in inputs])
+        shapes = (C.c_longlong * (4 * n_in))()
+        for i, a in enumerate(inputs):
+            for d, s in enumerate(a.shape):
+                shapes[4 * i + d] = s
+        optrs = (C.c_void_p * len(outputs))(*[a.ctypes.data for a in outputs])
+        err = C.create_string_buffer(512)
+        rc = self.lib.ref_run_kernel(name.encode(), n_in, ptrs, ranks, shapes, len(outputs), optrs, err, 512)
+        if rc != 0:
+            raise ValueError(err.value.decode())
+        return outputs

@@ -21,7 +21,7 @@ def engine(golden_weights):
 
 
 def _check_rooms(engine, raws, resolution, seed):
-    from learn_region_grow_b200 import rooms
+    from tools import rooms
     from oracle import metrics as om
     labels_raw, stats = engine.segment_raw_rooms(raws, resolution=resolution, seed=seed)
     f = engine.prepared_features()
@@ -51,7 +51,7 @@ def _check_rooms(engine, raws, resolution, seed):
 
 def test_scannet_shaped_variable_rooms(engine):
     """config 3: raw sizes drawn log-uniformly in [5 k, 60 k] (README.md:48-49), seeds 2000 + room."""
-    from learn_region_grow_b200 import rooms
+    from tools import rooms
     raws = rooms.generate_area(5, seed_base=2000, log_uniform=(5000, 60000))
     assert max(map(len, raws)) > 3 * min(map(len, raws))
     labels, stats = _check_rooms(engine, raws, 0.1, seed=0)
@@ -65,7 +65,7 @@ def test_kitti_shaped_scene_at_30cm(engine):
     """config 5: one outdoor scene (ground plane + vehicle / pole / building sized boxes), resolution 0.3
     (test_region_grow.py --resolution 0.3): six-figure point counts, multi-chunk scans, inlier sets far above the median's
     shared-memory capacity."""
-    from learn_region_grow_b200 import rooms
+    from tools import rooms
     scene = rooms.generate_outdoor_scene(3000, n_raw=150000, extent=70.0, n_boxes=80)
     labels, stats = _check_rooms(engine, [scene], 0.3, seed=1)
     assert stats['n_points'][0] > 60000 and stats['grow_steps'][0] > 1000

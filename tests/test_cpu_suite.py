@@ -251,7 +251,8 @@ def test_h5_standin_and_loadFromH5(tmp_path):
     standins = os.path.join(REPO, 'learn_region_grow_b200', 'dropin', 'standins')
     sys.path.append(standins)
     try:
-        from learn_region_grow_b200 import io_util, rooms
+        from learn_region_grow_b200 import io_util
+        from tools import rooms
         rs = [rooms.generate_room(1000, n_raw=500, n_boxes=2), rooms.generate_room(1001, n_raw=700, n_boxes=2)]
         path = str(tmp_path / 's3dis_area5.h5')
         io_util.saveToH5(path, rs)
@@ -274,7 +275,7 @@ def test_metrics_oracle_reproduces_the_reference_log(seed):
     """oracle/metrics.py is pinned by the statistics line the UNMODIFIED reference driver printed for the golden rooms
     (test_region_grow.py:349): same obj_id (raw column 6 at equalized_idx) and the reference's own final cluster labels."""
     from oracle import metrics as om
-    from learn_region_grow_b200 import rooms
+    from tools import rooms
     z = np.load(os.path.join(REPO, 'tests', 'golden', 'driver_trace_%d.npz' % seed), allow_pickle=True)
     room = z['room']
     f = feature_prep.prepare_features(room, 0.1)

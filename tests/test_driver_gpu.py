@@ -92,7 +92,7 @@ def test_device_driver_replays_on_oracle(engine, golden_weights, room_seed, rng_
 
 def test_multi_room_batch_matches_single_room_runs(engine, golden_weights):
     """Rooms are independent units: growing them together (any slot count) gives the labels of growing them alone."""
-    from learn_region_grow_b200 import rooms as R
+    from tools import rooms as R
     feats = [feature_prep.prepare_features(R.generate_room(1000 + i, n_raw=3000 + 1500 * i, n_boxes=5)) for i in range(4)]
     pts = [f['points'] for f in feats] + [np.zeros((0, 13), np.float32)]      # plus an empty room
     orders = [f['order'] for f in feats] + [np.zeros(0, np.int64)]
@@ -111,7 +111,7 @@ def test_multi_room_batch_matches_single_room_runs(engine, golden_weights):
 
 def test_full_size_room_properties(engine):
     """S3DIS-shaped rooms (~20k raw points, BASELINE.json config): invariants that hold at any size."""
-    from learn_region_grow_b200 import rooms as R
+    from tools import rooms as R
     feats = [feature_prep.prepare_features(R.generate_room(1000 + i)) for i in range(3)]
     pts, orders = [f['points'] for f in feats], [f['order'] for f in feats]
     labels, stats = engine.segment_rooms(pts, orders, resolution=0.1, seed=0)
@@ -152,7 +152,7 @@ def test_resolution_and_threshold_parameters(engine, golden_weights):
 def test_large_room_replays_on_oracle(engine, golden_weights):
     """A room larger than one scan chunk (N > 16,384 state words) with a floor region of several thousand inliers:
     multi-chunk scans, the >1024 and >2048 median paths and full 512-of-n sampling, replayed step by step on the oracle."""
-    from learn_region_grow_b200 import rooms as R
+    from tools import rooms as R
     f = feature_prep.prepare_features(R.generate_room(4242, n_raw=70000, n_boxes=6, dims=np.array([9.0, 9.0, 2.4])))
     points, order = f['points'], f['order']
     assert len(points) > 16384
@@ -169,7 +169,8 @@ def test_large_room_replays_on_oracle(engine, golden_weights):
 
 def test_scheduling_variants_give_identical_labels(engine):
     """Lock-step loop, persistent kernel, persistent kernel with the priority ring: same computation, same labels."""
-    from learn_region_grow_b200 import _lib, rooms as R
+    from learn_region_grow_b200 import _lib
+    from tools import rooms as R
     feats = [feature_prep.prepare_features(R.generate_room(1100 + i, n_raw=6000 + 2000 * i, n_boxes=6)) for i in range(5)]
     pts, orders = [f['points'] for f in feats], [f['order'] for f in feats]
     ref, st0 = engine.segment_rooms(pts, orders, resolution=0.1, seed=3)
@@ -197,7 +198,7 @@ def test_room_span_limit(engine):
 def test_projection_servers_give_identical_labels(engine, monkeypatch):
     """The pooled projection answered by the server CTAs (weights resident in shared memory, the default of the persistent
     kernel) and by work items that stream the weights from L2 (LRG_GSERVERS=0) sum in the same order: identical labels."""
-    from learn_region_grow_b200 import rooms as R
+    from tools import rooms as R
     feats = [feature_prep.prepare_features(R.generate_room(1200 + i, n_raw=5000 + 2500 * i, n_boxes=6)) for i in range(4)]
     pts, orders = [f['points'] for f in feats], [f['order'] for f in feats]
     monkeypatch.setenv('LRG_GSERVERS', '0')

@@ -28,7 +28,7 @@ def engine(golden_weights):
 
 @pytest.mark.parametrize('seed', [1000, 1001])
 def test_device_features_match_reference_run(engine, seed):
-    from learn_region_grow_b200 import rooms
+    from tools import rooms
     g = np.load(os.path.join(GOLDEN, 'driver_trace_%d.npz' % seed))
     raw, ref, ref_order = g['room'], g['points'], g['order']
     eq = engine.upload_raw_rooms([raw], resolution=0.1)
@@ -57,7 +57,7 @@ def test_device_features_match_reference_run(engine, seed):
 def test_raw_rooms_end_to_end(engine):
     """Raw points in, per-raw-point labels out; growing from device-prepared features equals growing from the same
     features uploaded through the feature API."""
-    from learn_region_grow_b200 import rooms
+    from tools import rooms
     raws = [rooms.generate_room(1200 + i, n_raw=5000 + 3000 * i, n_boxes=5) for i in range(3)] + [np.zeros((0, 8), np.float32)]
     labels_raw, stats = engine.segment_raw_rooms(raws, resolution=0.1, seed=2)
     f = engine.prepared_features()
@@ -86,7 +86,7 @@ def test_raw_rooms_end_to_end(engine):
 @pytest.mark.parametrize('F', [6, 9, 12])
 def test_feature_ablations(F):
     """The driver's --xyz / --xyzrgb / --xyzrgbn switches keep the leading columns (test_region_grow.py:70-83)."""
-    from learn_region_grow_b200 import rooms
+    from tools import rooms
     from learn_region_grow_b200.engine import Engine
     from oracle import lrg_forward
     raw = rooms.generate_room(1300, n_raw=4000, n_boxes=3)
@@ -106,7 +106,7 @@ def test_raw_points_resident_on_the_device(engine):
     """lrg_rooms_upload_raw_device: the raw rows are read where they are (a torch CUDA tensor here, plumbing only); same
     features, same labels as the host-buffer call; lrg_last_prepare_ms reports the preparation's device time."""
     import torch
-    from learn_region_grow_b200 import rooms
+    from tools import rooms
     raws = [rooms.generate_room(1400 + i, n_raw=4000 + 2500 * i, n_boxes=4) for i in range(3)]
     raw_off = np.zeros(len(raws) + 1, np.int64)
     np.cumsum([len(r) for r in raws], out=raw_off[1:])

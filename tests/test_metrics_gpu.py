@@ -79,7 +79,8 @@ def test_metrics_degenerate_rooms():
 def test_metrics_reproduce_the_reference_log():
     """The statistics line printed by the unmodified reference driver for the golden rooms (2 decimals)."""
     import re
-    from learn_region_grow_b200 import metrics, rooms
+    from learn_region_grow_b200 import metrics
+    from tools import rooms
     objs, labs, logged = [], [], []
     for seed in (1000, 1001):
         z = np.load(os.path.join(REPO, 'tests', 'golden', 'driver_trace_%d.npz' % seed), allow_pickle=True)
@@ -97,7 +98,7 @@ def test_metrics_reproduce_the_reference_log():
 def test_engine_room_metrics_raw_and_equalised(golden_weights):
     """Engine labels scored on the device: raw object ids (gathered with equalized_idx, :136) and equalised ids agree with
     the oracle on the labels the engine produced."""
-    from learn_region_grow_b200 import rooms
+    from tools import rooms
     from learn_region_grow_b200.engine import Engine
     from oracle import metrics as om
     e = Engine(1, 1, 512, 512, 13, 0)

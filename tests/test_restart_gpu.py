@@ -90,7 +90,7 @@ def test_restart_driver_replays_on_oracle(engine, golden_weights, R, flags):
 def test_restart_scheduling_invariance(engine):
     """Rooms stay independent units: any number of groups, the persistent kernel or the lock-step loop, rooms alone or
     together -- same labels.  num_restarts <= 1 is the plain driver."""
-    from learn_region_grow_b200 import rooms as Rm
+    from tools import rooms as Rm
     feats = [feature_prep.prepare_features(Rm.generate_room(1000 + i, n_raw=2500 + 1000 * i, n_boxes=4)) for i in range(3)]
     pts = [f['points'] for f in feats] + [np.zeros((0, 13), np.float32)]
     orders = [f['order'] for f in feats] + [np.zeros(0, np.int64)]

@@ -6,7 +6,7 @@ import numpy as np
 from oracle import feature_prep
 
 from conftest import GOLDEN
-from learn_region_grow_b200 import rooms
+from tools import rooms
 
 
 def test_prepare_features_matches_reference_run():

@@ -4,7 +4,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import bench
-from learn_region_grow_b200 import rooms
+from tools import rooms
 from learn_region_grow_b200.engine import Engine
 
 eng = Engine(1, 1, 512, 512, 13, 0); eng.load_weights(bench.load_weights())
