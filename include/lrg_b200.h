@@ -89,6 +89,12 @@ typedef struct LrgGrowParams {
                                   search_width times per round by one sampled grow step, the beam_width largest updated masks
                                   kept (:273); the beam_width * search_width expansions of a round run side by side on the
                                   device (product max 16).  Excludes num_restarts > 1. */
+  int spec_lanes;              /* test_region_grow.py only (no restarts / beam): > 1 grows up to spec_lanes regions of ONE room side
+                                  by side, speculatively, and commits them strictly in seed order (:183-217) -- a region grown on a
+                                  stale visited set is detected when it reaches the head of the order and grown again there, so the
+                                  labels are bit-identical to spec_lanes = 1.  0 = engine default, 1 = off,
+                                  max 16 */
+  int reserved[3];             /* zero */
 } LrgGrowParams;
 
 enum {
@@ -106,6 +112,9 @@ typedef struct LrgRoomStats {
   int32_t regions;             /* seeds grown (labelled or not) */
   int32_t clusters;            /* labelled regions (cluster_id - 1) */
   int32_t stop_noneighbor, stop_noexpand, stop_stuck, stop_other;
+  /* speculative lanes (spec_lanes > 1) only, else 0: grow steps of discarded attempts (not part of grow_steps), regions grown
+   * again at the head of the order, attempts dropped because an earlier region swallowed their seed */
+  int32_t spec_wasted_steps, spec_restarts, spec_dropped, reserved;
 } LrgRoomStats;
 
 /* One record per grow step when tracing (parity tests): everything needed to re-drive the CPU oracle. */

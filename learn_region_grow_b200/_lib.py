@@ -17,12 +17,13 @@ class GrowParams(C.Structure):
     _fields_ = [('resolution', C.c_float), ('cluster_threshold', C.c_int), ('seed', C.c_uint64),
                 ('max_slots', C.c_int), ('max_steps_per_region', C.c_int), ('room_id_base', C.c_int),
                 ('trace_capacity', C.c_int), ('flags', C.c_int), ('num_restarts', C.c_int), ('beam_width', C.c_int),
-                ('search_width', C.c_int)]
+                ('search_width', C.c_int), ('spec_lanes', C.c_int), ('reserved', C.c_int * 3)]
 
 
 class RoomStats(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('n_points', 'grow_steps', 'regions', 'clusters', 'stop_noneighbor',
-                                          'stop_noexpand', 'stop_stuck', 'stop_other')]
+                                          'stop_noexpand', 'stop_stuck', 'stop_other', 'spec_wasted_steps', 'spec_restarts',
+                                          'spec_dropped', 'reserved')]
 
 
 class StepTrace(C.Structure):

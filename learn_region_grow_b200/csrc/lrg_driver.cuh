@@ -25,6 +25,10 @@ struct SlotState {
   // random-restart driver only (lanes > 1): this lane has finished the current seed and waits for the other restarts /
   // the lane was handed a fresh seed by the lane that committed the previous one (skip the seed search)
   int parked, begin;
+  // speculative lanes only (DriverArgs::spec): the order ticket of the region this lane grows, the length of the group's commit
+  // log when the region began (what was committed later must stay outside the boxes it looked at), and -- once the region
+  // has stopped and waits for its turn to commit -- why it stopped (0: nothing waits)
+  int ticket, log_begin, fin_reason;
 };
 
 // Random-restart driver (test_random_restart.py): the NUM_RESTARTS restarts of a seed are `lanes` consecutive slots (a
@@ -49,6 +53,25 @@ struct LaneGroup {
   int seqMin[3], seqMax[3];
   int par_n[kMaxLanes];    // candidate q of Q: points, bounding box (its index list lives in DriverArgs::parI)
   int par_min[kMaxLanes][3], par_max[kMaxLanes][3];
+  // speculative lanes only: written by the lane that holds the head ticket (the commit critical section)
+  int commit_seq;          // ticket that commits next (published to the other lanes through SpecSync::commit_seq)
+  int next_ticket;         // tickets handed out so far = seeds issued in curvature order
+  int lane_ticket[kMaxLanes];   // ticket every lane holds, -1: the lane is idle
+  int log_n;               // entries in the group's commit log (DriverArgs::clog)
+  int useful_steps, wasted_steps, restarts, dropped;   // grow steps of committed regions / of discarded attempts
+  int stops[4];
+};
+
+// Speculative lanes (test_region_grow.py:183-217 with intra-room parallelism): the `lanes` slots of a group grow
+// the next unvisited seeds of ONE room side by side, each on its own copy of the state words (private CURRENT flags, VISITED
+// set by every commit in every copy).  Seeds are handed out in curvature order with increasing tickets; regions COMMIT
+// strictly in ticket order.  A region that stops waits until its ticket is the head, then validates itself against the log
+// of points committed since it began: a committed point inside the envelope it looked at (seqMin-1 .. seqMax+1) means it grew
+// on a stale visited set -> it is grown again, now as the head (exactly the sequential state); its own seed among them ->
+// dropped (the sequential driver would have skipped it).  What the other lanes of a group poll lives here.
+struct SpecSync {
+  int commit_seq;          // ticket that may commit now
+  int fin[kMaxLanes];      // 1: the lane's region has stopped and its state is at rest (claimed with a CAS by whoever makes it the head)
 };
 
 struct DriverArgs {
@@ -94,6 +117,12 @@ struct DriverArgs {
   // beam search (beam_width > 0): lanes = beam_width * search_width
   int beam_width, search_width;
   int* parI;                    // (n_slots / lanes, beam_width, maxN) ascending index lists of the candidates in Q
+  // speculative lanes (spec != 0, lanes > 1, no restarts / beam)
+  int spec;
+  SpecSync* spec_sync;          // (n_slots / lanes)
+  int* clog;                    // (n_slots / lanes, maxN) commit log: room-local indices of committed points, in commit order
+  const unsigned* q_ctr;        // persistent kernel: [0] head, [1] tail of the work queue (load hint for the window), or NULL
+  int spec_min_idle;            // hand a seed to another idle lane only when at least this many CTAs wait for work (0 = always)
 };
 
 struct FillArgs {

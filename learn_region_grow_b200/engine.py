@@ -210,11 +210,13 @@ class Engine:
         return self.raw_labels(True), stats
 
     def make_params(self, resolution=0.1, cluster_threshold=10, seed=0, max_slots=0, max_steps_per_region=0,
-                    room_id_base=0, trace_capacity=0, flags=0, num_restarts=0, beam_width=0, search_width=0):
+                    room_id_base=0, trace_capacity=0, flags=0, num_restarts=0, beam_width=0, search_width=0, spec_lanes=0):
         """``num_restarts`` > 1 selects the random-restart driver (test_random_restart.py, NUM_RESTARTS, 'np' scoring);
-        ``beam_width`` / ``search_width`` > 0 the beam-search driver (test_beam_search.py, BEAM_WIDTH, SEARCH_WIDTH, 'np')."""
-        return GrowParams(resolution, cluster_threshold, seed, max_slots, max_steps_per_region, room_id_base,
-                          trace_capacity, flags, num_restarts, beam_width, search_width)
+        ``beam_width`` / ``search_width`` > 0 the beam-search driver (test_beam_search.py, BEAM_WIDTH, SEARCH_WIDTH, 'np');
+        ``spec_lanes`` > 1 grows that many regions of a room side by side with in-order commits (same labels as 1)."""
+        p = GrowParams(resolution, cluster_threshold, seed, max_slots, max_steps_per_region, room_id_base,
+                       trace_capacity, flags, num_restarts, beam_width, search_width, spec_lanes)
+        return p
 
     def segment_resident(self, params=None, **kw):
         """Grow all uploaded rooms on the device; returns the per-room statistics (structured array)."""

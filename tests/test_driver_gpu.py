@@ -167,6 +167,25 @@ def test_large_room_replays_on_oracle(engine, golden_weights):
     np.testing.assert_array_equal(engine.labels(filled=True)[0], g.fill())
 
 
+@pytest.mark.parametrize('room_index', [0, 26])
+def test_bench_shaped_room_replays_on_oracle(engine, golden_weights, room_index):
+    """The rooms bench.py grows (tools/rooms.generate_room(1000 + i) with its defaults: ~20 k raw points, 20-40 boxes; index 26
+    is the longest chain of the 68-room workload) replayed step by step on the pinned oracle -- seeds, set sizes, medians,
+    sampled indices, masks, stop reasons, labels before and after the fill."""
+    from tools import rooms as R
+    f = feature_prep.prepare_features(R.generate_room(1000 + room_index))
+    points, order = f['points'], f['order']
+    engine.upload_rooms([points], [order], resolution=0.1)
+    stats = engine.segment_resident(resolution=0.1, seed=0, trace_capacity=8192, room_id_base=room_index)
+    trace, n_steps = engine.trace(0, 8192)
+    assert n_steps == stats['grow_steps'][0] and 1000 < n_steps <= 8192
+    g, adopted = _replay(points, order, golden_weights, trace, n_steps, 0, room_id=room_index)
+    print('bench room %d: %d points, %d steps, %d regions, %d near-tie bits adopted' % (room_index, len(points), n_steps, len(g.regions), adopted))
+    assert adopted <= 12
+    np.testing.assert_array_equal(engine.labels(filled=False)[0], g.cluster_label)
+    np.testing.assert_array_equal(engine.labels(filled=True)[0], g.fill())
+
+
 def test_scheduling_variants_give_identical_labels(engine):
     """Lock-step loop, persistent kernel, persistent kernel with the priority ring: same computation, same labels."""
     from learn_region_grow_b200 import _lib

@@ -1,6 +1,6 @@
 """Device feature preparation (test_region_grow.py:119-173 on the GPU) against the features the UNMODIFIED
 reference script computed for the golden rooms (tests/golden/driver_trace_*.npz, made by oracle/make_golden.py) and
-against the host restatement (learn_region_grow_b200/rooms.py), through the C ABI.
+against the host restatement (oracle/feature_prep.py), through the C ABI.
 
 Exact: equalisation maps, xyz, room coordinates, rgb.  Tolerance: normals / curvature go through a 3x3 decomposition of a
 covariance (LAPACK SVD in the reference, Jacobi eigen-solve here): 2e-3 absolute on all but the few isotropic cells whose
@@ -52,6 +52,29 @@ def test_device_features_match_reference_run(engine, seed):
     # the reference's own argsort is unstable, and the last bits of a curvature depend on the decomposition)
     np.testing.assert_allclose(curv, ref[ref_order, 12], atol=1e-6)
     assert np.mean(order == ref_order) > 0.9
+
+
+@pytest.mark.parametrize('seed', [1000, 1001])
+def test_what_the_feature_noise_costs_in_labels(engine, seed):
+    """The device's normals / curvature differ from the reference's in the last bits (Jacobi vs LAPACK SVD on near-degenerate
+    covariances), so the seed order equals the reference's in only >90 % of positions (above), and every swap can change which
+    region claims contested points.  Measured here: the adjusted Rand score between the labels grown from the device-prepared
+    features and from the features the UNMODIFIED reference script computed (golden), same Philox seed -- held against the
+    segmentation's own run-to-run noise: the score between two runs on the reference's features that differ only in the
+    RNG seed (the reference itself draws its masks, test_region_grow.py:266-267)."""
+    from sklearn.metrics import adjusted_rand_score
+    g = np.load(os.path.join(GOLDEN, 'driver_trace_%d.npz' % seed))
+    raw, ref, ref_order = g['room'], g['points'], g['order']
+    lab_ref = {s: engine.segment_rooms([ref], [ref_order], resolution=0.1, seed=s)[0][0] for s in (0, 1, 2)}
+    engine.upload_raw_rooms([raw], resolution=0.1)
+    f = engine.prepared_features()
+    lab_dev = engine.segment_rooms([f['points']], [f['order']], resolution=0.1, seed=0)[0][0]
+    ari_feat = adjusted_rand_score(lab_ref[0], lab_dev)
+    ari_rng = [adjusted_rand_score(lab_ref[0], lab_ref[1]), adjusted_rand_score(lab_ref[0], lab_ref[2]), adjusted_rand_score(lab_ref[1], lab_ref[2])]
+    print('room %d: ARI(device features vs reference features, same seed) = %.3f; ARI between RNG seeds on the reference features = %s'
+          % (seed, ari_feat, ', '.join('%.3f' % a for a in ari_rng)))
+    assert ari_feat >= min(ari_rng) - 0.05          # the feature noise costs no more than a different RNG seed does
+    assert ari_feat >= 0.5
 
 
 def test_raw_rooms_end_to_end(engine):
