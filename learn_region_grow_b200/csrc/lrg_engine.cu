@@ -119,6 +119,8 @@ struct LrgEngine {
   unsigned* d_pw_lanes = nullptr;
   LaneGroup* d_groups = nullptr;
   int* d_parI = nullptr;        // beam search: index lists of the candidates in every group's queue
+  SpecSync* d_spec_sync = nullptr;   // speculative lanes: per-group commit order; commit log
+  int* d_clog = nullptr;
   int* d_lane_steps = nullptr;
   int last_lanes = 1;
   // persistent grow kernel: work queue, per-slot stage counters, busy-time counters
@@ -228,7 +230,8 @@ static void free_rooms(LrgEngine* e) {
   pool_free(e, e->d_label_filled); pool_free(e, e->d_order); pool_free(e, e->d_lab_list); pool_free(e, e->d_unl_list);
   pool_free(e, e->d_n_lab); pool_free(e, e->d_n_unl); pool_free(e, e->d_stats);
   pool_free(e, e->d_pw_lanes); pool_free(e, e->d_groups); pool_free(e, e->d_lane_steps); pool_free(e, e->d_parI);
-  e->d_pw_lanes = nullptr; e->d_groups = nullptr; e->d_lane_steps = nullptr; e->d_parI = nullptr;
+  pool_free(e, e->d_spec_sync); pool_free(e, e->d_clog);
+  e->d_pw_lanes = nullptr; e->d_groups = nullptr; e->d_lane_steps = nullptr; e->d_parI = nullptr; e->d_spec_sync = nullptr; e->d_clog = nullptr;
   pool_free(e, e->d_raw_off); pool_free(e, e->d_equalized_idx); pool_free(e, e->d_unequalized_idx); pool_free(e, e->d_feat);
   e->d_raw_off = nullptr; e->d_equalized_idx = e->d_unequalized_idx = nullptr; e->d_feat = nullptr; e->raw_mode = false; e->total_raw = 0;
   e->d_room_off = nullptr; e->d_pts = nullptr; e->d_pw = nullptr; e->d_pw_off = nullptr; e->d_room_vmin = nullptr; e->d_label = nullptr;
@@ -790,17 +793,26 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
     LRG_REQUIRE((long long)params->beam_width * params->search_width <= kMaxLanes, "beam_width %d x search_width %d exceeds the limit of %d lanes",
                 params->beam_width, params->search_width, kMaxLanes);
   }
-  const int lanes = beam ? params->beam_width * params->search_width : params->num_restarts > 1 ? params->num_restarts : 1;
+  // speculative lanes: up to spec_lanes regions of one room side by side, committed in seed order (plain driver only)
+  LRG_REQUIRE(params->spec_lanes >= 0 && params->spec_lanes <= kMaxLanes, "spec_lanes %d out of range [0,%d]", params->spec_lanes, kMaxLanes);
+  const bool spec = params->spec_lanes > 1 && !beam && params->num_restarts <= 1;
+  LRG_REQUIRE(params->spec_lanes <= 1 || spec, "spec_lanes %d needs the plain driver (no restarts, no beam search)", params->spec_lanes);
+  const int lanes = beam ? params->beam_width * params->search_width : params->num_restarts > 1 ? params->num_restarts : spec ? params->spec_lanes : 1;
   const bool grouped = lanes > 1 || beam;     // slots form groups with a LaneGroup record (a 1 x 1 beam is a group of one lane)
   LRG_REQUIRE(lanes <= kMaxLanes, "num_restarts %d exceeds the limit of %d", lanes, kMaxLanes);
-  int n_slots = params->max_slots > 0 ? std::max(params->max_slots, lanes) : (lanes > 1 ? 296 : 148);
+  int n_slots = params->max_slots > 0 ? std::max(params->max_slots, lanes) : spec ? 148 * lanes : (lanes > 1 ? 296 : 148);
   int n_groups = std::max(1, std::min(n_slots / lanes, std::max(n_rooms, 1)));
   n_slots = n_groups * lanes;
   LRG_TRY(ensure_slots(e, n_slots));
   e->last_lanes = lanes;
   if (grouped) {
     pool_free(e, e->d_pw_lanes); pool_free(e, e->d_groups); pool_free(e, e->d_lane_steps); pool_free(e, e->d_parI);
-    e->d_pw_lanes = nullptr; e->d_groups = nullptr; e->d_lane_steps = nullptr; e->d_parI = nullptr;
+    pool_free(e, e->d_spec_sync); pool_free(e, e->d_clog);
+    e->d_pw_lanes = nullptr; e->d_groups = nullptr; e->d_lane_steps = nullptr; e->d_parI = nullptr; e->d_spec_sync = nullptr; e->d_clog = nullptr;
+    if (spec) {
+      LRG_TRY(pool_alloc(e, &e->d_spec_sync, (size_t)n_groups));
+      LRG_TRY(pool_alloc(e, &e->d_clog, (size_t)n_groups * std::max(e->slots_maxN, 1)));
+    }
     LRG_TRY(pool_alloc(e, &e->d_pw_lanes, (size_t)std::max<long long>(e->total_words, 4) * lanes));
     LRG_TRY(pool_alloc(e, &e->d_groups, (size_t)n_groups));
     LRG_TRY(pool_alloc(e, &e->d_lane_steps, (size_t)std::max(n_rooms, 1) * lanes));
@@ -827,6 +839,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
     for (auto& g : ginit) { g.room = -1; g.cluster_id = 1; }
     LRG_CUDA(cudaMemcpyAsync(e->d_groups, ginit.data(), sizeof(LaneGroup) * n_groups, cudaMemcpyHostToDevice, st));
     LRG_CUDA(cudaMemsetAsync(e->d_lane_steps, 0, sizeof(int) * (size_t)std::max(n_rooms, 1) * lanes, st));
+    if (spec) LRG_CUDA(cudaMemsetAsync(e->d_spec_sync, 0, sizeof(SpecSync) * (size_t)n_groups, st));
     LRG_CUDA(cudaStreamSynchronize(st));      // (ginit is a host temporary)
   }
   LRG_TRY(launch_reset_words(n_rooms, e->d_room_off, e->d_pw_off, d_words, lanes, e->total_words, st));
@@ -862,6 +875,8 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   da.stats = e->d_stats; da.trace = e->trace_capacity > 0 ? e->d_trace : nullptr; da.trace_capacity = e->trace_capacity;
   da.lanes = lanes; da.groups = e->d_groups; da.pw_lane_stride = e->total_words; da.lane_steps = grouped ? e->d_lane_steps : nullptr;
   da.beam_width = beam ? params->beam_width : 0; da.search_width = beam ? params->search_width : 0; da.parI = beam ? e->d_parI : nullptr;
+  da.spec = spec ? 1 : 0; da.spec_sync = e->d_spec_sync; da.clog = e->d_clog; da.q_ctr = nullptr;
+  da.spec_min_idle = getenv("LRG_SPEC_MIN_IDLE") ? atoi(getenv("LRG_SPEC_MIN_IDLE")) : 0;
 
   ForwardArgs fa{};
   fa.x[0] = e->d_tile[0]; fa.x[1] = e->d_tile[1]; fa.x_stride = 16;
@@ -914,6 +929,7 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
       GrowArgs ga{};
       ga.da = da;
       ga.da.done_flag = nullptr;
+      ga.da.q_ctr = e->d_qctr + 2;                  // head / tail of the work queue everybody pops (load hint of the speculative window)
       ga.fa = fa;
       ga.fa.active = nullptr;
       ga.net = e->tcnet;

@@ -201,7 +201,7 @@ __device__ __forceinline__ int pw_z(unsigned w) { return (int)((w >> 20) & 1023u
 // CTA barrier orders the former, the acquire fence at the start of a work item drops stale L1 lines for the latter.)
 constexpr int kScanU = 8;
 template <int NT, class Pred, class Visit>
-__device__ int scan_words(const unsigned* pw, int N, Pred pred, Visit visit, int* out, int* out_s, int cap_s, int* s_scan) {
+__device__ int scan_words(const unsigned* pw, int N, Pred pred, Visit visit, int* out, int* out_s, int cap_s, int* s_scan, bool l2 = false) {
   constexpr int U = kScanU;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n4 = (N + 3) >> 2;
@@ -213,7 +213,8 @@ __device__ int scan_words(const unsigned* pw, int N, Pred pred, Visit visit, int
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int q = q0 + u * 32;
-      v[u] = q < n4 ? reinterpret_cast<const uint4*>(pw)[q] : make_uint4(PW_VIS, PW_VIS, PW_VIS, PW_VIS);
+      // (l2: speculative lanes update the words with atomics, which act in L2 -- read them there)
+      v[u] = q >= n4 ? make_uint4(PW_VIS, PW_VIS, PW_VIS, PW_VIS) : l2 ? __ldcg(reinterpret_cast<const uint4*>(pw) + q) : reinterpret_cast<const uint4*>(pw)[q];
     }
     unsigned flags = 0;
     int offs[U], wtotal = 0;
@@ -538,12 +539,15 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
   // Philox coordinates of a draw: (room, seed point of the region, step within the region, stream, element) -- keyed by the
   // region, not by the room's running step count, so that a region's draws do not depend on what was grown before it;
   // restart lane l uses streams 8l + {0..5}
-  const unsigned lane_stream = 8u * (unsigned)lane_id;
+  // (speculative lanes: a region's draws must not depend on the lane that happens to grow it -- stream 0 like the plain driver)
+  const unsigned lane_stream = (da.spec != 0) ? 0u : 8u * (unsigned)lane_id;
   // beam search (test_beam_search.py): lane q * SW + s expands candidate q of the seed's queue for the s-th time
   const bool beam = da.beam_width > 0;
   const int BW = da.beam_width, SW = da.search_width;
-  if ((L > 1 || beam) && S.parked && !(beam && S.begin)) return;
-  if (beam && S.begin) {
+  // speculative lanes (DriverArgs::spec): the lanes of a group grow different regions of one room, commits in seed order
+  const bool spec = da.spec != 0 && L > 1;
+  if ((L > 1 || beam) && S.parked && !((beam || spec) && S.begin)) return;
+  if ((beam || spec) && S.begin) {
     // handed a candidate by the lane that closed the previous round: everything it wrote precedes the flag, so read the
     // state again behind an acquire fence (the lock-step loop may have loaded a torn record)
     __threadfence();
@@ -574,6 +578,11 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     vmin0 = vm.x; vmin1 = vm.y; vmin2 = vm.z;
   };
   if (S.room >= 0) bind_room();
+  // CURRENT flag updates of this lane's words.  Speculative lanes: another lane's commit may set VISITED in this copy at any
+  // time (atomicOr), so the flag goes in and out with atomics too (a plain read-modify-write could lose the commit's bit).
+  auto ldw = [&](int i) -> unsigned { return spec ? __ldcg(pw + i) : pw[i]; };   // (atomics act in L2: read them there)
+  auto set_cur = [&](int i, unsigned w) { if (spec) atomicOr(pw + i, PW_CUR); else pw[i] = w | PW_CUR; };
+  auto clr_cur = [&](int i, unsigned w) { if (spec) atomicAnd(pw + i, ~PW_CUR); else pw[i] = w & ~PW_CUR; };
 
   // next unvisited seed in curvature order from position `cursor` (:183-188); -1 when the room is exhausted
   auto find_seed = [&](int cursor) -> int {
@@ -581,7 +590,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     const int* order = da.order + base;
     for (int start = cursor; start < N; start += NT) {
       const int pos = start + tid;
-      const bool ok = pos < N && !(pw[order[pos]] & PW_VIS);
+      const bool ok = pos < N && !(ldw(order[pos]) & PW_VIS);
       const unsigned bal = __ballot_sync(0xffffffffu, ok);
       if (lane == 0) sh.red[warp] = bal ? (start + warp * 32 + __ffs(bal) - 1) : INT_MAX;
       __syncthreads();
@@ -940,9 +949,251 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     return 1;
   };
 
+  // ---- speculative lanes (SpecSync, lrg_driver.cuh) ---------------------------------------------------------------------
+  // The region of this lane has stopped (listI[0..n_cur) = the region): put the lane's state at rest, announce it, and find
+  // out whether its ticket is the head of the commit order.  Returns true to the lane that may commit now (it owns the
+  // group's critical section: sh.G is loaded), false when the lane waits -- whoever commits the ticket before it wakes it.
+  SpecSync* const ssync = spec ? da.spec_sync + slot / L : nullptr;
+  auto spec_load_group = [&]() {
+    if (tid == 0) {
+      __threadfence();                                       // acquire: everything the previous owners wrote
+      for (int i = 0; i < (int)(sizeof(LaneGroup) / 4); ++i)
+        reinterpret_cast<int*>(&sh.G)[i] = __ldcg(reinterpret_cast<const int*>(grp) + i);
+    }
+    __syncthreads();
+  };
+  auto spec_finish = [&](int reason, int n_cur) -> bool {
+    if (tid == 0) { S.active = 0; S.parked = 1; S.begin = 0; S.n_in = n_cur; S.fin_reason = reason; }
+    __syncthreads();
+    for (int i = tid; i < (int)(sizeof(SlotState) / 4); i += NT)
+      reinterpret_cast<int*>(gS)[i] = reinterpret_cast<const int*>(&sh.S)[i];
+    __syncthreads();
+    if (tid == 0) {
+      // Dekker with the committer of the ticket before mine: I raise `fin` then read commit_seq, it raises commit_seq then
+      // reads (claims) `fin`; the fences in between are sequentially consistent, so at least one side sees the other
+      __threadfence();
+      atomicExch(&ssync->fin[lane_id], 1);
+      __threadfence();
+      const int cs = *reinterpret_cast<volatile int*>(&ssync->commit_seq);
+      sh.flag = (cs == S.ticket && atomicCAS(&ssync->fin[lane_id], 1, 0) == 1) ? 1 : 0;
+    }
+    __syncthreads();
+    const bool head = sh.flag != 0;
+    __syncthreads();
+    if (!head) return false;
+    if (tid == 0) S.parked = 0;
+    spec_load_group();
+    return true;
+  };
+  // Owner: hand the next unvisited seed of the room (curvature order, :183-188) to lane l with the next ticket; false when the
+  // room has no seed left.  The lane is idle (or is this one), so its state is at rest.
+  auto spec_give_seed = [&](int l) -> bool {
+    LaneGroup& G = sh.G;
+    const int found = find_seed(G.cursor);
+    if (found < 0) return false;
+    const int seed = da.order[base + found];
+    unsigned* pwl = da.pw + (long long)l * da.pw_lane_stride + da.pw_off[G.room];
+    if (tid == 0) {
+      const unsigned w = __ldcg(pwl + seed);
+      const int vx = pw_x(w), vy = pw_y(w), vz = pw_z(w);
+      G.cursor = found + 1;
+      const int ticket = G.next_ticket++;
+      G.lane_ticket[l] = ticket;
+      atomicOr(pwl + seed, PW_CUR);
+      (da.listI + (size_t)(slot - lane_id + l) * da.maxN)[0] = seed;
+      SlotState* o = l == lane_id ? &S : da.slots + (slot - lane_id + l);
+      o->active = 0; o->finished = 0; o->room = G.room; o->seed = seed;
+      o->minD[0] = o->maxD[0] = o->seqMin[0] = o->seqMax[0] = vx;
+      o->minD[1] = o->maxD[1] = o->seqMin[1] = o->seqMax[1] = vy;
+      o->minD[2] = o->maxD[2] = o->seqMin[2] = o->seqMax[2] = vz;
+      o->stuck = 0; o->steps = 0; o->n_in = 1; o->n_nb = 0;
+      o->ticket = ticket; o->log_begin = G.log_n; o->fin_reason = 0;
+      if (l == lane_id) {
+        o->parked = 0; o->begin = 0;
+        sh.listI_s[0] = seed;
+      } else {
+        // (the flag is raised after the fence in spec_release; here only the record)
+        o->parked = 1;
+        sh.wake |= 1u << l;
+      }
+    }
+    __syncthreads();
+    return true;
+  };
+  // Owner (sh.G loaded): validate and commit (or discard) this lane's stopped region if it has one, hand out seeds, pass the
+  // head on.  Returns 0: the group has retired (no rooms left), 1: this lane grows a region (fresh seed, or the same seed
+  // again), 2: this lane is idle (parked; its state is written back).
+  auto spec_head = [&]() -> int {
+    LaneGroup& G = sh.G;
+    const int slot0 = slot - lane_id;
+    bool bump = false;
+    if (S.fin_reason != 0) {
+      const int n_cur = S.n_in, reason = S.fin_reason;
+      // what was committed since this region began: none of it may lie inside the boxes the region looked at
+      // (seqMin - 1 .. seqMax + 1 covers every neighbour shell of its life, :222-229), and its seed must still be unvisited
+      const int* clog = da.clog + (size_t)(slot / L) * da.maxN;
+      const int lo0 = S.seqMin[0] - 1, lo1 = S.seqMin[1] - 1, lo2 = S.seqMin[2] - 1;
+      const int hi0 = S.seqMax[0] + 1, hi1 = S.seqMax[1] + 1, hi2 = S.seqMax[2] + 1;
+      int bad = 0;
+      for (int j = S.log_begin + tid; j < G.log_n; j += NT) {
+        const int i = __ldcg(clog + j);
+        const unsigned w = __ldcg(pw + i);
+        const int x = pw_x(w), y = pw_y(w), z = pw_z(w);
+        if (i == S.seed) bad |= 2;
+        if (x >= lo0 && x <= hi0 && y >= lo1 && y <= hi1 && z >= lo2 && z <= hi2) bad |= 1;
+      }
+      // (__syncthreads_or is a logical OR: one call per bit)
+      bad = (__syncthreads_or(bad & 1) ? 1 : 0) | (__syncthreads_or(bad & 2) ? 2 : 0);
+      if (bad != 0) {
+        // grown on a stale visited set: forget the attempt
+        for (int j = tid; j < n_cur; j += NT) atomicAnd(pw + listI[j], ~PW_CUR);
+        __syncthreads();
+        if (tid == 0) G.wasted_steps += S.steps;
+        if (!(bad & 2)) {
+          // ... and grow the seed again: every earlier region is committed now, so this attempt sees exactly the visited set
+          // of the sequential driver (and nobody else can commit before it does)
+          if (tid == 0) {
+            const unsigned w = __ldcg(pw + S.seed);
+            G.restarts += 1;
+            atomicOr(pw + S.seed, PW_CUR);
+            listI[0] = S.seed; sh.listI_s[0] = S.seed;
+            S.minD[0] = S.maxD[0] = S.seqMin[0] = S.seqMax[0] = pw_x(w);
+            S.minD[1] = S.maxD[1] = S.seqMin[1] = S.seqMax[1] = pw_y(w);
+            S.minD[2] = S.maxD[2] = S.seqMin[2] = S.seqMax[2] = pw_z(w);
+            S.stuck = 0; S.steps = 0; S.n_in = 1; S.n_nb = 0; S.log_begin = G.log_n; S.fin_reason = 0; S.parked = 0;
+            grp->wasted_steps = G.wasted_steps; grp->restarts = G.restarts;      // (still the owner: nothing else changed)
+          }
+          __syncthreads();
+          return 1;
+        }
+        if (tid == 0) G.dropped += 1;                          // the seed was swallowed by an earlier region (:187-188)
+      } else {
+        // commit (stop_growing, :210-217): visited in every lane's copy of the words, label, log
+        const bool labelled = n_cur > da.cluster_threshold;
+        const int cid = G.cluster_id;
+        int* label = da.label + base;
+        unsigned* pw0 = da.pw + da.pw_off[G.room];
+        int* wlog = da.clog + (size_t)(slot / L) * da.maxN + G.log_n;
+        for (int j = tid; j < n_cur; j += NT) {
+          const int i = listI[j];
+          for (int l = 0; l < L; ++l) atomicOr(pw0 + (long long)l * da.pw_lane_stride + i, PW_VIS);
+          atomicAnd(pw + i, ~PW_CUR);
+          if (labelled) label[i] = cid;
+          __stcg(wlog + j, i);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          if (labelled) G.cluster_id += 1;
+          G.regions += 1;
+          G.visited += n_cur;
+          G.log_n += n_cur;
+          G.useful_steps += S.steps;
+          G.stops[reason == STOP_NONEIGHBOR ? 0 : reason == STOP_NOEXPAND ? 1 : reason == STOP_STUCK ? 2 : 3] += 1;
+        }
+      }
+      if (tid == 0) { S.fin_reason = 0; G.lane_ticket[lane_id] = -1; G.commit_seq += 1; }
+      __syncthreads();
+      bump = true;
+    }
+    // hand out seeds: this lane first, then the idle lanes while the window has room; when nothing is in flight and the
+    // room has no seed left, publish its statistics and move the group to the next room
+    bool mine = false;
+    while (true) {
+      if (G.room >= 0) {
+        // window: a seed goes to another idle lane only while CTAs are waiting for work (speculation costs SM time)
+        int idle_ctas = 1 << 30;
+        if (da.spec_min_idle > 0 && da.q_ctr != nullptr) {
+          const int b = (int)(*reinterpret_cast<const volatile unsigned*>(da.q_ctr + 1) - *reinterpret_cast<const volatile unsigned*>(da.q_ctr));
+          idle_ctas = b < 0 ? -b : 0;
+        }
+        for (int k = 0; k < L; ++k) {
+          const int l = (lane_id + k) % L;
+          if (G.lane_ticket[l] >= 0) continue;
+          if (k > 0 && G.next_ticket > G.commit_seq && idle_ctas < da.spec_min_idle) continue;
+          if (!spec_give_seed(l)) break;
+          if (l == lane_id) mine = true;
+        }
+      }
+      if (G.next_ticket > G.commit_seq) break;               // something is in flight
+      // the room is finished (or this is the first call of the run)
+      if (tid == 0) {
+        if (G.room >= 0) {
+          LrgRoomStats& st = da.stats[G.room];
+          st.n_points = N; st.grow_steps = G.useful_steps; st.regions = G.regions; st.clusters = G.cluster_id - 1;
+          st.stop_noneighbor = G.stops[0]; st.stop_noexpand = G.stops[1]; st.stop_stuck = G.stops[2]; st.stop_other = G.stops[3];
+          st.spec_wasted_steps = G.wasted_steps; st.spec_restarts = G.restarts; st.spec_dropped = G.dropped;
+          if (da.lane_steps != nullptr)
+            for (int l = 0; l < L; ++l) {
+              SlotState* o = l == lane_id ? &S : da.slots + slot0 + l;
+              da.lane_steps[(size_t)G.room * L + l] = l == lane_id ? S.total_steps : __ldcg(&o->total_steps);
+            }
+        }
+        const int nr = atomicAdd(da.next_room, 1);
+        G.room = nr < da.n_rooms ? nr : -1;
+        G.cursor = 0; G.cluster_id = 1; G.regions = 0; G.visited = 0;
+        G.commit_seq = 0; G.next_ticket = 0; G.log_n = 0;
+        G.useful_steps = G.wasted_steps = G.restarts = G.dropped = 0;
+        G.stops[0] = G.stops[1] = G.stops[2] = G.stops[3] = 0;
+        for (int l = 0; l < L; ++l) {
+          G.lane_ticket[l] = -1;
+          SlotState* o = l == lane_id ? &S : da.slots + slot0 + l;
+          o->total_steps = 0; o->room = G.room;
+        }
+        *reinterpret_cast<volatile int*>(&ssync->commit_seq) = 0;
+        S.active = 0;
+        bump = false;
+      }
+      __syncthreads();
+      if (G.room < 0) {
+        if (tid == 0) {
+          for (int l = 0; l < L; ++l)
+            if (l != lane_id) *reinterpret_cast<volatile int*>(&da.slots[slot0 + l].finished) = 1;
+          S.finished = 1;
+          *grp = G;
+          const int fin = atomicAdd(da.finished_slots, L) + L;
+          if (fin == da.n_slots) {
+            sh.all_done = 1;
+            if (da.done_flag != nullptr) { *da.done_flag = 1; __threadfence_system(); }
+          }
+        }
+        __syncthreads();
+        return 0;
+      }
+      bind_room();
+    }
+    // release the critical section: group record, lane records and word flags first, then the ticket that may commit
+    // next, then the lanes that were handed a seed / the lane that holds the new head ticket and already waits
+    if (tid == 0) {
+      *grp = G;
+      __threadfence();
+      const unsigned fresh = sh.wake;                           // lanes that were handed a seed in this call
+      if (bump) {
+        *reinterpret_cast<volatile int*>(&ssync->commit_seq) = G.commit_seq;
+        __threadfence();
+        for (int l = 0; l < L; ++l)
+          if (l != lane_id && G.lane_ticket[l] == G.commit_seq && !((fresh >> l) & 1u) && atomicCAS(&ssync->fin[l], 1, 0) == 1) {
+            *reinterpret_cast<volatile int*>(&da.slots[slot0 + l].begin) = 2;
+            sh.wake |= 1u << l;
+          }
+      }
+      for (int l = 0; l < L; ++l)
+        if ((fresh >> l) & 1u) *reinterpret_cast<volatile int*>(&da.slots[slot0 + l].begin) = 1;
+      if (!mine) { S.active = 0; S.parked = 1; S.begin = 0; }
+    }
+    __syncthreads();
+    if (!mine) {
+      for (int i = tid; i < (int)(sizeof(SlotState) / 4); i += NT)
+        reinterpret_cast<int*>(gS)[i] = reinterpret_cast<const int*>(&sh.S)[i];
+      __syncthreads();
+      return 2;
+    }
+    return 1;
+  };
+
   // stop_growing (:210-217): visited |= current; label when the region is larger than the threshold.
   // listI[0..n_cur) holds the current region.
   auto stop_region = [&](int reason, int n_cur) -> bool {
+    if (spec) return spec_finish(reason, n_cur);
     if (L > 1) return stop_lane(reason, n_cur);
     const bool labelled = n_cur > da.cluster_threshold;
     int* label = da.label + base;
@@ -975,6 +1226,17 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
         for (int i = 0; i < (int)(sizeof(LaneGroup) / 4); ++i)
           reinterpret_cast<int*>(&sh.G)[i] = __ldcg(reinterpret_cast<const int*>(grp) + i);
       __syncthreads();
+    }
+  } else if (spec && !S.active) {
+    const int begin_flag = S.begin;
+    __syncthreads();                    // (every thread has read the flag before thread 0 clears it)
+    if (begin_flag == 1) {              // a fresh seed handed over by the lane that held the head ticket (state re-read above)
+      if (tid == 0) { S.begin = 0; S.parked = 0; sh.listI_s[0] = S.seed; }
+      __syncthreads();
+      mode = MODE_SCAN;
+    } else {                            // woken as the new head with a stopped region (begin == 2), or the first call of the run
+      if (tid == 0) { S.begin = 0; S.parked = 0; }
+      spec_load_group();
     }
   } else if (L > 1 && !S.active) {
     if (S.begin) {                      // a fresh seed handed over by the lane that committed the previous one
@@ -1009,7 +1271,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       if (p_[k] >= 0) {
         lg_[k] = __ldcg(reinterpret_cast<const float2*>(da.logits[is_add ? 1 : 0] + ((size_t)slot * nrows + src_[k]) * 2));
         xy_[k] = *reinterpret_cast<const float2*>(pts + (size_t)p_[k] * 16);
-        w_[k] = pw[p_[k]];
+        w_[k] = ldw(p_[k]);
       }
     }
     // the uniform draws depend on nothing that was loaded: their ~80 integer instructions per row run under the loads' latency
@@ -1057,7 +1319,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
         }
       }
       // adds first, removes second (:283-286)
-      if (m && normal && is_add) { pw[p] = w_[k] | PW_CUR; upd = 1; }      // (a neighbour row is never CURRENT before this)
+      if (m && normal && is_add) { set_cur(p, w_[k]); upd = 1; }      // (a neighbour row is never CURRENT before this)
       m_[k] = m; normal_[k] = normal;
     }
     mark(11);
@@ -1066,25 +1328,25 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     const int n_odd = sh.n_odd;
     if (n_odd > 0) {
       for (int i = tid; i < N; i += NT) {
-        const unsigned w = pw[i];
+        const unsigned w = ldw(i);
         bool hit = false;
         for (int o = 0; o < n_odd; ++o) hit |= (sh.odd[o].w == 1 && sh.odd[o].x == pw_x(w) && sh.odd[o].y == pw_y(w) && sh.odd[o].z == pw_z(w));
-        if (hit && !(w & PW_CUR)) { pw[i] = w | PW_CUR; upd = 1; }
+        if (hit && !(w & PW_CUR)) { set_cur(i, w); upd = 1; }
       }
     }
     const int updated = __syncthreads_or(upd);
 #pragma unroll
     for (int k = 0; k < VT; ++k) {
       const bool is_add = (tid + k * NT) >= kMaxTilePts;
-      if (m_[k] && normal_[k] && !is_add) pw[p_[k]] = w_[k] & ~PW_CUR;      // (an inlier row is CURRENT and not VISITED)
+      if (m_[k] && normal_[k] && !is_add) clr_cur(p_[k], w_[k]);      // (an inlier row is CURRENT and not VISITED)
     }
     if (n_odd > 0) {
       __syncthreads();
       for (int i = tid; i < N; i += NT) {
-        const unsigned w = pw[i];
+        const unsigned w = ldw(i);
         bool hit = false;
         for (int o = 0; o < n_odd; ++o) hit |= (sh.odd[o].w == 0 && sh.odd[o].x == pw_x(w) && sh.odd[o].y == pw_y(w) && sh.odd[o].z == pw_z(w));
-        if (hit) pw[i] = w & ~PW_CUR;
+        if (hit) clr_cur(i, w);
       }
     }
     mark(13);
@@ -1118,7 +1380,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int j = tid * 4 + q;
-        kw[q] = j < n_old ? pw[li_[q]] : 0u;
+        kw[q] = j < n_old ? ldw(li_[q]) : 0u;
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
@@ -1176,7 +1438,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       n_in = nK + nA;
       __syncthreads();
     } else {
-      n_in = scan_words<NT>(pw, N, [](unsigned w) { return (w & PW_CUR) != 0; }, grow_box, listI, sh.listI_s, kListCap, sh.scan);
+      n_in = scan_words<NT>(pw, N, [](unsigned w) { return (w & PW_CUR) != 0; }, grow_box, listI, sh.listI_s, kListCap, sh.scan, spec);
     }
     int reason = STOP_NONE;
     if (!updated) {
@@ -1243,6 +1505,11 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       if (r == 0) break;
       if (r == 2) return;
       mode = MODE_SCAN;
+    } else if (mode == MODE_NEW_REGION && spec) {
+      const int r = spec_head();
+      if (r == 0) break;
+      if (r == 2) return;
+      mode = MODE_SCAN;
     } else if (mode == MODE_NEW_REGION && L > 1) {
       if (!advance_group()) break;
       mode = MODE_SCAN;
@@ -1305,7 +1572,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       if (w & (PW_CUR | PW_VIS)) return false;
       const int x = pw_x(w), y = pw_y(w), z = pw_z(w);
       return x >= lo0 && x <= hi0 && y >= lo1 && y <= hi1 && z >= lo2 && z <= hi2;
-    }, [](unsigned) {}, listJ, sh.listJ_s, kListCap, sh.scan);
+    }, [](unsigned) {}, listJ, sh.listJ_s, kListCap, sh.scan, spec);
     if (n_nb == 0 && beam) {                                  // empty shell: the candidate is not expanded (:206)
       if (!beam_park(false, S.n_in)) return;
       mode = MODE_NEW_REGION;
