@@ -328,7 +328,7 @@ def main():
         'note': 'algorithmic = 271.7 MFLOP per grow step (512+512 rows, factored heads); the kernel evaluates only distinct rows '
                 '(padding duplicates reuse logits) as 3xTF32 on tcgen05; the run is latency-bound by the longest room; '
                 'grid = one CTA per SM: 132 work-item CTAs + 16 pooled-projection server CTAs (weights resident in shared memory), '
-                'unless LRG_GSERVERS=0',
+                'unless LRG_FLAG_NO_PROJ_SERVERS',
     }
     # the driver phases' side of the roofline: algorithmic bytes per grow step = one pass over the room's state
     # (14 B per point) + the gathered tiles and logits (62,464 B) + the fp32 weights amortised over the rooms stepped together;
@@ -359,7 +359,7 @@ def main():
             roofline['reference_buckets'] = {
                 'feature_ms_device': float(np.mean(prep_ms_list)), 'net_sm_ms': net_ms, 'neighbor_plus_inlier_sm_ms': drv_ms,
                 'net_share_of_sm_time': net_ms / (net_ms + drv_ms) if (net_ms + drv_ms) > 0 else None,
-                'note': 'the pooled projection runs on 16 server CTAs and is not in net_sm_ms unless LRG_GSERVERS=0'}
+                'note': 'the pooled projection runs on 16 server CTAs and is not in net_sm_ms unless LRG_FLAG_NO_PROJ_SERVERS'}
         except Exception:
             pass
     if args.lockstep_timing:

@@ -26,7 +26,8 @@ enum {
   LRG_E_INVALID = -1,                  /* bad argument (the reference raises InvalidArgument via OP_REQUIRES) */
   LRG_E_CUDA = -2,                     /* a CUDA runtime call or kernel launch failed */
   LRG_E_STATE = -3,                    /* call order violated (e.g. forward before load_weights) */
-  LRG_E_NOMEM = -4
+  LRG_E_NOMEM = -4,
+  LRG_E_RANGE = -5                     /* LRG_FORWARD_TENSOR_F16 only: an activation left the fp16 range */
 };
 
 const char* lrg_last_error(void);
@@ -52,14 +53,25 @@ size_t lrg_engine_weight_count(const LrgEngine* e);
  * checkpoint-V2 files and hands over one flat float32 blob in the order above. */
 int lrg_engine_load_weights(LrgEngine* e, const float* blob, size_t n_floats);
 
-/* Which kernels evaluate the network.  AUTO = TENSOR when the model is the full one (lite=0), FMA otherwise.
- *   LRG_FORWARD_TENSOR  tcgen05 tensor cores, every contraction as 3xTF32 (hi/lo split operands, fp32 accumulation)
- *   LRG_FORWARD_FMA     fp32 FMA pipe (all lite variants; A/B reference for the tensor path)
+/* Which kernels evaluate the network.  AUTO = tensor cores when the model is the full one (lite=0), FMA otherwise.
+ *   LRG_FORWARD_TENSOR_F16  tcgen05 tensor cores, every contraction as a three-term split product of fp16 halves
+ *                           (x = hi + lo, D += hi.hi + lo.hi + hi.lo, fp32 accumulation; weights pre-scaled per layer by a
+ *                           power of two): ~22 mantissa bits per product at half the MMAs and half the weight bytes of
+ *                           3xTF32.  Valid while every activation stays below 65,000 (the shipped model: < 500); a
+ *                           synchronous call that sees a larger one fails with LRG_E_RANGE.
+ *   LRG_FORWARD_TENSOR      the same with tf32 halves (3xTF32): no range limit
+ *   LRG_FORWARD_AUTO        3xFP16; a synchronous call (lrg_forward_host, lrg_segment_resident, lrg_segment_rooms_host) that
+ *                           sees an activation beyond the fp16 range is repeated with 3xTF32 before it returns
+ *   LRG_FORWARD_FMA         fp32 FMA pipe (all lite variants; A/B reference for the tensor paths)
  * No reference equivalent (TF picks its own conv kernels). */
-enum { LRG_FORWARD_AUTO = 0, LRG_FORWARD_FMA = 1, LRG_FORWARD_TENSOR = 2 };
+enum { LRG_FORWARD_AUTO = 0, LRG_FORWARD_FMA = 1, LRG_FORWARD_TENSOR = 2, LRG_FORWARD_TENSOR_F16 = 3 };
 int lrg_engine_set_forward_mode(LrgEngine* e, int mode);
-/* The mode forward calls currently take (LRG_FORWARD_FMA or LRG_FORWARD_TENSOR; valid after load_weights). */
+/* The mode forward calls currently take (LRG_FORWARD_FMA, LRG_FORWARD_TENSOR or LRG_FORWARD_TENSOR_F16; valid after load_weights). */
 int lrg_engine_forward_mode(const LrgEngine* e);
+/* For callers of the asynchronous lrg_forward_device in 3xFP16: synchronises the device, reports (and clears) whether a tile
+ * saw an activation beyond the fp16 range since the last check, and how many synchronous calls were repeated with 3xTF32 so
+ * far.  Either pointer may be NULL. */
+int lrg_engine_range_overflow(LrgEngine* e, int* overflow, int* fallbacks);
 
 /* Replaces sess.run([net.add_output, net.remove_output], {inlier_pl, neighbor_pl}) (test_region_grow.py:257-258).
  * inlier (B, Ni, F), neighbor (B, Nj, F) float32 row-major; add_out (B, Nj, 2), remove_out (B, Ni, 2).
@@ -94,7 +106,13 @@ typedef struct LrgGrowParams {
                                   stale visited set is detected when it reaches the head of the order and grown again there, so the
                                   labels are bit-identical to spec_lanes = 1.  0 = engine default, 1 = off,
                                   max 16 */
-  int reserved[3];             /* zero */
+  int spec_top;                /* speculative lanes: only the spec_top rooms in flight with the most estimated work left (unvisited
+                                  points x grow steps per visited point so far) hand seeds to more than one lane -- the run ends
+                                  with its longest rooms, speculation elsewhere only costs SM time.  0 = engine default (8),
+                                  < 0 = every room speculates */
+  int spec_min_idle;           /* speculative lanes: a room outside the spec_top still speculates while at least this many CTAs of
+                                  the persistent kernel wait for work (the tail of a run).  0 = engine default (96), < 0 = never */
+  int reserved[1];             /* zero */
 } LrgGrowParams;
 
 enum {
@@ -102,8 +120,14 @@ enum {
   LRG_FLAG_NO_GRAPH = 2,       /* lock-step loop with direct kernel launches instead of a CUDA graph */
   LRG_FLAG_PRIORITY = 8,       /* persistent kernel: reserve 24 CTAs for the two slots with the most unvisited points (off by default:
                                   measured 1-3% slower than the plain FIFO; the loaded step latency is not queueing) */
-  LRG_FLAG_LOCKSTEP = 4        /* lock-step loop (one {step, branch, gproj, head} kernel quartet per iteration, CUDA graph)
+  LRG_FLAG_LOCKSTEP = 4,       /* lock-step loop (one {step, branch, gproj, head} kernel quartet per iteration, CUDA graph)
                                   instead of the persistent grow kernel; implied by the two flags above and by FMA mode */
+  /* A/B switches of the persistent kernel (the defaults are the measured best, profiles/README.md; results do not depend on
+   * any of them, tests/test_driver_gpu.py): */
+  LRG_FLAG_NO_PROJ_SERVERS = 16,   /* no pooled-projection server CTAs: 8 projection work items per grow step instead */
+  LRG_FLAG_NO_TILE_SPLIT = 32,     /* never split a branch tile over idle CTAs */
+  LRG_FLAG_HEADS_AFTER_PROJ = 64   /* publish the head tiles when the projection is complete instead of together with it
+                                      (only without projection servers) */
 };
 
 typedef struct LrgRoomStats {
@@ -130,7 +154,10 @@ typedef struct LrgStepTrace {
 
 /* Upload rooms: points (sum N, F) float32 rows = the 13-D features of test_region_grow.py:165-172,
  * room_offsets (n_rooms+1) prefix sums of N_r, seed_order (sum N) = argsort(curvatures) per room (:183),
- * room-local indices.  Replaces the numpy arrays the driver keeps per room (:175-183). */
+ * room-local indices.  Replaces the numpy arrays the driver keeps per room (:175-183).
+ * Preconditions, checked on the device (LRG_E_INVALID): every room holds at most ONE point per voxel at `resolution` -- the
+ * reference applies its masks by voxel (:282-287), the device by point, which is the same thing only after the reference's
+ * equalisation (:125-136; lrg_rooms_upload_raw does it) -- and seed_order is a permutation of 0..N_r-1 per room. */
 int lrg_rooms_upload(LrgEngine* e, int n_rooms, const int64_t* room_offsets, const float* points,
                      const int32_t* seed_order, float resolution);
 /* Upload rooms as RAW points and prepare the features on the device: replaces test_region_grow.py:119-173 (equalise to one
@@ -157,7 +184,10 @@ int lrg_rooms_features_download(LrgEngine* e, float* points, int32_t* seed_order
 int lrg_labels_download_raw(LrgEngine* e, int32_t* labels_raw, int filled);
 
 /* Grow every uploaded room to completion on the device (no host round trip per step), then fill unlabeled
- * points (:308-316).  stats may be NULL or n_rooms entries. */
+ * points (:308-316).  stats may be NULL or n_rooms entries.  params->resolution must be 0 or the resolution of the upload.
+ * One call at a time per engine handle: a second call that arrives while one is running returns LRG_E_STATE (use one
+ * engine per thread / stream); the persistent kernel needs the whole device -- a launch that cannot be co-resident
+ * returns LRG_E_STATE instead of spinning. */
 int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats* stats);
 /* labels (sum N) int32; filled != 0 returns the labels after the nearest-neighbour fill (:308-316),
  * otherwise the raw cluster_label with 0 = unlabeled (:176,214). */
@@ -182,16 +212,11 @@ int lrg_last_grow_profile(LrgEngine* e, int* persistent, double busy_ms[4], int6
 /* Summed time (ms) the items of each type waited in the device queue between publication and pick-up (same order). */
 int lrg_last_grow_queue_delay(LrgEngine* e, double delay_ms[4]);
 
-/* Environment switches read by lrg_segment_resident (A/B measurements; the defaults are the measured best, profiles/README.md):
- *   LRG_GSERVERS=0   persistent kernel without the pooled-projection server CTAs (8 projection work items per grow step instead)
- *   LRG_TUNE=bits    bit 0: split branch tiles over idle CTAs, bit 1: publish head tiles with the projection (default 3)
- *   LRG_HI="s,c"     reserve c CTAs for the s slots with the most unvisited points (what LRG_FLAG_PRIORITY sets to 2,24)
- * The results do not depend on any of them (tests/test_driver_gpu.py). */
-
-/* Diagnostics: with LRG_TILE_TIMING=1 in the environment at load_weights time the tensor tiles add the SM cycles of each
+/* Diagnostics: after lrg_engine_set_tile_timing(e, 1) the tensor tiles and the driver step add the SM cycles of each
  * of their stages to counters (out[0..13] branch tile stages, out[15] branch tiles; out[16..23] head tile stages,
  * out[31] head tiles; out[32..41] driver step stages, out[47] steps, out[48..59] median cycles / steps by set-size bucket);
  * tools/grow_profile.py prints them. */
+int lrg_engine_set_tile_timing(LrgEngine* e, int on);
 int lrg_tile_timing(LrgEngine* e, uint64_t out[64], int reset);
 
 /* With LRG_FLAG_KERNEL_TIMING: summed CUDA-event durations (ms) of the four kernels of the lock-step loop over the

@@ -17,7 +17,8 @@ class GrowParams(C.Structure):
     _fields_ = [('resolution', C.c_float), ('cluster_threshold', C.c_int), ('seed', C.c_uint64),
                 ('max_slots', C.c_int), ('max_steps_per_region', C.c_int), ('room_id_base', C.c_int),
                 ('trace_capacity', C.c_int), ('flags', C.c_int), ('num_restarts', C.c_int), ('beam_width', C.c_int),
-                ('search_width', C.c_int), ('spec_lanes', C.c_int), ('reserved', C.c_int * 3)]
+                ('search_width', C.c_int), ('spec_lanes', C.c_int), ('spec_top', C.c_int), ('spec_min_idle', C.c_int),
+                ('reserved', C.c_int * 1)]
 
 
 class RoomStats(C.Structure):
@@ -42,11 +43,14 @@ ROOM_METRICS_DTYPE = np.dtype([('nmi', '<f8'), ('ami', '<f8'), ('ars', '<f8'), (
                                ('n_points', '<i4'), ('n_classes', '<i4'), ('n_clusters', '<i4'), ('gt_match', '<i4')])
 assert STEP_TRACE_DTYPE.itemsize == C.sizeof(StepTrace) and ROOM_STATS_DTYPE.itemsize == C.sizeof(RoomStats)
 
-FORWARD_AUTO, FORWARD_FMA, FORWARD_TENSOR = 0, 1, 2
+FORWARD_AUTO, FORWARD_FMA, FORWARD_TENSOR, FORWARD_TENSOR_F16 = 0, 1, 2, 3
 FLAG_KERNEL_TIMING = 1
 FLAG_NO_GRAPH = 2
 FLAG_LOCKSTEP = 4
 FLAG_PRIORITY = 8
+FLAG_NO_PROJ_SERVERS = 16
+FLAG_NO_TILE_SPLIT = 32
+FLAG_HEADS_AFTER_PROJ = 64
 
 _P = C.c_void_p
 _I = C.c_int
@@ -60,6 +64,7 @@ _SIGNATURES = {
     'lrg_engine_load_weights': (_I, [_P, _P, C.c_size_t]),
     'lrg_engine_set_forward_mode': (_I, [_P, _I]),
     'lrg_engine_forward_mode': (_I, [_P]),
+    'lrg_engine_range_overflow': (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
     'lrg_forward_host': (_I, [_P, _I, _P, _P, _P, _P]),
     'lrg_forward_device': (_I, [_P, _I, _P, _P, _P, _P, _P]),
     'lrg_rooms_upload': (_I, [_P, _I, _P, _P, _P, C.c_float]),
@@ -79,6 +84,7 @@ _SIGNATURES = {
     'lrg_last_segment_profile': (_I, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int64),
                                       C.POINTER(C.c_int64), C.POINTER(C.c_float)]),
     'lrg_last_grow_profile': (_I, [_P, C.POINTER(_I), C.POINTER(C.c_double * 4), C.POINTER(C.c_int64 * 4)]),
+    'lrg_engine_set_tile_timing': (_I, [_P, _I]),
     'lrg_tile_timing': (_I, [_P, C.POINTER(C.c_uint64 * 64), _I]),
     'lrg_last_grow_queue_delay': (_I, [_P, C.POINTER(C.c_double * 4)]),
     'lrg_last_kernel_times': (_I, [_P, C.POINTER(C.c_float * 4)]),

@@ -60,6 +60,47 @@ __global__ void __launch_bounds__(1024) lrg_reset_words_kernel(const long long* 
   }
 }
 
+// Preconditions of the index-based driver (caller-prepared features, lrg_rooms_upload): the reference applies its masks by
+// VOXEL (every point whose voxel is in the add / remove set, test_region_grow.py:282-287), the device by point -- the two agree
+// only when every voxel holds exactly one point, which the reference's equalisation guarantees (:125-136) but a caller's
+// array may not.  One CTA per room: (a) seed_order must be a permutation of 0..N-1 (find_seed indexes the words with it),
+// (b) no two points of the room may share a voxel at the upload resolution (open-addressing hash set of the packed voxel
+// words in scratch, 2 entries per point).  err[0] = (room + 1) | kind << 28, kind 1 = seed order, 2 = duplicate voxel.
+__global__ void __launch_bounds__(1024) lrg_validate_rooms_kernel(const long long* __restrict__ room_off, const long long* __restrict__ pw_off,
+                                                                  const unsigned* __restrict__ pw, const int* __restrict__ order,
+                                                                  unsigned* __restrict__ scratch /* 3 * total_words, zeroed */, int* err) {
+  const int room = blockIdx.x, tid = threadIdx.x;
+  const long long base = room_off[room];
+  const int N = (int)(room_off[room + 1] - base);
+  if (N <= 0) return;
+  const unsigned* w = pw + pw_off[room];
+  unsigned* seen = scratch + 3 * pw_off[room];          // [N] marks of the seed order
+  unsigned* table = seen + ((N + 3) & ~3);               // [2 * n4] voxel word + 1, 0 = empty
+  const unsigned cap = 2u * (unsigned)((N + 3) & ~3);
+  int bad = 0;
+  for (int i = tid; i < N; i += 1024) {
+    const int o = order[base + i];
+    if (o < 0 || o >= N || atomicExch(&seen[o], 1u) != 0u) bad |= 1;
+    const unsigned key = (w[i] & PW_XYZ) + 1u;
+    unsigned h = (key * 2654435761u) % cap;
+    while (true) {
+      const unsigned prev = atomicCAS(&table[h], 0u, key);
+      if (prev == 0u) break;
+      if (prev == key) { bad |= 2; break; }
+      h = h + 1 == cap ? 0 : h + 1;
+    }
+  }
+  if (bad) atomicCAS(err, 0, (room + 1) | ((bad & 1 ? 1 : 2) << 28));
+}
+
+int launch_validate_rooms(int n_rooms, const long long* d_room_off, const long long* d_pw_off, const unsigned* d_pw, const int* d_order,
+                          unsigned* d_scratch, int* d_err, cudaStream_t stream) {
+  if (n_rooms <= 0) return LRG_OK;
+  lrg_validate_rooms_kernel<<<n_rooms, 1024, 0, stream>>>(d_room_off, d_pw_off, d_pw, d_order, d_scratch, d_err);
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
+}
+
 int launch_pack(const float* d_points, int F, int n_rooms, const long long* d_room_off, const long long* d_pw_off, float resolution,
                 float* d_pts16, unsigned* d_pw, int4* d_room_vmin, int* d_err, cudaStream_t stream) {
   if (n_rooms <= 0) return LRG_OK;
@@ -85,11 +126,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) lrg_step_kernel(const __grid_
 size_t step_smem_bytes() { return sizeof(StepShared); }
 
 int launch_step(const DriverArgs& da, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    LRG_CUDA(cudaFuncSetAttribute(lrg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepShared)));
-    configured = true;
-  }
+  // (per call: the attribute belongs to the current device / context, and an engine may live on any device)
+  LRG_CUDA(cudaFuncSetAttribute(lrg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepShared)));
   lrg_step_kernel<<<da.n_slots, kStepThreads, sizeof(StepShared), stream>>>(da);
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;

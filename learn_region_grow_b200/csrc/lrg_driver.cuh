@@ -122,7 +122,12 @@ struct DriverArgs {
   SpecSync* spec_sync;          // (n_slots / lanes)
   int* clog;                    // (n_slots / lanes, maxN) commit log: room-local indices of committed points, in commit order
   const unsigned* q_ctr;        // persistent kernel: [0] head, [1] tail of the work queue (load hint for the window), or NULL
-  int spec_min_idle;            // hand a seed to another idle lane only when at least this many CTAs wait for work (0 = always)
+  // which rooms speculate (a seed goes to a SECOND lane of a room only then): the spec_top groups with the largest estimate
+  // in spec_est (grow steps the group's room still needs; every owner refreshes its own entry), or anybody while at least
+  // spec_min_idle CTAs of the persistent kernel wait for work
+  int spec_top;
+  int spec_min_idle;
+  int* spec_est;                // (n_slots / lanes)
 };
 
 struct FillArgs {
@@ -141,6 +146,10 @@ struct FillArgs {
 // feature rows -> padded 16-float rows + state words; *d_err is set to a room index + 1 if a room spans > 1022 voxels
 int launch_pack(const float* d_points, int F, int n_rooms, const long long* d_room_off, const long long* d_pw_off, float resolution,
                 float* d_pts16, unsigned* d_pw, int4* d_room_vmin, int* d_err, cudaStream_t stream);
+// caller-prepared rooms: seed_order a permutation per room, one point per voxel; d_scratch = 3 * total_words zeroed words;
+// *d_err receives (room + 1) | kind << 28 (1 = bad seed order, 2 = two points in one voxel)
+int launch_validate_rooms(int n_rooms, const long long* d_room_off, const long long* d_pw_off, const unsigned* d_pw, const int* d_order,
+                          unsigned* d_scratch, int* d_err, cudaStream_t stream);
 // clears the CURRENT / VISITED flags of every room (start of a run)
 // (lanes > 1: also re-creates the copies 1..lanes-1 of the words, lane_stride words apart)
 int launch_reset_words(int n_rooms, const long long* d_room_off, const long long* d_pw_off, unsigned* d_pw, int lanes, long long lane_stride,

@@ -1,10 +1,13 @@
 // Host side of liblrg_b200.so: engine object (weights, workspaces, stream, CUDA graph of the lock-step grow loop) and
 // the extern "C" entry points of include/lrg_b200.h that concern LrgNet and the region-grow driver.
+#include <cuda_fp16.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <vector>
 
 #include "lrg_driver.cuh"
@@ -73,7 +76,12 @@ struct LrgEngine {
   // tensor-core path (full model only): operand images + descriptor
   bool tc_available = false;
   int forward_mode = LRG_FORWARD_AUTO;
-  float* d_tc_img = nullptr;
+  unsigned char* d_tc_img = nullptr;   // operand images of the tensor tiles: 3xTF32 set, then 3xFP16 set
+  int* d_range_flag = nullptr;         // 3xFP16 tiles: an activation left the fp16 range (TcNet::range_flag)
+  bool force_tf32 = false;             // set while a call is repeated with 3xTF32 after a range overflow
+  int last_kind = 0;                   // arithmetic of the last forward / segment call: 0 FMA, 1 3xTF32, 2 3xFP16
+  int range_fallbacks = 0;             // calls repeated with 3xTF32 so far
+  std::atomic<bool> busy{false};       // a segment call is running on this handle
   TcNet tcnet{};
   // forward workspaces for max_batch tile pairs (user-facing forward)
   int ws_batch = 0;
@@ -110,6 +118,7 @@ struct LrgEngine {
   int* d_tileidx[2] = {nullptr, nullptr};
   int* d_tilesrc[2] = {nullptr, nullptr};
   float *s_h1[2] = {nullptr, nullptr}, *s_pooled = nullptr, *s_gproj = nullptr, *s_logits[2] = {nullptr, nullptr};
+  uint2* s_gproj_tagged = nullptr;      // (n_slots, 2, H0) {value, tag} words written by the projection servers
   int* d_counters = nullptr;       // [0] next_room, [1] finished_slots
   int* h_done = nullptr;           // mapped pinned
   int* d_done = nullptr;
@@ -120,6 +129,7 @@ struct LrgEngine {
   LaneGroup* d_groups = nullptr;
   int* d_parI = nullptr;        // beam search: index lists of the candidates in every group's queue
   SpecSync* d_spec_sync = nullptr;   // speculative lanes: per-group commit order; commit log
+  int* d_spec_est = nullptr;         // speculative lanes: per-group estimate of the grow steps its room still needs
   int* d_clog = nullptr;
   int* d_lane_steps = nullptr;
   int last_lanes = 1;
@@ -230,8 +240,9 @@ static void free_rooms(LrgEngine* e) {
   pool_free(e, e->d_label_filled); pool_free(e, e->d_order); pool_free(e, e->d_lab_list); pool_free(e, e->d_unl_list);
   pool_free(e, e->d_n_lab); pool_free(e, e->d_n_unl); pool_free(e, e->d_stats);
   pool_free(e, e->d_pw_lanes); pool_free(e, e->d_groups); pool_free(e, e->d_lane_steps); pool_free(e, e->d_parI);
-  pool_free(e, e->d_spec_sync); pool_free(e, e->d_clog);
+  pool_free(e, e->d_spec_sync); pool_free(e, e->d_clog); pool_free(e, e->d_spec_est);
   e->d_pw_lanes = nullptr; e->d_groups = nullptr; e->d_lane_steps = nullptr; e->d_parI = nullptr; e->d_spec_sync = nullptr; e->d_clog = nullptr;
+  e->d_spec_est = nullptr;
   pool_free(e, e->d_raw_off); pool_free(e, e->d_equalized_idx); pool_free(e, e->d_unequalized_idx); pool_free(e, e->d_feat);
   e->d_raw_off = nullptr; e->d_equalized_idx = e->d_unequalized_idx = nullptr; e->d_feat = nullptr; e->raw_mode = false; e->total_raw = 0;
   e->d_room_off = nullptr; e->d_pts = nullptr; e->d_pw = nullptr; e->d_pw_off = nullptr; e->d_room_vmin = nullptr; e->d_label = nullptr;
@@ -246,7 +257,7 @@ static void free_slots(LrgEngine* e) {
     cudaFree(e->d_tile[i]); cudaFree(e->d_tileidx[i]); cudaFree(e->d_tilesrc[i]); cudaFree(e->s_h1[i]); cudaFree(e->s_logits[i]);
     e->d_tile[i] = nullptr; e->d_tileidx[i] = nullptr; e->d_tilesrc[i] = nullptr; e->s_h1[i] = nullptr; e->s_logits[i] = nullptr;
   }
-  cudaFree(e->s_pooled); cudaFree(e->s_gproj);
+  cudaFree(e->s_pooled); cudaFree(e->s_gproj); cudaFree(e->s_gproj_tagged); e->s_gproj_tagged = nullptr;
   e->d_slots = nullptr; e->d_listI = e->d_listJ = nullptr; e->d_keyI = e->d_keyJ = nullptr; e->s_pooled = e->s_gproj = nullptr;
   e->n_slots = 0; e->slots_maxN = 0;
 }
@@ -270,6 +281,7 @@ static int ensure_slots(LrgEngine* e, int n_slots) {
   }
   LRG_TRY(dev_alloc(&e->s_pooled, S * 2 * e->net.Clast));
   LRG_TRY(dev_alloc(&e->s_gproj, S * 2 * e->net.H0));
+  LRG_TRY(dev_alloc(&e->s_gproj_tagged, S * 2 * e->net.H0));
   e->n_slots = n_slots;
   e->slots_maxN = (int)M;
   return LRG_OK;
@@ -278,11 +290,28 @@ static int ensure_slots(LrgEngine* e, int n_slots) {
 static bool use_tc(const LrgEngine* e) {
   return e->tc_available && e->forward_mode != LRG_FORWARD_FMA;
 }
+// Arithmetic of the tensor tiles: 3xFP16 unless 3xTF32 was asked for (or a call is being repeated after a range overflow).
+static bool use_f16(const LrgEngine* e) {
+  return use_tc(e) && e->forward_mode != LRG_FORWARD_TENSOR && !e->force_tf32;
+}
 
 // The LrgNet forward over fa.B tile pairs on `stream`: tensor-core kernels for the full model, fp32-FMA kernels otherwise.
 static int run_forward(LrgEngine* e, const ForwardArgs& fa, cudaStream_t stream, cudaEvent_t* ev) {
-  if (use_tc(e)) return launch_forward_tc(e->tcnet, fa, stream, ev);
+  e->last_kind = use_tc(e) ? (use_f16(e) ? 2 : 1) : 0;
+  if (use_tc(e)) return launch_forward_tc(e->tcnet, fa, use_f16(e), stream, ev);
   return launch_forward_timed(e->net, fa, stream, ev);
+}
+// After a synchronised 3xFP16 call: did an activation leave the fp16 range?  (Clears the flag.)
+static int take_range_flag(LrgEngine* e, bool* overflow) {
+  *overflow = false;
+  if (e->d_range_flag == nullptr) return LRG_OK;
+  int f = 0;
+  LRG_CUDA(cudaMemcpy(&f, e->d_range_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (f != 0) {
+    LRG_CUDA(cudaMemset(e->d_range_flag, 0, sizeof(int)));
+    *overflow = true;
+  }
+  return LRG_OK;
 }
 
 // Operand image of W[k0:k0+Kc, n0:n0+Nc] (row-major [K][N] source) in the UMMA canonical no-swizzle K-major layout:
@@ -298,6 +327,33 @@ static void pack_chunk(std::vector<float>& out, const float* W, int K, int N, in
       const size_t off = (size_t)(k / 4) * (Nc * 4) + (size_t)n * 4 + (k % 4);
       umma::split_tf32(w, hi[off], lo[off]);
     }
+}
+
+// The same chunk for the 3xFP16 tiles: W * scale split into fp16 hi + fp16 lo, element (n, k) at half offset
+// (k/8)*(Nc*8) + n*8 + k%8 (core matrix = 8 rows x 8 halves = 128 bytes); hi image followed by lo image, appended as bytes.
+static void pack_chunk_f16(std::vector<unsigned char>& out, const float* W, int K, int N, int k0, int Kc, int n0, int Nc, float scale) {
+  const size_t base = out.size();
+  out.resize(base + (size_t)2 * Nc * Kc * 2, 0);
+  uint16_t* hi = reinterpret_cast<uint16_t*>(out.data() + base);
+  uint16_t* lo = hi + (size_t)Nc * Kc;
+  for (int k = 0; k < Kc; ++k)
+    for (int n = 0; n < Nc; ++n) {
+      const float w = (k0 + k < K) ? W[(size_t)(k0 + k) * N + n0 + n] * scale : 0.f;
+      const __half h = __float2half_rn(w);
+      const __half l = __float2half_rn(w - __half2float(h));
+      const size_t off = (size_t)(k / 8) * (Nc * 8) + (size_t)n * 8 + (k % 8);
+      memcpy(&hi[off], &h, 2);
+      memcpy(&lo[off], &l, 2);
+    }
+}
+// Power of two that brings the largest weight of a layer just below 2^15: the fp16 lo parts of all but negligible weights are
+// then normal numbers, and hi never overflows.
+static float f16_weight_scale(const float* W, size_t n) {
+  float m = 0.f;
+  for (size_t i = 0; i < n; ++i) m = std::max(m, std::fabs(W[i]));
+  if (!(m > 0.f) || !std::isfinite(m)) return 1.f;
+  const int ex = (int)std::floor(std::log2(32768.0 / (double)m));
+  return std::ldexp(1.f, std::max(-20, std::min(30, ex)));
 }
 
 }  // namespace lrg
@@ -348,7 +404,7 @@ int lrg_engine_destroy(LrgEngine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   free_forward_ws(e); free_rooms(e); free_slots(e);
-  cudaFree(e->d_weights); cudaFree(e->d_tc_img); cudaFree(e->d_counters); cudaFree(e->d_trace);
+  cudaFree(e->d_weights); cudaFree(e->d_tc_img); cudaFree(e->d_range_flag); cudaFree(e->d_counters); cudaFree(e->d_trace);
   cudaFree(e->d_qring); cudaFree(e->d_qctr); cudaFree(e->d_sync); cudaFree(e->d_busy); cudaFree(e->d_tile_dbg); cudaFree(e->d_remaining);
   for (auto& b : e->pool) cudaFree(b.p);
   e->pool.clear();
@@ -362,8 +418,9 @@ size_t lrg_engine_weight_count(const LrgEngine* e) { return e ? e->n_weights : 0
 
 int lrg_engine_set_forward_mode(LrgEngine* e, int mode) {
   LRG_REQUIRE(e != nullptr, "engine is NULL");
-  LRG_REQUIRE(mode == LRG_FORWARD_AUTO || mode == LRG_FORWARD_FMA || mode == LRG_FORWARD_TENSOR, "unknown forward mode %d", mode);
-  if (mode == LRG_FORWARD_TENSOR && e->weights_loaded && !e->tc_available) {
+  LRG_REQUIRE(mode == LRG_FORWARD_AUTO || mode == LRG_FORWARD_FMA || mode == LRG_FORWARD_TENSOR || mode == LRG_FORWARD_TENSOR_F16,
+              "unknown forward mode %d", mode);
+  if ((mode == LRG_FORWARD_TENSOR || mode == LRG_FORWARD_TENSOR_F16) && e->weights_loaded && !e->tc_available) {
     set_error("the tensor-core forward covers the full model only (lite=0, feature_size<=16)");
     return LRG_E_STATE;
   }
@@ -373,7 +430,18 @@ int lrg_engine_set_forward_mode(LrgEngine* e, int mode) {
 
 int lrg_engine_forward_mode(const LrgEngine* e) {
   if (e == nullptr) return LRG_E_INVALID;
-  return use_tc(e) ? LRG_FORWARD_TENSOR : LRG_FORWARD_FMA;
+  return use_tc(e) ? (use_f16(e) ? LRG_FORWARD_TENSOR_F16 : LRG_FORWARD_TENSOR) : LRG_FORWARD_FMA;
+}
+
+int lrg_engine_range_overflow(LrgEngine* e, int* overflow, int* fallbacks) {
+  LRG_REQUIRE(e != nullptr, "engine is NULL");
+  LRG_CUDA(cudaSetDevice(e->device));
+  LRG_CUDA(cudaDeviceSynchronize());
+  bool over = false;
+  LRG_TRY(take_range_flag(e, &over));
+  if (overflow) *overflow = over ? 1 : 0;
+  if (fallbacks) *fallbacks = e->range_fallbacks;
+  return LRG_OK;
 }
 
 int lrg_engine_load_weights(LrgEngine* e, const float* blob, size_t n_floats) {
@@ -454,15 +522,21 @@ int lrg_engine_load_weights(LrgEngine* e, const float* blob, size_t n_floats) {
   // tensor-core path: pre-packed hi/lo operand images of the full model (lrg_forward_tc.cu)
   e->tc_available = false;
   if (e->lite == 0 && e->F <= 16) {
-    std::vector<float> img;
-    img.reserve(2 * kBranchImgFloats + 2 * kHeadImgFloats);
-    size_t branch_off[2], head_off[2];
+    std::vector<float> img;                                // 3xTF32 images
+    std::vector<unsigned char> img16;                      // 3xFP16 images
+    img.reserve((2 * kBranchImgBytesTf32 + 2 * kHeadImgBytesTf32) / 4);
+    img16.reserve(2 * kBranchImgBytesF16 + 2 * kHeadImgBytesF16);
+    size_t branch_off[2], head_off[2], branch_off16[2], head_off16[2];
+    float branch_inv[2][5], head_inv[2][2];
     const float* q = blob;
     for (int br = 0; br < 2; ++br) {
       const float* Wl[kMaxConv];
+      float sc[kMaxConv];
       for (int i = 0; i < nc; ++i) {
         const int K = i == 0 ? e->F : e->conv[i - 1];
         Wl[i] = q;
+        sc[i] = f16_weight_scale(q, (size_t)K * e->conv[i]);
+        branch_inv[br][i] = 1.f / sc[i];
         q += (size_t)K * e->conv[i] + e->conv[i];
       }
       branch_off[br] = img.size();
@@ -473,7 +547,15 @@ int lrg_engine_load_weights(LrgEngine* e, const float* blob, size_t n_floats) {
       pack_chunk(img, Wl[3], 64, 128, 32, 32, 0, 128);
       for (int nb = 0; nb < 4; ++nb)
         for (int kc = 0; kc < 4; ++kc) pack_chunk(img, Wl[4], 128, 512, kc * 32, 32, nb * 128, 128);
-      if (img.size() - branch_off[br] != kBranchImgFloats) { set_error("internal: branch image size"); return LRG_E_INVALID; }
+      if ((img.size() - branch_off[br]) * 4 != kBranchImgBytesTf32) { set_error("internal: branch image size"); return LRG_E_INVALID; }
+      branch_off16[br] = img16.size();
+      pack_chunk_f16(img16, Wl[0], e->F, 64, 0, 16, 0, 64, sc[0]);
+      pack_chunk_f16(img16, Wl[1], 64, 64, 0, 64, 0, 64, sc[1]);
+      pack_chunk_f16(img16, Wl[2], 64, 64, 0, 64, 0, 64, sc[2]);
+      pack_chunk_f16(img16, Wl[3], 64, 128, 0, 64, 0, 128, sc[3]);
+      for (int nb = 0; nb < 4; ++nb)
+        for (int kc = 0; kc < 2; ++kc) pack_chunk_f16(img16, Wl[4], 128, 512, kc * 64, 64, nb * 128, 128, sc[4]);
+      if (img16.size() - branch_off16[br] != kBranchImgBytesF16) { set_error("internal: branch image size (fp16)"); return LRG_E_INVALID; }
     }
     for (int hb = 0; hb < 2; ++hb) {
       const int h = hb == 0 ? 1 : 0;                       // blob: add head first; device index 1 = add
@@ -489,30 +571,44 @@ int lrg_engine_load_weights(LrgEngine* e, const float* blob, size_t n_floats) {
         pack_chunk(img, K1, 256, 128, kc * 64 + 32, 32, 0, 128);
       };
       W0(0); W0(1); W1(0); W0(2); W1(1); W0(3); W1(2); W1(3);   // the order lrg_tc_head_kernel consumes them in
-      if (img.size() - head_off[h] != kHeadImgFloats) { set_error("internal: head image size"); return LRG_E_INVALID; }
+      if ((img.size() - head_off[h]) * 4 != kHeadImgBytesTf32) { set_error("internal: head image size"); return LRG_E_INVALID; }
+      const float s0 = f16_weight_scale(K0local, (size_t)64 * 256), s1 = f16_weight_scale(K1, (size_t)256 * 128);
+      head_inv[h][0] = 1.f / s0; head_inv[h][1] = 1.f / s1;
+      head_off16[h] = img16.size();
+      auto W0h = [&](int nb) { pack_chunk_f16(img16, K0local, 64, 256, 0, 64, nb * 64, 64, s0); };
+      auto W1h = [&](int kc) {
+        pack_chunk_f16(img16, K1, 256, 128, kc * 64, 32, 0, 128, s1);
+        pack_chunk_f16(img16, K1, 256, 128, kc * 64 + 32, 32, 0, 128, s1);
+      };
+      W0h(0); W0h(1); W1h(0); W0h(2); W1h(1); W0h(3); W1h(2); W1h(3);
+      if (img16.size() - head_off16[h] != kHeadImgBytesF16) { set_error("internal: head image size (fp16)"); return LRG_E_INVALID; }
     }
     cudaFree(e->d_tc_img);
     e->d_tc_img = nullptr;
-    LRG_TRY(dev_alloc(&e->d_tc_img, img.size()));
-    LRG_CUDA(cudaMemcpy(e->d_tc_img, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const size_t tf32_bytes = img.size() * sizeof(float);
+    LRG_TRY(dev_alloc(&e->d_tc_img, tf32_bytes + img16.size()));
+    LRG_CUDA(cudaMemcpy(e->d_tc_img, img.data(), tf32_bytes, cudaMemcpyHostToDevice));
+    LRG_CUDA(cudaMemcpy(e->d_tc_img + tf32_bytes, img16.data(), img16.size(), cudaMemcpyHostToDevice));
+    if (e->d_range_flag == nullptr) LRG_TRY(dev_alloc(&e->d_range_flag, 1));
+    LRG_CUDA(cudaMemset(e->d_range_flag, 0, sizeof(int)));
     TcNet& t = e->tcnet;
     memset(&t, 0, sizeof(t));
     t.F = e->F;
+    t.range_flag = e->d_range_flag;
     for (int br = 0; br < 2; ++br) {
-      t.branch_img[br] = e->d_tc_img + branch_off[br];
-      for (int i = 0; i < 5; ++i) t.conv_bias[br][i] = net.conv[br][i].bias;
+      t.branch_img[0][br] = e->d_tc_img + branch_off[br] * sizeof(float);
+      t.branch_img[1][br] = e->d_tc_img + tf32_bytes + branch_off16[br];
+      for (int i = 0; i < 5; ++i) { t.conv_bias[br][i] = net.conv[br][i].bias; t.branch_inv[br][i] = branch_inv[br][i]; }
     }
     for (int h = 0; h < 2; ++h) {
       t.W0g[h] = net.W0g[h];
-      t.head_img[h] = e->d_tc_img + head_off[h];
+      t.head_img[0][h] = e->d_tc_img + head_off[h] * sizeof(float);
+      t.head_img[1][h] = e->d_tc_img + tf32_bytes + head_off16[h];
+      t.head_inv[h][0] = head_inv[h][0]; t.head_inv[h][1] = head_inv[h][1];
       t.head_bias0[h] = net.head0_local[h].bias;
       t.head_bias1[h] = net.hidden[h][0].bias;
       t.head_W2[h] = net.out[h].W;
       t.head_bias2[h] = net.out[h].bias;
-    }
-    if (getenv("LRG_TILE_TIMING") != nullptr && e->d_tile_dbg == nullptr) {
-      LRG_TRY(dev_alloc(&e->d_tile_dbg, 64));
-      LRG_CUDA(cudaMemset(e->d_tile_dbg, 0, 64 * sizeof(unsigned long long)));
     }
     t.dbg = e->d_tile_dbg;
     LRG_TRY(tc_forward_configure());
@@ -553,6 +649,20 @@ int lrg_forward_host(LrgEngine* e, int B, const float* inlier, const float* neig
   LRG_CUDA(cudaMemcpyAsync(e->d_x[0], inlier, sizeof(float) * (size_t)B * e->Ni * e->F, cudaMemcpyHostToDevice, e->stream));
   LRG_CUDA(cudaMemcpyAsync(e->d_x[1], neighbor, sizeof(float) * (size_t)B * e->Nj * e->F, cudaMemcpyHostToDevice, e->stream));
   LRG_TRY(lrg_forward_device(e, B, e->d_x[0], e->d_x[1], e->d_logits[1], e->d_logits[0], e->stream));
+  if (e->last_kind == 2) {
+    // 3xFP16 tiles: an activation beyond the fp16 range voids the result -- repeat with 3xTF32 (or report it when 3xFP16 was asked for)
+    LRG_CUDA(cudaStreamSynchronize(e->stream));
+    bool over = false;
+    LRG_TRY(take_range_flag(e, &over));
+    if (over) {
+      if (e->forward_mode == LRG_FORWARD_TENSOR_F16) { set_error("lrg_forward: an activation exceeds the fp16 range (use LRG_FORWARD_AUTO or LRG_FORWARD_TENSOR)"); return LRG_E_RANGE; }
+      e->force_tf32 = true;
+      e->range_fallbacks += 1;
+      const int rc = lrg_forward_device(e, B, e->d_x[0], e->d_x[1], e->d_logits[1], e->d_logits[0], e->stream);
+      e->force_tf32 = false;
+      LRG_TRY(rc);
+    }
+  }
   LRG_CUDA(cudaMemcpyAsync(add_out, e->d_logits[1], sizeof(float) * (size_t)B * e->Nj * 2, cudaMemcpyDeviceToHost, e->stream));
   LRG_CUDA(cudaMemcpyAsync(remove_out, e->d_logits[0], sizeof(float) * (size_t)B * e->Ni * 2, cudaMemcpyDeviceToHost, e->stream));
   LRG_CUDA(cudaStreamSynchronize(e->stream));
@@ -595,7 +705,7 @@ static int alloc_rooms(LrgEngine* e, int n_rooms, const int64_t* room_offsets, f
 }
 
 // Dense (T, F) device feature rows -> padded rows + packed state words (e->d_order must already hold the seed order).
-static int pack_rooms(LrgEngine* e, const float* d_dense) {
+static int pack_rooms(LrgEngine* e, const float* d_dense, bool validate = false) {
   if (e->total_pts <= 0) return LRG_OK;
   LRG_CUDA(cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(int), e->stream));
   LRG_TRY(launch_pack(d_dense, e->F, e->n_rooms, e->d_room_off, e->d_pw_off, e->resolution, e->d_pts, e->d_pw, e->d_room_vmin, e->d_counters, e->stream));
@@ -603,6 +713,24 @@ static int pack_rooms(LrgEngine* e, const float* d_dense) {
   LRG_CUDA(cudaMemcpyAsync(&bad_room, e->d_counters, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   LRG_CUDA(cudaStreamSynchronize(e->stream));
   LRG_REQUIRE(bad_room == 0, "room %d spans more than 1022 voxels along an axis at resolution %g (state words hold 10 bits per axis)", bad_room - 1, (double)e->resolution);
+  if (validate) {
+    // caller-prepared features: the device applies the masks by point, the reference by voxel (test_region_grow.py:282-287)
+    unsigned* d_scratch = nullptr;
+    LRG_TRY(pool_alloc(e, &d_scratch, (size_t)3 * e->total_words));
+    cudaError_t ce = cudaMemsetAsync(d_scratch, 0, sizeof(unsigned) * 3 * (size_t)e->total_words, e->stream);
+    int rc = ce == cudaSuccess ? launch_validate_rooms(e->n_rooms, e->d_room_off, e->d_pw_off, e->d_pw, e->d_order, d_scratch, e->d_counters, e->stream) : LRG_E_CUDA;
+    if (ce == cudaSuccess && rc == LRG_OK) ce = cudaMemcpyAsync(&bad_room, e->d_counters, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    pool_free(e, d_scratch);
+    LRG_TRY(rc);
+    LRG_CUDA(ce);
+    if (bad_room != 0) {
+      const int room = (bad_room & 0x0FFFFFFF) - 1;
+      if ((bad_room >> 28) == 1) set_error("room %d: seed_order is not a permutation of 0..N-1", room);
+      else set_error("room %d: two points share a voxel at resolution %g -- the driver needs one point per voxel (equalise like test_region_grow.py:125-136, or upload raw points with lrg_rooms_upload_raw)", room, (double)e->resolution);
+      return LRG_E_INVALID;
+    }
+  }
   return LRG_OK;
 }
 
@@ -621,7 +749,7 @@ int lrg_rooms_upload(LrgEngine* e, int n_rooms, const int64_t* room_offsets, con
     LRG_TRY(pool_alloc(e, &d_raw, T * e->F));
     cudaError_t ce = cudaMemcpyAsync(d_raw, points, sizeof(float) * T * e->F, cudaMemcpyHostToDevice, e->stream);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(e->d_order, seed_order, sizeof(int) * T, cudaMemcpyHostToDevice, e->stream);
-    int rc = ce == cudaSuccess ? pack_rooms(e, d_raw) : LRG_E_CUDA;
+    int rc = ce == cudaSuccess ? pack_rooms(e, d_raw, true) : LRG_E_CUDA;
     if (ce != cudaSuccess) set_error("rooms upload -> %s", cudaGetErrorString(ce));
     cudaStreamSynchronize(e->stream);
     pool_free(e, d_raw);
@@ -777,9 +905,48 @@ int lrg_labels_download_raw(LrgEngine* e, int32_t* labels_raw, int filled) {
   return LRG_OK;
 }
 
+namespace {
+// CUDA events that are destroyed on every return path.
+struct EventSet {
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  int create() {
+    for (auto& x : ev) LRG_CUDA(cudaEventCreate(&x));
+    return LRG_OK;
+  }
+  ~EventSet() {
+    for (auto x : ev)
+      if (x) cudaEventDestroy(x);
+  }
+};
+}  // namespace
+
+static int segment_resident_impl(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats* stats);
+
 int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats* stats) {
   LRG_REQUIRE(e != nullptr && params != nullptr, "engine/params is NULL");
   if (!e->weights_loaded) { set_error("lrg_segment: weights not loaded"); return LRG_E_STATE; }
+  LRG_REQUIRE(params->resolution == 0.f || params->resolution == e->resolution,
+              "params->resolution %g differs from the resolution the rooms were uploaded with (%g)", params->resolution, e->resolution);
+  // one call at a time per engine handle (the slot arrays, queues and the stream are the engine's): fail fast instead of racing
+  if (e->busy.exchange(true)) { set_error("lrg_segment_resident: the engine handle is in use by another call (one call at a time per handle)"); return LRG_E_STATE; }
+  struct Release { LrgEngine* e; ~Release() { e->busy.store(false); } } release{e};
+  int rc = segment_resident_impl(e, params, stats);
+  if (rc == LRG_OK && e->last_kind == 2) {
+    // 3xFP16 tiles: an activation beyond the fp16 range voids the run -- repeat it with 3xTF32 (or report it when 3xFP16 was asked for)
+    bool over = false;
+    LRG_TRY(take_range_flag(e, &over));
+    if (over) {
+      if (e->forward_mode == LRG_FORWARD_TENSOR_F16) { set_error("lrg_segment_resident: an activation exceeds the fp16 range (use LRG_FORWARD_AUTO or LRG_FORWARD_TENSOR)"); return LRG_E_RANGE; }
+      e->force_tf32 = true;
+      e->range_fallbacks += 1;
+      rc = segment_resident_impl(e, params, stats);
+      e->force_tf32 = false;
+    }
+  }
+  return rc;
+}
+
+static int segment_resident_impl(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats* stats) {
   LRG_CUDA(cudaSetDevice(e->device));
   const int n_rooms = e->n_rooms;
   const size_t T = (size_t)e->total_pts;
@@ -810,6 +977,8 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
     pool_free(e, e->d_spec_sync); pool_free(e, e->d_clog);
     e->d_pw_lanes = nullptr; e->d_groups = nullptr; e->d_lane_steps = nullptr; e->d_parI = nullptr; e->d_spec_sync = nullptr; e->d_clog = nullptr;
     if (spec) {
+      pool_free(e, e->d_spec_est); e->d_spec_est = nullptr;
+      LRG_TRY(pool_alloc(e, &e->d_spec_est, (size_t)n_groups));
       LRG_TRY(pool_alloc(e, &e->d_spec_sync, (size_t)n_groups));
       LRG_TRY(pool_alloc(e, &e->d_clog, (size_t)n_groups * std::max(e->slots_maxN, 1)));
     }
@@ -819,8 +988,6 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
     if (beam) LRG_TRY(pool_alloc(e, &e->d_parI, (size_t)n_groups * params->beam_width * std::max(e->slots_maxN, 1)));
   }
   cudaStream_t st = e->stream;
-  cudaEvent_t ev0, ev1, ev2;
-  LRG_CUDA(cudaEventCreate(&ev0)); LRG_CUDA(cudaEventCreate(&ev1)); LRG_CUDA(cudaEventCreate(&ev2));
   if (params->trace_capacity > 0 && (e->d_trace == nullptr || e->trace_capacity != params->trace_capacity || e->trace_rooms < n_rooms * lanes)) {
     cudaFree(e->d_trace);
     e->d_trace = nullptr;
@@ -828,6 +995,9 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
     e->trace_rooms = n_rooms * lanes;
   }
   *e->h_done = 0;
+  EventSet evs;
+  LRG_TRY(evs.create());
+  const cudaEvent_t ev0 = evs.ev[0], ev1 = evs.ev[1], ev2 = evs.ev[2];
   LRG_CUDA(cudaEventRecord(ev0, st));
   // reset per-run state (inside the timed region: it is part of one pass over the rooms)
   unsigned* d_words = e->d_pw;
@@ -839,7 +1009,10 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
     for (auto& g : ginit) { g.room = -1; g.cluster_id = 1; }
     LRG_CUDA(cudaMemcpyAsync(e->d_groups, ginit.data(), sizeof(LaneGroup) * n_groups, cudaMemcpyHostToDevice, st));
     LRG_CUDA(cudaMemsetAsync(e->d_lane_steps, 0, sizeof(int) * (size_t)std::max(n_rooms, 1) * lanes, st));
-    if (spec) LRG_CUDA(cudaMemsetAsync(e->d_spec_sync, 0, sizeof(SpecSync) * (size_t)n_groups, st));
+    if (spec) {
+      LRG_CUDA(cudaMemsetAsync(e->d_spec_sync, 0, sizeof(SpecSync) * (size_t)n_groups, st));
+      LRG_CUDA(cudaMemsetAsync(e->d_spec_est, 0, sizeof(int) * (size_t)n_groups, st));
+    }
     LRG_CUDA(cudaStreamSynchronize(st));      // (ginit is a host temporary)
   }
   LRG_TRY(launch_reset_words(n_rooms, e->d_room_off, e->d_pw_off, d_words, lanes, e->total_words, st));
@@ -876,7 +1049,10 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   da.lanes = lanes; da.groups = e->d_groups; da.pw_lane_stride = e->total_words; da.lane_steps = grouped ? e->d_lane_steps : nullptr;
   da.beam_width = beam ? params->beam_width : 0; da.search_width = beam ? params->search_width : 0; da.parI = beam ? e->d_parI : nullptr;
   da.spec = spec ? 1 : 0; da.spec_sync = e->d_spec_sync; da.clog = e->d_clog; da.q_ctr = nullptr;
-  da.spec_min_idle = getenv("LRG_SPEC_MIN_IDLE") ? atoi(getenv("LRG_SPEC_MIN_IDLE")) : 0;
+  // which rooms speculate: the spec_top rooms with the most estimated work left, and anybody while CTAs idle (the tail)
+  da.spec_top = params->spec_top == 0 ? 8 : params->spec_top < 0 ? (1 << 30) : params->spec_top;
+  da.spec_min_idle = params->spec_min_idle == 0 ? 96 : params->spec_min_idle < 0 ? (1 << 30) : params->spec_min_idle;
+  da.spec_est = e->d_spec_est;
 
   ForwardArgs fa{};
   fa.x[0] = e->d_tile[0]; fa.x[1] = e->d_tile[1]; fa.x_stride = 16;
@@ -938,28 +1114,37 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
         ga.q[k].head = e->d_qctr + 2 * k; ga.q[k].tail = e->d_qctr + 2 * k + 1;
       }
       ga.sync = e->d_sync;
+      ga.progress = e->d_qctr + 5; ga.abort = reinterpret_cast<int*>(e->d_qctr + 6);
       ga.busy_ns = e->d_busy;
       ga.remaining = e->d_remaining;
       // reserved CTAs for the slots with the most work left (LRG_FLAG_PRIORITY; LRG_HI="slots,ctas" overrides for experiments)
       ga.hi_slots = 0; ga.hi_ctas = 0;
       if (lanes == 1 && !beam) {
-        int hs = (params->flags & LRG_FLAG_PRIORITY) ? 2 : 0, hc = (params->flags & LRG_FLAG_PRIORITY) ? 24 : 0;
-        if (const char* env = getenv("LRG_HI")) sscanf(env, "%d,%d", &hs, &hc);
+        const int hs = (params->flags & LRG_FLAG_PRIORITY) ? 2 : 0, hc = (params->flags & LRG_FLAG_PRIORITY) ? 24 : 0;
         const int n_ctas = e->sm_count > 0 ? e->sm_count : 148;
         if (hs > 0 && hc > 0 && hc < n_ctas) { ga.hi_slots = std::min(hs, 8); ga.hi_ctas = hc; }
       }
       // pooled-projection servers: 16 of the CTAs keep W0[:1024] of both heads in shared memory (LRG_GSERVERS=0 turns them off)
       const int n_ctas_total = e->sm_count > 0 ? e->sm_count : 148;
-      ga.n_servers = (getenv("LRG_GSERVERS") ? atoi(getenv("LRG_GSERVERS")) != 0 : true) && n_ctas_total >= 4 * kProjServers ? kProjServers : 0;
+      ga.n_servers = !(params->flags & LRG_FLAG_NO_PROJ_SERVERS) && n_ctas_total >= 4 * kProjServers ? kProjServers : 0;
       ga.greq_ring = e->d_qring + (size_t)2 * e->q_capacity; ga.greq_mask = e->q_capacity - 1; ga.greq_tail = e->d_qctr + 4;
+      ga.gproj_tagged = e->s_gproj_tagged;
+      if (ga.n_servers > 0) LRG_CUDA(cudaMemsetAsync(e->s_gproj_tagged, 0, sizeof(uint2) * (size_t)n_slots * 2 * e->net.H0, st));   // (tags restart with the run)
       if (ga.hi_ctas + ga.n_servers >= n_ctas_total) { ga.hi_ctas = 0; ga.hi_slots = 0; }
-      ga.tune = getenv("LRG_TUNE") ? atoi(getenv("LRG_TUNE")) : 3;   // both measured positive (profiles/README.md)
-      rc = launch_grow(ga, e->sm_count > 0 ? e->sm_count : 148, st);
+      // both measured positive (profiles/README.md): bit 0 = split branch tiles over idle CTAs, bit 1 = head tiles go out with the projection
+      ga.tune = ((params->flags & LRG_FLAG_NO_TILE_SPLIT) ? 0 : 1) | ((params->flags & LRG_FLAG_HEADS_AFTER_PROJ) ? 0 : 2);
+      e->last_kind = use_f16(e) ? 2 : 1;
+      rc = launch_grow(ga, e->sm_count > 0 ? e->sm_count : 148, use_f16(e), st);
       if (rc == LRG_OK) {
         cudaError_t se = cudaStreamSynchronize(st);
         if (se != cudaSuccess) { set_error("persistent grow kernel -> %s", cudaGetErrorString(se)); rc = LRG_E_CUDA; }
       }
       if (rc == LRG_OK) LRG_CUDA(cudaMemcpy(e->h_busy, e->d_busy, sizeof(e->h_busy), cudaMemcpyDeviceToHost));
+      if (rc == LRG_OK) {
+        unsigned aborted = 0;
+        LRG_CUDA(cudaMemcpy(&aborted, e->d_qctr + 6, sizeof(unsigned), cudaMemcpyDeviceToHost));
+        if (aborted != 0) { set_error("persistent grow kernel: no work item retired anywhere for 20 s -- the run was abandoned"); rc = LRG_E_STATE; }
+      }
       e->iterations = 0;
       e->launches = 1;
     } else if (use_graph) {
@@ -1028,7 +1213,6 @@ int lrg_segment_resident(LrgEngine* e, const LrgGrowParams* params, LrgRoomStats
   LRG_CUDA(cudaStreamSynchronize(st));
   LRG_CUDA(cudaEventElapsedTime(&e->grow_ms, ev0, ev1));
   LRG_CUDA(cudaEventElapsedTime(&e->fill_ms, ev1, ev2));
-  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
   if (stats != nullptr && n_rooms > 0)
     LRG_CUDA(cudaMemcpy(stats, e->d_stats, sizeof(LrgRoomStats) * n_rooms, cudaMemcpyDeviceToHost));
   return LRG_OK;
@@ -1109,9 +1293,24 @@ int lrg_last_grow_profile(LrgEngine* e, int* persistent, double busy_ms[4], int6
   return LRG_OK;
 }
 
+int lrg_engine_set_tile_timing(LrgEngine* e, int on) {
+  LRG_REQUIRE(e != nullptr, "engine is NULL");
+  LRG_CUDA(cudaSetDevice(e->device));
+  if (on && e->d_tile_dbg == nullptr) {
+    LRG_TRY(dev_alloc(&e->d_tile_dbg, 64));
+    LRG_CUDA(cudaMemset(e->d_tile_dbg, 0, 64 * sizeof(unsigned long long)));
+  } else if (!on && e->d_tile_dbg != nullptr) {
+    LRG_CUDA(cudaDeviceSynchronize());
+    cudaFree(e->d_tile_dbg);
+    e->d_tile_dbg = nullptr;
+  }
+  e->tcnet.dbg = e->d_tile_dbg;
+  return LRG_OK;
+}
+
 int lrg_tile_timing(LrgEngine* e, uint64_t out[64], int reset) {
   LRG_REQUIRE(e != nullptr && out != nullptr, "NULL argument");
-  if (e->d_tile_dbg == nullptr) { set_error("tile timing is off (set LRG_TILE_TIMING=1 before load_weights)"); return LRG_E_STATE; }
+  if (e->d_tile_dbg == nullptr) { set_error("tile timing is off (call lrg_engine_set_tile_timing(e, 1) first)"); return LRG_E_STATE; }
   LRG_CUDA(cudaSetDevice(e->device));
   LRG_CUDA(cudaMemcpy(out, e->d_tile_dbg, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   if (reset) LRG_CUDA(cudaMemset(e->d_tile_dbg, 0, 64 * sizeof(uint64_t)));

@@ -3,9 +3,12 @@
 // the lock-step loop and of lrg_forward_device.  The tile bodies live in lrg_tc_tiles.cuh (shared with the persistent
 // grow kernel).
 //
-// Precision: the parity bar is the fp32 TF graph, so every contraction runs as 3xTF32 -- each fp32 operand is split
-// into hi + lo (both TF32-exact) and D += hi.hi + lo.hi + hi.lo with fp32 accumulation in TMEM, which carries ~21
-// mantissa bits per product (tools/umma_probe.cu: 5e-6..4e-5 per GEMM where an fp32 FMA chain has 2e-6..1e-5).
+// Precision: the parity bar is the fp32 TF graph, so every contraction runs as a three-term split product -- each fp32
+// operand is split into hi + lo and D += hi.hi + lo.hi + hi.lo with fp32 accumulation in TMEM, which carries ~21-22
+// mantissa bits per product.  Two kinds: 3xFP16 (kind::f16, hi / lo are fp16, weights pre-scaled by a power of two per
+// layer; half the MMAs and half the weight bytes; tools/umma_f16_probe.cu: 2e-7..9e-7 relative per GEMM) is the default;
+// 3xTF32 (kind::tf32; tools/umma_probe.cu: 5e-6..4e-5 absolute per GEMM where an fp32 FMA chain has 2e-6..1e-5) is what a
+// call falls back to when an activation leaves the fp16 range (TcNet::range_flag).
 //
 //   lrg_tc_branch_kernel  one CTA per (128-point tile, branch, tile pair): x -> 64 -> 64 -> 64 -> 128 -> 512 -> column max.
 //                         Activations never leave the SM: the epilogue warps read the accumulator from TMEM, add bias,
@@ -28,6 +31,7 @@ namespace lrg {
 
 constexpr int kTcThreads = 192;
 
+template <bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1) lrg_tc_branch_kernel(const __grid_constant__ TcNet net, const __grid_constant__ ForwardArgs fa) {
   const int b = blockIdx.z, br = blockIdx.y, tile = blockIdx.x;
   if (fa.active != nullptr && fa.active[(size_t)b * fa.active_stride] == 0) return;
@@ -41,7 +45,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) lrg_tc_branch_kernel(const __gr
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_base;
-  tc_branch_tile(net, fa, b, br, tile, nvalid, 0, 4, smem, st, tmem);
+  tc_branch_tile<F16>(net, fa, b, br, tile, nvalid, 0, 4, smem, st, tmem);
   if ((threadIdx.x >> 5) == 4) tmem_dealloc(tmem, kTmemCols);
 }
 
@@ -53,6 +57,7 @@ __global__ void __launch_bounds__(512) lrg_tc_gproj_kernel(const __grid_constant
   tc_gproj_block(net, fa, b, h, cb, sP, sR);
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(kTcThreads, 1) lrg_tc_head_kernel(const __grid_constant__ TcNet net, const __grid_constant__ ForwardArgs fa) {
   const int b = blockIdx.z, h = blockIdx.y, tile = blockIdx.x;   // h: 0 = remove head on inlier rows, 1 = add head on neighbor rows
   if (fa.active != nullptr && fa.active[(size_t)b * fa.active_stride] == 0) return;
@@ -66,27 +71,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) lrg_tc_head_kernel(const __grid
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_base;
-  tc_head_tile(net, fa, b, h, tile, nvalid, nullptr, smem, st, tmem);
+  tc_head_tile<F16>(net, fa, b, h, tile, nvalid, nullptr, nullptr, 0u, smem, st, tmem);
   if ((threadIdx.x >> 5) == 4) tmem_dealloc(tmem, kTmemCols);
 }
 
 int tc_forward_configure() {
-  LRG_CUDA(cudaFuncSetAttribute(lrg_tc_branch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-  LRG_CUDA(cudaFuncSetAttribute(lrg_tc_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  LRG_CUDA(cudaFuncSetAttribute(lrg_tc_branch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  LRG_CUDA(cudaFuncSetAttribute(lrg_tc_head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  LRG_CUDA(cudaFuncSetAttribute(lrg_tc_branch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  LRG_CUDA(cudaFuncSetAttribute(lrg_tc_head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
   return LRG_OK;
 }
 
-// pooled must be zero for the active tile pairs on entry.
-int launch_forward_tc(const TcNet& net, const ForwardArgs& fa, cudaStream_t stream, cudaEvent_t* ev) {
+// pooled must be zero for the active tile pairs on entry.  f16: 3xFP16 tiles (net.range_flag reports a range overflow).
+int launch_forward_tc(const TcNet& net, const ForwardArgs& fa, bool f16, cudaStream_t stream, cudaEvent_t* ev) {
   if (fa.B <= 0) return LRG_OK;
   const int nmax = fa.n_pts[0] > fa.n_pts[1] ? fa.n_pts[0] : fa.n_pts[1];
   dim3 grid((nmax + 127) / 128, 2, fa.B);
   if (ev) cudaEventRecord(ev[0], stream);
-  lrg_tc_branch_kernel<<<grid, kTcThreads, kTcSmem, stream>>>(net, fa);
+  if (f16) lrg_tc_branch_kernel<true><<<grid, kTcThreads, kTcSmem, stream>>>(net, fa);
+  else lrg_tc_branch_kernel<false><<<grid, kTcThreads, kTcSmem, stream>>>(net, fa);
   if (ev) cudaEventRecord(ev[1], stream);
   lrg_tc_gproj_kernel<<<dim3(4, 2, fa.B), 512, 0, stream>>>(net, fa);
   if (ev) cudaEventRecord(ev[2], stream);
-  lrg_tc_head_kernel<<<grid, kTcThreads, kTcSmem, stream>>>(net, fa);
+  if (f16) lrg_tc_head_kernel<true><<<grid, kTcThreads, kTcSmem, stream>>>(net, fa);
+  else lrg_tc_head_kernel<false><<<grid, kTcThreads, kTcSmem, stream>>>(net, fa);
   if (ev) cudaEventRecord(ev[3], stream);
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;

@@ -43,91 +43,202 @@ __device__ __forceinline__ void queue_push(const GrowQueue& q, const unsigned* i
   }
 }
 
+// Watchdog of the spinning CTAs.  Idle CTAs are normal (one large room keeps ~10 of 148 busy), so the test is GLOBAL progress:
+// thread 0 of every CTA bumps GrowArgs::progress after each item; a spinner that has seen that counter stand still for
+// kStallNs (20 s of globaltimer -- independent of the SM clock, profilers and throttling slow the run but items keep retiring)
+// raises GrowArgs::abort, and every spinner that sees the flag leaves.  The host then returns LRG_E_STATE; nothing traps, the
+// context stays usable.
+constexpr unsigned long long kStallNs = 20000000000ull;
+struct StallWatch {
+  unsigned last;
+  unsigned long long t_last;
+  unsigned spins;
+  __device__ __forceinline__ void start(const GrowArgs& ga) { last = *reinterpret_cast<volatile unsigned*>(ga.progress); t_last = global_ns(); spins = 0; }
+  // true: give up (the run is wedged, or somebody else found it to be)
+  __device__ __forceinline__ bool stalled(const GrowArgs& ga) {
+    if ((++spins & 1023u) != 0) return false;
+    if (*reinterpret_cast<volatile int*>(ga.abort) != 0) return true;
+    const unsigned p = *reinterpret_cast<volatile unsigned*>(ga.progress);
+    const unsigned long long now = global_ns();
+    if (p != last) { last = p; t_last = now; return false; }
+    if (now - t_last > kStallNs) {
+      *reinterpret_cast<volatile int*>(ga.abort) = 1;
+      __threadfence();
+      return true;
+    }
+    return false;
+  }
+};
+
 // Blocking pop of the normal ring: take a ticket, spin on that ticket's own entry (idle CTAs poll distinct addresses).
-__device__ __forceinline__ unsigned queue_pop(const GrowQueue& q) {
+__device__ __forceinline__ unsigned queue_pop(const GrowArgs& ga, const GrowQueue& q) {
   const unsigned h = atomicAdd(q.head, 1u);
   const unsigned long long gen = (unsigned long long)(h / (q.cap_mask + 1u)) + 1ull;
   const volatile unsigned long long* e = q.ring + (h & q.cap_mask);
   unsigned long long v = *e;
   if ((v >> 32) != gen) {
-    const long long t0 = clock64();
+    StallWatch w;
+    w.start(ga);
     while (((v = *e) >> 32) != gen) {
       __nanosleep(32);
-      if (clock64() - t0 > 60000000000ll) asm volatile("trap;");   // ~30 s without work: the run is wedged, fail loudly
+      if (w.stalled(ga)) return make_item(ITEM_EXIT, 0, 0, 0);
     }
   }
   return (unsigned)v;                                // (the caller issues the acquire fence where the item needs one)
 }
 
 // Pooled-projection server: gproj[slot][h][c0 + c] = bias0_h[c0 + c] + sum_k pooled[slot][k] * W0g_h[k][c0 + c] for the 32
-// columns of this CTA, the weights resident in shared memory (128 KB) instead of being streamed from L2 by every grow step
-// (256 KB per 64-column block item).  Four request groups of 128 threads work on different requests at once (group g takes
-// the tickets = g mod 4 of the broadcast ring); summation order = tc_gproj_block's (32 K-groups of 32 rows, each a
-// sequential fmaf chain from 0, combined in order on top of the bias), so both paths give the same bits.
+// columns of this CTA.  The CTA's 1024 x 32 weights live in REGISTERS for the whole run -- lane c of warp j keeps the 64
+// weights of column c0 + c in K-groups 2j and 2j+1 (rows 64j .. 64j+63) -- so nothing is streamed from L2 per grow step
+// (256 KB per 64-column block item otherwise) and the weights are not re-read from shared memory either (a first version
+// kept them there: 128 KB of shared-memory reads per request, ~2k cycles of the port, 64 % utilisation at the bench's request
+// rate -- the head tiles waited 7.8 us for their projection under load against 2.4 us on an idle machine).
+// The 16 warps run free of one another (no CTA barrier in the loop).  Requests are numbered by ticket; for ticket t
+//   * warp t mod 16 is its LOADER: it polls the broadcast request ring in global memory (one polling warp per server and
+//     ticket -- 256 warps polling one L2 line made the producers' stores queue behind them), copies the slot's pooled row
+//     (4 KB) into a ring of row buffers in shared memory and then publishes the request in a shared-memory ring; it does this
+//     up to kProjLook tickets AHEAD of its own arithmetic, so under load the two L2 round trips are off the request path;
+//   * EVERY warp waits for the request in the shared-memory ring, reads its 64 values of the row (broadcast 128-bit loads),
+//     runs its two 32-long fmaf chains and drops the two partial sums per column into a ring of partial-sum buffers;
+//   * warp t mod 16 is also its REDUCER: it waits for the 16 arrivals on the buffer's mbarrier, combines the 32 K-groups in
+//     order on top of the bias and stores every value together with the tag of the slot's forward as one 8-byte word -- the
+//     head tiles poll the tags, so the server needs no fence and no counter (a fence + atomic per request kept the reducer
+//     ~800 cycles from the next request's arithmetic, which every request needs from every warp: a serial chain).
+// Summation order = tc_gproj_block's (32 K-groups of 32 rows, each a sequential fmaf chain from 0, combined in order on top of
+// the bias), so both paths give the same bits.
+constexpr int kProjBufs = 8;                         // row / partial-sum buffers in flight per server
+constexpr int kProjLook = 4;                         // tickets a loader runs ahead of its own arithmetic (< kProjBufs)
+constexpr int kProjReqRing = 32;                     // shared-memory request ring (> kProjBufs + kProjLook)
 __device__ void proj_server(const GrowArgs& ga, unsigned char* smem) {
-  const int tid = threadIdx.x, grp = tid >> 7, t = tid & 127, c = t & 31, kq = t >> 5;
+  const int tid = threadIdx.x, c = tid & 31, j = tid >> 5;           // j = warp: K-groups 2j, 2j + 1
   const int h = (int)blockIdx.x / 8, c0 = ((int)blockIdx.x % 8) * 32;
-  float* const sW = reinterpret_cast<float*>(smem);                 // [1024][32]
-  float* const sP = sW + 1024 * 32 + grp * 2048;                    // [1024] pooled row of this group's request
-  float* const sR = sP + 1024;                                      // [32][32] K-group partial sums
+  float* const sP = reinterpret_cast<float*>(smem);                  // [kProjBufs][1024] pooled rows
+  float* const sR = sP + kProjBufs * 1024;                           // [kProjBufs][32 K-groups][32 columns]
+  volatile unsigned long long* const s_req = reinterpret_cast<volatile unsigned long long*>(sR + kProjBufs * 1024);   // [kProjReqRing]
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(const_cast<unsigned long long*>(s_req) + kProjReqRing);        // full[], empty[]
+  if (tid < kProjReqRing) s_req[tid] = 0ull;
+  if (tid == 0) {
+    for (int i = 0; i < kProjBufs; ++i) { mbar_init(smem_u32(&bars[i]), 16); mbar_init(smem_u32(&bars[kProjBufs + i]), 1); }
+    fence_barrier_init();
+  }
+  float w[64];
   {
-    const float4* W = reinterpret_cast<const float4*>(ga.net.W0g[h] + c0);
-    for (int i = tid; i < 1024 * 8; i += kGrowThreads) {
-      const int k = i >> 3, q = i & 7;
-      reinterpret_cast<float4*>(sW)[i] = __ldg(W + (size_t)k * 64 + q);
-    }
+    const float* W = ga.net.W0g[h] + (size_t)(64 * j) * 256 + c0 + c;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) w[i] = __ldg(W + (size_t)i * 256);
   }
   const float bias = __ldg(ga.net.head_bias0[h] + c0 + c);
-  __syncthreads();
-  for (unsigned ticket = (unsigned)grp;; ticket += 4u) {
-    const unsigned long long gen = (unsigned long long)(ticket / (ga.greq_mask + 1u)) + 1ull;
-    const volatile unsigned long long* e = ga.greq_ring + (ticket & ga.greq_mask);
-    unsigned long long v = *e;
-    if ((v >> 32) != gen) {
-      const long long t0 = clock64();
-      while (((v = *e) >> 32) != gen) {
+  __syncthreads();                                                   // (ring and barriers initialised: the only CTA barrier)
+  auto gen_of = [&](unsigned ticket) { return (unsigned long long)(ticket / (ga.greq_mask + 1u)) + 1ull; };
+  // Loader duty for ticket t2 (whole warp): 1 = done, 0 = not possible yet (non-blocking only), -1 = the run was abandoned
+  auto load_request = [&](unsigned t2, bool blocking) -> int {
+    const int buf = (int)(t2 % kProjBufs);
+    if (t2 >= (unsigned)kProjBufs) {
+      // the row buffer is free once all 16 warps have arrived for ticket t2 - kProjBufs (they read the row before they arrive)
+      const uint32_t par = ((t2 - kProjBufs) / kProjBufs) & 1u;
+      if (blocking) mbar_wait(smem_u32(&bars[buf]), par);
+      else {
+        int ok = 0;                                    // (one lane asks: the answer must be warp-uniform)
+        if (c == 0) ok = (int)mbar_try_wait(smem_u32(&bars[buf]), par);
+        if (!__shfl_sync(0xffffffffu, ok, 0)) return 0;
+      }
+    }
+    const volatile unsigned long long* e = ga.greq_ring + (t2 & ga.greq_mask);
+    unsigned long long v = 0;
+    if (c == 0) v = *e;
+    v = __shfl_sync(0xffffffffu, v, 0);
+    if ((v >> 32) != gen_of(t2)) {
+      if (!blocking) return 0;
+      int state = 0;                                   // lane 0 polls; 1 = there, -1 = give up
+      if (c == 0) {
+        StallWatch sw;
+        sw.start(ga);
+        while (((v = *e) >> 32) != gen_of(t2)) {
+          __nanosleep(20);
+          if (sw.stalled(ga)) { state = -1; break; }
+        }
+      }
+      state = __shfl_sync(0xffffffffu, state, 0);
+      if (state < 0) return -1;
+      v = __shfl_sync(0xffffffffu, v, 0);
+    }
+    const unsigned slot = (unsigned)v & 0x1FFFu;
+    if (slot != kProjExit) {
+      const float4* src = reinterpret_cast<const float4*>(ga.fa.pooled + (size_t)slot * 1024);
+      float4 r[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) r[q] = __ldcg(src + q * 32 + c);
+      float4* dst = reinterpret_cast<float4*>(sP + buf * 1024);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dst[q * 32 + c] = r[q];
+    }
+    __syncwarp();
+    if (c == 0) {
+      __threadfence_block();
+      s_req[t2 % kProjReqRing] = ((unsigned long long)(t2 + 1u) << 32) | (unsigned)v;   // (tagged by ticket: the ring is shorter than a generation)
+    }
+    return 1;
+  };
+  unsigned next_duty = (unsigned)j;                    // my next ticket as loader
+  for (unsigned ticket = 0;; ++ticket) {
+    if (next_duty <= ticket + (unsigned)kProjLook) {
+      const int r = load_request(next_duty, next_duty == ticket);
+      if (r < 0) break;
+      if (r > 0) next_duty += 16u;
+    }
+    // the request, once its loader has staged the row
+    unsigned long long v = s_req[ticket % kProjReqRing];
+    if ((v >> 32) != (unsigned long long)(ticket + 1u)) {
+      unsigned spins = 0;
+      bool give_up = false;
+      while (((v = s_req[ticket % kProjReqRing]) >> 32) != (unsigned long long)(ticket + 1u)) {
         __nanosleep(20);
-        if (clock64() - t0 > 60000000000ll) asm volatile("trap;");
+        if ((++spins & 0xFFFFu) == 0 && *reinterpret_cast<volatile int*>(ga.abort) != 0) { give_up = true; break; }
+        // (my own loader duty may have become possible meanwhile: rows are staged kProjLook tickets ahead)
+        if ((spins & 63u) == 0 && next_duty <= ticket + (unsigned)kProjLook && next_duty != ticket) {
+          const int r = load_request(next_duty, false);
+          if (r > 0) next_duty += 16u;
+        }
       }
+      if (give_up) break;
     }
-    const unsigned slot = (unsigned)v;
+    __threadfence_block();
+    const unsigned slot = (unsigned)v & 0x1FFFu, tag = proj_tag((unsigned)v >> 13);
     if (slot == kProjExit) break;
-    // (every thread polled the entry itself: no broadcast through shared memory, no barrier before the loads)
-    const float4* prow = reinterpret_cast<const float4*>(ga.fa.pooled + (size_t)slot * 1024);
-    reinterpret_cast<float4*>(sP)[t] = __ldcg(prow + t);
-    reinterpret_cast<float4*>(sP)[t + 128] = __ldcg(prow + t + 128);
-    asm volatile("bar.sync %0, 128;" ::"r"(grp + 1));
+    const int buf = (int)(ticket % kProjBufs);
+    const uint32_t phase = (ticket / kProjBufs) & 1u;
+    float a0 = 0.f, a1 = 0.f;
     {
-      // eight K-groups per thread as eight independent fmaf chains (each chain sequential in k like tc_gproj_block)
-      float acc[8];
+      const float4* p4 = reinterpret_cast<const float4*>(sP + buf * 1024 + 64 * j);
 #pragma unroll
-      for (int g8 = 0; g8 < 8; ++g8) acc[g8] = 0.f;
-      const float* w = sW + (kq * 8 * 32) * 32 + c;
-      const float* p = sP + kq * 8 * 32;
-#pragma unroll 4
-      for (int i = 0; i < 32; ++i) {
-#pragma unroll
-        for (int g8 = 0; g8 < 8; ++g8) acc[g8] = fmaf(p[g8 * 32 + i], w[(g8 * 32 + i) * 32], acc[g8]);
+      for (int q = 0; q < 8; ++q) {
+        const float4 x = p4[q], y = p4[8 + q];
+        a0 = fmaf(x.x, w[q * 4 + 0], a0); a1 = fmaf(y.x, w[32 + q * 4 + 0], a1);
+        a0 = fmaf(x.y, w[q * 4 + 1], a0); a1 = fmaf(y.y, w[32 + q * 4 + 1], a1);
+        a0 = fmaf(x.z, w[q * 4 + 2], a0); a1 = fmaf(y.z, w[32 + q * 4 + 2], a1);
+        a0 = fmaf(x.w, w[q * 4 + 3], a0); a1 = fmaf(y.w, w[32 + q * 4 + 3], a1);
       }
-#pragma unroll
-      for (int g8 = 0; g8 < 8; ++g8) sR[(kq * 8 + g8) * 32 + c] = acc[g8];
     }
-    asm volatile("bar.sync %0, 128;" ::"r"(grp + 1));
-    if (t < 32) {
+    mbar_wait(smem_u32(&bars[kProjBufs + buf]), phase ^ 1u);         // the buffer's previous request has been reduced
+    float* R = sR + buf * 1024;
+    R[(2 * j) * 32 + c] = a0;
+    R[(2 * j + 1) * 32 + c] = a1;
+    __syncwarp();
+    if (c == 0) mbar_arrive(smem_u32(&bars[buf]));
+    if (j == (int)(ticket & 15u)) {
+      mbar_wait(smem_u32(&bars[buf]), phase);
       float s2 = bias;
 #pragma unroll
-      for (int g2 = 0; g2 < 32; ++g2) s2 += sR[g2 * 32 + t];
-      ga.fa.gproj[((size_t)slot * 2 + h) * 256 + c0 + t] = s2;
+      for (int g2 = 0; g2 < 32; ++g2) s2 += R[g2 * 32 + c];
+      // value and tag in ONE 8-byte store: whoever reads the tag of this forward has the value -- no fence, no counter
+      __stcg(ga.gproj_tagged + ((size_t)slot * 2 + h) * 256 + c0 + c, make_uint2(__float_as_uint(s2), tag));
       __syncwarp();
-      if (t == 0) {
-        __threadfence();
-        atomicSub(&ga.sync[slot].gproj_left, 1);
-      }
+      if (c == 0) mbar_arrive(smem_u32(&bars[kProjBufs + buf]));
     }
-    asm volatile("bar.sync %0, 128;" ::"r"(grp + 1));     // sP / sR are reused by the group's next request
   }
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_constant__ GrowArgs ga) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(16) TcStatic st;
@@ -158,7 +269,7 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
     if (tid == 0) {
       unsigned it = chained;
       chained = 0;
-      if (it == 0) it = queue_pop(ga.q[my_ring]);
+      if (it == 0) it = queue_pop(ga, ga.q[my_ring]);
       // acquire: the driver step reads state other CTAs wrote with plain stores (drop stale L1 lines); the tensor tiles and
       // the projection read everything produced in this launch with ld.global.cg and need no fence
       if ((it & 7u) == ITEM_STEP) __threadfence();
@@ -184,14 +295,11 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
         if (sh.S.finished) *reinterpret_cast<volatile int*>(ga.remaining + slot) = 0;
         if (sh.all_done) {
           // the last slot has retired: nothing is in flight any more, release every CTA
-          if (ga.n_servers > 0) {                          // one closing request per request group of the servers
+          if (ga.n_servers > 0) {                          // one closing request: every server reads every entry
             __threadfence();
-            const unsigned t4 = atomicAdd(ga.greq_tail, 4u);
-            for (unsigned i = 0; i < 4u; ++i) {
-              const unsigned idx = t4 + i;
-              *reinterpret_cast<volatile unsigned long long*>(ga.greq_ring + (idx & ga.greq_mask)) =
-                  (((unsigned long long)(idx / (ga.greq_mask + 1u)) + 1ull) << 32) | kProjExit;
-            }
+            const unsigned idx = atomicAdd(ga.greq_tail, 1u);
+            *reinterpret_cast<volatile unsigned long long*>(ga.greq_ring + (idx & ga.greq_mask)) =
+                (((unsigned long long)(idx / (ga.greq_mask + 1u)) + 1ull) << 32) | kProjExit;
           }
           for (int ring = 0; ring < 2; ++ring)
             for (unsigned left = ring == 0 ? (unsigned)ga.hi_ctas : gridDim.x - (unsigned)(ga.hi_ctas + ga.n_servers); left > 0;) {
@@ -232,7 +340,8 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
           const int lg = !(ga.tune & 1) ? 0 : idle >= 8 * (tilesI + tilesJ) ? 2 : idle >= 4 * (tilesI + tilesJ) ? 1 : 0;
           const int parts = 1 << lg;
           sy->branch_left = (tilesI + tilesJ) * parts;
-          sy->gproj_left = ga.n_servers > 0 ? ga.n_servers : 8;
+          sy->seq += 1u;                                 // (this CTA owns the slot between a STEP and its publication)
+          sy->gproj_left = 8;
           sy->head_left = tilesI + tilesJ;
           sy->tiles[0] = tilesI;
           sy->tiles[1] = tilesJ;
@@ -252,7 +361,7 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
     } else if (type == ITEM_BRANCH) {
       {
         const int br = a & 1, part = t >> 2, nbs = 4 >> (a >> 1);
-        tc_branch_tile(ga.net, ga.fa, slot, br, t & 3, forward_valid_rows(ga.fa, slot, br), part * nbs, (part + 1) * nbs, smem, st, tmem);
+        tc_branch_tile<F16>(ga.net, ga.fa, slot, br, t & 3, forward_valid_rows(ga.fa, slot, br), part * nbs, (part + 1) * nbs, smem, st, tmem);
       }
       if (tid == 0) {
         __threadfence();
@@ -268,7 +377,7 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
             // plain, 1350 vs 1180 ms with 10 restarts.)
             const unsigned idx = atomicAdd(ga.greq_tail, 1u);
             *reinterpret_cast<volatile unsigned long long*>(ga.greq_ring + (idx & ga.greq_mask)) =
-                (((unsigned long long)(idx / (ga.greq_mask + 1u)) + 1ull) << 32) | (unsigned)slot;
+                (((unsigned long long)(idx / (ga.greq_mask + 1u)) + 1ull) << 32) | (unsigned)slot | ((__ldcg(&sy->seq) & kProjSeqMask) << 13);
           } else {
             for (int h = 0; h < 2; ++h)
               for (int cb = 0; cb < 4; ++cb) next[n_next++] = make_item(ITEM_GPROJ, slot, h, cb);
@@ -291,7 +400,11 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
         }
       }
     } else if (type == ITEM_HEAD) {
-      tc_head_tile(ga.net, ga.fa, slot, a, t, forward_valid_rows(ga.fa, slot, a), &sy->gproj_left, smem, st, tmem);
+      if (ga.n_servers > 0)
+        tc_head_tile<F16>(ga.net, ga.fa, slot, a, t, forward_valid_rows(ga.fa, slot, a), nullptr, ga.gproj_tagged + ((size_t)slot * 2 + a) * 256,
+                          proj_tag(__ldcg(&sy->seq)), smem, st, tmem);
+      else
+        tc_head_tile<F16>(ga.net, ga.fa, slot, a, t, forward_valid_rows(ga.fa, slot, a), &sy->gproj_left, nullptr, 0u, smem, st, tmem);
       if (tid == 0) {
         __threadfence();
         // the CTA that retires the slot's last head tile runs the slot's next driver step itself: no queue hop, and under
@@ -320,6 +433,7 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
         atomicAdd(ga.busy_ns + type, global_ns() - t0);
         atomicAdd(ga.busy_ns + 8 + type, 1ull);
       }
+      atomicAdd(ga.progress, 1u);                      // (the watchdog of the spinning CTAs looks at this)
     }
     __syncthreads();
   }
@@ -329,14 +443,35 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
 }
 
 int grow_configure() {
-  LRG_CUDA(cudaFuncSetAttribute(lrg_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  LRG_CUDA(cudaFuncSetAttribute(lrg_grow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+  LRG_CUDA(cudaFuncSetAttribute(lrg_grow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
   return LRG_OK;
 }
 
-int launch_grow(const GrowArgs& ga, int n_ctas, cudaStream_t stream) {
+// Cooperative launch: the kernel's CTAs wait for one another (work queue, projection servers), so they must all be resident
+// -- one per SM, each with all 512 TMEM columns.  cudaLaunchCooperativeKernel guarantees co-residency (the launch is held
+// back until the grid fits) and refuses a grid that can never fit, which is reported as LRG_E_STATE instead of a spin.
+int launch_grow(const GrowArgs& ga, int n_ctas, bool f16, cudaStream_t stream) {
   static_assert(sizeof(StepShared) <= kTcSmem, "driver scratch must fit the shared memory it aliases");
-  lrg_grow_kernel<<<n_ctas, kGrowThreads, kTcSmem, stream>>>(ga);
-  LRG_CUDA(cudaGetLastError());
+  const void* fn = f16 ? (const void*)lrg_grow_kernel<true> : (const void*)lrg_grow_kernel<false>;
+  int per_sm = 0, dev = 0, sms = 0, coop = 0;
+  LRG_CUDA(cudaGetDevice(&dev));
+  LRG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  LRG_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  LRG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kGrowThreads, kTcSmem));
+  if (per_sm < 1 || n_ctas > per_sm * sms || !coop) {
+    set_error("persistent grow kernel: %d CTAs cannot be co-resident on this device (%d SMs x %d CTAs per SM, cooperative launch %s)",
+              n_ctas, sms, per_sm, coop ? "supported" : "unsupported");
+    return LRG_E_STATE;
+  }
+  void* args[] = {const_cast<GrowArgs*>(&ga)};
+  const cudaError_t err = cudaLaunchCooperativeKernel(fn, dim3((unsigned)n_ctas), dim3(kGrowThreads), args, kTcSmem, stream);
+  if (err == cudaErrorCooperativeLaunchTooLarge) {
+    cudaGetLastError();
+    set_error("persistent grow kernel: the device cannot hold %d co-resident CTAs right now", n_ctas);
+    return LRG_E_STATE;
+  }
+  LRG_CUDA(err);
   return LRG_OK;
 }
 

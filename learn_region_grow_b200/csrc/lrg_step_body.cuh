@@ -1100,16 +1100,34 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     bool mine = false;
     while (true) {
       if (G.room >= 0) {
-        // window: a seed goes to another idle lane only while CTAs are waiting for work (speculation costs SM time)
-        int idle_ctas = 1 << 30;
-        if (da.spec_min_idle > 0 && da.q_ctr != nullptr) {
-          const int b = (int)(*reinterpret_cast<const volatile unsigned*>(da.q_ctr + 1) - *reinterpret_cast<const volatile unsigned*>(da.q_ctr));
-          idle_ctas = b < 0 ? -b : 0;
+        // Window: speculation costs SM time (discarded attempts) and pays only on the run's critical path, so a seed goes to
+        // a SECOND lane only (a) in the spec_top rooms with the most estimated work left -- the run ends with them -- or
+        // (b) while many CTAs wait for work anyway (the tail).  Estimate = unvisited points x grow steps per visited point
+        // of this room so far (prior: 0.2 steps per point).
+        bool speculate = true;
+        if (da.spec_est != nullptr) {
+          const int gi = slot / L, ng = da.n_slots / L;
+          const int mine = (int)(((long long)(N - G.visited) * (G.useful_steps + 20)) / (G.visited + 100));
+          if (tid == 0) *reinterpret_cast<volatile int*>(da.spec_est + gi) = mine;
+          int ahead = 0;
+          for (int g0 = 0; g0 < ng; g0 += NT) {
+            const int g = g0 + tid;
+            const int other = (g < ng && g != gi) ? __ldcg(da.spec_est + g) : -1;
+            ahead += __syncthreads_count(other > mine || (other == mine && g < gi));
+          }
+          // (the queue counters move while they are read: ONE thread looks, the verdict must be the same for the whole CTA)
+          int idle_ok = 0;
+          if (tid == 0 && da.q_ctr != nullptr) {
+            const int b = (int)(*reinterpret_cast<const volatile unsigned*>(da.q_ctr + 1) - *reinterpret_cast<const volatile unsigned*>(da.q_ctr));
+            idle_ok = (b < 0 ? -b : 0) >= da.spec_min_idle;
+          }
+          idle_ok = __syncthreads_or(idle_ok);
+          speculate = ahead < da.spec_top || idle_ok != 0;
         }
         for (int k = 0; k < L; ++k) {
           const int l = (lane_id + k) % L;
           if (G.lane_ticket[l] >= 0) continue;
-          if (k > 0 && G.next_ticket > G.commit_seq && idle_ctas < da.spec_min_idle) continue;
+          if (k > 0 && G.next_ticket > G.commit_seq && !speculate) continue;
           if (!spec_give_seed(l)) break;
           if (l == lane_id) mine = true;
         }
@@ -1146,6 +1164,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       __syncthreads();
       if (G.room < 0) {
         if (tid == 0) {
+          if (da.spec_est != nullptr) *reinterpret_cast<volatile int*>(da.spec_est + slot / L) = 0;
           for (int l = 0; l < L; ++l)
             if (l != lane_id) *reinterpret_cast<volatile int*>(&da.slots[slot0 + l].finished) = 1;
           S.finished = 1;

@@ -30,6 +30,7 @@ constexpr uint32_t kTmemCols = 512;
 //           [384,448) / [448,512) 64-channel slice of the hidden layer hi / lo
 constexpr uint32_t kTmAhi = 256, kTmAlo = 384;
 constexpr uint32_t kTmH1hi = 256, kTmH1lo = 320, kTmChi = 384, kTmClo = 448;
+constexpr float kF16Limit = 65000.f;                   // 3xFP16: activations must stay below this (fp16 max = 65504)
 
 struct TcBarriers {
   uint64_t full[kRingSlots], empty[kRingSlots];
@@ -61,21 +62,28 @@ __device__ __forceinline__ void mbar_inval(uint32_t bar) { asm volatile("mbarrie
 
 // One weight chunk = hi image + lo image of an [Nc x Kc] K-major operand in shared memory; the activations' hi / lo parts
 // sit in TMEM columns a_hi.. / a_lo..:  D[tmem] (+)= A(hi,lo)[128 x Kc] . chunk^T as hi.hi + lo.hi + hi.lo.
+// F16 = false: kind::tf32, one 32-bit TMEM column and 4 bytes of the image per element, K = 8 per instruction;
+// F16 = true:  kind::f16, two elements per TMEM column (packed fp16 pairs) and 2 bytes per element, K = 16 per instruction
+// -- either way one instruction consumes 8 TMEM columns of A and two K-adjacent core matrices of B, so the descriptor
+// arithmetic is the same; the fp16 form needs half the instructions (and half the weight bytes) for the same K.
 // Fully unrolled with compile-time shapes: the single issuing thread must sustain one tcgen05.mma per <= 32..64 cycles,
 // so per instruction there is only a descriptor add (the start-address field advances by a constant) left to do.
-template <int Nc, int Kc>
+template <bool F16, int Nc, int Kc>
 __device__ __forceinline__ void mma_chunk(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t d_tmem, bool first) {
   constexpr uint32_t kdirB = (uint32_t)Nc * 16;                 // bytes between K-adjacent core matrices of the image
-  constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Nc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t idesc = (F16 ? 0u : ((2u << 7) | (2u << 10))) | (1u << 4) | ((uint32_t)(Nc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr int KS = F16 ? Kc / 16 : Kc / 8;
   const uint64_t bd_hi = make_desc(b_hi, kdirB, kMNdir);
-  const uint64_t bd_lo = make_desc(b_hi + (uint32_t)(Nc * Kc * 4), kdirB, kMNdir);
+  const uint64_t bd_lo = make_desc(b_hi + (uint32_t)(Nc * Kc * (F16 ? 2 : 4)), kdirB, kMNdir);
 #pragma unroll
   for (int term = 0; term < 3; ++term) {
     const uint32_t a0 = (term == 1) ? a_lo : a_hi;
     const uint64_t bd = (term == 2) ? bd_lo : bd_hi;
 #pragma unroll
-    for (int ks = 0; ks < Kc / 8; ++ks)
-      umma_tf32_ts(d_tmem, a0 + ks * 8, bd + (uint64_t)((ks * 2 * kdirB) >> 4), idesc, (term == 0 && ks == 0 && first) ? 0u : 1u);
+    for (int ks = 0; ks < KS; ++ks) {
+      if (F16) umma_f16_ts(d_tmem, a0 + ks * 8, bd + (uint64_t)((ks * 2 * kdirB) >> 4), idesc, (term == 0 && ks == 0 && first) ? 0u : 1u);
+      else umma_tf32_ts(d_tmem, a0 + ks * 8, bd + (uint64_t)((ks * 2 * kdirB) >> 4), idesc, (term == 0 && ks == 0 && first) ? 0u : 1u);
+    }
   }
 }
 
@@ -85,24 +93,41 @@ __device__ __forceinline__ void split_fast(float x, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(__fsub_rn(x, __uint_as_float(hi)));
 }
 
-// bias + ReLU + hi/lo split of 32 accumulator columns of this thread's row, stored as the A operand of the next layer
-// (TMEM columns t_hi.. / t_lo..); optionally mirrored to global memory as fp32.
-__device__ __forceinline__ void store_act32(uint32_t (&v)[32], const float* s_bias, uint32_t t_hi, uint32_t t_lo, float* g_row) {
-  uint32_t lo[32];
+// scale + bias + ReLU + hi/lo split of 32 accumulator columns (channels c0..c0+31) of this thread's row, stored as the A
+// operand of the next layer: TMEM columns t_hi + c0.. / t_lo + c0.. (3xTF32, one column per channel) or t_hi + c0/2.. /
+// t_lo + c0/2.. (3xFP16, packed pairs); optionally mirrored to global memory as fp32.  inv = 1 for 3xTF32 (the fmaf is then
+// an exactly rounded add).  over: set when a value leaves the fp16 range.
+template <bool F16>
+__device__ __forceinline__ void store_act32(uint32_t (&v)[32], const float* s_bias, float inv, uint32_t t_hi, uint32_t t_lo, int c0,
+                                            float* g_row, bool& over) {
+  float x[32];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(s_bias + q * 4);
-    float4 x;
-    x.x = fmaxf(__uint_as_float(v[q * 4 + 0]) + b.x, 0.f);
-    x.y = fmaxf(__uint_as_float(v[q * 4 + 1]) + b.y, 0.f);
-    x.z = fmaxf(__uint_as_float(v[q * 4 + 2]) + b.z, 0.f);
-    x.w = fmaxf(__uint_as_float(v[q * 4 + 3]) + b.w, 0.f);
-    if (g_row != nullptr) *reinterpret_cast<float4*>(g_row + q * 4) = x;
-    split_fast(x.x, v[q * 4 + 0], lo[q * 4 + 0]); split_fast(x.y, v[q * 4 + 1], lo[q * 4 + 1]);
-    split_fast(x.z, v[q * 4 + 2], lo[q * 4 + 2]); split_fast(x.w, v[q * 4 + 3], lo[q * 4 + 3]);
+    x[q * 4 + 0] = fmaxf(fmaf(__uint_as_float(v[q * 4 + 0]), inv, b.x), 0.f);
+    x[q * 4 + 1] = fmaxf(fmaf(__uint_as_float(v[q * 4 + 1]), inv, b.y), 0.f);
+    x[q * 4 + 2] = fmaxf(fmaf(__uint_as_float(v[q * 4 + 2]), inv, b.z), 0.f);
+    x[q * 4 + 3] = fmaxf(fmaf(__uint_as_float(v[q * 4 + 3]), inv, b.w), 0.f);
+    if (g_row != nullptr) *reinterpret_cast<float4*>(g_row + q * 4) = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
   }
-  tmem_st32(t_hi, v);
-  tmem_st32(t_lo, lo);
+  if (F16) {
+    uint32_t hi[16], lo[16];
+    float mx = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      mx = fmaxf(mx, fmaxf(x[2 * i], x[2 * i + 1]));
+      split_f16x2(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
+    }
+    over |= !(mx < kF16Limit);                    // (also catches NaN)
+    tmem_st16(t_hi + (uint32_t)(c0 >> 1), hi);
+    tmem_st16(t_lo + (uint32_t)(c0 >> 1), lo);
+  } else {
+    uint32_t lo[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) split_fast(x[i], v[i], lo[i]);
+    tmem_st32(t_hi + (uint32_t)c0, v);
+    tmem_st32(t_lo + (uint32_t)c0, lo);
+  }
 }
 
 __device__ __forceinline__ void tc_init_barriers(TcBarriers& bars, bool head) {
@@ -124,20 +149,32 @@ __device__ __forceinline__ void tc_inval_barriers(TcBarriers& bars) {
   for (int i = 0; i < kTcBarrierCount; ++i) mbar_inval(smem_u32(p + i));
 }
 
+// Chunk c of a branch / head operand image: size and offset in bytes (lrg_tc.cuh has the chunk lists).
+template <bool F16> __device__ __forceinline__ uint32_t branch_chunk_bytes(int c) {
+  if (F16) return c == 0 ? 4096u : c <= 2 ? 16384u : 32768u;
+  return c == 0 ? 8192u : 32768u;
+}
+template <bool F16> __device__ __forceinline__ uint32_t branch_chunk_off(int c) {
+  if (F16) return c == 0 ? 0u : c == 1 ? 4096u : c == 2 ? 20480u : 36864u + (uint32_t)(c - 3) * 32768u;
+  return c == 0 ? 0u : 8192u + (uint32_t)(c - 1) * 32768u;
+}
+template <bool F16> __device__ __forceinline__ uint32_t head_chunk_bytes() { return F16 ? 16384u : 32768u; }
+
 // Weight loader (one thread): streams the operand-image chunks [first, n_head) and [gap_to, gap_to + n_tail) through the
-// ring in that order (the ring position is the running count); chunk 0 of the image may be short (bytes0).
-__device__ __forceinline__ void tc_stream_weights(TcBarriers& bars, uint32_t ring_u32, const float* img, int first, int n_head,
-                                                  int gap_to, int n_tail, uint32_t bytes0) {
-  auto chunk_off = [&](int c) { return c == 0 ? (size_t)0 : (size_t)bytes0 / 4 + (size_t)(c - 1) * (kSlotBytes / 4); };
+// ring in that order (the ring position is the running count).
+template <bool F16, bool HEAD>
+__device__ __forceinline__ void tc_stream_weights(TcBarriers& bars, uint32_t ring_u32, const unsigned char* img, int first, int n_head,
+                                                  int gap_to, int n_tail) {
   int i = first;                                   // position in the ring sequence
   const int total = n_head + n_tail;
   for (; i < total; ++i) {
     const int c = i < n_head ? i : gap_to + (i - n_head);
     const int slot = i % kRingSlots;
-    const uint32_t bytes = (c == 0) ? bytes0 : kSlotBytes;
+    const uint32_t bytes = HEAD ? head_chunk_bytes<F16>() : branch_chunk_bytes<F16>(c);
+    const uint32_t off = HEAD ? (uint32_t)c * head_chunk_bytes<F16>() : branch_chunk_off<F16>(c);
     mbar_wait(smem_u32(&bars.empty[slot]), ((uint32_t)(i / kRingSlots) & 1u) ^ 1u);
     mbar_expect_tx(smem_u32(&bars.full[slot]), bytes);
-    bulk_g2s(ring_u32 + slot * kSlotBytes, img + chunk_off(c), bytes, smem_u32(&bars.full[slot]));
+    bulk_g2s(ring_u32 + slot * kSlotBytes, img + off, bytes, smem_u32(&bars.full[slot]));
   }
 }
 
@@ -145,6 +182,7 @@ __device__ __forceinline__ void tc_stream_weights(TcBarriers& bars, uint32_t rin
 // x (rows x F) -> 64 -> 64 -> 64 -> 128 -> 512 -> column max merged into pooled (learn_region_grow_util.py:106-123).
 // nb0..nb1: which 128-column blocks of the last layer this call reduces (a tile may be split over several CTAs, each
 // recomputing the cheap first four layers, to shorten the critical path when SMs are idle); h1 is written when nb0 == 0.
+template <bool F16>
 __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardArgs& fa, int b, int br, int tile, int nvalid,
                                                int nb0, int nb1, unsigned char* smem, TcStatic& st, uint32_t tmem) {
   const int n = fa.n_pts[br];
@@ -175,6 +213,7 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
     const int r = tid;
     const bool valid = r < rows;
     const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    bool over = false;
     {
       const float* xrow = fa.x[br] + ((size_t)b * n + row0 + r) * fa.x_stride;
       float xv[16];
@@ -188,13 +227,26 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
 #pragma unroll
         for (int c = 0; c < 16; ++c) xv[c] = (valid && c < net.F) ? __ldcg(xrow + c) : 0.f;
       }
-      uint32_t hi[32], lo[32];
+      if (F16) {
+        uint32_t hi[16], lo[16];
+        float mx = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        if (c < 16) split_fast(xv[c], hi[c], lo[c]); else { hi[c] = 0u; lo[c] = 0u; }
+        for (int c = 0; c < 16; ++c) {
+          if (c < 8) { split_f16x2(xv[2 * c], xv[2 * c + 1], hi[c], lo[c]); mx = fmaxf(mx, fmaxf(fabsf(xv[2 * c]), fabsf(xv[2 * c + 1]))); }
+          else { hi[c] = 0u; lo[c] = 0u; }
+        }
+        over |= !(mx < kF16Limit);
+        tmem_st16(tlane + kTmAhi, hi);
+        tmem_st16(tlane + kTmAlo, lo);
+      } else {
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (c < 16) split_fast(xv[c], hi[c], lo[c]); else { hi[c] = 0u; lo[c] = 0u; }
+        }
+        tmem_st32(tlane + kTmAhi, hi);
+        tmem_st32(tlane + kTmAlo, lo);
       }
-      tmem_st32(tlane + kTmAhi, hi);
-      tmem_st32(tlane + kTmAlo, lo);
       tmem_st_wait();
       tcgen05_fence_before();
       mbar_arrive(smem_u32(&bars.act_ready));
@@ -208,11 +260,12 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
       tcgen05_fence_after();
       const int N = (l == 3) ? 128 : 64;
       const float* s_bias = st.vec + l * 64;
+      const float inv = F16 ? net.branch_inv[br][l] : 1.f;
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tlane + buf * 128 + c0, v);
         tmem_ld_wait();
-        store_act32(v, s_bias + c0, tlane + kTmAhi + c0, tlane + kTmAlo + c0, (l == 1 && g_h1 != nullptr) ? g_h1 + c0 : nullptr);
+        store_act32<F16>(v, s_bias + c0, inv, tlane + kTmAhi, tlane + kTmAlo, c0, (l == 1 && g_h1 != nullptr) ? g_h1 + c0 : nullptr, over);
       }
       tmem_st_wait();
       tcgen05_fence_before();
@@ -223,6 +276,7 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
     // last layer: column max over the tile's rows, bias and ReLU after the max (both monotone)
     int* gmax = reinterpret_cast<int*>(fa.pooled) + (size_t)b * 1024 + br * 512;
     const float* bias4 = net.conv_bias[br][4];
+    const float inv4 = F16 ? net.branch_inv[br][4] : 1.f;
 #pragma unroll 1
     for (int nb = nb0; nb < nb1; ++nb) {
       const int j = 4 + (nb - nb0), buf = j & 1;
@@ -251,12 +305,13 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
           }
         }
         const int col = nb * 128 + c * 32 + lane;    // lane L ends up with column c*32 + L
-        atomicMax(gmax + col, __float_as_int(fmaxf(m[0] + b4[c], 0.f)));
+        atomicMax(gmax + col, __float_as_int(fmaxf(fmaf(m[0], inv4, b4[c]), 0.f)));
       }
       tcgen05_fence_before();
       mbar_arrive(smem_u32(&bars.acc_empty[buf]));
       tc_stamp(net.dbg, 6 + (nb - nb0), tstamp);
     }
+    if (F16 && over && net.range_flag != nullptr) *reinterpret_cast<volatile int*>(net.range_flag) = 1;
   } else if (warp == 4) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
@@ -284,11 +339,12 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
         timed_wait(smem_u32(&bars.acc_empty[buf]), ((uint32_t)(l >> 1) & 1u) ^ 1u, w_acc);
         tcgen05_fence_after();
         const uint32_t d = tmem + buf * 128;
-        if (l == 0) { mma_chunk<64, 16>(a_hi, a_lo, wait_chunk(), d, true); done_chunk(); }
-        else if (l < 3) { mma_chunk<64, 64>(a_hi, a_lo, wait_chunk(), d, true); done_chunk(); }
+        if (l == 0) { mma_chunk<F16, 64, 16>(a_hi, a_lo, wait_chunk(), d, true); done_chunk(); }
+        else if (l < 3) { mma_chunk<F16, 64, 64>(a_hi, a_lo, wait_chunk(), d, true); done_chunk(); }
+        else if (F16) { mma_chunk<true, 128, 64>(a_hi, a_lo, wait_chunk(), d, true); done_chunk(); }
         else {
-          mma_chunk<128, 32>(a_hi, a_lo, wait_chunk(), d, true); done_chunk();
-          mma_chunk<128, 32>(a_hi + 32, a_lo + 32, wait_chunk(), d, false); done_chunk();
+          mma_chunk<false, 128, 32>(a_hi, a_lo, wait_chunk(), d, true); done_chunk();
+          mma_chunk<false, 128, 32>(a_hi + 32, a_lo + 32, wait_chunk(), d, false); done_chunk();
         }
         umma_commit(smem_u32(&bars.acc_full[buf]));
       }
@@ -298,9 +354,10 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
         const int j = 4 + (nb - nb0), buf = j & 1;
         timed_wait(smem_u32(&bars.acc_empty[buf]), ((uint32_t)(j >> 1) & 1u) ^ 1u, w_acc);
         tcgen05_fence_after();
+        // (a chunk covers 32 TMEM columns of A in both kinds: 32 channels as tf32, 64 channels as packed fp16 pairs)
 #pragma unroll 1
-        for (int kc = 0; kc < 4; ++kc) {
-          mma_chunk<128, 32>(a_hi + kc * 32, a_lo + kc * 32, wait_chunk(), tmem + buf * 128, kc == 0);
+        for (int kc = 0; kc < (F16 ? 2 : 4); ++kc) {
+          mma_chunk<F16, 128, F16 ? 64 : 32>(a_hi + kc * 32, a_lo + kc * 32, wait_chunk(), tmem + buf * 128, kc == 0);
           done_chunk();
         }
         umma_commit(smem_u32(&bars.acc_full[buf]));
@@ -313,7 +370,10 @@ __device__ __forceinline__ void tc_branch_tile(const TcNet& net, const ForwardAr
     }
   } else if (warp == 5) {
     // ===================================================================== weight loader
-    if (lane == 0) tc_stream_weights(bars, ring_u32, net.branch_img[br], 0, 5, 5 + 4 * nb0, 4 * (nb1 - nb0), 8192u);
+    if (lane == 0) {
+      if (F16) tc_stream_weights<true, false>(bars, ring_u32, net.branch_img[1][br], 0, 4, 4 + 2 * nb0, 2 * (nb1 - nb0));
+      else tc_stream_weights<false, false>(bars, ring_u32, net.branch_img[0][br], 0, 5, 5 + 4 * nb0, 4 * (nb1 - nb0));
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -368,9 +428,12 @@ __device__ __forceinline__ void tc_gproj_block(const TcNet& net, const ForwardAr
 // 32-channel K-chunks the moment its epilogue has written them (c_ready / c_free per half).
 // gproj_pending: optional counter that reaches 0 when this tile pair's pooled projection has been written (the
 // persistent kernel publishes head tiles together with the projection blocks so that the tile's prologue and first MMAs
-// overlap them); NULL = the projection is already there.
+// overlap them); NULL = the projection is already there.  gproj_tagged (persistent kernel with projection servers): the
+// 256 {value, tag} words of this (slot, head) instead of fa.gproj; a word is valid once its tag equals `tag`.
+template <bool F16>
 __device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs& fa, int b, int h, int tile, int nvalid,
-                                             const int* gproj_pending, unsigned char* smem, TcStatic& st, uint32_t tmem) {
+                                             const int* gproj_pending, const uint2* gproj_tagged, unsigned tag, unsigned char* smem,
+                                             TcStatic& st, uint32_t tmem) {
   const int n = fa.n_pts[h];
   const int row0 = tile * 128;
   const int rows = min(128, nvalid - row0);
@@ -396,17 +459,29 @@ __device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs
       float4 x[16];
 #pragma unroll
       for (int q = 0; q < 16; ++q) x[q] = valid ? __ldcg(hrow + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      if (F16) {
+        // (h1 was produced by a branch tile of this kind, which already checked its range)
         uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 v = x[half * 8 + q];
-          split_fast(v.x, hi[q * 4 + 0], lo[q * 4 + 0]); split_fast(v.y, hi[q * 4 + 1], lo[q * 4 + 1]);
-          split_fast(v.z, hi[q * 4 + 2], lo[q * 4 + 2]); split_fast(v.w, hi[q * 4 + 3], lo[q * 4 + 3]);
+        for (int q = 0; q < 16; ++q) {
+          split_f16x2(x[q].x, x[q].y, hi[q * 2 + 0], lo[q * 2 + 0]);
+          split_f16x2(x[q].z, x[q].w, hi[q * 2 + 1], lo[q * 2 + 1]);
         }
-        tmem_st32(tlane + kTmH1hi + half * 32, hi);
-        tmem_st32(tlane + kTmH1lo + half * 32, lo);
+        tmem_st32(tlane + kTmH1hi, hi);
+        tmem_st32(tlane + kTmH1lo, lo);
+      } else {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 v = x[half * 8 + q];
+            split_fast(v.x, hi[q * 4 + 0], lo[q * 4 + 0]); split_fast(v.y, hi[q * 4 + 1], lo[q * 4 + 1]);
+            split_fast(v.z, hi[q * 4 + 2], lo[q * 4 + 2]); split_fast(v.w, hi[q * 4 + 3], lo[q * 4 + 3]);
+          }
+          tmem_st32(tlane + kTmH1hi + half * 32, hi);
+          tmem_st32(tlane + kTmH1lo + half * 32, lo);
+        }
       }
       tmem_st_wait();
       tcgen05_fence_before();
@@ -414,6 +489,8 @@ __device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs
     }
     mbar_wait(smem_u32(&bars.vec_ready), 0u);          // st.vec is complete
     tc_stamp(net.dbg, 17, tstamp);
+    bool over = false;
+    const float inv0 = F16 ? net.head_inv[h][0] : 1.f, inv1 = F16 ? net.head_inv[h][1] : 1.f;
 #pragma unroll 1
     for (int nb = 0; nb < 4; ++nb) {
       const int buf = nb & 1;
@@ -428,7 +505,7 @@ __device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs
           mbar_wait(smem_u32(&bars.c_free[half]), (uint32_t)(nb - 1) & 1u);
           tcgen05_fence_after();
         }
-        store_act32(v, sG + nb * 64 + half * 32, tlane + kTmChi + half * 32, tlane + kTmClo + half * 32, nullptr);
+        store_act32<F16>(v, sG + nb * 64 + half * 32, inv0, tlane + kTmChi, tlane + kTmClo, half * 32, nullptr, over);
         tmem_st_wait();
         tcgen05_fence_before();
         if (half == 1) mbar_arrive(smem_u32(&bars.acc_empty[buf]));
@@ -446,13 +523,14 @@ __device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float x = fmaxf(__uint_as_float(v[i]) + sB1[c0 + i], 0.f);
+        const float x = fmaxf(fmaf(__uint_as_float(v[i]), inv1, sB1[c0 + i]), 0.f);
         const float2 w = *reinterpret_cast<const float2*>(sW2 + 2 * (c0 + i));
         o0 = fmaf(x, w.x, o0);
         o1 = fmaf(x, w.y, o1);
       }
     }
     if (valid) *reinterpret_cast<float2*>(fa.logits[h] + ((size_t)b * n + row0 + r) * 2) = make_float2(o0, o1);
+    if (F16 && over && net.range_flag != nullptr) *reinterpret_cast<volatile int*>(net.range_flag) = 1;
     tc_stamp(net.dbg, 22, tstamp);
   } else if (warp == 4) {
     if (lane == 0) {
@@ -471,7 +549,7 @@ __device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs
         const int buf = nb & 1;
         mbar_wait(smem_u32(&bars.acc_empty[buf]), ((uint32_t)(nb >> 1) & 1u) ^ 1u);
         tcgen05_fence_after();
-        mma_chunk<64, 64>(tmem + kTmH1hi, tmem + kTmH1lo, wait_chunk(), tmem + buf * 64, true);
+        mma_chunk<F16, 64, 64>(tmem + kTmH1hi, tmem + kTmH1lo, wait_chunk(), tmem + buf * 64, true);
         done_chunk();
         umma_commit(smem_u32(&bars.acc_full[buf]));
       };
@@ -480,7 +558,8 @@ __device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs
         for (int half = 0; half < 2; ++half) {
           mbar_wait(smem_u32(&bars.c_ready[half]), (uint32_t)kc & 1u);
           tcgen05_fence_after();
-          mma_chunk<128, 32>(tmem + kTmChi + half * 32, tmem + kTmClo + half * 32, wait_chunk(), tmem + 128, kc == 0 && half == 0);
+          constexpr uint32_t hc = F16 ? 16 : 32;             // TMEM columns of a 32-channel half of the hidden slice
+          mma_chunk<F16, 128, 32>(tmem + kTmChi + half * hc, tmem + kTmClo + half * hc, wait_chunk(), tmem + 128, kc == 0 && half == 0);
           done_chunk();
           umma_commit(smem_u32(&bars.c_free[half]));
         }
@@ -492,11 +571,11 @@ __device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs
     }
   } else if (warp == 5) {
     // loader warp: first fill the ring, then stage the small vectors, then keep the ring fed
-    const float* img = net.head_img[h];
+    const unsigned char* img = net.head_img[F16 ? 1 : 0][h];
     if (lane == 0) {
       for (int i = 0; i < kRingSlots; ++i) {
-        mbar_expect_tx(smem_u32(&bars.full[i]), kSlotBytes);
-        bulk_g2s(ring_u32 + i * kSlotBytes, img + (size_t)i * (kSlotBytes / 4), kSlotBytes, smem_u32(&bars.full[i]));
+        mbar_expect_tx(smem_u32(&bars.full[i]), head_chunk_bytes<F16>());
+        bulk_g2s(ring_u32 + i * kSlotBytes, img + (size_t)i * head_chunk_bytes<F16>(), head_chunk_bytes<F16>(), smem_u32(&bars.full[i]));
       }
     }
     const float* g = fa.gproj + ((size_t)b * 2 + h) * 256;
@@ -505,19 +584,38 @@ __device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs
     for (int i = 0; i < 4; ++i) tb[i] = __ldg(net.head_bias1[h] + lane + 32 * i);
 #pragma unroll
     for (int i = 0; i < 8; ++i) tw[i] = __ldg(net.head_W2[h] + lane + 32 * i);
-    if (gproj_pending != nullptr) {
-      if (lane == 0) {
-        const long long t0 = clock64();
-        while (*reinterpret_cast<const volatile int*>(gproj_pending) != 0) {
+    if (gproj_tagged != nullptr) {
+      // answered by the projection servers: every value arrives as one 8-byte {value, tag} word; a lane is done when its eight
+      // words carry the tag of this forward
+      const long long t0 = clock64();
+      unsigned pending = 0xFFu;
+      while (pending != 0u) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if ((pending >> i) & 1u) {
+            const uint2 x = __ldcg(gproj_tagged + lane + 32 * i);
+            if (x.y == tag) { tg[i] = __uint_as_float(x.x); pending &= ~(1u << i); }
+          }
+        if (pending != 0u) {
           __nanosleep(40);
           if (clock64() - t0 > 4000000000ll) asm volatile("trap;");
         }
-        __threadfence();
       }
-      __syncwarp();
-    }
+    } else {
+      if (gproj_pending != nullptr) {
+        if (lane == 0) {
+          const long long t0 = clock64();
+          while (*reinterpret_cast<const volatile int*>(gproj_pending) != 0) {
+            __nanosleep(40);
+            if (clock64() - t0 > 4000000000ll) asm volatile("trap;");
+          }
+          __threadfence();
+        }
+        __syncwarp();
+      }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) tg[i] = __ldcg(g + lane + 32 * i);
+      for (int i = 0; i < 8; ++i) tg[i] = __ldcg(g + lane + 32 * i);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) sG[lane + 32 * i] = tg[i];
 #pragma unroll
@@ -526,7 +624,7 @@ __device__ __forceinline__ void tc_head_tile(const TcNet& net, const ForwardArgs
     for (int i = 0; i < 8; ++i) sW2[lane + 32 * i] = tw[i];
     if (lane < 2) sB2[lane] = __ldg(net.head_bias2[h] + lane);
     mbar_arrive(smem_u32(&bars.vec_ready));
-    if (lane == 0) tc_stream_weights(bars, ring_u32, img, kRingSlots, kHeadChunks, 0, 0, kSlotBytes);
+    if (lane == 0) tc_stream_weights<F16, true>(bars, ring_u32, img, kRingSlots, kHeadChunks, 0, 0);
   }
   tcgen05_fence_before();
   __syncthreads();

@@ -68,13 +68,20 @@ class Engine:
         self._weights = None
         self._room_offsets = None
         if forward_mode is None:
-            forward_mode = {'': 0, 'auto': 0, 'fma': 1, 'tensor': 2}[os.environ.get('LRG_FORWARD_MODE', '').lower()]
+            forward_mode = {'': 0, 'auto': 0, 'fma': 1, 'tensor': 2, 'tf32': 2, 'f16': 3}[os.environ.get('LRG_FORWARD_MODE', '').lower()]
         if forward_mode:
             self.set_forward_mode(forward_mode)
 
     def set_forward_mode(self, mode):
-        """0 auto, 1 fp32-FMA kernels, 2 tcgen05 3xTF32 kernels (full model only)."""
+        """0 auto (3xFP16 tensor tiles, repeated with 3xTF32 if an activation leaves the fp16 range), 1 fp32-FMA kernels,
+        2 tcgen05 3xTF32, 3 tcgen05 3xFP16 without the fallback (tensor modes: full model only)."""
         _lib.check(self.lib.lrg_engine_set_forward_mode(self._h, int(mode)))
+
+    def range_overflow(self):
+        """(overflow seen since the last check, synchronous calls repeated with 3xTF32 so far)."""
+        over, fb = C.c_int(0), C.c_int(0)
+        _lib.check(self.lib.lrg_engine_range_overflow(self._h, C.byref(over), C.byref(fb)))
+        return bool(over.value), fb.value
 
     def forward_mode(self):
         return self.lib.lrg_engine_forward_mode(self._h)
@@ -210,12 +217,14 @@ class Engine:
         return self.raw_labels(True), stats
 
     def make_params(self, resolution=0.1, cluster_threshold=10, seed=0, max_slots=0, max_steps_per_region=0,
-                    room_id_base=0, trace_capacity=0, flags=0, num_restarts=0, beam_width=0, search_width=0, spec_lanes=0):
+                    room_id_base=0, trace_capacity=0, flags=0, num_restarts=0, beam_width=0, search_width=0, spec_lanes=0,
+                    spec_top=0, spec_min_idle=0):
         """``num_restarts`` > 1 selects the random-restart driver (test_random_restart.py, NUM_RESTARTS, 'np' scoring);
         ``beam_width`` / ``search_width`` > 0 the beam-search driver (test_beam_search.py, BEAM_WIDTH, SEARCH_WIDTH, 'np');
-        ``spec_lanes`` > 1 grows that many regions of a room side by side with in-order commits (same labels as 1)."""
+        ``spec_lanes`` > 1 grows that many regions of a room side by side with in-order commits (same labels as 1), in the
+        ``spec_top`` rooms with the most work left and wherever ``spec_min_idle`` CTAs idle (0 = defaults, < 0 = all / never)."""
         p = GrowParams(resolution, cluster_threshold, seed, max_slots, max_steps_per_region, room_id_base,
-                       trace_capacity, flags, num_restarts, beam_width, search_width, spec_lanes)
+                       trace_capacity, flags, num_restarts, beam_width, search_width, spec_lanes, spec_top, spec_min_idle)
         return p
 
     def segment_resident(self, params=None, **kw):

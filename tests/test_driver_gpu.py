@@ -134,7 +134,9 @@ def test_full_size_room_properties(engine):
 
 def test_resolution_and_threshold_parameters(engine, golden_weights):
     """--resolution (test_region_grow.py:63) and cluster_threshold (:33) reach the device."""
-    points, order = golden_room(1000)
+    from tools import rooms as R
+    f = feature_prep.prepare_features(R.generate_room(1000, n_raw=6000, n_boxes=4), 0.3)      # equalised at 0.3 m: one point per voxel
+    points, order = f['points'], f['order']
     labels, stats = engine.segment_rooms([points], [order], resolution=0.3, seed=1, cluster_threshold=25, trace_capacity=2048)
     trace, n_steps = engine.trace(0, 2048)
     fwd = lambda a, b: lrg_forward.forward(golden_weights, a, b)
@@ -214,22 +216,52 @@ def test_room_span_limit(engine):
     assert stats['n_points'][0] == 4 and labels[0].shape == (4,)
 
 
-def test_projection_servers_give_identical_labels(engine, monkeypatch):
+def test_upload_checks_the_drivers_preconditions(engine):
+    """The device applies add / remove masks by point, the reference by voxel (test_region_grow.py:282-287): the same thing
+    only with one point per voxel (what the reference's equalisation guarantees, :125-136).  An upload that breaks this, or
+    whose seed order is not a permutation, is refused instead of silently giving other labels."""
+    from learn_region_grow_b200._lib import LrgError
+    f = feature_prep.prepare_features(__import__('tools.rooms', fromlist=['x']).generate_room(1300, n_raw=3000, n_boxes=3, dims=np.array([3.0, 2.5, 2.2])))
+    pts, order = f['points'], f['order']
+    engine.upload_rooms([pts], [order], resolution=0.1)                      # the equalised room is fine
+    with pytest.raises(LrgError, match='share a voxel'):
+        engine.upload_rooms([pts], [order], resolution=0.3)                  # ... but not at a coarser resolution
+    dup = pts.copy()
+    dup[7, :3] = dup[3, :3]
+    with pytest.raises(LrgError, match='share a voxel'):
+        engine.upload_rooms([pts, dup], [order, order], resolution=0.1)
+    for bad in (np.where(np.arange(len(order)) == 5, order[6], order), np.where(np.arange(len(order)) == 9, len(order), order),
+                np.where(np.arange(len(order)) == 9, -1, order)):
+        with pytest.raises(LrgError, match='permutation'):
+            engine.upload_rooms([pts], [bad.astype(np.int32)], resolution=0.1)
+    with pytest.raises(LrgError, match='resolution'):
+        engine.upload_rooms([pts], [order], resolution=0.1)
+        engine.segment_resident(resolution=0.2)
+    labels, stats = engine.segment_rooms([pts], [order], resolution=0.1, seed=0)
+    assert labels[0].min() >= 1
+
+
+def test_projection_servers_give_identical_labels(engine):
     """The pooled projection answered by the server CTAs (weights resident in shared memory, the default of the persistent
-    kernel) and by work items that stream the weights from L2 (LRG_GSERVERS=0) sum in the same order: identical labels."""
+    kernel) and by work items that stream the weights from L2 (LRG_FLAG_NO_PROJ_SERVERS) sum in the same order: identical
+    labels; so do the other A/B switches of the persistent kernel (no tile splitting, head tiles after the projection)."""
     from tools import rooms as R
+    from learn_region_grow_b200 import _lib
     feats = [feature_prep.prepare_features(R.generate_room(1200 + i, n_raw=5000 + 2500 * i, n_boxes=6)) for i in range(4)]
     pts, orders = [f['points'] for f in feats], [f['order'] for f in feats]
-    monkeypatch.setenv('LRG_GSERVERS', '0')
-    ref, st0 = engine.segment_rooms(pts, orders, resolution=0.1, seed=11)
+    noserv = _lib.FLAG_NO_PROJ_SERVERS
+    ref, st0 = engine.segment_rooms(pts, orders, resolution=0.1, seed=11, flags=noserv)
     assert engine.profile()['persistent'] and engine.profile()['items']['gproj'] == 8 * st0['grow_steps'].sum()
-    monkeypatch.setenv('LRG_GSERVERS', '1')
     for kw in ({}, dict(num_restarts=3), dict(beam_width=2, search_width=2)):
-        monkeypatch.setenv('LRG_GSERVERS', '0')
-        a, sa = engine.segment_rooms(pts, orders, resolution=0.1, seed=11, **kw)
-        monkeypatch.setenv('LRG_GSERVERS', '1')
+        a, sa = engine.segment_rooms(pts, orders, resolution=0.1, seed=11, flags=noserv, **kw)
         b, sb = engine.segment_rooms(pts, orders, resolution=0.1, seed=11, **kw)
         assert engine.profile()['persistent'] and engine.profile()['items']['gproj'] == 0
         for x, y in zip(a, b):
             np.testing.assert_array_equal(x, y)
         assert sa['grow_steps'].tolist() == sb['grow_steps'].tolist()
+    for flags in (_lib.FLAG_NO_TILE_SPLIT, noserv | _lib.FLAG_HEADS_AFTER_PROJ, noserv | _lib.FLAG_NO_TILE_SPLIT | _lib.FLAG_HEADS_AFTER_PROJ):
+        c, sc = engine.segment_rooms(pts, orders, resolution=0.1, seed=11, flags=flags)
+        assert engine.profile()['persistent']
+        for x, y in zip(ref, c):
+            np.testing.assert_array_equal(x, y)
+        assert sc['grow_steps'].tolist() == st0['grow_steps'].tolist()

@@ -20,6 +20,9 @@ def main():
     raw_off, raw = bench.make_workload(args.rooms, 1000)
     eng = Engine(1, 1, 512, 512, 13, 0)
     eng.load_weights(bench.load_weights())
+    if os.environ.get('LRG_TILE_TIMING'):          # (this tool's own switch; the library has an explicit call for it)
+        from learn_region_grow_b200 import _lib
+        _lib.check(eng.lib.lrg_engine_set_tile_timing(eng._h, 1))
     eng.upload_raw_concatenated(raw_off, raw, 0.1)
     for _ in range(args.repeat):
         stats = eng.segment_resident(resolution=0.1, seed=0, max_slots=args.slots, flags=args.flags)

@@ -1,10 +1,11 @@
-"""Pooled-projection servers on/off (LRG_GSERVERS): grow time of the bench workload, one room alone, restarts and beam; labels
+"""Pooled-projection servers on/off (LRG_FLAG_NO_PROJ_SERVERS): grow time of the bench workload, one room alone, restarts and beam; labels
 checked against the run without servers."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import bench
 from learn_region_grow_b200.engine import Engine
+from learn_region_grow_b200 import _lib
 
 rooms = int(sys.argv[1]) if len(sys.argv) > 1 else 68
 raw_off, raw = bench.make_workload(rooms, 1000)
@@ -13,10 +14,9 @@ eng.upload_raw_concatenated(raw_off, raw, 0.1)
 for name, kw in (('plain', {}), ('restarts 10', dict(num_restarts=10)), ('beam 3x3', dict(beam_width=3, search_width=3))):
     ref = None
     for s in ('0', '1', '0', '1'):
-        os.environ['LRG_GSERVERS'] = s
         ms = []
         for it in range(3):
-            st = eng.segment_resident(resolution=0.1, seed=0, **kw)
+            st = eng.segment_resident(resolution=0.1, seed=0, flags=0 if s == '1' else _lib.FLAG_NO_PROJ_SERVERS, **kw)
             ms.append(eng.profile()['grow_ms'])
         lab = np.concatenate(eng.labels(True))
         if ref is None:

@@ -1,5 +1,5 @@
-"""Speculative-lane probe: grow time, committed / discarded steps for spec_lanes in {1,2,3,4,6,8}, on one long room and on the
-68 bench rooms.  python tools/spec_probe.py [rooms]"""
+"""Speculative-lane probe: grow time, committed / discarded steps by spec_lanes and by which rooms speculate (spec_top rooms
+with the most work left, anybody while spec_min_idle CTAs idle; -1 = all / never), on one long room and on the 68 bench rooms.  python tools/spec_probe.py [rooms]"""
 import os
 import sys
 import time
@@ -20,18 +20,19 @@ for sel, name in ((slice(26, 27) if n_rooms > 26 else slice(0, 1), 'longest room
     base = sel.start
     e.upload_raw_rooms(rooms_raw, 0.1)
     ref = None
-    for lanes in (1, 2, 3, 4, 6, 8):
-        for min_idle in ((0,) if lanes == 1 else (0, 8, 32)):
-            os.environ['LRG_SPEC_MIN_IDLE'] = str(min_idle)
-            ms = []
-            for rep in range(3):
-                st = e.segment_resident(resolution=0.1, seed=0, room_id_base=base, spec_lanes=lanes)
-                ms.append(e.profile()['grow_ms'])
-            lab = np.concatenate(e.labels(True))
-            if ref is None:
-                ref = lab
-            pr = e.profile()
-            busy = sum(pr['busy_ms'].values())
-            print('%-13s lanes %d min_idle %2d: grow %7.2f ms (min of 3; %s)  steps %7d  discarded %6d (regrown %4d dropped %4d)  SM busy %.2f  same labels %s'
-                  % (name, lanes, min_idle, min(ms), ' '.join('%.1f' % m for m in ms), st['grow_steps'].sum(), st['spec_wasted_steps'].sum(),
-                     st['spec_restarts'].sum(), st['spec_dropped'].sum(), busy / (148 * pr['grow_ms']), np.array_equal(lab, ref)), flush=True)
+    for lanes, top, min_idle in ((1, 0, 0), (2, -1, -1), (4, -1, -1), (4, 4, -1), (4, 8, -1), (4, 16, -1), (4, 8, 96), (4, 8, 64), (3, 8, 96),
+                                 (6, 8, 96), (4, 12, 48)):
+        if name == 'longest room' and (top, min_idle) not in ((0, 0), (-1, -1)):
+            continue
+        ms = []
+        for rep in range(3):
+            st = e.segment_resident(resolution=0.1, seed=0, room_id_base=base, spec_lanes=lanes, spec_top=top, spec_min_idle=min_idle)
+            ms.append(e.profile()['grow_ms'])
+        lab = np.concatenate(e.labels(True))
+        if ref is None:
+            ref = lab
+        pr = e.profile()
+        busy = sum(pr['busy_ms'].values())
+        print('%-13s lanes %d top %2d min_idle %3d: grow %7.2f ms (min of 3; %s)  steps %7d  discarded %6d (regrown %4d dropped %4d)  SM busy %.2f  same labels %s'
+              % (name, lanes, top, min_idle, min(ms), ' '.join('%.1f' % m for m in ms), st['grow_steps'].sum(), st['spec_wasted_steps'].sum(),
+                 st['spec_restarts'].sum(), st['spec_dropped'].sum(), busy / (148 * pr['grow_ms']), np.array_equal(lab, ref)), flush=True)
