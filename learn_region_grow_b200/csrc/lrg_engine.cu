@@ -962,9 +962,14 @@ static int segment_resident_impl(LrgEngine* e, const LrgGrowParams* params, LrgR
   }
   // speculative lanes: up to spec_lanes regions of one room side by side, committed in seed order (plain driver only)
   LRG_REQUIRE(params->spec_lanes >= 0 && params->spec_lanes <= kMaxLanes, "spec_lanes %d out of range [0,%d]", params->spec_lanes, kMaxLanes);
-  const bool spec = params->spec_lanes > 1 && !beam && params->num_restarts <= 1;
+  // (0 = engine default: 4 lanes for the plain driver in the persistent kernel -- same labels, shorter chains; a traced run keeps
+  // one lane so that lrg_trace_download sees one step sequence per room)
+  const bool plain = !beam && params->num_restarts <= 1;
+  const bool persistent_path = use_tc(e) && !(params->flags & (LRG_FLAG_KERNEL_TIMING | LRG_FLAG_NO_GRAPH | LRG_FLAG_LOCKSTEP));
+  const int spec_lanes = params->spec_lanes != 0 ? params->spec_lanes : (plain && persistent_path && params->trace_capacity == 0) ? 4 : 1;
+  const bool spec = spec_lanes > 1 && plain;
   LRG_REQUIRE(params->spec_lanes <= 1 || spec, "spec_lanes %d needs the plain driver (no restarts, no beam search)", params->spec_lanes);
-  const int lanes = beam ? params->beam_width * params->search_width : params->num_restarts > 1 ? params->num_restarts : spec ? params->spec_lanes : 1;
+  const int lanes = beam ? params->beam_width * params->search_width : params->num_restarts > 1 ? params->num_restarts : spec ? spec_lanes : 1;
   const bool grouped = lanes > 1 || beam;     // slots form groups with a LaneGroup record (a 1 x 1 beam is a group of one lane)
   LRG_REQUIRE(lanes <= kMaxLanes, "num_restarts %d exceeds the limit of %d", lanes, kMaxLanes);
   int n_slots = params->max_slots > 0 ? std::max(params->max_slots, lanes) : spec ? 148 * lanes : (lanes > 1 ? 296 : 148);
@@ -1050,7 +1055,7 @@ static int segment_resident_impl(LrgEngine* e, const LrgGrowParams* params, LrgR
   da.beam_width = beam ? params->beam_width : 0; da.search_width = beam ? params->search_width : 0; da.parI = beam ? e->d_parI : nullptr;
   da.spec = spec ? 1 : 0; da.spec_sync = e->d_spec_sync; da.clog = e->d_clog; da.q_ctr = nullptr;
   // which rooms speculate: the spec_top rooms with the most estimated work left, and anybody while CTAs idle (the tail)
-  da.spec_top = params->spec_top == 0 ? 8 : params->spec_top < 0 ? (1 << 30) : params->spec_top;
+  da.spec_top = params->spec_top == 0 ? 4 : params->spec_top < 0 ? (1 << 30) : params->spec_top;
   da.spec_min_idle = params->spec_min_idle == 0 ? 96 : params->spec_min_idle < 0 ? (1 << 30) : params->spec_min_idle;
   da.spec_est = e->d_spec_est;
 

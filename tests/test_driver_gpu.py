@@ -250,7 +250,7 @@ def test_projection_servers_give_identical_labels(engine):
     feats = [feature_prep.prepare_features(R.generate_room(1200 + i, n_raw=5000 + 2500 * i, n_boxes=6)) for i in range(4)]
     pts, orders = [f['points'] for f in feats], [f['order'] for f in feats]
     noserv = _lib.FLAG_NO_PROJ_SERVERS
-    ref, st0 = engine.segment_rooms(pts, orders, resolution=0.1, seed=11, flags=noserv)
+    ref, st0 = engine.segment_rooms(pts, orders, resolution=0.1, seed=11, flags=noserv, spec_lanes=1)
     assert engine.profile()['persistent'] and engine.profile()['items']['gproj'] == 8 * st0['grow_steps'].sum()
     for kw in ({}, dict(num_restarts=3), dict(beam_width=2, search_width=2)):
         a, sa = engine.segment_rooms(pts, orders, resolution=0.1, seed=11, flags=noserv, **kw)

@@ -38,7 +38,9 @@ def _same(a, b):
 @pytest.mark.parametrize('lanes', [2, 3, 4, 8])
 def test_golden_room_equals_oracle_and_plain_driver(engine, golden_weights, lanes):
     points, order = golden_room(1001)
-    plain = _run(engine, [points], [order], seed=12345)
+    plain = _run(engine, [points], [order], seed=12345, spec_lanes=1)
+    default = _run(engine, [points], [order], seed=12345)          # (engine default: 4 lanes in the persistent kernel)
+    _same(plain, default)
     spec = _run(engine, [points], [order], seed=12345, spec_lanes=lanes)
     _same(plain, spec)
     assert plain[2]['spec_wasted_steps'][0] == 0
@@ -58,7 +60,7 @@ def test_many_rooms_and_scheduling_variants(engine):
     feats = [feature_prep.prepare_features(R.generate_room(1500 + i, n_raw=4000 + 2500 * i, n_boxes=4 + i)) for i in range(5)]
     pts = [f['points'] for f in feats] + [np.zeros((0, 13), np.float32), feats[0]['points'][:7]]
     orders = [f['order'] for f in feats] + [np.zeros(0, np.int64), np.arange(7)]
-    plain = _run(engine, pts, orders, seed=3)
+    plain = _run(engine, pts, orders, seed=3, spec_lanes=1)
     for kw in (dict(spec_lanes=4), dict(spec_lanes=2, max_slots=4), dict(spec_lanes=4, flags=_lib.FLAG_LOCKSTEP), dict(spec_lanes=3, max_slots=3)):
         spec = _run(engine, pts, orders, seed=3, **kw)
         _same(plain, spec)

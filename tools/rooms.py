@@ -17,24 +17,25 @@ COLOR_VARIATION = np.array([0.15274304, 0.15051211, 0.15046296])
 XYZ_NOISE = 0.01
 
 
-def _surface(rng, n, origin, u, v, obj_id, cls_id):
+def _surface(rng, n, origin, u, v, obj_id, cls_id, xyz_noise=XYZ_NOISE):
     """n points on the parallelogram origin + a*u + b*v with the reference's noise and colour model."""
     P = np.zeros((n, 8))
     a = rng.random_sample(n)[:, None]
     b = rng.random_sample(n)[:, None]
     P[:, :3] = origin + a * u + b * v
-    P[:, :3] += rng.randn(n, 3) * XYZ_NOISE                       # generate_synthetic_rooms.py:46
+    P[:, :3] += rng.randn(n, 3) * xyz_noise                       # generate_synthetic_rooms.py:46
     return P
 
 
-def _colorize(rng, P):
+def _colorize(rng, P, color_jitter=0.5):
     mean_color = rng.random_sample(3) - 0.5                        # :47
-    P[:, 3:6] = mean_color + rng.randn(len(P), 3) * COLOR_VARIATION * 0.5
+    P[:, 3:6] = mean_color + rng.randn(len(P), 3) * COLOR_VARIATION * color_jitter
     P[:, 3:6] = np.clip(P[:, 3:6], -0.5, 0.5)                      # :49-50
 
 
-def generate_room(seed, n_raw=20000, n_boxes=None, dims=None, max_dim=12.0):
-    """One synthetic room, (N,8) float32, N ~= n_raw."""
+def generate_room(seed, n_raw=20000, n_boxes=None, dims=None, max_dim=12.0, color_jitter=0.5, xyz_noise=XYZ_NOISE):
+    """One synthetic room, (N,8) float32, N ~= n_raw.  ``color_jitter`` scales the per-point colour noise (the reference's generator:
+    0.5, :48), ``xyz_noise`` is the per-point position noise in metres (the reference: 0.01, :46)."""
     rng = np.random.RandomState(seed)
     if dims is None:
         dims = ROOM_DIMENSIONS + rng.randn(3) * ROOM_VARIATION     # :104-106
@@ -69,9 +70,9 @@ def generate_room(seed, n_raw=20000, n_boxes=None, dims=None, max_dim=12.0):
         parts = []
         for (o, u, v), a in zip(faces, fa):
             n = max(1, int(round(n_raw * a / total)))
-            parts.append(_surface(rng, n, np.array(o, float), np.array(u, float), np.array(v, float), oid + 1, classes[oid]))
+            parts.append(_surface(rng, n, np.array(o, float), np.array(u, float), np.array(v, float), oid + 1, classes[oid], xyz_noise))
         P = np.vstack(parts)
-        _colorize(rng, P)
+        _colorize(rng, P, color_jitter)
         P[:, 6] = oid + 1
         P[:, 7] = classes[oid]
         out.append(P)

@@ -20,8 +20,8 @@ for sel, name in ((slice(26, 27) if n_rooms > 26 else slice(0, 1), 'longest room
     base = sel.start
     e.upload_raw_rooms(rooms_raw, 0.1)
     ref = None
-    for lanes, top, min_idle in ((1, 0, 0), (2, -1, -1), (4, -1, -1), (4, 4, -1), (4, 8, -1), (4, 16, -1), (4, 8, 96), (4, 8, 64), (3, 8, 96),
-                                 (6, 8, 96), (4, 12, 48)):
+    for lanes, top, min_idle in ((1, 0, 0), (2, -1, -1), (4, -1, -1), (4, 4, -1), (4, 2, -1), (3, 4, -1), (4, 6, -1), (4, 8, -1), (0, 0, 0), (4, 4, 120),
+                                 (4, 4, 64), (6, 4, 96), (8, 2, -1)):
         if name == 'longest room' and (top, min_idle) not in ((0, 0), (-1, -1)):
             continue
         ms = []
