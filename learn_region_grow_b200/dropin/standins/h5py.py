@@ -1,40 +1,25 @@
-"""Stand-in for h5py (absent from this image) covering the reference's dataset access pattern
-(/root/reference/learn_region_grow_util.py:11-20): ``f = File(name, 'r'|'w'); f['points'][:]; f.close()``
-and ``create_dataset(name, data=..., dtype=...)`` (tools/generate_synthetic_rooms.py:112-115).
-
-Storage is a numpy ``.npz`` archive written at the *same path* the HDF5 file would have; real HDF5 files
-need the real h5py (SURVEY.md 8f-4 lists a native HDF5 reader as a later row).
+"""Stand-in for h5py (absent from this image) over the repository's own HDF5 reader / writer
+(learn_region_grow_b200/hdf5.py): ``f = File(name, 'r'); f['points'][:]; f.close()``
+(/root/reference/learn_region_grow_util.py:11-20) and ``File(name, 'w').create_dataset(name, data=, dtype=[, compression='gzip',
+compression_opts=4])`` (tools/generate_synthetic_rooms.py:112-115, stage_data.py:249-256).  Files written here are real
+HDF5; files written by the real h5py with default settings are read directly.  (``.npz`` payloads written by the first
+version of this stand-in are still opened for reading.)
 """
 import numpy as np
 
+from learn_region_grow_b200.hdf5 import Dataset, Group, Hdf5Error, Hdf5Unsupported, Reader, Writer, SIGNATURE  # noqa: F401
 
-class _Dataset:
-    def __init__(self, arr):
-        self._arr = arr
-        self.shape = arr.shape
-        self.dtype = arr.dtype
-
-    def __getitem__(self, key):
-        return self._arr[key]
-
-    def __len__(self):
-        return len(self._arr)
+__version__ = '0.0+lrg_b200'
 
 
-class File:
-    def __init__(self, name, mode='r', **kw):
-        self.filename, self.mode = name, mode
-        self._data = {}
-        if mode.startswith('r'):
-            with open(name, 'rb') as f:
-                magic = f.read(8)
-            if magic.startswith(b'\x89HDF'):
-                raise OSError('%s is a real HDF5 file; install h5py to read it (this stand-in reads .npz payloads)' % name)
-            with np.load(name, allow_pickle=False) as z:
-                self._data = {k: z[k] for k in z.files}
+class _NpzFile:
+    def __init__(self, name):
+        self.filename, self.mode = name, 'r'
+        with np.load(name, allow_pickle=False) as z:
+            self._data = {k: z[k] for k in z.files}
 
     def __getitem__(self, key):
-        return _Dataset(self._data[key])
+        return self._data[key]
 
     def __contains__(self, key):
         return key in self._data
@@ -42,15 +27,7 @@ class File:
     def keys(self):
         return self._data.keys()
 
-    def create_dataset(self, name, data=None, dtype=None, shape=None, **kw):
-        arr = np.zeros(shape, dtype=dtype) if data is None else np.asarray(data, dtype=dtype)
-        self._data[name] = arr
-        return _Dataset(arr)
-
     def close(self):
-        if not self.mode.startswith('r') and self._data is not None:
-            with open(self.filename, 'wb') as f:
-                np.savez(f, **self._data)
         self._data = None
 
     def __enter__(self):
@@ -59,3 +36,15 @@ class File:
     def __exit__(self, *a):
         self.close()
         return False
+
+
+def File(name, mode='r', **kw):
+    if mode == 'r':
+        with open(name, 'rb') as f:
+            magic = f.read(4)
+        if magic == b'PK\x03\x04':
+            return _NpzFile(name)
+        return Reader(name)
+    if mode in ('w', 'w-', 'x'):
+        return Writer(name)
+    raise Hdf5Unsupported("File mode %r (only 'r' and 'w')" % mode)

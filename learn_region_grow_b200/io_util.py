@@ -31,6 +31,44 @@ def saveToH5(filename, rooms):
     f.close()
 
 
+STAGED_KEYS = ('points', 'count', 'neighbor_points', 'neighbor_count', 'add', 'remove', 'steps', 'complete')
+
+
+def saveStagedH5(filename, staged):
+    """The staged-training layout of stage_data.py:249-256: per grow step the centred inlier set (``points`` rows split by
+    ``count``) with its ``remove`` mask, the neighbour shell (``neighbor_points`` / ``neighbor_count``) with its ``add``
+    mask, the step index within its region (``steps``) and the completeness of the region (``complete``); every dataset
+    gzip level 4 like the reference's."""
+    import h5py
+    kinds = dict(points=numpy.float32, neighbor_points=numpy.float32, complete=numpy.float32)
+    f = h5py.File(filename, 'w')
+    for k in STAGED_KEYS:
+        f.create_dataset(k, data=staged[k], compression='gzip', compression_opts=4, dtype=kinds.get(k, numpy.int32))
+    f.close()
+
+
+def loadStagedH5(filename, feature_size=None):
+    """Inverse, split per step the way train_region_grow.py:82-110 consumes it: lists of per-step inlier / neighbour arrays
+    (columns ``:feature_size``) and their remove / add masks, plus ``steps`` and ``complete``."""
+    import h5py
+    f = h5py.File(filename, 'r')
+    d = {k: f[k][:] for k in STAGED_KEYS}
+    f.close()
+    out = dict(inlier_count=d['count'], neighbor_count=d['neighbor_count'], steps=d['steps'], complete=d['complete'],
+               inlier_points=[], remove=[], neighbor_points=[], add=[])
+    idp = 0
+    for c in d['count']:
+        out['inlier_points'].append(d['points'][idp:idp + c, :feature_size])
+        out['remove'].append(d['remove'][idp:idp + c])
+        idp += c
+    idp = 0
+    for c in d['neighbor_count']:
+        out['neighbor_points'].append(d['neighbor_points'][idp:idp + c, :feature_size])
+        out['add'].append(d['add'][idp:idp + c])
+        idp += c
+    return out
+
+
 def savePCD(filename, points):
     """ASCII PCD v0.7 with packed rgb (util.py:33-55)."""
     if len(points) == 0:
