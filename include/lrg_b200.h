@@ -126,8 +126,13 @@ enum {
    * any of them, tests/test_driver_gpu.py): */
   LRG_FLAG_NO_PROJ_SERVERS = 16,   /* no pooled-projection server CTAs: 8 projection work items per grow step instead */
   LRG_FLAG_NO_TILE_SPLIT = 32,     /* never split a branch tile over idle CTAs */
-  LRG_FLAG_HEADS_AFTER_PROJ = 64   /* publish the head tiles when the projection is complete instead of together with it
+  LRG_FLAG_HEADS_AFTER_PROJ = 64,  /* publish the head tiles when the projection is complete instead of together with it
                                       (only without projection servers) */
+  /* beam search only: 'ml' scoring (test_beam_search.py:46-47,238-256,263-264) -- a candidate's score is its parent's score plus
+   * the log-probability of the step under the network's confidences: over all padded tile rows of each set log(conf) where
+   * the row's re-rounded voxel is in the sampled add / remove set, log(1 - conf) elsewhere, each / NUM_NEIGHBOR_POINT,
+   * accumulated row by row in float32 like the reference's numpy scalars.  Without the flag: 'np' (:41,266). */
+  LRG_FLAG_SCORE_ML = 128
 };
 
 typedef struct LrgRoomStats {
@@ -150,6 +155,9 @@ typedef struct LrgStepTrace {
   uint32_t add_mask[16];       /* bit r of word r/32: tile row r sampled True */
   uint32_t remove_mask[16];
   uint32_t inlier_idx_crc, neighbor_idx_crc;   /* sum-of-products checksums of the sampled point indices */
+  float log_prob[2];           /* LRG_FLAG_SCORE_ML: addLogProb, rmvLogProb of this expansion (test_beam_search.py:238-256) */
+  float score;                 /* LRG_FLAG_SCORE_ML: parent's score + addLogProb + rmvLogProb (:264) */
+  int32_t reserved;            /* zero */
 } LrgStepTrace;
 
 /* Upload rooms: points (sum N, F) float32 rows = the 13-D features of test_region_grow.py:165-172,

@@ -31,13 +31,15 @@ class StepTrace(C.Structure):
     _fields_ = [('seed_point', C.c_int32), ('step_in_region', C.c_int32), ('n_inlier', C.c_int32),
                 ('n_neighbor', C.c_int32), ('stop_reason', C.c_int32), ('size_after', C.c_int32),
                 ('center', C.c_float * 16), ('add_mask', C.c_uint32 * 16), ('remove_mask', C.c_uint32 * 16),
-                ('inlier_idx_crc', C.c_uint32), ('neighbor_idx_crc', C.c_uint32)]
+                ('inlier_idx_crc', C.c_uint32), ('neighbor_idx_crc', C.c_uint32), ('log_prob', C.c_float * 2), ('score', C.c_float),
+                ('reserved', C.c_int32)]
 
 
 STEP_TRACE_DTYPE = np.dtype([('seed_point', '<i4'), ('step_in_region', '<i4'), ('n_inlier', '<i4'), ('n_neighbor', '<i4'),
                              ('stop_reason', '<i4'), ('size_after', '<i4'), ('center', '<f4', (16,)),
                              ('add_mask', '<u4', (16,)), ('remove_mask', '<u4', (16,)),
-                             ('inlier_idx_crc', '<u4'), ('neighbor_idx_crc', '<u4')])
+                             ('inlier_idx_crc', '<u4'), ('neighbor_idx_crc', '<u4'), ('log_prob', '<f4', (2,)), ('score', '<f4'),
+                             ('reserved', '<i4')])
 ROOM_STATS_DTYPE = np.dtype([(n, '<i4') for n, _ in RoomStats._fields_])
 ROOM_METRICS_DTYPE = np.dtype([('nmi', '<f8'), ('ami', '<f8'), ('ars', '<f8'), ('prc', '<f8'), ('rcl', '<f8'), ('iou', '<f8'),
                                ('n_points', '<i4'), ('n_classes', '<i4'), ('n_clusters', '<i4'), ('gt_match', '<i4')])
@@ -51,6 +53,7 @@ FLAG_PRIORITY = 8
 FLAG_NO_PROJ_SERVERS = 16
 FLAG_NO_TILE_SPLIT = 32
 FLAG_HEADS_AFTER_PROJ = 64
+FLAG_SCORE_ML = 128
 
 _P = C.c_void_p
 _I = C.c_int

@@ -53,6 +53,8 @@ struct LaneGroup {
   int seqMin[3], seqMax[3];
   int par_n[kMaxLanes];    // candidate q of Q: points, bounding box (its index list lives in DriverArgs::parI)
   int par_min[kMaxLanes][3], par_max[kMaxLanes][3];
+  float fscore[kMaxLanes];    // 'ml' scoring (DriverArgs::score_ml): log-probability score of every lane's expansion (:264)
+  float par_score[kMaxLanes]; // ... and of candidate q of Q (0 for the seed alone, :164)
   // speculative lanes only: written by the lane that holds the head ticket (the commit critical section)
   int commit_seq;          // ticket that commits next (published to the other lanes through SpecSync::commit_seq)
   int next_ticket;         // tickets handed out so far = seeds issued in curvature order
@@ -116,6 +118,7 @@ struct DriverArgs {
   int* lane_steps;              // (n_rooms, lanes) out: grow steps every lane took in the room (trace lengths)
   // beam search (beam_width > 0): lanes = beam_width * search_width
   int beam_width, search_width;
+  int score_ml;                 // beam search: rank candidates by accumulated log-probability instead of size (LRG_FLAG_SCORE_ML)
   int* parI;                    // (n_slots / lanes, beam_width, maxN) ascending index lists of the candidates in Q
   // speculative lanes (spec != 0, lanes > 1, no restarts / beam)
   int spec;

@@ -960,6 +960,8 @@ static int segment_resident_impl(LrgEngine* e, const LrgGrowParams* params, LrgR
     LRG_REQUIRE((long long)params->beam_width * params->search_width <= kMaxLanes, "beam_width %d x search_width %d exceeds the limit of %d lanes",
                 params->beam_width, params->search_width, kMaxLanes);
   }
+  LRG_REQUIRE(beam || !(params->flags & LRG_FLAG_SCORE_ML), "LRG_FLAG_SCORE_ML ('ml' scoring) needs the beam-search driver (beam_width, search_width > 0): "
+              "the reference's restart driver is broken with it (test_random_restart.py:196)");
   // speculative lanes: up to spec_lanes regions of one room side by side, committed in seed order (plain driver only)
   LRG_REQUIRE(params->spec_lanes >= 0 && params->spec_lanes <= kMaxLanes, "spec_lanes %d out of range [0,%d]", params->spec_lanes, kMaxLanes);
   // (0 = engine default: 4 lanes for the plain driver in the persistent kernel -- same labels, shorter chains; a traced run keeps
@@ -1052,6 +1054,7 @@ static int segment_resident_impl(LrgEngine* e, const LrgGrowParams* params, LrgR
   da.dbg = e->d_tile_dbg ? e->d_tile_dbg + 32 : nullptr;
   da.stats = e->d_stats; da.trace = e->trace_capacity > 0 ? e->d_trace : nullptr; da.trace_capacity = e->trace_capacity;
   da.lanes = lanes; da.groups = e->d_groups; da.pw_lane_stride = e->total_words; da.lane_steps = grouped ? e->d_lane_steps : nullptr;
+  da.score_ml = (beam && (params->flags & LRG_FLAG_SCORE_ML)) ? 1 : 0;
   da.beam_width = beam ? params->beam_width : 0; da.search_width = beam ? params->search_width : 0; da.parI = beam ? e->d_parI : nullptr;
   da.spec = spec ? 1 : 0; da.spec_sync = e->d_spec_sync; da.clog = e->d_clog; da.q_ctr = nullptr;
   // which rooms speculate: the spec_top rooms with the most estimated work left, and anybody while CTAs idle (the tail)

@@ -274,6 +274,9 @@ struct StepShared {
   int red[32 * 6];
   int flag;
   int all_done;                 // set when this call retired the last slot of the run
+  float lp[2];                  // beam search, 'ml' scoring: addLogProb, rmvLogProb of the step being applied
+  float lane_score;             // ... and the expansion's score (parent + both)
+  int nsel[2];                  // ... selected rows per set
   unsigned wake;                // random restarts / beam search: lanes of this group (bit l) this call handed work to (they need a STEP)
   LaneGroup G;                  // random restarts: the group's room-level state while this CTA owns it
   unsigned nextkey[16];         // median: smallest key above the lower median, per channel
@@ -528,7 +531,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
   SlotState* gS = da.slots + slot;
   for (int i = tid; i < (int)(sizeof(SlotState) / 4); i += NT)
     reinterpret_cast<int*>(&sh.S)[i] = __ldcg(reinterpret_cast<const int*>(gS) + i);
-  if (tid == 0) { sh.n_odd = 0; sh.flag = 0; sh.all_done = 0; sh.wake = 0; }
+  if (tid == 0) { sh.n_odd = 0; sh.flag = 0; sh.all_done = 0; sh.wake = 0; sh.nsel[0] = sh.nsel[1] = 0; sh.lp[0] = sh.lp[1] = 0.f; sh.lane_score = 0.f; }
   __syncthreads();
   SlotState& S = sh.S;
   if (S.finished) return;
@@ -784,6 +787,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
     __syncthreads();
     if (tid == 0) {
       *reinterpret_cast<volatile int*>(&grp->score[lane_id]) = candidate ? n_cur : -1;
+      if (da.score_ml) *reinterpret_cast<volatile float*>(&grp->fscore[lane_id]) = sh.lane_score;
       __threadfence();
       const int expect = __ldcg(&grp->expect);
       const int done = atomicAdd(&grp->done, 1) + 1;
@@ -814,7 +818,8 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
         for (int q = 0; q < BW; ++q) {
           int best = -1;
           for (int l = 0; l < G.expect; ++l)
-            if (!((used >> l) & 1u) && G.score[l] >= 0 && (best < 0 || G.score[l] > G.score[best])) best = l;
+            if (!((used >> l) & 1u) && G.score[l] >= 0 &&
+                (best < 0 || (da.score_ml ? G.fscore[l] > G.fscore[best] : G.score[l] > G.score[best]))) best = l;
           if (best < 0) break;
           used |= 1u << best;
           sh.red[1 + nc++] = best;
@@ -834,6 +839,9 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
           for (int j = tid; j < n; j += NT) __stcg(dst + j, l == lane_id ? sl[j] : __ldcg(sl + j));
         }
         if (tid == 0) {
+          float ps[kMaxLanes];
+          for (int q = 0; q < nc; ++q) ps[q] = G.fscore[sh.red[1 + q]];
+          for (int q = 0; q < nc; ++q) G.par_score[q] = ps[q];
           for (int q = 0; q < nc; ++q) {
             const int l = sh.red[1 + q];
             const SlotState* o = da.slots + slot0 + l;
@@ -898,6 +906,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
           G.seed = seed;
           __stcg(par0, seed);
           G.par_n[0] = 1;
+          G.par_score[0] = 0.f;
           const int v[3] = {pw_x(w), pw_y(w), pw_z(w)};
           for (int a = 0; a < 3; ++a) G.par_min[0][a] = G.par_max[0][a] = G.seqMin[a] = G.seqMax[a] = v[a];
           G.stuck = 1;                  // the head of the first round finds the seed's box inside itself (:180-184)
@@ -1341,6 +1350,53 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       if (m && normal && is_add) { set_cur(p, w_[k]); upd = 1; }      // (a neighbour row is never CURRENT before this)
       m_[k] = m; normal_[k] = normal;
     }
+    if (beam && da.score_ml) {
+      // 'ml' scoring (test_beam_search.py:238-256): every padded tile row asks whether ITS re-rounded voxel is in the set of the
+      // re-rounded voxels of the rows that sampled True (rows of one source point agree; a row that re-rounds into another
+      // point's voxel is handled by comparing the voxels themselves), takes log(conf) or log(1 - conf), / NUM_NEIGHBOR_POINT
+      unsigned* selkey = reinterpret_cast<unsigned*>(sh.planes);          // [2][kMaxTilePts]   (the median planes are not live here)
+      float* terms = reinterpret_cast<float*>(selkey + 2 * kMaxTilePts);  // [2][kMaxTilePts]
+      unsigned key_[VT];
+#pragma unroll
+      for (int k = 0; k < VT; ++k) {
+        const int vt = tid + k * NT;
+        const bool is_add = vt >= kMaxTilePts;
+        key_[k] = 0;
+        if (p_[k] >= 0) {
+          const float cx = S.center[0], cy = S.center[1];
+          const float x = __fadd_rn(__fsub_rn(xy_[k].x, cx), cx);
+          const float y = __fadd_rn(__fsub_rn(xy_[k].y, cy), cy);
+          const int vx = voxel_of(x, res) - vmin0, vy = voxel_of(y, res) - vmin1;
+          key_[k] = ((unsigned)(vx + 1) & 0x7ffu) | (((unsigned)(vy + 1) & 0x7ffu) << 11) | ((unsigned)pw_z(w_[k]) << 22);
+          if (m_[k]) selkey[(is_add ? 1 : 0) * kMaxTilePts + atomicAdd(&sh.nsel[is_add ? 1 : 0], 1)] = key_[k];
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < VT; ++k) {
+        const int vt = tid + k * NT;
+        const bool is_add = vt >= kMaxTilePts;
+        const int r = is_add ? vt - kMaxTilePts : vt;
+        float t = 0.f;
+        if (p_[k] >= 0) {
+          const unsigned* sk = selkey + (is_add ? 1 : 0) * kMaxTilePts;
+          const int ns = sh.nsel[is_add ? 1 : 0];
+          bool hit = false;
+          for (int j = 0; j < ns; ++j) hit |= sk[j] == key_[k];
+          const float conf = confidence(lg_[k].x, lg_[k].y);
+          t = __fdiv_rn(logf(hit ? conf : __fsub_rn(1.f, conf)), (float)da.Nj);
+        }
+        terms[(is_add ? 1 : 0) * kMaxTilePts + r] = t;
+      }
+      __syncthreads();
+      if (tid == 0 || tid == 32) {                             // row-by-row float32 accumulation, one thread per set (:243-245,255-257)
+        const int set = tid == 0 ? 1 : 0;
+        const int nrows = set ? da.Nj : da.Ni;
+        float acc = 0.f;
+        for (int r = 0; r < nrows; ++r) acc = __fadd_rn(acc, terms[set * kMaxTilePts + r]);
+        sh.lp[set ? 0 : 1] = acc;                               // lp[0] = addLogProb, lp[1] = rmvLogProb
+      }
+    }
     mark(11);
     __syncthreads();
     mark(12);
@@ -1503,6 +1559,11 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       __syncthreads();
     }
     if (tr != nullptr && tid == 0) { tr->stop_reason = reason; tr->size_after = n_in; }
+    if (beam && da.score_ml && tid == 0) {                     // newScore = currentScore + addLogProb + rmvLogProb (:264)
+      const float parent = __ldcg(&grp->par_score[lane_id / SW]);
+      sh.lane_score = __fadd_rn(__fadd_rn(parent, sh.lp[0]), sh.lp[1]);
+      if (tr != nullptr) { tr->log_prob[0] = sh.lp[0]; tr->log_prob[1] = sh.lp[1]; tr->score = sh.lane_score; }
+    }
     stamp(2);
     if (beam) {
       // one expansion per lane and round: the mask joins newQ if it added a point (:262-267)

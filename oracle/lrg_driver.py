@@ -330,7 +330,10 @@ class BeamRoomGrower(RoomGrower):
     runs on its bounding box; the search ends when it sticks twice or no expansion added anything, and ``bestMask`` becomes
     visited / labelled (:276-279).
 
-    ('ml' scoring accumulates log-probabilities over the *padded* tile rows, :236-256; not restated -- 'np' is the default.)
+    ``scoring='ml'`` (:46-47): a candidate's score is its parent's score plus the log-probability of the step under the
+    network's own confidences (:238-256,263-264) -- over ALL 512 (padded) tile rows of each set, ``log(conf)`` for a row whose
+    re-rounded voxel is in the sampled add / remove set and ``log(1 - conf)`` otherwise, each divided by NUM_NEIGHBOR_POINT
+    (both sets, :243,255) and accumulated row by row in float32 (numpy float32 scalars).
 
     The script as shipped needs Python 2 (``range(n) + list(...)``, :212,224); oracle/make_golden.py runs it unmodified with
     a list-returning ``range`` in its globals (oracle/run_reference.py).
@@ -340,8 +343,11 @@ class BeamRoomGrower(RoomGrower):
     device can run the expansions of a round side by side.
     """
 
-    def __init__(self, *args, beam_width=3, search_width=3, **kw):
+    def __init__(self, *args, beam_width=3, search_width=3, scoring='np', **kw):
         super().__init__(*args, **kw)
+        assert scoring in ('np', 'ml')
+        self.scoring = scoring
+        self.step_log_prob = None   # 'ml': addLogProb + rmvLogProb of the last expansion (float32)
         self.B, self.W = int(beam_width), int(search_width)
         self.lane = 0
         self.round = 0
@@ -403,6 +409,19 @@ class BeamRoomGrower(RoomGrower):
         rmvPoints = st['inlier'][0, :, :][st['rmv_mask']]                         # :245-248
         rmvPoints[:, :2] += center[:2]
         rmvVoxels = voxelize(rmvPoints[:, :3], self.resolution)
+        if self.scoring == 'ml':                                                  # :238-256
+            parts = []
+            for tile, conf, sel in ((st['neighbor'][0], add_conf, addVoxels), (st['inlier'][0], rmv_conf, rmvVoxels)):
+                rows = np.array(tile[:, :3])
+                rows[:, :2] += center[:2]                                         # :240,252 (the tile row is un-centred in place)
+                hit = _rows_in(voxelize(rows, self.resolution), sel)
+                with np.errstate(divide='ignore'):
+                    terms = np.log(np.where(hit, conf, np.float32(1) - conf)) / np.float32(self.Nj)
+                acc = np.float32(0)
+                for t in terms:                                                   # row-by-row float32 accumulation (:243-245)
+                    acc = acc + t
+                parts.append(acc)
+            self.step_log_parts = parts
         in_add = _rows_in(self.point_voxels, addVoxels)                           # :251-258
         in_rmv = _rows_in(self.point_voxels, rmvVoxels)
         updated = bool(np.any(np.logical_and(~self.currentMask, in_add)))
@@ -446,7 +465,13 @@ class BeamRoomGrower(RoomGrower):
                         break                                                     # empty shell: no expansion of this candidate (:206)
                     updated, newMask = r
                     if updated:                                                   # :262-267 ('np': the score is the region size)
-                        newQ.append((int(np.sum(newMask)), newMask))
+                        if self.scoring == 'ml':                                  # :263-264
+                            new_score = score + self.step_log_parts[0] + self.step_log_parts[1]
+                            if forced is not None and getattr(forced, 'score', None) is not None:
+                                new_score = forced.score(lane, score, self.step_log_parts, new_score)
+                        else:
+                            new_score = int(np.sum(newMask))
+                        newQ.append((new_score, newMask))
             Q = sorted(newQ, key=lambda x: x[0], reverse=True)[:self.B]           # :273
             self.round += 1
         self.visited[bestMask] = True                                             # :276

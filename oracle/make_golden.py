@@ -125,10 +125,12 @@ def golden_restart_trace(seed, n_raw, n_boxes):
     print(log[-300:])
 
 
-def golden_beam_trace(seed, n_raw, n_boxes):
+def golden_beam_trace(seed, n_raw, n_boxes, scoring='np'):
     """4. ``beam_trace_<seed>.npz`` - the UNMODIFIED /root/reference/test_beam_search.py (BEAM_WIDTH 3, SEARCH_WIDTH 3, 'np'
     scoring) on the room of driver_trace_<seed>.npz.  The script concatenates ``range(n) + list(...)`` (:212,224), which is
-    Python 2; it is executed as it is with a list-returning ``range`` among its module globals (run_reference.py2_range)."""
+    Python 2; it is executed as it is with a list-returning ``range`` among its module globals (run_reference.py2_range).
+    ``scoring='ml'`` passes ``--scoring ml`` (:46-47,263-264: candidates ranked by accumulated log-probability) and writes
+    ``beam_ml_trace_<seed>.npz``."""
     room = rooms.generate_room(seed, n_raw=n_raw, n_boxes=n_boxes, dims=np.array([3.0, 2.5, 2.2]))
     scratch = '/tmp/lrg_golden_bs_%d' % seed
     os.makedirs(os.path.join(scratch, 'data'), exist_ok=True)
@@ -151,8 +153,9 @@ def golden_beam_trace(seed, n_raw, n_boxes):
         buf = io.StringIO()
         t0 = time.time()
         with contextlib.redirect_stdout(buf):
-            g = run_reference.run(os.path.join(REF, 'test_beam_search.py'), ['--area', '5'],
+            g = run_reference.run(os.path.join(REF, 'test_beam_search.py'), ['--area', '5'] + (['--scoring', scoring] if scoring != 'np' else []),
                                   init_globals={'range': run_reference.py2_range})
+        assert g['scoring'] == scoring
         wall = time.time() - t0
         trace = shim_util.TRACE
         shim_util.TRACE = None
@@ -165,8 +168,8 @@ def golden_beam_trace(seed, n_raw, n_boxes):
                neighbor_crc=np.array([t['neighbor_crc'] for t in trace], dtype=np.uint32),
                log=np.array(log), reference_wall_s=np.array(wall),
                beam_width=np.array(g['BEAM_WIDTH']), search_width=np.array(g['SEARCH_WIDTH']))
-    np.savez_compressed(os.path.join(GOLD, 'beam_trace_%d.npz' % seed), **out)
-    print('beam trace %d: steps %d wall %.1fs' % (seed, len(trace), wall))
+    np.savez_compressed(os.path.join(GOLD, 'beam%s_trace_%d.npz' % ('' if scoring == 'np' else '_' + scoring, seed)), **out)
+    print('beam trace %d (%s): steps %d wall %.1fs' % (seed, scoring, len(trace), wall))
     print(log[-300:])
 
 
@@ -214,6 +217,9 @@ if __name__ == '__main__':
     if sys.argv[1:] == ['beam']:
         golden_beam_trace(1000, 2500, 4)
         sys.exit(0)
+    if sys.argv[1:] == ['beam_ml']:
+        golden_beam_trace(1000, 2500, 4, scoring='ml')
+        sys.exit(0)
     if sys.argv[1:] == ['forward']:
         golden_forward_pin()
         sys.exit(0)
@@ -222,4 +228,5 @@ if __name__ == '__main__':
     golden_trace(1001, 6000, 8)
     golden_restart_trace(1000, 2500, 4)
     golden_beam_trace(1000, 2500, 4)
+    golden_beam_trace(1000, 2500, 4, scoring='ml')
     golden_forward_pin()

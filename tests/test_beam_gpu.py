@@ -29,9 +29,12 @@ def engine(golden_weights):
     e.close()
 
 
-def _replay(points, order, weights, traces, seed, B, W):
+LOG_PROB_TOL = 4e-4   # |d log p / d logit| <= 1 per row and the sums are means over the rows: twice the 2e-4 logit tolerance
+
+
+def _replay(points, order, weights, traces, seed, B, W, scoring='np', score_err=None):
     fwd = lambda a, b: lrg_forward.forward(weights, a, b)
-    g = lrg_driver.BeamRoomGrower(points, order, fwd, lrg_driver.PhiloxRng(seed), beam_width=B, search_width=W)
+    g = lrg_driver.BeamRoomGrower(points, order, fwd, lrg_driver.PhiloxRng(seed), beam_width=B, search_width=W, scoring=scoring)
     pos = [0] * (B * W)
     adopted = [0]
 
@@ -56,6 +59,21 @@ def _replay(points, order, weights, traces, seed, B, W):
             adopted[0] += int(differ.sum())
         return add, rmv, dev_add, dev_rmv
 
+    def adopt_score(lane, parent, parts, new_score):
+        # 'ml': the device's log-probabilities must be the oracle's within the forward tolerance; its score must be EXACTLY
+        # float32(parent + add + rmv) of its own parts (:264); the oracle then ranks with the device's number, so that a
+        # near-tie between two candidates cannot send the two searches down different paths
+        rec = traces[lane][0][pos[lane] - 1]
+        lp = rec['log_prob'].astype(np.float32)
+        for mine, theirs in zip(parts, lp):
+            if np.isfinite(mine) or np.isfinite(theirs):
+                assert abs(float(mine) - float(theirs)) <= LOG_PROB_TOL, (lane, parts, lp)
+                score_err.append(abs(float(mine) - float(theirs)))
+        assert np.float32(rec['score']) == np.float32(np.float32(np.float32(parent) + lp[0]) + lp[1]), (lane, parent, lp, rec['score'])
+        return np.float32(rec['score'])
+
+    if scoring == 'ml':
+        forced.score = adopt_score
     g.run(forced)
     for lane in range(B * W):
         trace, n_steps = traces[lane]
@@ -83,6 +101,34 @@ def test_beam_driver_replays_on_oracle(engine, golden_weights, B, W, flags):
     assert stats['regions'][0] == len(g.regions) and stats['clusters'][0] == g.cluster_id - 1
     by_reason = {r: sum(1 for x in g.regions if x[3] == r) for r in ('exhausted', 'stuck')}
     assert (stats['stop_noexpand'][0], stats['stop_stuck'][0]) == (by_reason['exhausted'], by_reason['stuck'])
+
+
+@pytest.mark.parametrize('B,W,flags', [(3, 3, 0), (2, 3, _lib.FLAG_LOCKSTEP)])
+def test_beam_ml_scoring_replays_on_oracle(engine, golden_weights, B, W, flags):
+    """``--scoring ml`` (test_beam_search.py:46-47,238-256,263-264; LRG_FLAG_SCORE_ML): candidates ranked by accumulated
+    log-probability.  The oracle restatement of it is pinned bit for bit to the unmodified script
+    (tests/test_oracle_driver.py::test_beam_ml_scoring_replays_reference_trace); here the device's per-expansion
+    log-probabilities are held to it within LOG_PROB_TOL, its score arithmetic exactly, and -- ranking with the device's scores --
+    the labels must be identical."""
+    points, order = golden_room(1000)
+    engine.upload_rooms([points], [order], resolution=0.1)
+    stats = engine.segment_resident(resolution=0.1, seed=3, trace_capacity=2048, beam_width=B, search_width=W, flags=flags, scoring='ml')
+    traces = [engine.trace(0, 2048, lane=l) for l in range(B * W)]
+    assert sum(t[1] for t in traces) == stats['grow_steps'][0] and stats['grow_steps'][0] > 50
+    errs = []
+    g, adopted = _replay(points, order, golden_weights, traces, 3, B, W, scoring='ml', score_err=errs)
+    assert adopted <= 3 * B * W and len(errs) > 100
+    print('ml scoring: %d expansions scored, max |log-prob difference| %.2e, mean %.2e' % (len(errs) // 2, max(errs), np.mean(errs)))
+    np.testing.assert_array_equal(engine.labels(filled=False)[0], g.cluster_label)
+    np.testing.assert_array_equal(engine.labels(filled=True)[0], g.fill())
+    assert stats['regions'][0] == len(g.regions) and stats['clusters'][0] == g.cluster_id - 1
+    # the two scorings search differently (same seed, same streams)
+    engine.segment_resident(resolution=0.1, seed=3, beam_width=B, search_width=W, flags=flags)
+    assert not np.array_equal(engine.labels(filled=False)[0], g.cluster_label)
+    with pytest.raises(_lib.LrgError):
+        engine.segment_resident(resolution=0.1, seed=3, scoring='ml')                      # needs the beam-search driver
+    with pytest.raises(_lib.LrgError):
+        engine.segment_resident(resolution=0.1, seed=3, num_restarts=3, scoring='ml')      # broken in the reference (:196)
 
 
 def test_beam_scheduling_invariance(engine):

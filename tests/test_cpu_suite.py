@@ -301,7 +301,7 @@ def test_abi_struct_layouts_match_the_header(tmp_path):
 int main(void) {
   printf("LrgGrowParams %zu %zu %zu %zu %zu %zu\\n", sizeof(LrgGrowParams), offsetof(LrgGrowParams, seed), offsetof(LrgGrowParams, flags), offsetof(LrgGrowParams, num_restarts), offsetof(LrgGrowParams, beam_width), offsetof(LrgGrowParams, search_width));
   printf("LrgRoomStats %zu %zu\\n", sizeof(LrgRoomStats), offsetof(LrgRoomStats, stop_other));
-  printf("LrgStepTrace %zu %zu %zu\\n", sizeof(LrgStepTrace), offsetof(LrgStepTrace, center), offsetof(LrgStepTrace, neighbor_idx_crc));
+  printf("LrgStepTrace %zu %zu %zu %zu\\n", sizeof(LrgStepTrace), offsetof(LrgStepTrace, center), offsetof(LrgStepTrace, neighbor_idx_crc), offsetof(LrgStepTrace, score));
   printf("LrgRoomMetrics %zu %zu %zu\\n", sizeof(LrgRoomMetrics), offsetof(LrgRoomMetrics, iou), offsetof(LrgRoomMetrics, gt_match));
   return 0;
 }
@@ -313,6 +313,6 @@ int main(void) {
     assert out['LrgGrowParams'] == [ctypes.sizeof(G), G.seed.offset, G.flags.offset, G.num_restarts.offset, G.beam_width.offset, G.search_width.offset]
     assert out['LrgRoomStats'] == [_lib.ROOM_STATS_DTYPE.itemsize, _lib.ROOM_STATS_DTYPE.fields['stop_other'][1]]
     T = _lib.STEP_TRACE_DTYPE
-    assert out['LrgStepTrace'] == [T.itemsize, T.fields['center'][1], T.fields['neighbor_idx_crc'][1]]
+    assert out['LrgStepTrace'] == [T.itemsize, T.fields['center'][1], T.fields['neighbor_idx_crc'][1], T.fields['score'][1]]
     M = _lib.ROOM_METRICS_DTYPE
     assert out['LrgRoomMetrics'] == [M.itemsize, M.fields['iou'][1], M.fields['gt_match'][1]]

@@ -107,6 +107,37 @@ def test_beam_driver_replays_reference_trace(golden_weights):
         assert int(tok[6]) == steps and int(tok[7].split('/')[0]) == size
 
 
+def test_beam_ml_scoring_replays_reference_trace(golden_weights):
+    """'ml' scoring (``--scoring ml``, test_beam_search.py:46-47,238-256,263-264): oracle BeamRoomGrower(scoring='ml') vs the
+    UNMODIFIED script (tests/golden/beam_ml_trace_1000.npz, oracle/make_golden.py beam_ml).  The ranking by accumulated
+    log-probability decides which masks survive a round, so every tile of the 2,781 Session.run calls, the final labels and
+    the printed region lines only agree when the float32 scores order the candidates like the script's own."""
+    base = np.load(os.path.join(GOLDEN, 'driver_trace_1000.npz'))
+    g = np.load(os.path.join(GOLDEN, 'beam_ml_trace_1000.npz'))
+    np_run = np.load(os.path.join(GOLDEN, 'beam_trace_1000.npz'))
+    assert len(g['inlier_crc']) != len(np_run['inlier_crc'])              # the two scorings really search differently
+    calls = []
+
+    def fwd(inlier, neighbor):
+        calls.append((_crc(inlier), _crc(neighbor)))
+        add, rmv = lrg_forward.forward(golden_weights, inlier, neighbor, dtype=np.float64)
+        return add.astype(np.float32), rmv.astype(np.float32)
+
+    grower = lrg_driver.BeamRoomGrower(base['points'], base['order'], fwd, lrg_driver.NumpyLegacyRng(0), resolution=0.1,
+                                       beam_width=int(g['beam_width']), search_width=int(g['search_width']), scoring='ml')
+    grower.run()
+    assert len(calls) == len(g['inlier_crc'])
+    assert [c[0] for c in calls] == [int(x) for x in g['inlier_crc']]
+    assert [c[1] for c in calls] == [int(x) for x in g['neighbor_crc']]
+    np.testing.assert_array_equal(grower.fill(), g['cluster_label'])
+    lines = [l for l in str(g['log']).split('\n') if l.startswith('room ')]
+    labelled = [r for r in grower.regions if r[4]]
+    assert len(lines) == len(labelled)
+    for line, (seed_id, steps, size, reason, _) in zip(lines, labelled):
+        tok = line.split()
+        assert int(tok[6]) == steps and int(tok[7].split('/')[0]) == size
+
+
 def test_beam_driver_philox_lanes_and_forced_replay(golden_weights):
     """The Philox form of the beam-search oracle (expansion (q, s) of round r draws at lane q * SEARCH_WIDTH + s, step r): a
     run is deterministic, and re-driving it with the masks it sampled (the hook tests/test_beam_gpu.py feeds with the device's
