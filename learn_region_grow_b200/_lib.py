@@ -54,6 +54,8 @@ FLAG_NO_PROJ_SERVERS = 16
 FLAG_NO_TILE_SPLIT = 32
 FLAG_HEADS_AFTER_PROJ = 64
 FLAG_SCORE_ML = 128
+FLAG_NO_SPATIAL_INDEX = 256
+FLAG_NO_STEP_OVERLAP = 512
 
 _P = C.c_void_p
 _I = C.c_int

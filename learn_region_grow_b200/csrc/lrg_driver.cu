@@ -60,6 +60,90 @@ __global__ void __launch_bounds__(1024) lrg_reset_words_kernel(const long long* 
   }
 }
 
+// Spatial index of a room (DriverArgs::sp_*): the neighbour shell of a grow step (test_region_grow.py:221-229) is a small box,
+// but the reference's point order (first-seen voxels of the raw file, :125-136) is not spatial -- a whole-room scan reads all
+// N state words per step.  One CTA per room sorts the points by the Morton code of their voxel (bitonic sort of
+// code << 32 | index in global scratch), stores the permutation and the coordinates in that order, and the bounding box
+// of every run of kSpBlock points; a step then reads the block boxes, and only the blocks that meet its shell.
+__device__ __forceinline__ unsigned morton_spread10(unsigned v) {       // 10 bits -> every third bit
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+__global__ void __launch_bounds__(1024) lrg_spatial_index_kernel(const long long* __restrict__ room_off, const long long* __restrict__ pw_off,
+                                                                 const unsigned* __restrict__ pw, const long long* __restrict__ sp_off,
+                                                                 const long long* __restrict__ key_off, unsigned long long* __restrict__ keys_all,
+                                                                 int* __restrict__ sp_perm, unsigned* __restrict__ sp_vox, uint2* __restrict__ sp_box) {
+  const int room = blockIdx.x, tid = threadIdx.x;
+  const int N = (int)(room_off[room + 1] - room_off[room]);
+  if (N <= 0) return;
+  const unsigned* w = pw + pw_off[room];
+  unsigned long long* keys = keys_all + key_off[room];
+  const int P = (int)(key_off[room + 1] - key_off[room]);
+  for (int i = tid; i < P; i += 1024) {
+    unsigned long long k = ~0ull;
+    if (i < N) {
+      const unsigned v = w[i];
+      const unsigned code = morton_spread10(v & 1023u) | (morton_spread10((v >> 10) & 1023u) << 1) | (morton_spread10((v >> 20) & 1023u) << 2);
+      k = ((unsigned long long)code << 32) | (unsigned)i;
+    }
+    keys[i] = k;
+  }
+  __syncthreads();
+  const int half = P >> 1;
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < half; t += 1024) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const unsigned long long a = keys[i], b = keys[i | j];
+        if ((a > b) == ((i & k) == 0)) { keys[i] = b; keys[i | j] = a; }
+      }
+      __syncthreads();
+    }
+  const long long so = sp_off[room];
+  const int npad = (int)(sp_off[room + 1] - so);
+  for (int m = tid; m < npad; m += 1024) {
+    const int i = m < N ? (int)(keys[m] & 0xFFFFFFFFull) : 0;
+    sp_perm[so + m] = i;
+    sp_vox[so + m] = m < N ? (w[i] & 0x3FFFFFFFu) : 0x3FFFFFFFu;
+  }
+  __syncthreads();
+  const int lane = tid & 31;
+  for (int b = tid >> 5; b < npad / kSpBlock; b += 32) {
+    int mn[3] = {1023, 1023, 1023}, mx[3] = {0, 0, 0};
+    for (int q = lane; q < kSpBlock; q += 32) {
+      const int m = b * kSpBlock + q;
+      if (m < N) {
+        const unsigned v = sp_vox[so + m];
+        const int c[3] = {(int)(v & 1023u), (int)((v >> 10) & 1023u), (int)((v >> 20) & 1023u)};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], c[a]); mx[a] = max(mx[a], c[a]); }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        mn[a] = min(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], d));
+        mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], d));
+      }
+    if (lane == 0) sp_box[so / kSpBlock + b] = make_uint2((unsigned)mn[0] | ((unsigned)mn[1] << 10) | ((unsigned)mn[2] << 20),
+                                                          (unsigned)mx[0] | ((unsigned)mx[1] << 10) | ((unsigned)mx[2] << 20));
+  }
+}
+
+int launch_spatial_index(int n_rooms, const long long* d_room_off, const long long* d_pw_off, const unsigned* d_pw, const long long* d_sp_off,
+                         const long long* d_key_off, unsigned long long* d_keys, int* d_sp_perm, unsigned* d_sp_vox, uint2* d_sp_box,
+                         cudaStream_t stream) {
+  if (n_rooms <= 0) return LRG_OK;
+  lrg_spatial_index_kernel<<<n_rooms, 1024, 0, stream>>>(d_room_off, d_pw_off, d_pw, d_sp_off, d_key_off, d_keys, d_sp_perm, d_sp_vox, d_sp_box);
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
+}
+
 // Preconditions of the index-based driver (caller-prepared features, lrg_rooms_upload): the reference applies its masks by
 // VOXEL (every point whose voxel is in the add / remove set, test_region_grow.py:282-287), the device by point -- the two agree
 // only when every voxel holds exactly one point, which the reference's equalisation guarantees (:125-136) but a caller's

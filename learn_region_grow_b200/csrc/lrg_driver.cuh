@@ -83,6 +83,13 @@ struct DriverArgs {
   unsigned* pw;                 // per-point state words: 10+10+10 bits of room-relative voxel coordinates (:175), bit 30 CURRENT, bit 31 VISITED
   const long long* pw_off;      // (n_rooms+1) word offset of every room in pw (rooms padded to a multiple of 4 words)
   const int4* room_vmin;        // (n_rooms) voxel coordinates the words are relative to
+  // spatial index of every room (static; built at upload by lrg_spatial_index_kernel): the room's points in Morton order of
+  // their voxels, cut into blocks of kSpBlock; NULL = off (every shell scan reads all N state words)
+  const long long* sp_off;      // (n_rooms+1) offset of every room in sp_perm / sp_vox (rooms padded to whole blocks)
+  const int* sp_perm;           // room-local point index of the m-th point in Morton order (padding: 0)
+  const unsigned* sp_vox;       // its packed voxel coordinates (padding: 0x3FFFFFFF, outside every shell)
+  const uint2* sp_box;          // (sp_off / kSpBlock) per block: packed minimum / maximum voxel coordinates
+  int tune_step;                // A/B switches of the step: bit 0 = never run the median beside the indexed shell scan
   int* label;                   // (T) cluster_label (:176)
   const int* order;             // (T) room-local seed order (:183)
   SlotState* slots;
@@ -146,6 +153,13 @@ struct FillArgs {
   int F;
 };
 
+constexpr int kSpBlock = 128;          // points per block of the spatial index (one 128-bit load per lane of a warp)
+constexpr int kSpMaxN = 262144;        // rooms up to this many points use the index (bitmap of the hits in shared memory)
+constexpr int kSpMinN = 2048;          // ... and smaller rooms are not worth the extra round trip
+// Morton order + block boxes of every room; d_keys: (sum of P_r) sort scratch, P_r = power of two >= N_r at d_key_off[r]
+int launch_spatial_index(int n_rooms, const long long* d_room_off, const long long* d_pw_off, const unsigned* d_pw, const long long* d_sp_off,
+                         const long long* d_key_off, unsigned long long* d_keys, int* d_sp_perm, unsigned* d_sp_vox, uint2* d_sp_box,
+                         cudaStream_t stream);
 // feature rows -> padded 16-float rows + state words; *d_err is set to a room index + 1 if a room spans > 1022 voxels
 int launch_pack(const float* d_points, int F, int n_rooms, const long long* d_room_off, const long long* d_pw_off, float resolution,
                 float* d_pts16, unsigned* d_pw, int4* d_room_vmin, int* d_err, cudaStream_t stream);

@@ -97,6 +97,11 @@ struct LrgEngine {
   float* d_pts = nullptr;
   unsigned* d_pw = nullptr;              // packed per-point state words (rooms padded to 4 words)
   long long* d_pw_off = nullptr;
+  // spatial index of the rooms (DriverArgs::sp_*, built at upload)
+  long long* d_sp_off = nullptr;
+  int* d_sp_perm = nullptr;
+  unsigned* d_sp_vox = nullptr;
+  uint2* d_sp_box = nullptr;
   int4* d_room_vmin = nullptr;
   long long total_words = 0;
   int *d_label = nullptr, *d_label_filled = nullptr, *d_order = nullptr;
@@ -237,6 +242,8 @@ static int ensure_forward_ws(LrgEngine* e, int B) {
 
 static void free_rooms(LrgEngine* e) {
   pool_free(e, e->d_room_off); pool_free(e, e->d_pts); pool_free(e, e->d_pw); pool_free(e, e->d_pw_off); pool_free(e, e->d_room_vmin); pool_free(e, e->d_label);
+  pool_free(e, e->d_sp_off); pool_free(e, e->d_sp_perm); pool_free(e, e->d_sp_vox); pool_free(e, e->d_sp_box);
+  e->d_sp_off = nullptr; e->d_sp_perm = nullptr; e->d_sp_vox = nullptr; e->d_sp_box = nullptr;
   pool_free(e, e->d_label_filled); pool_free(e, e->d_order); pool_free(e, e->d_lab_list); pool_free(e, e->d_unl_list);
   pool_free(e, e->d_n_lab); pool_free(e, e->d_n_unl); pool_free(e, e->d_stats);
   pool_free(e, e->d_pw_lanes); pool_free(e, e->d_groups); pool_free(e, e->d_lane_steps); pool_free(e, e->d_parI);
@@ -713,6 +720,39 @@ static int pack_rooms(LrgEngine* e, const float* d_dense, bool validate = false)
   LRG_CUDA(cudaMemcpyAsync(&bad_room, e->d_counters, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   LRG_CUDA(cudaStreamSynchronize(e->stream));
   LRG_REQUIRE(bad_room == 0, "room %d spans more than 1022 voxels along an axis at resolution %g (state words hold 10 bits per axis)", bad_room - 1, (double)e->resolution);
+  {
+    // spatial index: Morton order of every room's voxels + block boxes (the shell scans of the grow steps read only the blocks
+    // that meet the shell)
+    const int R = e->n_rooms;
+    std::vector<long long> h_sp_off((size_t)R + 1, 0), h_key_off((size_t)R + 1, 0);
+    for (int r = 0; r < R; ++r) {
+      const long long n = e->h_room_off[r + 1] - e->h_room_off[r];
+      long long P = 1;
+      while (P < n) P <<= 1;
+      h_sp_off[r + 1] = h_sp_off[r] + (n + kSpBlock - 1) / kSpBlock * kSpBlock;
+      h_key_off[r + 1] = h_key_off[r] + (n > 0 ? std::max<long long>(P, 2) : 0);
+    }
+    long long* d_key_off = nullptr;
+    unsigned long long* d_keys = nullptr;
+    LRG_TRY(pool_alloc(e, &e->d_sp_off, (size_t)R + 1));
+    LRG_TRY(pool_alloc(e, &e->d_sp_perm, (size_t)h_sp_off[R]));
+    LRG_TRY(pool_alloc(e, &e->d_sp_vox, (size_t)h_sp_off[R]));
+    LRG_TRY(pool_alloc(e, &e->d_sp_box, (size_t)(h_sp_off[R] / kSpBlock)));
+    LRG_TRY(pool_alloc(e, &d_key_off, (size_t)R + 1));
+    int rc = pool_alloc(e, &d_keys, (size_t)h_key_off[R]);
+    cudaError_t ce = cudaSuccess;
+    if (rc == LRG_OK) {
+      ce = cudaMemcpyAsync(e->d_sp_off, h_sp_off.data(), sizeof(long long) * (R + 1), cudaMemcpyHostToDevice, e->stream);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_key_off, h_key_off.data(), sizeof(long long) * (R + 1), cudaMemcpyHostToDevice, e->stream);
+      if (ce == cudaSuccess)
+        rc = launch_spatial_index(R, e->d_room_off, e->d_pw_off, e->d_pw, e->d_sp_off, d_key_off, d_keys, e->d_sp_perm, e->d_sp_vox, e->d_sp_box, e->stream);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);       // (the host vectors and the scratch go away)
+    }
+    pool_free(e, d_key_off);
+    pool_free(e, d_keys);
+    LRG_TRY(rc);
+    LRG_CUDA(ce);
+  }
   if (validate) {
     // caller-prepared features: the device applies the masks by point, the reference by voxel (test_region_grow.py:282-287)
     unsigned* d_scratch = nullptr;
@@ -1041,6 +1081,9 @@ static int segment_resident_impl(LrgEngine* e, const LrgGrowParams* params, LrgR
 
   DriverArgs da{};
   da.n_rooms = n_rooms; da.room_off = e->d_room_off; da.pts = e->d_pts; da.pw = d_words; da.pw_off = e->d_pw_off; da.room_vmin = e->d_room_vmin;
+  da.tune_step = (params->flags & LRG_FLAG_NO_STEP_OVERLAP) ? 1 : 0;
+  const bool no_sp = (params->flags & LRG_FLAG_NO_SPATIAL_INDEX) != 0;
+  da.sp_off = no_sp ? nullptr : e->d_sp_off; da.sp_perm = no_sp ? nullptr : e->d_sp_perm; da.sp_vox = no_sp ? nullptr : e->d_sp_vox; da.sp_box = no_sp ? nullptr : e->d_sp_box;
   da.label = e->d_label; da.order = e->d_order; da.slots = e->d_slots; da.n_slots = n_slots; da.maxN = e->slots_maxN;
   da.listI = e->d_listI; da.listJ = e->d_listJ; da.keyI = e->d_keyI; da.keyJ = e->d_keyJ;
   da.tile[0] = e->d_tile[0]; da.tile[1] = e->d_tile[1]; da.tileidx[0] = e->d_tileidx[0]; da.tileidx[1] = e->d_tileidx[1];

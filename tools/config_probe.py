@@ -22,10 +22,12 @@ if which in ('scannet', 'both'):
            int(st['grow_steps'].sum()), int(st['grow_steps'].max()), sum(map(len, area)) / (t3 - t0) / 1e6, m['nmi'].mean()), flush=True)
 if which in ('kitti', 'both'):
     scene = rooms.generate_outdoor_scene(3000)
-    for it in range(2):
+    from learn_region_grow_b200 import _lib
+    for flags in (0, 0, _lib.FLAG_NO_STEP_OVERLAP, _lib.FLAG_NO_SPATIAL_INDEX):
         t0 = time.perf_counter(); eq = eng.upload_raw_rooms([scene], 0.3); t1 = time.perf_counter()
-        st = eng.segment_resident(resolution=0.3, seed=0); t2 = time.perf_counter()
+        st = eng.segment_resident(resolution=0.3, seed=0, flags=flags); t2 = time.perf_counter()
         lab = eng.raw_labels(); t3 = time.perf_counter()
+        print('flags %3d grow %.1f ms ' % (flags, eng.profile()['grow_ms']), end='')
         print('kitti-shaped: raw %d, equalised %d | prep %.1f ms grow+fill %.1f ms labels %.1f ms | %d steps %d regions %d clusters | %.2f M raw points/s' %
               (len(scene), int(eq[-1]), 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), int(st['grow_steps'][0]), int(st['regions'][0]),
                int(st['clusters'][0]), len(scene) / (t3 - t0) / 1e6), flush=True)
