@@ -581,6 +581,11 @@ def tfops_extras(rig, peaks):
             ('query_ball_point', lambda: chk(L.lrg_query_ball_point(B, n, m, radius, ns, p(xyz), p(q), p(gi), p(cnt), None)), B * (n * 12 + m * (16 + 4 * ns))),
             ('group_point', lambda: chk(L.lrg_group_point(B, n, c, m, ns, p(feat), p(gi), p(g), None)), B * m * ns * (4 + 8 * c)),
         ]
+        nx = torch.zeros(B, m, 3, device='cuda')
+        npts = torch.zeros(B, m, ns, 3 + c, device='cuda')
+        gx = torch.zeros(B, m, ns, 3, device='cuda')
+        ops.append(('sample_and_group', lambda: chk(L.lrg_sample_and_group(B, n, m, radius, ns, c, p(xyz), p(feat), None, p(idx), p(nx), p(npts), p(gi), p(cnt),
+                                                                           p(gx), None)), B * (n * (12 + 4 * c) + m * ns * (4 + 4 * (3 + c)))))
         row = {}
         for name, fn, nbytes in ops:
             us = timeit(fn)
@@ -598,6 +603,13 @@ def tfops_extras(rig, peaks):
         nb = B * (n * (24 + 4 * 256) + m * 256 * 4)
         row['three_interpolate'] = {'us': us, 'algorithmic_gbs': nb / us / 1e3, 'frac_of_hbm_peak': nb / us / 1e3 / hbm}
         out['B%d_n1024_m256' % B] = row
+    # one large cloud: 65,536 points in the registers of a cluster of 8 CTAs (argmax through distributed shared memory)
+    n, m = 65536, 256
+    xyz = torch.from_numpy(rng.rand(1, n, 3).astype(np.float32)).cuda()
+    idx = torch.zeros(1, m, dtype=torch.int32, device='cuda')
+    us = timeit(lambda: chk(L.lrg_farthest_point_sampling(1, n, m, p(xyz), None, p(idx), None)), reps=5, warm=1)
+    out['B1_n65536_m256'] = {'farthest_point_sample': {'us': us, 'us_per_round': us / m, 'algorithmic_gbs': (n * 12 + m * 4) / us / 1e3,
+                                                       'kernel': 'lrg_fps_cluster_kernel<8> (thread-block cluster, DSMEM exchange)'}}
     out['note'] = 'CUDA events, 20 launches after 3 warm-up; arrays of a few MB are L2-resident (stated, not flushed); hbm peak = MEASURED_PEAKS hbm_gbs'
     return out
 
@@ -650,7 +662,9 @@ def main():
                                     'mean': {k: float(np.nanmean(mt[k])) for k in ('nmi', 'ami', 'ars', 'prc', 'rcl', 'iou')},
                                     'scope': 'obj_id of the raw points in, NMI/AMI/ARS/PRC/RCL/IOU per room out (test_region_grow.py:319-349)'}
             for key, kw, scope in (('random_restart', dict(num_restarts=10), 'test_random_restart.py: 10 restarts per seed as parallel lanes, largest region kept'),
-                                   ('beam_search', dict(beam_width=3, search_width=3), 'test_beam_search.py: 3 candidates x 3 expansions per round as parallel lanes')):
+                                   ('beam_search', dict(beam_width=3, search_width=3), 'test_beam_search.py: 3 candidates x 3 expansions per round as parallel lanes'),
+                                   ('beam_search_ml', dict(beam_width=3, search_width=3, scoring='ml'),
+                                    'test_beam_search.py --scoring ml: candidates ranked by accumulated log-probability (:238-256,263-264)')):
                 kw2 = dict(params)
                 kw2.pop('spec_lanes', None)
                 kw2.update(kw)

@@ -276,6 +276,17 @@ int lrg_room_metrics(LrgEngine* e, const int32_t* obj_id, int raw, int filled, L
 int lrg_farthest_point_sampling(int b, int n, int m, const float* d_inp, float* d_temp, int* d_out, lrg_stream_t s);
 /* tf_sampling_g.cu:206 gatherpointLauncher(b,n,m,inp,idx,out) */
 int lrg_gather_point(int b, int n, int m, const float* d_inp, const int* d_idx, float* d_out, lrg_stream_t s);
+/* train_pointnet.py:113-123 sample_and_group(npoint, radius, nsample, xyz, points) as two launches instead of four custom ops
+ * and four graph ops: farthest point sampling, then gather_point of the centres (new_xyz) + ball query + group_point of xyz with
+ * the translation normalisation (:117) + group_point of the features + concat (:119-120) in one kernel (a store per round or an
+ * epilogue inside the sampling kernel was measured to slow its serial loop by 27 %, so the gather rides with the queries).
+ * xyz (b,n,3), points (b,n,c) or NULL with c = 0; out: fps_idx (b,npoint), new_xyz (b,npoint,3), new_points
+ * (b,npoint,nsample,3+c), idx (b,npoint,nsample), pts_cnt (b,npoint), grouped_xyz (b,npoint,nsample,3) or NULL.  temp: the
+ * (32,n) workspace of farthestpointsamplingLauncher, only read for n > 65,536.  Results equal the separate ops bit for bit. */
+int lrg_sample_and_group(int b, int n, int npoint, float radius, int nsample, int c, const float* d_xyz, const float* d_points, float* d_temp,
+                         int* d_fps_idx, float* d_new_xyz, float* d_new_points, int* d_idx, int* d_pts_cnt, float* d_grouped_xyz, lrg_stream_t s);
+/* tests: clouds larger than n use the thread-block-cluster FPS kernel (default 8,192 = where one CTA runs out of registers) */
+int lrg_fps_set_cluster_min(int n);
 /* tf_sampling_g.cu:209 scatteraddpointLauncher(b,n,m,out_g,idx,inp_g); inp_g must be zeroed (tf_sampling.cpp:174) */
 int lrg_scatter_add_point(int b, int n, int m, const float* d_out_g, const int* d_idx, float* d_inp_g, lrg_stream_t s);
 /* tf_sampling_g.cu:198 probsampleLauncher(b,n,m,inp_p,inp_r,temp,out); temp (b,n) workspace */
@@ -286,6 +297,9 @@ int lrg_query_ball_point(int b, int n, int m, float radius, int nsample, const f
                          int* d_idx, int* d_pts_cnt, lrg_stream_t s);
 /* tf_grouping_g.cu:129 selectionSortLauncher(b,n,m,k,dist,outi,out) */
 int lrg_selection_sort(int b, int n, int m, int k, const float* d_dist, int* d_outi, float* d_out, lrg_stream_t s);
+/* tf_grouping.py:66-68 (knn_point's graph ops tile / subtract / square / reduce_sum): dist (b,m,n) = squared distances between
+ * every xyz2 (b,m,c) query and every xyz1 (b,n,c) point; the input of selectionSortLauncher in knn_point (:70) */
+int lrg_pairwise_sqdist(int b, int n, int m, int c, const float* d_xyz1, const float* d_xyz2, float* d_dist, lrg_stream_t s);
 /* tf_grouping_g.cu:133 groupPointLauncher(b,n,c,m,nsample,points,idx,out) */
 int lrg_group_point(int b, int n, int c, int m, int nsample, const float* d_points, const int* d_idx, float* d_out, lrg_stream_t s);
 /* tf_grouping_g.cu:137 groupPointGradLauncher(b,n,c,m,nsample,grad_out,idx,grad_points); grad_points zeroed (tf_grouping.cpp:204) */

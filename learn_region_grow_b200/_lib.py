@@ -96,6 +96,9 @@ _SIGNATURES = {
     'lrg_labels_device_ptr': (_I, [_P, _I, C.POINTER(_P)]),
     'lrg_farthest_point_sampling': (_I, [_I, _I, _I, _P, _P, _P, _P]),
     'lrg_gather_point': (_I, [_I, _I, _I, _P, _P, _P, _P]),
+    'lrg_sample_and_group': (_I, [_I, _I, _I, C.c_float, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'lrg_fps_set_cluster_min': (_I, [_I]),
+    'lrg_pairwise_sqdist': (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     'lrg_scatter_add_point': (_I, [_I, _I, _I, _P, _P, _P, _P]),
     'lrg_prob_sample': (_I, [_I, _I, _I, _P, _P, _P, _P, _P]),
     'lrg_query_ball_point': (_I, [_I, _I, _I, C.c_float, _I, _P, _P, _P, _P, _P]),

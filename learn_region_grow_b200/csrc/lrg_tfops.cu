@@ -1,6 +1,7 @@
 // sm_100a replacements for the PointNet++ custom ops of /root/reference/tf_ops (sampling, grouping, 3d_interpolation).
 // Index-exact with the reference kernels: same distance expressions (so nvcc contracts them identically), same scan
 // order, same tie rules.  All pointers are device pointers.
+#include <cooperative_groups.h>
 #include <float.h>
 
 #include "lrg_common.cuh"
@@ -81,6 +82,75 @@ __global__ void __launch_bounds__(NT) lrg_fps_kernel(int n, int m, const float* 
   }
 }
 
+// Clouds of 8,193 .. 65,536 points: a thread-block CLUSTER of CL CTAs per cloud keeps the points and the running minimum
+// distances in registers (16 per thread) -- CTA r, thread t holds the points t + 512 (r + CL q), so that within a thread the
+// tie rule's order is still ascending q -- where the one-CTA kernel above runs out of registers and the reference's layout
+// (min-distances in a global workspace, lrg_fps_big_kernel below) re-reads 16 n bytes per round.  Per round: the CTA's argmax
+// as above, then every CTA writes its (distance, tie) word into the round's slot of EVERY CTA's shared memory (distributed
+// shared memory), one cluster barrier, and everybody takes the maximum of the CL words -- no global memory in the loop but the
+// three coordinates of the last sample.  The slots are double-buffered by round parity: a CTA can only be one barrier ahead.
+template <int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kFpsThreads) lrg_fps_cluster_kernel(int n, int m, const float* __restrict__ dataset,
+                                                                                               int* __restrict__ idxs) {
+  namespace cg = cooperative_groups;
+  constexpr int NT = kFpsThreads, PPT = 16;
+  __shared__ uint2 sred[2][NT / 32];
+  __shared__ uint2 ckey[2][8];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / CL, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* pts = dataset + (size_t)b * n * 3;
+  float px[PPT], py[PPT], pz[PPT], td[PPT];
+#pragma unroll
+  for (int q = 0; q < PPT; ++q) {
+    const int k = tid + NT * (rank + CL * q);
+    px[q] = py[q] = pz[q] = 0.f;
+    if (k < n) { px[q] = pts[k * 3 + 0]; py[q] = pts[k * 3 + 1]; pz[q] = pts[k * 3 + 2]; }
+    td[q] = 1e38f;
+  }
+  int old = 0;
+  if (rank == 0 && tid == 0) idxs[(size_t)b * m] = 0;
+  cluster.sync();                                     // (every CTA of the cluster is running before anybody writes into it)
+  for (int j = 1; j < m; ++j) {
+    const float x1 = pts[old * 3 + 0], y1 = pts[old * 3 + 1], z1 = pts[old * 3 + 2];
+    float best = -1.f;
+    int besti = 0;
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      const int k = tid + NT * (rank + CL * q);
+      if (k < n) {
+        const float x2 = px[q], y2 = py[q], z2 = pz[q];
+        const float d = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1);
+        const float d2 = min(d, td[q]);
+        td[q] = d2;
+        if (d2 > best) { best = d2; besti = k; }
+      }
+    }
+    const unsigned long long key = best < 0.f ? 0ull : fps_key(best, besti);
+    const unsigned d = (unsigned)(key >> 32), t = (unsigned)key;
+    const unsigned dmax = __reduce_max_sync(0xffffffffu, d);
+    const unsigned tmax = __reduce_max_sync(0xffffffffu, d == dmax ? t : 0u);
+    if (lane == 0) sred[j & 1][warp] = make_uint2(dmax, tmax);
+    __syncthreads();
+    if (warp == 0) {
+      const uint2 w = lane < NT / 32 ? sred[j & 1][lane] : make_uint2(0u, 0u);
+      const unsigned d2 = __reduce_max_sync(0xffffffffu, w.x);
+      const unsigned t2 = __reduce_max_sync(0xffffffffu, w.x == d2 ? w.y : 0u);
+      if (lane < CL) *cluster.map_shared_rank(&ckey[j & 1][rank], lane) = make_uint2(d2, t2);
+    }
+    cluster.sync();
+    const uint2 w = lane < CL ? ckey[j & 1][lane] : make_uint2(0u, 0u);
+    const unsigned d3 = __reduce_max_sync(0xffffffffu, w.x);
+    const unsigned t3 = __reduce_max_sync(0xffffffffu, w.x == d3 ? w.y : 0u);
+    if (d3 == 0u && t3 == 0u) old = 0;
+    else {
+      const unsigned tie = 0x7FFFFFFFu - t3;
+      old = (int)(((tie & 0x3FFFFFu) << 9) | (tie >> 22));
+    }
+    if (rank == 0 && tid == 0) idxs[(size_t)b * m + j] = old;
+  }
+}
+
 // Large clouds: min-distances in the caller's workspace (same layout as the reference: one row per CTA).
 __global__ void __launch_bounds__(kFpsThreads) lrg_fps_big_kernel(int b_total, int n, int m, const float* __restrict__ dataset,
                                                                 float* __restrict__ temp, int* __restrict__ idxs) {
@@ -95,7 +165,7 @@ __global__ void __launch_bounds__(kFpsThreads) lrg_fps_big_kernel(int b_total, i
     __syncthreads();
     for (int j = 1; j < m; ++j) {
       const float x1 = pts[old * 3 + 0], y1 = pts[old * 3 + 1], z1 = pts[old * 3 + 2];
-      float best = -1.f;
+        float best = -1.f;
       int besti = 0;
       for (int k = tid; k < n; k += kFpsThreads) {
         const float x2 = pts[k * 3 + 0], y2 = pts[k * 3 + 1], z2 = pts[k * 3 + 2];
@@ -272,6 +342,70 @@ __global__ void __launch_bounds__(256) lrg_query_ball_kernel(int b, int n, int m
   }
 }
 
+// sample_and_group (train_pointnet.py:113-123) behind the sampling: gather_point of the sampled centres (:114), ball query,
+// group_point of the coordinates with the translation normalisation (grouped_xyz -= new_xyz, :117), group_point of the
+// features and the concat (:119-120) in ONE kernel -- a warp finds its query's nsample neighbours as above and writes their rows at once, instead of a (b,m,nsample)
+// index tensor going through memory into two gather launches and two elementwise graph ops.
+// TPQ threads per query: 32 (a warp does everything; narrow rows) or 256 (one CTA per query: its first warp runs the ball query,
+// then all 256 threads copy the nsample x (3 + c) output rows -- wide feature rows, few queries).
+template <int TPQ>
+__global__ void __launch_bounds__(256) lrg_ball_group_kernel(int b, int n, int m, float radius, int nsample, int c, const float* __restrict__ xyz,
+                                                             const float* __restrict__ points, const int* __restrict__ fps_idx,
+                                                             float* __restrict__ new_xyz, int* __restrict__ idx, int* __restrict__ pts_cnt, float* __restrict__ grouped_xyz,
+                                                             float* __restrict__ new_points) {
+  const int lane = threadIdx.x & 31;
+  const int tq = threadIdx.x % TPQ;                    // thread within the query's group
+  const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / TPQ;
+  const long long ngroups = ((long long)gridDim.x * blockDim.x) / TPQ;
+  const int cw = 3 + (points != nullptr ? c : 0);
+  for (long long q = gid; q < (long long)b * m; q += ngroups) {      // (uniform per CTA when TPQ == 256)
+    const long long bi = q / m;
+    const float* p1 = xyz + bi * n * 3;
+    const int ci = fps_idx[q];                          // gather_point: the query is the sampled point itself
+    const float x2 = p1[(size_t)ci * 3 + 0], y2 = p1[(size_t)ci * 3 + 1], z2 = p1[(size_t)ci * 3 + 2];
+    int* out = idx + q * nsample;
+    if (tq < 32) {
+      if (lane < 3) new_xyz[q * 3 + lane] = lane == 0 ? x2 : lane == 1 ? y2 : z2;
+      int cnt = 0, first = -1;
+      for (int k0 = 0; k0 < n && cnt < nsample; k0 += 32) {
+        const int k = k0 + lane;
+        bool hit = false;
+        if (k < n) {
+          const float x1 = p1[k * 3 + 0], y1 = p1[k * 3 + 1], z1 = p1[k * 3 + 2];
+          const float d = max(sqrtf((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1)), 1e-20f);
+          hit = d < radius;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) {
+          if (first < 0) first = k0 + __ffs(bal) - 1;
+          const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+          if (hit && pos < nsample) out[pos] = k;
+          cnt = min(nsample, cnt + __popc(bal));
+        }
+      }
+      if (first >= 0)
+        for (int l = cnt + lane; l < nsample; l += 32) out[l] = first;
+      if (lane == 0) pts_cnt[q] = cnt;
+    }
+    // the row of indices was written by other threads of the group
+    if constexpr (TPQ == 32) __syncwarp(); else { __threadfence_block(); __syncthreads(); }
+    const float ctr[3] = {x2, y2, z2};
+    for (int t = tq; t < nsample * cw; t += TPQ) {
+      const int s = t / cw, l = t - s * cw;
+      const int i = out[s];                            // (an empty ball leaves the row as the caller initialised it, like the reference)
+      float v;
+      if (l < 3) {
+        v = __fsub_rn(p1[(size_t)i * 3 + l], ctr[l]);
+        if (grouped_xyz != nullptr) grouped_xyz[(q * nsample + s) * 3 + l] = v;
+      } else {
+        v = points[(bi * n + i) * c + (l - 3)];
+      }
+      new_points[(q * nsample + s) * cw + l] = v;
+    }
+    if constexpr (TPQ != 32) __syncthreads();           // (the next query of this CTA rewrites nothing of this one; keeps the group together)
+  }
+}
+
 // ------------------------------------------------------------------------------------- group / grad
 __global__ void lrg_group_point_kernel(long long rows, int n, int c, int per_batch_rows, const float* __restrict__ points,
                                        const int* __restrict__ idx, float* __restrict__ out) {
@@ -305,6 +439,26 @@ __global__ void lrg_group_point_grad_kernel(long long rows, int n, int c, int pe
     const int l = (int)(t - r * c);
     const long long bi = r / per_batch_rows;
     atomicAdd(grad_points + (bi * n + idx[r]) * c + l, grad_out[t]);
+  }
+}
+
+// ------------------------------------------------------------------------------------- knn_point's distance matrix
+// tf_grouping.py:66-68: dist[b][j][i] = sum_c (xyz1[b][i][c] - xyz2[b][j][c])^2 (tile + subtract + square + reduce_sum in the
+// reference's graph), float32, channels summed left to right.  One thread per entry, rows of xyz1 contiguous across a warp.
+__global__ void lrg_pairwise_sqdist_kernel(long long total, int n, int m, int c, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                                           float* __restrict__ dist) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long bj = e / n;
+    const int i = (int)(e - bj * n);
+    const long long b = bj / m;
+    const float* p1 = xyz1 + ((size_t)b * n + i) * c;
+    const float* p2 = xyz2 + (size_t)bj * c;
+    float s = 0.f;
+    for (int k = 0; k < c; ++k) {
+      const float d = __fsub_rn(p1[k], p2[k]);
+      s = __fadd_rn(s, __fmul_rn(d, d));
+    }
+    dist[e] = s;
   }
 }
 
@@ -419,6 +573,27 @@ static inline int grid_for(long long work, int threads, int max_blocks = 148 * 1
   return (int)blocks;
 }
 
+// FPS by cloud size: registers of one CTA up to 8,192 points, of a cluster of 2 / 4 / 8 CTAs up to 65,536, else the
+// reference's layout (min-distances in the caller's (32,n) workspace).  LRG_FPS_CLUSTER_MIN (tests) moves the first boundary.
+static int g_fps_cluster_min = 512 * 16;
+static int launch_fps(int b, int n, int m, const float* d_inp, float* d_temp, int* d_out, cudaStream_t st) {
+  if (n <= g_fps_cluster_min && n <= 512 * 16) {
+    if (n <= 512 * 1) lrg_fps_kernel<512, 1><<<b, 512, 0, st>>>(n, m, d_inp, d_out);
+    else if (n <= 512 * 2) lrg_fps_kernel<512, 2><<<b, 512, 0, st>>>(n, m, d_inp, d_out);
+    else if (n <= 512 * 4) lrg_fps_kernel<512, 4><<<b, 512, 0, st>>>(n, m, d_inp, d_out);
+    else if (n <= 512 * 8) lrg_fps_kernel<512, 8><<<b, 512, 0, st>>>(n, m, d_inp, d_out);
+    else lrg_fps_kernel<512, 16><<<b, 512, 0, st>>>(n, m, d_inp, d_out);
+  } else if (n <= 8192 * 2) lrg_fps_cluster_kernel<2><<<b * 2, kFpsThreads, 0, st>>>(n, m, d_inp, d_out);
+  else if (n <= 8192 * 4) lrg_fps_cluster_kernel<4><<<b * 4, kFpsThreads, 0, st>>>(n, m, d_inp, d_out);
+  else if (n <= 8192 * 8) lrg_fps_cluster_kernel<8><<<b * 8, kFpsThreads, 0, st>>>(n, m, d_inp, d_out);
+  else {
+    LRG_REQUIRE(d_temp != nullptr, "FarthestPointSample with n=%d > %d needs the (32,n) temp workspace", n, 8192 * 8);
+    lrg_fps_big_kernel<<<b < 32 ? b : 32, kFpsThreads, 0, st>>>(b, n, m, d_inp, d_temp, d_out);
+  }
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
+}
+
 }  // namespace lrg
 
 using namespace lrg;
@@ -426,21 +601,33 @@ using namespace lrg;
 extern "C" {
 #pragma GCC visibility push(default)
 
+int lrg_fps_set_cluster_min(int n) { g_fps_cluster_min = n > 0 ? n : 512 * 16; return LRG_OK; }
+
 int lrg_farthest_point_sampling(int b, int n, int m, const float* d_inp, float* d_temp, int* d_out, lrg_stream_t s) {
   LRG_REQUIRE(b >= 0 && n > 0 && m >= 0, "FarthestPointSample expects b>=0, n>0, npoint>=0 (got b=%d n=%d m=%d)", b, n, m);
   if (b == 0 || m == 0) return LRG_OK;
   LRG_REQUIRE(d_inp && d_out, "NULL tensor pointer");
   cudaStream_t st = (cudaStream_t)s;
-  // (fewer, fatter threads were measured slower: 1024 points as 128 threads x 8 take 466 us for 1024 samples, 512 x 2 take 265 us)
-  if (n <= 512 * 1) lrg_fps_kernel<512, 1><<<b, 512, 0, st>>>(n, m, d_inp, d_out);
-  else if (n <= 512 * 2) lrg_fps_kernel<512, 2><<<b, 512, 0, st>>>(n, m, d_inp, d_out);
-  else if (n <= 512 * 4) lrg_fps_kernel<512, 4><<<b, 512, 0, st>>>(n, m, d_inp, d_out);
-  else if (n <= 512 * 8) lrg_fps_kernel<512, 8><<<b, 512, 0, st>>>(n, m, d_inp, d_out);
-  else if (n <= 512 * 16) lrg_fps_kernel<512, 16><<<b, 512, 0, st>>>(n, m, d_inp, d_out);
-  else {
-    LRG_REQUIRE(d_temp != nullptr, "FarthestPointSample with n=%d > %d needs the (32,n) temp workspace", n, kFpsThreads * 16);
-    lrg_fps_big_kernel<<<b < 32 ? b : 32, kFpsThreads, 0, st>>>(b, n, m, d_inp, d_temp, d_out);
-  }
+  // (one CTA: fewer, fatter threads were measured slower: 1024 points as 128 threads x 8 take 466 us for 1024 samples, 512 x 2 take 265 us)
+  return launch_fps(b, n, m, d_inp, d_temp, d_out, st);
+}
+
+int lrg_sample_and_group(int b, int n, int npoint, float radius, int nsample, int c, const float* d_xyz, const float* d_points, float* d_temp,
+                         int* d_fps_idx, float* d_new_xyz, float* d_new_points, int* d_idx, int* d_pts_cnt, float* d_grouped_xyz, lrg_stream_t s) {
+  LRG_REQUIRE(b >= 0 && n > 0 && npoint > 0 && nsample > 0 && c >= 0, "sample_and_group: bad shape (b=%d n=%d npoint=%d nsample=%d c=%d)", b, n, npoint, nsample, c);
+  if (b == 0) return LRG_OK;
+  LRG_REQUIRE(d_xyz && d_fps_idx && d_new_xyz && d_new_points && d_idx && d_pts_cnt, "NULL tensor pointer");
+  LRG_REQUIRE(c == 0 || d_points != nullptr, "sample_and_group: c=%d feature channels but points is NULL", c);
+  cudaStream_t st = (cudaStream_t)s;
+  const int rc = launch_fps(b, n, npoint, d_xyz, d_temp, d_fps_idx, st);
+  if (rc != LRG_OK) return rc;
+  // wide rows and too few queries to fill the machine with one warp each: a CTA per query
+  if ((3 + c) * nsample >= 2048 && (long long)b * npoint <= 148 * 64)
+    lrg_ball_group_kernel<256><<<grid_for((long long)b * npoint * 256, 256), 256, 0, st>>>(b, n, npoint, radius, nsample, c, d_xyz, c > 0 ? d_points : nullptr,
+                                                                                          d_fps_idx, d_new_xyz, d_idx, d_pts_cnt, d_grouped_xyz, d_new_points);
+  else
+    lrg_ball_group_kernel<32><<<grid_for((long long)b * npoint * 32, 256), 256, 0, st>>>(b, n, npoint, radius, nsample, c, d_xyz, c > 0 ? d_points : nullptr,
+                                                                                        d_fps_idx, d_new_xyz, d_idx, d_pts_cnt, d_grouped_xyz, d_new_points);
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;
 }
@@ -488,6 +675,15 @@ int lrg_selection_sort(int b, int n, int m, int k, const float* d_dist, int* d_o
   LRG_REQUIRE(b >= 0 && n > 0 && m >= 0, "SelectionSort: bad shape");
   if ((long long)b * m == 0) return LRG_OK;
   lrg_selection_sort_kernel<<<grid_for((long long)b * m * 32, 256), 256, 0, (cudaStream_t)s>>>((long long)b * m, n, k, d_dist, d_outi, d_out);
+  LRG_CUDA(cudaGetLastError());
+  return LRG_OK;
+}
+
+int lrg_pairwise_sqdist(int b, int n, int m, int c, const float* d_xyz1, const float* d_xyz2, float* d_dist, lrg_stream_t s) {
+  LRG_REQUIRE(b >= 0 && n > 0 && m >= 0 && c > 0, "pairwise_sqdist: bad shape");
+  const long long total = (long long)b * m * n;
+  if (total == 0) return LRG_OK;
+  lrg_pairwise_sqdist_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)s>>>(total, n, m, c, d_xyz1, d_xyz2, d_dist);
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;
 }

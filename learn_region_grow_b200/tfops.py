@@ -19,6 +19,13 @@ class _DeviceBuffer:
             _lib.lib().lrg_free(self.ptr)
             self.ptr = C.c_void_p()
 
+    def __del__(self):
+        # an op that raises between inp()/out() and finish() drops its _Call: the buffers go with it
+        try:
+            self.free()
+        except Exception:
+            pass
+
 
 class _Call:
     """Marshals numpy / torch arguments to device pointers for one op call."""
@@ -104,11 +111,40 @@ def farthest_point_sample(npoint, inp):
     b, n, _ = s
     c = _Call(inp)
     d_inp = c.inp(inp, np.float32)
-    d_tmp = c.out((32, n), np.float32) if n > 8192 else None
+    d_tmp = c.out((32, n), np.float32) if n > 65536 else None     # (up to 65,536 points live in registers: one CTA or a cluster)
     d_out = c.out((b, npoint), np.int32)
     _lib.check(_lib.lib().lrg_farthest_point_sampling(b, n, npoint, d_inp, d_tmp, d_out, c.stream()))
     res = c.finish()
     return res[-1] if isinstance(res, tuple) else res
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points=None):
+    """train_pointnet.py:113-123: ``new_xyz = gather_point(xyz, farthest_point_sample(npoint, xyz))``, ball query around new_xyz,
+    ``grouped_xyz = group_point(xyz, idx) - new_xyz``, ``new_points = concat(grouped_xyz, group_point(points, idx))`` -- two
+    launches (lrg_sample_and_group).  Returns (new_xyz, new_points, idx, grouped_xyz) like the reference."""
+    s = _shape(xyz)
+    _require(len(s) == 3 and s[2] == 3, 'FarthestPointSample expects (batch_size,num_points,3) inp shape')   # tf_sampling.cpp:105
+    b, n, _ = s
+    ch = 0
+    if points is not None:
+        sp = _shape(points)
+        _require(len(sp) == 3 and sp[0] == b and sp[1] == n, 'GroupPoint expects (batch_size, num_points, channel) points shape')   # tf_grouping.cpp:148
+        ch = sp[2]
+    c = _Call(*([xyz] + ([points] if points is not None else [])))
+    d_xyz = c.inp(xyz, np.float32)
+    d_pts = c.inp(points, np.float32) if ch else None
+    d_tmp = c.out((32, n), np.float32) if n > 65536 else None
+    d_fps = c.out((b, npoint), np.int32)
+    d_new_xyz = c.out((b, npoint, 3), np.float32)
+    d_new_points = c.out((b, npoint, nsample, 3 + ch), np.float32)
+    d_idx = c.out((b, npoint, nsample), np.int32)
+    d_cnt = c.out((b, npoint), np.int32)
+    d_gxyz = c.out((b, npoint, nsample, 3), np.float32)
+    _lib.check(_lib.lib().lrg_sample_and_group(b, n, npoint, C.c_float(radius), nsample, ch, d_xyz, d_pts, d_tmp, d_fps, d_new_xyz, d_new_points,
+                                               d_idx, d_cnt, d_gxyz, c.stream()))
+    res = c.finish()
+    new_xyz, new_points, idx, _, grouped_xyz = res[-5:]
+    return new_xyz, new_points, idx, grouped_xyz
 
 
 def gather_point(inp, idx):
@@ -208,10 +244,19 @@ def group_point_grad(points, idx, grad_out):
 
 def knn_point(k, xyz1, xyz2):
     """tf_grouping.py:48-73: brute-force squared distances (B,M,N) then select_top_k; returns (val, idx) (B,M,k)."""
-    a1, a2 = np.asarray(xyz1, np.float32), np.asarray(xyz2, np.float32)
-    dist = ((a2[:, :, None, :] - a1[:, None, :, :]) ** 2).sum(-1, dtype=np.float32)
-    outi, out = select_top_k(k, dist)
-    return out[:, :, :k], outi[:, :, :k]
+    s1, s2 = _shape(xyz1), _shape(xyz2)
+    _require(len(s1) == 3 and len(s2) == 3 and s1[0] == s2[0] and s1[2] == s2[2], 'knn_point expects (b,n,c) xyz1 and (b,m,c) xyz2')
+    b, n, ch = s1
+    m = s2[1]
+    c = _Call(xyz1, xyz2)
+    d1, d2 = c.inp(xyz1, np.float32), c.inp(xyz2, np.float32)
+    d_dist = c.out((b, m, n), np.float32)
+    d_outi = c.out((b, m, n), np.int32)
+    d_out = c.out((b, m, n), np.float32)
+    _lib.check(_lib.lib().lrg_pairwise_sqdist(b, n, m, ch, d1, d2, d_dist, c.stream()))              # :66-68
+    _lib.check(_lib.lib().lrg_selection_sort(b, n, m, k, d_dist, d_outi, d_out, c.stream()))         # :70
+    _, outi, out = c.finish()
+    return out[:, :, :k], outi[:, :, :k]                                                             # :71-72
 
 
 # ----------------------------------------------------------------------------- tf_interpolate.py

@@ -195,3 +195,86 @@ def test_against_reference_kernels_themselves():
         np.testing.assert_array_equal(host(g_new, (b, m, ns, 16), np.float32), host(g_ref, (b, m, ns, 16), np.float32))
         for p in (dx, tmp, o_ref, o_new, dq, i_ref, i_new, c_ref, c_new, df, g_ref, g_new):
             L.lrg_free(p)
+
+
+@pytest.mark.parametrize('b,n,m,dup', [(1, 9000, 96, False), (2, 16384, 64, True), (1, 30000, 128, False), (1, 65536, 48, False),
+                                       (1, 70000, 32, False)])
+def test_farthest_point_sample_large_clouds(b, n, m, dup):
+    """8,193 .. 65,536 points: the thread-block-cluster kernel (2 / 4 / 8 CTAs per cloud, points in registers, argmax exchanged
+    through distributed shared memory); above that the workspace kernel.  Index-exact against the C restatement (itself pinned
+    to the reference's own kernel in test_against_reference_kernels_themselves)."""
+    from learn_region_grow_b200 import tfops as T
+    x = _clouds(b, n, n + m, dup)
+    got = T.farthest_point_sample(m, x)
+    np.testing.assert_array_equal(got, O.farthest_point_sample(m, x))
+
+
+def test_cluster_fps_equals_the_one_cta_kernel_and_the_reference_kernel():
+    """Forcing the cluster kernel onto small clouds (lrg_fps_set_cluster_min) gives the indices of the one-CTA kernel, ties
+    included; and on a 20,000-point cloud the reference's own farthestpointsamplingKernel agrees where it is available."""
+    from learn_region_grow_b200 import _lib, tfops as T
+    L = _lib.lib()
+    clouds = [(_clouds(2, 600, 7, True), 600), (_clouds(1, 3000, 8), 257), (_clouds(3, 8192, 9), 40)]
+    one = [T.farthest_point_sample(m, x) for x, m in clouds]
+    try:
+        _lib.check(L.lrg_fps_set_cluster_min(256))
+        for (x, m), ref in zip(clouds, one):
+            np.testing.assert_array_equal(T.farthest_point_sample(m, x), ref)
+    finally:
+        _lib.check(L.lrg_fps_set_cluster_min(0))
+    if O.ReferenceKernels.available():
+        R = O.ReferenceKernels()
+        x = _clouds(1, 20000, 11)
+        p, tmp, out = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        for ptr, nbytes in ((p, x.nbytes), (tmp, 32 * 20000 * 4), (out, 200 * 4)):
+            _lib.check(L.lrg_malloc(C.byref(ptr), nbytes))
+        _lib.check(L.lrg_memcpy_h2d(p, _lib.ptr(x), x.nbytes))
+        R.fps(1, 20000, 200, p, tmp, out)
+        ref = np.empty((1, 200), np.int32)
+        _lib.check(L.lrg_device_synchronize())
+        _lib.check(L.lrg_memcpy_d2h(_lib.ptr(ref), out, ref.nbytes))
+        np.testing.assert_array_equal(T.farthest_point_sample(200, x), ref)
+        for ptr in (p, tmp, out):
+            L.lrg_free(ptr)
+
+
+@pytest.mark.parametrize('b,n,npoint,radius,ns,c', [(2, 1024, 256, 0.15, 32, 6), (1, 4096, 512, 0.1, 32, 0), (3, 500, 64, 0.3, 16, 13),
+                                                    (1, 12000, 128, 0.05, 8, 4)])
+def test_sample_and_group_fused(b, n, npoint, radius, ns, c):
+    """lrg_sample_and_group (train_pointnet.py:113-123 in two launches) == the separate ops == the oracle's composition, bit for
+    bit: new_xyz, idx, grouped_xyz (translation-normalised) and new_points = concat(grouped_xyz, grouped features)."""
+    from learn_region_grow_b200 import tfops as T
+    x = _clouds(b, n, 50 + n)
+    feat = np.random.RandomState(3).randn(b, n, c).astype(np.float32) if c else None
+    new_xyz, new_points, idx, grouped_xyz = T.sample_and_group(npoint, radius, ns, x, feat)
+    # the reference's own sequence through the separate drop-in ops
+    s_new = T.gather_point(x, T.farthest_point_sample(npoint, x))
+    s_idx, s_cnt = T.query_ball_point(radius, ns, x, s_new)
+    s_g = T.group_point(x, s_idx) - s_new[:, :, None, :]
+    s_np = np.concatenate([s_g, T.group_point(feat, s_idx)], -1) if c else s_g
+    # ... and on the CPU oracle
+    o_new = O.gather_point(x, O.farthest_point_sample(npoint, x))
+    o_idx, _ = O.query_ball_point(radius, ns, x, o_new)
+    o_g = O.group_point(x, o_idx) - o_new[:, :, None, :]
+    for got, sep, ora in ((new_xyz, s_new, o_new), (idx, s_idx, o_idx), (grouped_xyz, s_g, o_g)):
+        np.testing.assert_array_equal(got, sep)
+        np.testing.assert_array_equal(got, ora)
+    np.testing.assert_array_equal(new_points, s_np)
+    assert new_points.shape == (b, npoint, ns, 3 + c)
+
+
+def test_knn_point_on_the_device():
+    """tf_grouping.py:48-73: distance matrix (lrg_pairwise_sqdist) + selection sort, both on the device; numpy and torch inputs."""
+    from learn_region_grow_b200 import tfops as T
+    x1, x2 = _clouds(2, 300, 1), _clouds(2, 40, 2)
+    val, idx = T.knn_point(5, x1, x2)
+    d = ((x1[:, None, :, :] - x2[:, :, None, :]) ** 2)
+    dist = (d[..., 0] + d[..., 1]) + d[..., 2]
+    ri, ro = O.select_top_k(5, dist.astype(np.float32))
+    np.testing.assert_array_equal(idx, ri[:, :, :5])
+    np.testing.assert_array_equal(val, ro[:, :, :5])
+    torch = pytest.importorskip('torch')
+    tv, ti = T.knn_point(5, torch.from_numpy(x1).cuda(), torch.from_numpy(x2).cuda())
+    assert ti.is_cuda
+    np.testing.assert_array_equal(ti.cpu().numpy(), idx)
+    np.testing.assert_array_equal(tv.cpu().numpy(), val)

@@ -79,6 +79,47 @@ def test_tfops_beside_reference_kernels():
             assert torch.equal(g_new, g_ref)
             lines.append('%-22s %5d %5d %5d %4d | %10.1f %10.1f %7.2f | %9.2f' % ('group_point', B, n, m, c, t_new, t_ref, t_ref / t_new,
                                                                                    B * m * NSAMPLE * (4 + 8 * c) / t_new / 1e3))
+            # sample_and_group (train_pointnet.py:113-123) as lrg_sample_and_group's two launches beside the reference's five
+            # kernel launches (FPS, gather, ball query, group xyz, group features; its two elementwise graph ops not counted)
+            gx_ref = torch.zeros(B, m, NSAMPLE, 3, device='cuda')
+            np_new = torch.zeros(B, m, NSAMPLE, 3 + c, device='cuda')
+            gx_new = torch.zeros(B, m, NSAMPLE, 3, device='cuda')
+            nx_new = torch.zeros(B, m, 3, device='cuda')
+            f_new = torch.zeros(B, m, dtype=torch.int32, device='cuda')
+
+            def ref_chain():
+                R.fps(B, n, m, p(xyz), p(tmp), p(o_ref))
+                R.gather(B, n, m, p(xyz), p(o_ref), p(q_ref))
+                R.query_ball(B, n, m, radius, NSAMPLE, p(xyz), p(q_ref), p(i_ref), p(c_ref))
+                R.group(B, n, 3, m, NSAMPLE, p(xyz), p(i_ok), p(gx_ref))
+                R.group(B, n, c, m, NSAMPLE, p(feat), p(i_ok), p(g_ref))
+            i_new.zero_()
+            t_new = _time(torch, lambda: _lib.check(L.lrg_sample_and_group(B, n, m, radius, NSAMPLE, c, p(xyz), p(feat), None, p(f_new), p(nx_new),
+                                                                           p(np_new), p(i_new), p(c_new), p(gx_new), None)))
+            t_ref = _time(torch, ref_chain)
+            assert torch.equal(f_new, o_ref) and torch.equal(nx_new, q_ref) and torch.equal(i_new[hit], i_ref[hit])
+            assert torch.equal(np_new[..., 3:][hit], g_ref[hit]) and torch.equal(gx_new[hit], (gx_ref - q_ref[:, :, None, :])[hit])
+            lines.append('%-22s %5d %5d %5d %4d | %10.1f %10.1f %7.2f | %9.2f' % ('sample_and_group', B, n, m, c, t_new, t_ref, t_ref / t_new,
+                                                                                   B * (n * (12 + 4 * c) + m * NSAMPLE * (4 + 4 * (3 + c))) / t_new / 1e3))
+        if B == 1:
+            # large clouds: one CTA up to 8,192 points, a cluster of 2 / 4 / 8 CTAs (distributed shared memory) up to 65,536
+            for n, m in [(8192, 256), (16384, 256), (32768, 256), (65536, 256)]:
+                xyz = torch.from_numpy(rng.rand(B, n, 3).astype(np.float32)).cuda()
+                tmp = torch.zeros(32, n, device='cuda')
+                o_new = torch.zeros(B, m, dtype=torch.int32, device='cuda')
+                o_ref = torch.zeros_like(o_new)
+                t_new = _time(torch, lambda: _lib.check(L.lrg_farthest_point_sampling(B, n, m, p(xyz), p(tmp), p(o_new), None)), reps=5, warm=1)
+                t_ref = _time(torch, lambda: R.fps(B, n, m, p(xyz), p(tmp), p(o_ref)), reps=5, warm=1)
+                assert torch.equal(o_new, o_ref)
+                lines.append('%-22s %5d %5d %5d %4s | %10.1f %10.1f %7.2f | %9.2f' % ('fps (large cloud)', B, n, m, '-', t_new, t_ref, t_ref / t_new,
+                                                                                       B * (n * 12 + m * 4) / t_new / 1e3))
+                if n == 8192:
+                    _lib.check(L.lrg_fps_set_cluster_min(4096))
+                    t_cl = _time(torch, lambda: _lib.check(L.lrg_farthest_point_sampling(B, n, m, p(xyz), p(tmp), p(o_new), None)), reps=5, warm=1)
+                    _lib.check(L.lrg_fps_set_cluster_min(0))
+                    assert torch.equal(o_new, o_ref)
+                    lines.append('%-22s %5d %5d %5d %4s | %10.1f %10.1f %7.2f | %9.2f' % ('fps (8192 as cluster)', B, n, m, '-', t_cl, t_ref, t_ref / t_cl,
+                                                                                           B * (n * 12 + m * 4) / t_cl / 1e3))
         for (n, m) in [(1024, 1024), (20000, 4096)]:                      # prob_sample: n categories, m draws per row
             pr = torch.from_numpy(rng.rand(B, n).astype(np.float32)).cuda()
             un = torch.from_numpy(rng.rand(B, m).astype(np.float32)).cuda()

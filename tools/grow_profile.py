@@ -14,18 +14,28 @@ def main():
     ap.add_argument('--repeat', type=int, default=2)
     ap.add_argument('--slots', type=int, default=0)
     ap.add_argument('--flags', type=int, default=0)
+    ap.add_argument('--lanes', type=int, default=0)
+    ap.add_argument('--kitti', type=int, default=0, help='N Semantic-KITTI-shaped scenes at 0.3 m instead of rooms')
     args = ap.parse_args()
     import bench
     from learn_region_grow_b200.engine import Engine
-    raw_off, raw = bench.make_workload(args.rooms, 1000)
+    res = 0.3 if args.kitti else 0.1
+    if args.kitti:
+        import numpy as np
+        from tools import rooms as Rm
+        scenes = [Rm.generate_outdoor_scene(3000 + i)[:, :6] for i in range(args.kitti)]
+        raw_off = np.concatenate([[0], np.cumsum([len(s) for s in scenes])]).astype(np.int64)
+        raw = np.ascontiguousarray(np.vstack(scenes), dtype=np.float32)
+    else:
+        raw_off, raw = bench.make_workload(args.rooms, 1000)
     eng = Engine(1, 1, 512, 512, 13, 0)
     eng.load_weights(bench.load_weights())
     if os.environ.get('LRG_TILE_TIMING'):          # (this tool's own switch; the library has an explicit call for it)
         from learn_region_grow_b200 import _lib
         _lib.check(eng.lib.lrg_engine_set_tile_timing(eng._h, 1))
-    eng.upload_raw_concatenated(raw_off, raw, 0.1)
+    eng.upload_raw_concatenated(raw_off, raw, res)
     for _ in range(args.repeat):
-        stats = eng.segment_resident(resolution=0.1, seed=0, max_slots=args.slots, flags=args.flags)
+        stats = eng.segment_resident(resolution=res, seed=0, max_slots=args.slots, flags=args.flags, spec_lanes=args.lanes)
         pr = eng.profile()
     steps = int(stats['grow_steps'].sum())
     print('rooms %d  grow steps %d (max/room %d)  grow %.1f ms  fill %.1f ms  persistent %s' %
