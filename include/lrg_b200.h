@@ -108,11 +108,16 @@ typedef struct LrgGrowParams {
                                   persistent kernel when no trace is recorded, else 1), 1 = off, max 16 */
   int spec_top;                /* speculative lanes: only the spec_top rooms in flight with the most estimated work left (unvisited
                                   points x grow steps per visited point so far) hand seeds to more than one lane -- the run ends
-                                  with its longest rooms, speculation elsewhere only costs SM time.  0 = engine default (4),
-                                  < 0 = every room speculates */
+                                  with its longest rooms, speculation elsewhere only costs SM time.  A cap on top of spec_crit below.
+                                  0 = engine default (8), < 0 = no cap */
   int spec_min_idle;           /* speculative lanes: a room outside the spec_top still speculates while at least this many CTAs of
                                   the persistent kernel wait for work (the tail of a run).  0 = engine default (96), < 0 = never */
-  int reserved[1];             /* zero */
+  int spec_crit;               /* speculative lanes: a room among the spec_top speculates only while it is CRITICAL -- its estimated
+                                  remaining grow steps x spec_crit >= the estimated remaining grow steps of the whole run (rooms in
+                                  flight + rooms not started): a chain link costs ~50 us of latency but a grow step only ~1 us of the
+                                  machine's time (130 us of SM time over 132 SMs), so a room whose share of the remaining work is
+                                  below ~1/50 finishes inside the throughput bound anyway and speculation would only add discarded
+                                  steps to it.  0 = engine default (40), < 0 = every room counts as critical */
 } LrgGrowParams;
 
 enum {

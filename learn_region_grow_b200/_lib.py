@@ -18,7 +18,7 @@ class GrowParams(C.Structure):
                 ('max_slots', C.c_int), ('max_steps_per_region', C.c_int), ('room_id_base', C.c_int),
                 ('trace_capacity', C.c_int), ('flags', C.c_int), ('num_restarts', C.c_int), ('beam_width', C.c_int),
                 ('search_width', C.c_int), ('spec_lanes', C.c_int), ('spec_top', C.c_int), ('spec_min_idle', C.c_int),
-                ('reserved', C.c_int * 1)]
+                ('spec_crit', C.c_int)]
 
 
 class RoomStats(C.Structure):

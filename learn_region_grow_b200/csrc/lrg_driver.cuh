@@ -137,6 +137,8 @@ struct DriverArgs {
   // spec_min_idle CTAs of the persistent kernel wait for work
   int spec_top;
   int spec_min_idle;
+  int spec_crit;                // ... and only while its estimate x spec_crit >= the estimate of all remaining work (0: always)
+  long long total_pts;          // points of all rooms (the rooms not yet started enter the estimate with 0.2 grow steps per point)
   int* spec_est;                // (n_slots / lanes)
 };
 

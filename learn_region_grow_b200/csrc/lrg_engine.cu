@@ -1101,8 +1101,10 @@ static int segment_resident_impl(LrgEngine* e, const LrgGrowParams* params, LrgR
   da.beam_width = beam ? params->beam_width : 0; da.search_width = beam ? params->search_width : 0; da.parI = beam ? e->d_parI : nullptr;
   da.spec = spec ? 1 : 0; da.spec_sync = e->d_spec_sync; da.clog = e->d_clog; da.q_ctr = nullptr;
   // which rooms speculate: the spec_top rooms with the most estimated work left, and anybody while CTAs idle (the tail)
-  da.spec_top = params->spec_top == 0 ? 4 : params->spec_top < 0 ? (1 << 30) : params->spec_top;
+  da.spec_top = params->spec_top == 0 ? 8 : params->spec_top < 0 ? (1 << 30) : params->spec_top;
   da.spec_min_idle = params->spec_min_idle == 0 ? 96 : params->spec_min_idle < 0 ? (1 << 30) : params->spec_min_idle;
+  da.spec_crit = params->spec_crit == 0 ? 40 : params->spec_crit < 0 ? 0 : params->spec_crit;
+  da.total_pts = e->total_pts;
   da.spec_est = e->d_spec_est;
 
   ForwardArgs fa{};

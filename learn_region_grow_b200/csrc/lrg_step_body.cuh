@@ -369,6 +369,7 @@ struct StepShared {
   float lane_score;             // ... and the expansion's score (parent + both)
   int nsel[2];                  // ... selected rows per set
   int sp_cnt;                   // indexed shell scan: blocks that meet the shell
+  unsigned long long est_sum;   // speculative lanes: sum of the other rooms' work estimates
   int sp_total;                 // ... and its result when only half of the CTA ran it
   unsigned wake;                // random restarts / beam search: lanes of this group (bit l) this call handed work to (they need a STEP)
   LaneGroup G;                  // random restarts: the group's room-level state while this CTA owns it
@@ -1212,11 +1213,26 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
           const int mine = (int)(((long long)(N - G.visited) * (G.useful_steps + 20)) / (G.visited + 100));
           if (tid == 0) *reinterpret_cast<volatile int*>(da.spec_est + gi) = mine;
           int ahead = 0;
+          long long part = 0;
+          if (tid == 0) sh.est_sum = 0ull;
           for (int g0 = 0; g0 < ng; g0 += NT) {
             const int g = g0 + tid;
             const int other = (g < ng && g != gi) ? __ldcg(da.spec_est + g) : -1;
+            if (other > 0) part += other;
             ahead += __syncthreads_count(other > mine || (other == mine && g < gi));
           }
+          // the estimate of everything that is left: the other rooms in flight, this one, and the rooms nobody has started
+          // (0.2 grow steps per point, the prior of the estimate above)
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+          if (lane == 0 && part != 0) atomicAdd(&sh.est_sum, (unsigned long long)part);
+          __syncthreads();
+          long long total_est = (long long)sh.est_sum + mine;
+          {
+            const int nr = min(*reinterpret_cast<volatile int*>(da.next_room), da.n_rooms);
+            total_est += (da.total_pts - da.room_off[nr]) / 5;
+          }
+          const bool critical = da.spec_crit <= 0 || (long long)mine * da.spec_crit >= total_est;
           // (the queue counters move while they are read: ONE thread looks, the verdict must be the same for the whole CTA)
           int idle_ok = 0;
           if (tid == 0 && da.q_ctr != nullptr) {
@@ -1224,7 +1240,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
             idle_ok = (b < 0 ? -b : 0) >= da.spec_min_idle;
           }
           idle_ok = __syncthreads_or(idle_ok);
-          speculate = ahead < da.spec_top || idle_ok != 0;
+          speculate = (ahead < da.spec_top && critical) || idle_ok != 0;
         }
         for (int k = 0; k < L; ++k) {
           const int l = (lane_id + k) % L;

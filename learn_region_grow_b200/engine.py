@@ -218,18 +218,19 @@ class Engine:
 
     def make_params(self, resolution=0.1, cluster_threshold=10, seed=0, max_slots=0, max_steps_per_region=0,
                     room_id_base=0, trace_capacity=0, flags=0, num_restarts=0, beam_width=0, search_width=0, spec_lanes=0,
-                    spec_top=0, spec_min_idle=0, scoring='np'):
+                    spec_top=0, spec_min_idle=0, scoring='np', spec_crit=0):
         """``num_restarts`` > 1 selects the random-restart driver (test_random_restart.py, NUM_RESTARTS, 'np' scoring);
         ``beam_width`` / ``search_width`` > 0 the beam-search driver (test_beam_search.py, BEAM_WIDTH, SEARCH_WIDTH) with
         ``scoring`` 'np' (region size, the default, :41) or 'ml' (accumulated log-probability, ``--scoring ml``, :46-47,263-264);
         ``spec_lanes`` > 1 grows that many regions of a room side by side with in-order commits (same labels as 1), in the
-        ``spec_top`` rooms with the most work left and wherever ``spec_min_idle`` CTAs idle (0 = defaults, < 0 = all / never)."""
+        ``spec_top`` rooms with the most work left while they hold at least 1 / ``spec_crit`` of the run's remaining work, and
+        wherever ``spec_min_idle`` CTAs idle (0 = defaults, < 0 = all / never)."""
         if scoring not in ('np', 'ml'):
             raise ValueError("scoring must be 'np' or 'ml'")
         if scoring == 'ml':
             flags |= _lib.FLAG_SCORE_ML
         p = GrowParams(resolution, cluster_threshold, seed, max_slots, max_steps_per_region, room_id_base,
-                       trace_capacity, flags, num_restarts, beam_width, search_width, spec_lanes, spec_top, spec_min_idle)
+                       trace_capacity, flags, num_restarts, beam_width, search_width, spec_lanes, spec_top, spec_min_idle, spec_crit)
         return p
 
     def segment_resident(self, params=None, **kw):
