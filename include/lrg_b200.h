@@ -104,8 +104,9 @@ typedef struct LrgGrowParams {
   int spec_lanes;              /* test_region_grow.py only (no restarts / beam): > 1 grows up to spec_lanes regions of ONE room side
                                   by side, speculatively, and commits them strictly in seed order (:183-217) -- a region grown on a
                                   stale visited set is detected when it reaches the head of the order and grown again there, so the
-                                  labels are bit-identical to spec_lanes = 1.  0 = engine default (4 in the
-                                  persistent kernel when no trace is recorded, else 1), 1 = off, max 16 */
+                                  labels are bit-identical to spec_lanes = 1.  0 = engine default (in the
+                                  persistent kernel when no trace is recorded: 4, or 8 when the rooms average >= 65,536 points; else
+                                  1), 1 = off, max 16 */
   int spec_top;                /* speculative lanes: only the spec_top rooms in flight with the most estimated work left (unvisited
                                   points x grow steps per visited point so far) hand seeds to more than one lane -- the run ends
                                   with its longest rooms, speculation elsewhere only costs SM time.  A cap on top of spec_crit below.

@@ -1008,7 +1008,10 @@ static int segment_resident_impl(LrgEngine* e, const LrgGrowParams* params, LrgR
   // one lane so that lrg_trace_download sees one step sequence per room)
   const bool plain = !beam && params->num_restarts <= 1;
   const bool persistent_path = use_tc(e) && !(params->flags & (LRG_FLAG_KERNEL_TIMING | LRG_FLAG_NO_GRAPH | LRG_FLAG_LOCKSTEP));
-  const int spec_lanes = params->spec_lanes != 0 ? params->spec_lanes : (plain && persistent_path && params->trace_capacity == 0) ? 4 : 1;
+  // (default: 4 lanes; 8 when the rooms are large -- a 177 k-point outdoor scene holds far more regions that do not touch one
+  // another than a 12 k-point room: 19 scenes 1.34 -> 1.09 s with 8 lanes, while 8 lanes on rooms only add discarded steps)
+  const int dflt_lanes = (e->n_rooms > 0 && e->total_pts / e->n_rooms >= 65536) ? 8 : 4;
+  const int spec_lanes = params->spec_lanes != 0 ? params->spec_lanes : (plain && persistent_path && params->trace_capacity == 0) ? dflt_lanes : 1;
   const bool spec = spec_lanes > 1 && plain;
   LRG_REQUIRE(params->spec_lanes <= 1 || spec, "spec_lanes %d needs the plain driver (no restarts, no beam search)", params->spec_lanes);
   const int lanes = beam ? params->beam_width * params->search_width : params->num_restarts > 1 ? params->num_restarts : spec ? spec_lanes : 1;

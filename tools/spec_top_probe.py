@@ -21,13 +21,11 @@ for cfg in configs:
         raw_off, raw = bench.concat_rooms([r[:, :6] for r in rr])
         e.upload_raw_concatenated(raw_off, raw, res)
         ref = None
-        for label, kw in (('top 4 crit off', dict(spec_top=4, spec_crit=-1)), ('top 2 crit off', dict(spec_top=2, spec_crit=-1)),
-                          ('top 4 crit 40', dict(spec_top=4, spec_crit=40)), ('top 8 crit 40', dict(spec_top=8, spec_crit=40)),
-                          ('top all crit 40', dict(spec_top=-1, spec_crit=40)), ('top 4 crit 25', dict(spec_top=4, spec_crit=25)),
-                          ('top 8 crit 25', dict(spec_top=8, spec_crit=25)), ('top 8 crit 60', dict(spec_top=8, spec_crit=60)), ('1 lane', dict(spec_lanes=1))):
+        for label, kw in (('4 lanes (default)', dict()), ('6 lanes', dict(spec_lanes=6)), ('8 lanes', dict(spec_lanes=8)), ('8 lanes crit 30', dict(spec_lanes=8, spec_crit=30)),
+                          ('6 lanes idle 64', dict(spec_lanes=6, spec_min_idle=64)), ('1 lane', dict(spec_lanes=1))):
             ms = []
             for rep in range(2):
-                st = e.segment_resident(resolution=res, seed=0, spec_lanes=kw.get('spec_lanes', 4), spec_top=kw.get('spec_top', 0), flags=kw.get('flags', 0), spec_crit=kw.get('spec_crit', 0))
+                st = e.segment_resident(resolution=res, seed=0, spec_lanes=kw.get('spec_lanes', 4), spec_top=kw.get('spec_top', 0), flags=kw.get('flags', 0), spec_crit=kw.get('spec_crit', 0), spec_min_idle=kw.get('spec_min_idle', 0))
                 ms.append(e.profile()['grow_ms'])
             lab = np.concatenate(e.labels(True))
             ref = lab if ref is None else ref
