@@ -306,20 +306,47 @@ __device__ int scan_box_spatial(const DriverArgs& da, int room, const unsigned* 
     const int x = pw_x(v), y = pw_y(v), z = pw_z(v);
     return x >= lo[0] && x <= hi[0] && y >= lo[1] && y <= hi[1] && z >= lo[2] && z <= hi[2];
   };
-  for (int i = warp; i < nhit; i += NT / 32) {
-    const int q = blklist[i] * (kSpBlock / 4) + lane;
-    const uint4 v = __ldg(vox4 + q);
-    const int4 p = __ldg(perm4 + q);
-    const bool f0 = inside(v.x), f1 = inside(v.y), f2 = inside(v.z), f3 = inside(v.w);
-    // (l2: speculative lanes update the words with atomics, which act in L2 -- read them there)
-    const unsigned w0 = !f0 ? PW_VIS : l2 ? __ldcg(pw + p.x) : pw[p.x];
-    const unsigned w1 = !f1 ? PW_VIS : l2 ? __ldcg(pw + p.y) : pw[p.y];
-    const unsigned w2 = !f2 ? PW_VIS : l2 ? __ldcg(pw + p.z) : pw[p.z];
-    const unsigned w3 = !f3 ? PW_VIS : l2 ? __ldcg(pw + p.w) : pw[p.w];
-    if (f0 && pred(w0)) { atomicOr(bitmap + (p.x >> 5), 1u << (p.x & 31)); visit(w0); }
-    if (f1 && pred(w1)) { atomicOr(bitmap + (p.y >> 5), 1u << (p.y & 31)); visit(w1); }
-    if (f2 && pred(w2)) { atomicOr(bitmap + (p.z >> 5), 1u << (p.z & 31)); visit(w2); }
-    if (f3 && pred(w3)) { atomicOr(bitmap + (p.w >> 5), 1u << (p.w & 31)); visit(w3); }
+  // kSpU blocks per warp and round, every load of the round in flight before any is used: a round is two dependent L2 round
+  // trips (static coordinates + indices, then the state words of the points inside the box) whatever kSpU is, and the ~19
+  // blocks a room's shell meets fit one round (one block per warp and round took three)
+  constexpr int kSpU = 4;
+  for (int i0 = warp; i0 < nhit; i0 += (NT / 32) * kSpU) {      // (block i0 + u * warps: the hits spread evenly over the warps)
+    uint4 v[kSpU];
+    int4 p[kSpU];
+#pragma unroll
+    for (int u = 0; u < kSpU; ++u) {
+      v[u] = make_uint4(PW_XYZ, PW_XYZ, PW_XYZ, PW_XYZ);        // (coordinates 1023: outside every box)
+      p[u] = make_int4(0, 0, 0, 0);
+      if (i0 + u * (NT / 32) < nhit) {
+        const int q = blklist[i0 + u * (NT / 32)] * (kSpBlock / 4) + lane;
+        v[u] = __ldg(vox4 + q);
+        p[u] = __ldg(perm4 + q);
+      }
+    }
+    unsigned w[kSpU][4];
+    unsigned f = 0;
+#pragma unroll
+    for (int u = 0; u < kSpU; ++u) {
+      const bool f0 = inside(v[u].x), f1 = inside(v[u].y), f2 = inside(v[u].z), f3 = inside(v[u].w);
+      f |= ((f0 ? 1u : 0u) | (f1 ? 2u : 0u) | (f2 ? 4u : 0u) | (f3 ? 8u : 0u)) << (4 * u);
+      // (l2: speculative lanes update the words with atomics, which act in L2 -- read them there)
+      w[u][0] = !f0 ? PW_VIS : l2 ? __ldcg(pw + p[u].x) : pw[p[u].x];
+      w[u][1] = !f1 ? PW_VIS : l2 ? __ldcg(pw + p[u].y) : pw[p[u].y];
+      w[u][2] = !f2 ? PW_VIS : l2 ? __ldcg(pw + p[u].z) : pw[p[u].z];
+      w[u][3] = !f3 ? PW_VIS : l2 ? __ldcg(pw + p[u].w) : pw[p[u].w];
+    }
+    if (f) {
+#pragma unroll
+      for (int u = 0; u < kSpU; ++u) {
+        const unsigned fu = (f >> (4 * u)) & 15u;
+        if (fu) {
+          if ((fu & 1u) && pred(w[u][0])) { atomicOr(bitmap + (p[u].x >> 5), 1u << (p[u].x & 31)); visit(w[u][0]); }
+          if ((fu & 2u) && pred(w[u][1])) { atomicOr(bitmap + (p[u].y >> 5), 1u << (p[u].y & 31)); visit(w[u][1]); }
+          if ((fu & 4u) && pred(w[u][2])) { atomicOr(bitmap + (p[u].z >> 5), 1u << (p[u].z & 31)); visit(w[u][2]); }
+          if ((fu & 8u) && pred(w[u][3])) { atomicOr(bitmap + (p[u].w >> 5), 1u << (p[u].w & 31)); visit(w[u][3]); }
+        }
+      }
+    }
   }
   group_sync<BAR, NT>();
   const int wpt = (nwords + NT - 1) / NT;
@@ -1789,22 +1816,23 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
       auto free_word = [](unsigned w) { return (w & (PW_CUR | PW_VIS)) == 0u; };
       if (S.n_in <= kMedianSmall && !(da.tune_step & 1)) {
         // The indexed scan is a chain of L2 round trips with little arithmetic, and the 9-channel median of a small region
-        // (:241; needs only the inlier list) is independent of it: the lower half of the CTA scans, the upper half selects.
-        constexpr int G = NT / 2;
-        if (tid < G) {
-          const int r = scan_box_spatial<G, 1>(da, S.room, pw, N, lo, hi, free_word, [](unsigned) {}, listJ, sh.listJ_s, kListCap, sh.scan,
-                                               bitmap, blklist, &sh.sp_cnt, spec);
+        // (:241; needs only the inlier list) is independent of it: part of the CTA scans, the rest selects.
+        // (NT = 512: 7 warps scan, 9 warps take one median channel each -- with 8 + 8 one warp selected two channels in a row)
+        constexpr int GA = NT == 512 ? 224 : NT / 2, GB = NT - GA;
+        if (tid < GA) {
+          const int r = scan_box_spatial<GA, 1>(da, S.room, pw, N, lo, hi, free_word, [](unsigned) {}, listJ, sh.listJ_s, kListCap, sh.scan,
+                                                bitmap, blklist, &sh.sp_cnt, spec);
           if (tid == 0) sh.sp_total = r;
         } else {
-          const int t2 = tid - G, n_cur = S.n_in;
-          for (int j = t2; j < n_cur; j += G) {
+          const int t2 = tid - GA, n_cur = S.n_in;
+          for (int j = t2; j < n_cur; j += GB) {
             unsigned k[9];
             row_keys(j, k);
 #pragma unroll
             for (int s = 0; s < 9; ++s) sh.mkeys[s][j] = k[s];
           }
-          group_sync<2, G>();
-          for (int c = t2 >> 5; c < nch; c += G / 32) {
+          group_sync<2, GB>();
+          for (int c = t2 >> 5; c < nch; c += GB / 32) {
             unsigned lo_k, hi_k;
             warp_median<1>(sh.mkeys[c], n_cur, lo_k, hi_k);
             if (lane == 0) { sh.prefix[c] = lo_k; sh.nextkey[c] = hi_k; }
