@@ -21,13 +21,13 @@ for cfg in configs:
         raw_off, raw = bench.concat_rooms([r[:, :6] for r in rr])
         e.upload_raw_concatenated(raw_off, raw, res)
         ref = None
-        for label, kw in (('4 lanes (default)', dict()), ('6 lanes', dict(spec_lanes=6)), ('8 lanes', dict(spec_lanes=8)), ('8 lanes crit 30', dict(spec_lanes=8, spec_crit=30)),
-                          ('6 lanes idle 64', dict(spec_lanes=6, spec_min_idle=64)), ('1 lane', dict(spec_lanes=1))):
+        for label, kw in (('default', dict()), ('top 4 crit off (first rule)', dict(spec_top=4, spec_crit=-1)), ('crit 25', dict(spec_crit=25)),
+                          ('8 lanes', dict(spec_lanes=8)), ('1 lane', dict(spec_lanes=1))):
             ms = []
             for rep in range(2):
-                st = e.segment_resident(resolution=res, seed=0, spec_lanes=kw.get('spec_lanes', 4), spec_top=kw.get('spec_top', 0), flags=kw.get('flags', 0), spec_crit=kw.get('spec_crit', 0), spec_min_idle=kw.get('spec_min_idle', 0))
+                st = e.segment_resident(resolution=res, seed=0, spec_lanes=kw.get('spec_lanes', 0), spec_top=kw.get('spec_top', 0), flags=kw.get('flags', 0), spec_crit=kw.get('spec_crit', 0), spec_min_idle=kw.get('spec_min_idle', 0))
                 ms.append(e.profile()['grow_ms'])
             lab = np.concatenate(e.labels(True))
             ref = lab if ref is None else ref
-            print('config %d %-12s %-16s grow %8.1f ms | steps %d longest %d | labels %s' % (cfg, cname, label, min(ms), int(st['grow_steps'].sum()),
+            print('config %d %-12s %-28s grow %8.1f ms | steps %d longest %d | labels %s' % (cfg, cname, label, min(ms), int(st['grow_steps'].sum()),
                   int(st['grow_steps'].max()), 'same' if np.array_equal(lab, ref) else 'DIFFERENT'), flush=True)
