@@ -1277,7 +1277,10 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
           if (l == lane_id) mine = true;
         }
       }
-      if (G.next_ticket > G.commit_seq) break;               // something is in flight
+      const bool in_flight = G.next_ticket > G.commit_seq;
+      __syncthreads();                                       // (every thread has compared the two counters before thread 0 resets them below,
+                                                             //  one after the other -- compute-sanitizer racecheck, profiles/r2aa_*)
+      if (in_flight) break;                                  // something is in flight
       // the room is finished (or this is the first call of the run)
       if (tid == 0) {
         if (G.room >= 0) {
