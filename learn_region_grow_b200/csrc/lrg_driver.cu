@@ -291,10 +291,118 @@ __global__ void __launch_bounds__(256) lrg_fill_kernel(const __grid_constant__ F
   }
 }
 
+// The same search through the room's spatial index (lrg_spatial_index_kernel): the 13-D squared distance is at least its x, y, z
+// part, and that is at least the distance from the query to the bounding box of a block of Morton-ordered points -- a block
+// whose bound exceeds the best distance found so far cannot hold the nearest labelled point.  One warp per unlabeled point:
+// (1) the bound of every block, the block with the smallest bound is searched first (it usually holds the query's own
+// surroundings); (2) every other block whose bound does not exceed the best distance so far is searched, best first updated
+// after each.  Distances are numpy_sqdist as above and ties go to the smallest point index, so the result is the brute-force
+// kernel's, bit for bit -- with ~1 % of its distance evaluations on a 12 k-point room and ~0.1 % on a 177 k-point scene.
+// Bounds are computed from voxel boxes (coordinate = rint(x / resolution), so x lies within 0.51 voxels of its voxel's centre
+// -- 0.5 plus the rounding of the division) and shaved by 1e-4 so that no float rounding can put a bound above a distance.
+__global__ void __launch_bounds__(256) lrg_fill_spatial_kernel(const __grid_constant__ FillArgs fa) {
+  const int room = blockIdx.y;
+  const long long base = fa.room_off[room];
+  const int N = (int)(fa.room_off[room + 1] - base);
+  const int nl = fa.n_lab[room], nu = fa.n_unl[room];
+  if (nl == 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* pts = fa.pts + base * 16;
+  const int* label = fa.label + base;
+  const long long so = fa.sp_off[room];
+  const int nblk = (N + kSpBlock - 1) / kSpBlock;
+  const uint2* box = fa.sp_box + so / kSpBlock;
+  const int4* perm4 = reinterpret_cast<const int4*>(fa.sp_perm + so);
+  const int4 vm = fa.room_vmin[room];
+  const float res = fa.resolution;
+  for (int u = blockIdx.x * 8 + warp; u < nu; u += gridDim.x * 8) {
+    const int i = fa.unl_list[base + u];
+    float q[16];
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) {
+      float4 t = *reinterpret_cast<const float4*>(pts + (size_t)i * 16 + c);
+      q[c] = t.x; q[c + 1] = t.y; q[c + 2] = t.z; q[c + 3] = t.w;
+    }
+    auto bound = [&](int b) -> float {
+      const uint2 bb = __ldg(box + b);
+      float s = 0.f;
+      const int lo[3] = {(int)(bb.x & 1023u) + vm.x, (int)((bb.x >> 10) & 1023u) + vm.y, (int)((bb.x >> 20) & 1023u) + vm.z};
+      const int hi[3] = {(int)(bb.y & 1023u) + vm.x, (int)((bb.y >> 10) & 1023u) + vm.y, (int)((bb.y >> 20) & 1023u) + vm.z};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float l = ((float)lo[a] - 0.51f) * res, h = ((float)hi[a] + 0.51f) * res;
+        const float d = fmaxf(0.f, fmaxf(l - q[a], q[a] - h));
+        s += d * d;
+      }
+      return s * 0.9999f;
+    };
+    float best = INFINITY;
+    int bestidx = INT_MAX;
+    auto search = [&](int b) {                             // (warp-uniform b) the labelled points of block b against the query
+      const int m0 = b * kSpBlock + lane * 4;
+      const int4 p = __ldg(perm4 + (m0 >> 2));
+      const int idx[4] = {p.x, p.y, p.z, p.w};
+      int lab[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lab[k] = (m0 + k < N) ? label[idx[k]] : 0;
+      float lb = INFINITY;
+      int li = INT_MAX;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (lab[k] != 0) {
+          const float* row = pts + (size_t)idx[k] * 16;
+          float rv[16];
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) {
+            float4 t = *reinterpret_cast<const float4*>(row + c);
+            rv[c] = t.x; rv[c + 1] = t.y; rv[c + 2] = t.z; rv[c + 3] = t.w;
+          }
+          const float d = numpy_sqdist(rv, q, fa.F);
+          if (d < lb || (d == lb && idx[k] < li)) { lb = d; li = idx[k]; }
+        }
+#pragma unroll
+      for (int dlt = 16; dlt > 0; dlt >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, lb, dlt);
+        const int oi = __shfl_xor_sync(0xffffffffu, li, dlt);
+        if (ob < lb || (ob == lb && oi < li)) { lb = ob; li = oi; }
+      }
+      if (lb < best || (lb == best && li < bestidx)) { best = lb; bestidx = li; }
+    };
+    // (1) the most promising block first
+    float mb = INFINITY;
+    int mblk = INT_MAX;
+    for (int b = lane; b < nblk; b += 32) {
+      const float s = bound(b);
+      if (s < mb) { mb = s; mblk = b; }
+    }
+#pragma unroll
+    for (int dlt = 16; dlt > 0; dlt >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, mb, dlt);
+      const int oi = __shfl_xor_sync(0xffffffffu, mblk, dlt);
+      if (ob < mb || (ob == mb && oi < mblk)) { mb = ob; mblk = oi; }
+    }
+    search(mblk);
+    // (2) every other block that can still hold a nearer (or equally near, lower-indexed) labelled point
+    for (int b0 = 0; b0 < nblk; b0 += 32) {
+      const int b = b0 + lane;
+      const float s = (b < nblk && b != mblk) ? bound(b) : INFINITY;
+      unsigned todo = __ballot_sync(0xffffffffu, s <= best);
+      while (todo) {
+        const int l = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float sl = __shfl_sync(0xffffffffu, s, l);
+        if (sl <= best) search(b0 + l);                    // (best may have dropped since the ballot)
+      }
+    }
+    if (lane == 0 && bestidx != INT_MAX) fa.label_filled[base + i] = label[bestidx];
+  }
+}
+
 int launch_fill(const FillArgs& fa, cudaStream_t stream) {
   if (fa.n_rooms <= 0) return LRG_OK;
   lrg_fill_lists_kernel<<<fa.n_rooms, kStepThreads, 0, stream>>>(fa);
-  lrg_fill_kernel<<<dim3(64, fa.n_rooms), 256, 0, stream>>>(fa);
+  if (fa.sp_perm != nullptr) lrg_fill_spatial_kernel<<<dim3(64, fa.n_rooms), 256, 0, stream>>>(fa);
+  else lrg_fill_kernel<<<dim3(64, fa.n_rooms), 256, 0, stream>>>(fa);
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;
 }

@@ -153,6 +153,12 @@ struct FillArgs {
   int* n_lab;                   // (n_rooms)
   int* n_unl;
   int F;
+  // spatial index of the rooms (DriverArgs::sp_*; sp_perm == NULL: every unlabeled point scans every labelled point)
+  const long long* sp_off;
+  const int* sp_perm;
+  const uint2* sp_box;
+  const int4* room_vmin;
+  float resolution;
 };
 
 constexpr int kSpBlock = 128;          // points per block of the spatial index (one 128-bit load per lane of a warp)

@@ -1263,6 +1263,9 @@ static int segment_resident_impl(LrgEngine* e, const LrgGrowParams* params, LrgR
   FillArgs fl{};
   fl.n_rooms = n_rooms; fl.room_off = e->d_room_off; fl.pts = e->d_pts; fl.label = e->d_label; fl.label_filled = e->d_label_filled;
   fl.lab_list = e->d_lab_list; fl.unl_list = e->d_unl_list; fl.n_lab = e->d_n_lab; fl.n_unl = e->d_n_unl; fl.F = e->F;
+  if (!(params->flags & LRG_FLAG_NO_SPATIAL_INDEX)) {     // nearest labelled point through the rooms' spatial index (same labels)
+    fl.sp_off = e->d_sp_off; fl.sp_perm = e->d_sp_perm; fl.sp_box = e->d_sp_box; fl.room_vmin = e->d_room_vmin; fl.resolution = e->resolution;
+  }
   LRG_TRY(launch_fill(fl, st));
   e->launches += 2;
   LRG_CUDA(cudaEventRecord(ev2, st));

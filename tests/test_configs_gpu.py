@@ -72,3 +72,29 @@ def test_kitti_shaped_scene_at_30cm(engine):
     again, stats2 = engine.segment_raw_rooms([scene], resolution=0.3, seed=1)
     np.testing.assert_array_equal(again[0], labels[0])
     assert stats2['grow_steps'][0] == stats['grow_steps'][0]
+
+
+def test_spatial_index_changes_no_label(engine):
+    """The Morton-ordered spatial index (shell scans of the grow steps, nearest-labelled-point search of the fill) against the
+    whole-room scans / the all-pairs fill (LRG_FLAG_NO_SPATIAL_INDEX) on rooms of three shapes at two resolutions: unfilled and
+    filled labels and the per-room statistics must be identical -- the fill's block bounds may prune, never decide."""
+    from tools import rooms
+    from learn_region_grow_b200 import _lib
+    cases = [([rooms.generate_room(1000 + i)[:, :6] for i in range(3)], 0.1),
+             ([rooms.generate_room(2000 + i, n_raw=n)[:, :6] for i, n in enumerate((5000, 35000))], 0.1),
+             ([rooms.generate_outdoor_scene(3000)[:, :6]], 0.3)]
+    for raws, res in cases:
+        out = []
+        for flags in (0, _lib.FLAG_NO_SPATIAL_INDEX):
+            engine.upload_raw_rooms(raws, res)
+            st = engine.segment_resident(resolution=res, seed=1, flags=flags)
+            out.append((engine.labels(False), engine.labels(True), st, engine.profile()['fill_ms']))
+        (u0, f0, s0, ms0), (u1, f1, s1, ms1) = out
+        for a, b in zip(u0, u1):
+            np.testing.assert_array_equal(a, b)
+        for a, b in zip(f0, f1):
+            np.testing.assert_array_equal(a, b)
+        assert s0['grow_steps'].tolist() == s1['grow_steps'].tolist() and s0['regions'].tolist() == s1['regions'].tolist()
+        assert all((u == 0).sum() > 0 for u in u0)                     # there was something to fill
+        print('fill: %d points, %d unlabeled: %.2f ms through the index, %.2f ms all pairs' %
+              (sum(len(u) for u in u0), sum(int((u == 0).sum()) for u in u0), ms0, ms1))
