@@ -283,19 +283,29 @@ __device__ int scan_box_spatial(const DriverArgs& da, int room, const unsigned* 
   if (tid == 0) *s_cnt = 0;
   group_sync<BAR, NT>();
   const uint2* box = da.sp_box + so / kSpBlock;
-  for (int b0 = 0; b0 < nblk; b0 += NT) {
-    const int b = b0 + tid;
-    bool hit = false;
-    if (b < nblk) {
-      const uint2 bb = __ldg(box + b);
-      hit = pw_x(bb.x) <= hi[0] && pw_x(bb.y) >= lo[0] && pw_y(bb.x) <= hi[1] && pw_y(bb.y) >= lo[1] && pw_z(bb.x) <= hi[2] && pw_z(bb.y) >= lo[2];
+  // (eight boxes per thread and round, loaded before any is tested: a large scene has more blocks than the group has threads,
+  //  and one box per round made every round a round trip of its own)
+  constexpr int kBoxU = 8;
+  for (int b0 = 0; b0 < nblk; b0 += NT * kBoxU) {
+    uint2 bb[kBoxU];
+#pragma unroll
+    for (int u = 0; u < kBoxU; ++u) {
+      const int b = b0 + u * NT + tid;
+      bb[u] = b < nblk ? __ldg(box + b) : make_uint2(PW_XYZ, 0u);
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, hit);
-    if (bal) {
-      int base = 0;
-      if (lane == 0) base = atomicAdd(s_cnt, __popc(bal));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (hit) blklist[base + __popc(bal & ((1u << lane) - 1u))] = b;
+#pragma unroll
+    for (int u = 0; u < kBoxU; ++u) {
+      if (b0 + u * NT >= nblk) break;                                       // (uniform)
+      const int b = b0 + u * NT + tid;
+      const bool hit = b < nblk && pw_x(bb[u].x) <= hi[0] && pw_x(bb[u].y) >= lo[0] && pw_y(bb[u].x) <= hi[1] && pw_y(bb[u].y) >= lo[1] &&
+                       pw_z(bb[u].x) <= hi[2] && pw_z(bb[u].y) >= lo[2];
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (bal) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(s_cnt, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hit) blklist[base + __popc(bal & ((1u << lane) - 1u))] = b;
+      }
     }
   }
   group_sync<BAR, NT>();
