@@ -31,10 +31,10 @@ def engine(golden_weights):
     e.close()
 
 
-def _replay(points, order, weights, trace, n_steps, seed, room_id=0):
+def _replay(points, order, weights, trace, n_steps, seed, room_id=0, resolution=0.1):
     """Re-drive the oracle with the device's trace.  Returns (grower, adopted near-tie bits)."""
     fwd = lambda a, b: lrg_forward.forward(weights, a, b)
-    g = lrg_driver.RoomGrower(points, order, fwd, lrg_driver.PhiloxRng(seed), room_id=room_id)
+    g = lrg_driver.RoomGrower(points, order, fwd, lrg_driver.PhiloxRng(seed), room_id=room_id, resolution=resolution)
     adopted = 0
     t = 0
     for seed_id in np.arange(len(points))[order]:
@@ -166,6 +166,30 @@ def test_large_room_replays_on_oracle(engine, golden_weights):
     g, adopted = _replay(points, order, golden_weights, trace, n_steps, 5)
     assert adopted <= 8
     np.testing.assert_array_equal(engine.labels(filled=False)[0], g.cluster_label)
+    np.testing.assert_array_equal(engine.labels(filled=True)[0], g.fill())
+
+
+def test_outdoor_shaped_scene_at_30cm_replays_on_oracle(engine, golden_weights):
+    """BASELINE config 5's shape at a size the oracle finishes: a 36 x 36 m ground plane with boxes on it at resolution 0.3
+    (tools/rooms.generate_outdoor_scene) -- the ground region reaches thousands of inliers (block median, box query for the
+    inlier list, full 512-of-n sampling) and every shell scan goes through the spatial index; replayed step by step."""
+    from tools import rooms as R
+    f = feature_prep.prepare_features(R.generate_outdoor_scene(3100, n_raw=40000, extent=36.0, n_boxes=30), 0.3)
+    points, order = f['points'], f['order']
+    assert len(points) > 8192
+    engine.upload_rooms([points], [order], resolution=0.3)
+    stats = engine.segment_resident(resolution=0.3, seed=2, trace_capacity=16384)
+    trace, n_steps = engine.trace(0, 16384)
+    assert n_steps == stats['grow_steps'][0] and 200 < n_steps <= 16384
+    assert trace['n_inlier'].max() > 2048
+    g, adopted = _replay(points, order, golden_weights, trace, n_steps, 2, resolution=0.3)
+    print('outdoor scene: %d points, %d steps, %d regions, largest region %d, %d near-tie bits adopted' %
+          (len(points), n_steps, len(g.regions), int(trace['n_inlier'].max()), adopted))
+    assert adopted <= 12
+    np.testing.assert_array_equal(engine.labels(filled=False)[0], g.cluster_label)
+    np.testing.assert_array_equal(engine.labels(filled=True)[0], g.fill())
+    # the same scene with eight speculative lanes (the engine's default for large scenes): the same labels
+    engine.segment_resident(resolution=0.3, seed=2, spec_lanes=8)
     np.testing.assert_array_equal(engine.labels(filled=True)[0], g.fill())
 
 
