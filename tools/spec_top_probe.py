@@ -21,8 +21,8 @@ for cfg in configs:
         raw_off, raw = bench.concat_rooms([r[:, :6] for r in rr])
         e.upload_raw_concatenated(raw_off, raw, res)
         ref = None
-        for label, kw in (('default', dict()), ('top 4 crit off (first rule)', dict(spec_top=4, spec_crit=-1)), ('crit 25', dict(spec_crit=25)),
-                          ('8 lanes', dict(spec_lanes=8)), ('1 lane', dict(spec_lanes=1))):
+        for label, kw in (('default', dict()), ('no tile split', dict(flags=_lib.FLAG_NO_TILE_SPLIT)), ('default again', dict()),
+                          ('no tile split again', dict(flags=_lib.FLAG_NO_TILE_SPLIT))):
             ms = []
             for rep in range(2):
                 st = e.segment_resident(resolution=res, seed=0, spec_lanes=kw.get('spec_lanes', 0), spec_top=kw.get('spec_top', 0), flags=kw.get('flags', 0), spec_crit=kw.get('spec_crit', 0), spec_min_idle=kw.get('spec_min_idle', 0))
