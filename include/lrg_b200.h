@@ -135,6 +135,8 @@ enum {
   LRG_FLAG_NO_SPATIAL_INDEX = 256, /* every neighbour-shell scan reads all N state words of the room instead of the blocks of the
                                       room's Morton-ordered spatial index that meet the shell, and the fill compares every unlabeled
                                       point with every labelled point instead of pruning blocks by their distance bound */
+  LRG_FLAG_ROOMS_IN_ORDER = 1024,  /* rooms are started in index order instead of largest first (a run that holds more rooms than
+                                      slots then tends to end with a long room that was started late) */
   LRG_FLAG_NO_STEP_OVERLAP = 512,  /* the median of a small region is selected after the indexed shell scan instead of beside it */
   LRG_FLAG_HEADS_AFTER_PROJ = 64,  /* publish the head tiles when the projection is complete instead of together with it
                                       (only without projection servers) */

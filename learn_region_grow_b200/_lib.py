@@ -56,6 +56,7 @@ FLAG_HEADS_AFTER_PROJ = 64
 FLAG_SCORE_ML = 128
 FLAG_NO_SPATIAL_INDEX = 256
 FLAG_NO_STEP_OVERLAP = 512
+FLAG_ROOMS_IN_ORDER = 1024
 
 _P = C.c_void_p
 _I = C.c_int

@@ -112,6 +112,10 @@ struct DriverArgs {
   int max_steps;
   int room_id_base;
   int* next_room;
+  // The order in which rooms are started (NULL: by index): largest first, so that the run does not end with a long room that was
+  // started late -- a room's label set does not depend on when it runs.  pending_pts[k] = points of the rooms order[k..]).
+  const int* room_order;        // (n_rooms)
+  const long long* pending_pts; // (n_rooms + 1)
   int* finished_slots;
   volatile int* done_flag;      // mapped pinned host memory
   LrgRoomStats* stats;          // (n_rooms)

@@ -134,6 +134,8 @@ struct LrgEngine {
   LaneGroup* d_groups = nullptr;
   int* d_parI = nullptr;        // beam search: index lists of the candidates in every group's queue
   SpecSync* d_spec_sync = nullptr;   // speculative lanes: per-group commit order; commit log
+  int* d_room_order = nullptr;         // rooms in the order they are started (largest first)
+  long long* d_pending_pts = nullptr;  // suffix sums of their point counts
   int* d_spec_est = nullptr;         // speculative lanes: per-group estimate of the grow steps its room still needs
   int* d_clog = nullptr;
   int* d_lane_steps = nullptr;
@@ -248,6 +250,7 @@ static void free_rooms(LrgEngine* e) {
   pool_free(e, e->d_n_lab); pool_free(e, e->d_n_unl); pool_free(e, e->d_stats);
   pool_free(e, e->d_pw_lanes); pool_free(e, e->d_groups); pool_free(e, e->d_lane_steps); pool_free(e, e->d_parI);
   pool_free(e, e->d_spec_sync); pool_free(e, e->d_clog); pool_free(e, e->d_spec_est);
+  pool_free(e, e->d_room_order); pool_free(e, e->d_pending_pts); e->d_room_order = nullptr; e->d_pending_pts = nullptr;
   e->d_pw_lanes = nullptr; e->d_groups = nullptr; e->d_lane_steps = nullptr; e->d_parI = nullptr; e->d_spec_sync = nullptr; e->d_clog = nullptr;
   e->d_spec_est = nullptr;
   pool_free(e, e->d_raw_off); pool_free(e, e->d_equalized_idx); pool_free(e, e->d_unequalized_idx); pool_free(e, e->d_feat);
@@ -1097,6 +1100,24 @@ static int segment_resident_impl(LrgEngine* e, const LrgGrowParams* params, LrgR
   da.resolution = e->resolution; da.cluster_threshold = params->cluster_threshold; da.seed = params->seed;
   da.max_steps = params->max_steps_per_region; da.room_id_base = params->room_id_base;
   da.next_room = e->d_counters; da.finished_slots = e->d_counters + 1; da.done_flag = e->d_done;
+  if (n_rooms > 1 && !(params->flags & LRG_FLAG_ROOMS_IN_ORDER)) {
+    // start the largest rooms first (more points = more grow steps, roughly): the tail of the run is then made of short rooms
+    std::vector<int> ord((size_t)n_rooms);
+    for (int r = 0; r < n_rooms; ++r) ord[r] = r;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
+      return e->h_room_off[a + 1] - e->h_room_off[a] > e->h_room_off[b + 1] - e->h_room_off[b];
+    });
+    std::vector<long long> pend((size_t)n_rooms + 1, 0);
+    for (int k = n_rooms - 1; k >= 0; --k) pend[k] = pend[k + 1] + (e->h_room_off[ord[k] + 1] - e->h_room_off[ord[k]]);
+    pool_free(e, e->d_room_order); pool_free(e, e->d_pending_pts);
+    e->d_room_order = nullptr; e->d_pending_pts = nullptr;
+    LRG_TRY(pool_alloc(e, &e->d_room_order, (size_t)n_rooms));
+    LRG_TRY(pool_alloc(e, &e->d_pending_pts, (size_t)n_rooms + 1));
+    LRG_CUDA(cudaMemcpyAsync(e->d_room_order, ord.data(), sizeof(int) * n_rooms, cudaMemcpyHostToDevice, st));
+    LRG_CUDA(cudaMemcpyAsync(e->d_pending_pts, pend.data(), sizeof(long long) * (n_rooms + 1), cudaMemcpyHostToDevice, st));
+    LRG_CUDA(cudaStreamSynchronize(st));      // (host temporaries)
+    da.room_order = e->d_room_order; da.pending_pts = e->d_pending_pts;
+  }
   da.dbg = e->d_tile_dbg ? e->d_tile_dbg + 32 : nullptr;
   da.stats = e->d_stats; da.trace = e->trace_capacity > 0 ? e->d_trace : nullptr; da.trace_capacity = e->trace_capacity;
   da.lanes = lanes; da.groups = e->d_groups; da.pw_lane_stride = e->total_words; da.lane_steps = grouped ? e->d_lane_steps : nullptr;

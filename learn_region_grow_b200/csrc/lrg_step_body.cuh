@@ -822,7 +822,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
           st.stop_noneighbor = stops[0]; st.stop_noexpand = stops[1]; st.stop_stuck = stops[2]; st.stop_other = stops[3];
         }
         const int nr = atomicAdd(da.next_room, 1);
-        G.room = nr < da.n_rooms ? nr : -1;
+        G.room = nr < da.n_rooms ? (da.room_order != nullptr ? da.room_order[nr] : nr) : -1;
         G.cursor = 0; G.cluster_id = 1; G.regions = 0; G.visited = 0;
         for (int l = 0; l < L; ++l) {                      // per-room counters of every lane (the others are parked)
           SlotState* o = l == lane_id ? &S : da.slots + (slot - lane_id + l);
@@ -1267,7 +1267,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
           long long total_est = (long long)sh.est_sum + mine;
           {
             const int nr = min(*reinterpret_cast<volatile int*>(da.next_room), da.n_rooms);
-            total_est += (da.total_pts - da.room_off[nr]) / 5;
+            total_est += (da.pending_pts != nullptr ? da.pending_pts[nr] : da.total_pts - da.room_off[nr]) / 5;
           }
           const bool critical = da.spec_crit <= 0 || (long long)mine * da.spec_crit >= total_est;
           // (the queue counters move while they are read: ONE thread looks, the verdict must be the same for the whole CTA)
@@ -1305,7 +1305,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
             }
         }
         const int nr = atomicAdd(da.next_room, 1);
-        G.room = nr < da.n_rooms ? nr : -1;
+        G.room = nr < da.n_rooms ? (da.room_order != nullptr ? da.room_order[nr] : nr) : -1;
         G.cursor = 0; G.cluster_id = 1; G.regions = 0; G.visited = 0;
         G.commit_seq = 0; G.next_ticket = 0; G.log_n = 0;
         G.useful_steps = G.wasted_steps = G.restarts = G.dropped = 0;
@@ -1776,7 +1776,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
             st.stop_noneighbor = S.stops[0]; st.stop_noexpand = S.stops[1]; st.stop_stuck = S.stops[2]; st.stop_other = S.stops[3];
           }
           const int nr = atomicAdd(da.next_room, 1);
-          S.room = nr < da.n_rooms ? nr : -1;
+          S.room = nr < da.n_rooms ? (da.room_order != nullptr ? da.room_order[nr] : nr) : -1;
           S.cursor = 0; S.cluster_id = 1; S.total_steps = 0; S.regions = 0; S.visited = 0;
           S.stops[0] = S.stops[1] = S.stops[2] = S.stops[3] = 0;
           S.active = 0;

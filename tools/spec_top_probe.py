@@ -21,13 +21,14 @@ for cfg in configs:
         raw_off, raw = bench.concat_rooms([r[:, :6] for r in rr])
         e.upload_raw_concatenated(raw_off, raw, res)
         ref = None
-        for label, kw in (('default', dict()), ('no tile split', dict(flags=_lib.FLAG_NO_TILE_SPLIT)), ('default again', dict()),
-                          ('no tile split again', dict(flags=_lib.FLAG_NO_TILE_SPLIT))):
+        for label, kw in (('default (largest rooms first)', dict()), ('rooms in index order', dict(flags=_lib.FLAG_ROOMS_IN_ORDER)), ('default again', dict()),
+                          ('rooms in index order again', dict(flags=_lib.FLAG_ROOMS_IN_ORDER)), ('1 lane', dict(spec_lanes=1)),
+                          ('1 lane, index order', dict(spec_lanes=1, flags=_lib.FLAG_ROOMS_IN_ORDER))):
             ms = []
             for rep in range(2):
                 st = e.segment_resident(resolution=res, seed=0, spec_lanes=kw.get('spec_lanes', 0), spec_top=kw.get('spec_top', 0), flags=kw.get('flags', 0), spec_crit=kw.get('spec_crit', 0), spec_min_idle=kw.get('spec_min_idle', 0))
                 ms.append(e.profile()['grow_ms'])
             lab = np.concatenate(e.labels(True))
             ref = lab if ref is None else ref
-            print('config %d %-12s %-28s grow %8.1f ms | steps %d longest %d | labels %s' % (cfg, cname, label, min(ms), int(st['grow_steps'].sum()),
+            print('config %d %-12s %-30s grow %8.1f ms | steps %d longest %d | labels %s' % (cfg, cname, label, min(ms), int(st['grow_steps'].sum()),
                   int(st['grow_steps'].max()), 'same' if np.array_equal(lab, ref) else 'DIFFERENT'), flush=True)
