@@ -21,9 +21,8 @@ for cfg in configs:
         raw_off, raw = bench.concat_rooms([r[:, :6] for r in rr])
         e.upload_raw_concatenated(raw_off, raw, res)
         ref = None
-        for label, kw in (('default (largest rooms first)', dict()), ('rooms in index order', dict(flags=_lib.FLAG_ROOMS_IN_ORDER)), ('default again', dict()),
-                          ('rooms in index order again', dict(flags=_lib.FLAG_ROOMS_IN_ORDER)), ('1 lane', dict(spec_lanes=1)),
-                          ('1 lane, index order', dict(spec_lanes=1, flags=_lib.FLAG_ROOMS_IN_ORDER))):
+        for label, kw in (('default', dict()), ('rooms in index order', dict(flags=_lib.FLAG_ROOMS_IN_ORDER)), ('top 4 crit off (first rule)', dict(spec_top=4, spec_crit=-1)),
+                          ('crit 25', dict(spec_crit=25)), ('8 lanes', dict(spec_lanes=8)), ('1 lane', dict(spec_lanes=1))):
             ms = []
             for rep in range(2):
                 st = e.segment_resident(resolution=res, seed=0, spec_lanes=kw.get('spec_lanes', 0), spec_top=kw.get('spec_top', 0), flags=kw.get('flags', 0), spec_crit=kw.get('spec_crit', 0), spec_min_idle=kw.get('spec_min_idle', 0))
