@@ -2,6 +2,7 @@
 // the lock-step step kernel (one CTA per room in flight advances its room by one grow step per launch; the body is
 // lrg_step_body.cuh, shared with the persistent grow kernel) and the final nearest-neighbour fill.
 #include "lrg_step_body.cuh"
+#include "lrg_sort.cuh"
 
 namespace lrg {
 
@@ -73,17 +74,15 @@ __device__ __forceinline__ unsigned morton_spread10(unsigned v) {       // 10 bi
   return v;
 }
 
-__global__ void __launch_bounds__(1024) lrg_spatial_index_kernel(const long long* __restrict__ room_off, const long long* __restrict__ pw_off,
-                                                                 const unsigned* __restrict__ pw, const long long* __restrict__ sp_off,
-                                                                 const long long* __restrict__ key_off, unsigned long long* __restrict__ keys_all,
-                                                                 int* __restrict__ sp_perm, unsigned* __restrict__ sp_vox, uint2* __restrict__ sp_box) {
-  const int room = blockIdx.x, tid = threadIdx.x;
+__global__ void lrg_spatial_keys_kernel(const long long* __restrict__ room_off, const long long* __restrict__ pw_off, const unsigned* __restrict__ pw,
+                                        const long long* __restrict__ key_off, unsigned long long* __restrict__ keys_all) {
+  const int room = blockIdx.y;
   const int N = (int)(room_off[room + 1] - room_off[room]);
   if (N <= 0) return;
   const unsigned* w = pw + pw_off[room];
   unsigned long long* keys = keys_all + key_off[room];
   const int P = (int)(key_off[room + 1] - key_off[room]);
-  for (int i = tid; i < P; i += 1024) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
     unsigned long long k = ~0ull;
     if (i < N) {
       const unsigned v = w[i];
@@ -92,32 +91,30 @@ __global__ void __launch_bounds__(1024) lrg_spatial_index_kernel(const long long
     }
     keys[i] = k;
   }
-  __syncthreads();
-  const int half = P >> 1;
-  for (int k = 2; k <= P; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < half; t += 1024) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const unsigned long long a = keys[i], b = keys[i | j];
-        if ((a > b) == ((i & k) == 0)) { keys[i] = b; keys[i | j] = a; }
-      }
-      __syncthreads();
-    }
+}
+
+// behind the sort: permutation and coordinates in Morton order, one warp per block of kSpBlock points for its bounding box
+__global__ void __launch_bounds__(256) lrg_spatial_blocks_kernel(const long long* __restrict__ room_off, const long long* __restrict__ pw_off,
+                                                                const unsigned* __restrict__ pw, const long long* __restrict__ sp_off,
+                                                                const long long* __restrict__ key_off, const unsigned long long* __restrict__ keys_all,
+                                                                int* __restrict__ sp_perm, unsigned* __restrict__ sp_vox, uint2* __restrict__ sp_box) {
+  const int room = blockIdx.y;
+  const int N = (int)(room_off[room + 1] - room_off[room]);
+  if (N <= 0) return;
+  const unsigned* w = pw + pw_off[room];
+  const unsigned long long* keys = keys_all + key_off[room];
   const long long so = sp_off[room];
-  const int npad = (int)(sp_off[room + 1] - so);
-  for (int m = tid; m < npad; m += 1024) {
-    const int i = m < N ? (int)(keys[m] & 0xFFFFFFFFull) : 0;
-    sp_perm[so + m] = i;
-    sp_vox[so + m] = m < N ? (w[i] & 0x3FFFFFFFu) : 0x3FFFFFFFu;
-  }
-  __syncthreads();
-  const int lane = tid & 31;
-  for (int b = tid >> 5; b < npad / kSpBlock; b += 32) {
+  const int nblk = (int)(sp_off[room + 1] - so) / kSpBlock;
+  const int lane = threadIdx.x & 31;
+  for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nblk; b += (gridDim.x * blockDim.x) >> 5) {
     int mn[3] = {1023, 1023, 1023}, mx[3] = {0, 0, 0};
     for (int q = lane; q < kSpBlock; q += 32) {
       const int m = b * kSpBlock + q;
+      const int i = m < N ? (int)(keys[m] & 0xFFFFFFFFull) : 0;
+      const unsigned v = m < N ? (w[i] & 0x3FFFFFFFu) : 0x3FFFFFFFu;
+      sp_perm[so + m] = i;
+      sp_vox[so + m] = v;
       if (m < N) {
-        const unsigned v = sp_vox[so + m];
         const int c[3] = {(int)(v & 1023u), (int)((v >> 10) & 1023u), (int)((v >> 20) & 1023u)};
 #pragma unroll
         for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], c[a]); mx[a] = max(mx[a], c[a]); }
@@ -136,10 +133,14 @@ __global__ void __launch_bounds__(1024) lrg_spatial_index_kernel(const long long
 }
 
 int launch_spatial_index(int n_rooms, const long long* d_room_off, const long long* d_pw_off, const unsigned* d_pw, const long long* d_sp_off,
-                         const long long* d_key_off, unsigned long long* d_keys, int* d_sp_perm, unsigned* d_sp_vox, uint2* d_sp_box,
-                         cudaStream_t stream) {
+                         const long long* d_key_off, unsigned long long* d_keys, long long max_keys, int* d_sp_perm, unsigned* d_sp_vox,
+                         uint2* d_sp_box, cudaStream_t stream) {
   if (n_rooms <= 0) return LRG_OK;
-  lrg_spatial_index_kernel<<<n_rooms, 1024, 0, stream>>>(d_room_off, d_pw_off, d_pw, d_sp_off, d_key_off, d_keys, d_sp_perm, d_sp_vox, d_sp_box);
+  const int per_room = std::max(4, std::min(148, (4 * 148 + n_rooms - 1) / n_rooms));
+  lrg_spatial_keys_kernel<<<dim3(per_room, n_rooms), 256, 0, stream>>>(d_room_off, d_pw_off, d_pw, d_key_off, d_keys);
+  RoomSort rs{d_keys, nullptr, 0, d_key_off, nullptr};
+  launch_room_sort<false>(rs, n_rooms, max_keys, stream);
+  lrg_spatial_blocks_kernel<<<dim3(per_room, n_rooms), 256, 0, stream>>>(d_room_off, d_pw_off, d_pw, d_sp_off, d_key_off, d_keys, d_sp_perm, d_sp_vox, d_sp_box);
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;
 }

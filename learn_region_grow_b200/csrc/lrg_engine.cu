@@ -728,12 +728,14 @@ static int pack_rooms(LrgEngine* e, const float* d_dense, bool validate = false)
     // that meet the shell)
     const int R = e->n_rooms;
     std::vector<long long> h_sp_off((size_t)R + 1, 0), h_key_off((size_t)R + 1, 0);
+    long long max_keys = 0;
     for (int r = 0; r < R; ++r) {
       const long long n = e->h_room_off[r + 1] - e->h_room_off[r];
       long long P = 1;
       while (P < n) P <<= 1;
       h_sp_off[r + 1] = h_sp_off[r] + (n + kSpBlock - 1) / kSpBlock * kSpBlock;
       h_key_off[r + 1] = h_key_off[r] + (n > 0 ? std::max<long long>(P, 2) : 0);
+      max_keys = std::max<long long>(max_keys, h_key_off[r + 1] - h_key_off[r]);
     }
     long long* d_key_off = nullptr;
     unsigned long long* d_keys = nullptr;
@@ -748,7 +750,7 @@ static int pack_rooms(LrgEngine* e, const float* d_dense, bool validate = false)
       ce = cudaMemcpyAsync(e->d_sp_off, h_sp_off.data(), sizeof(long long) * (R + 1), cudaMemcpyHostToDevice, e->stream);
       if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_key_off, h_key_off.data(), sizeof(long long) * (R + 1), cudaMemcpyHostToDevice, e->stream);
       if (ce == cudaSuccess)
-        rc = launch_spatial_index(R, e->d_room_off, e->d_pw_off, e->d_pw, e->d_sp_off, d_key_off, d_keys, e->d_sp_perm, e->d_sp_vox, e->d_sp_box, e->stream);
+        rc = launch_spatial_index(R, e->d_room_off, e->d_pw_off, e->d_pw, e->d_sp_off, d_key_off, d_keys, max_keys, e->d_sp_perm, e->d_sp_vox, e->d_sp_box, e->stream);
       if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);       // (the host vectors and the scratch go away)
     }
     pool_free(e, d_key_off);
@@ -871,6 +873,7 @@ static int upload_raw_impl(LrgEngine* e, int n_rooms, const int64_t* raw_offsets
   fp.n_rooms = n_rooms; fp.C = n_cols; fp.F = e->F; fp.res = resolution;
   fp.raw_off = d_raw_off; fp.raw = device_src ? raw_points : d_raw; fp.sort_off = d_sort_off; fp.keys = d_keys; fp.keys2 = d_keys2; fp.raw_vmin = d_vmin;
   fp.n_eq = d_neq; fp.err = d_err; fp.uniq_vox = d_uvox; fp.uniq_start = d_ustart; fp.eq_of_uniq = d_equ; fp.sums = d_sums; fp.raw_rank = d_rank;
+  for (int r = 0; r < n_rooms; ++r) fp.max_sort = std::max<long long>(fp.max_sort, sort_off[r + 1] - sort_off[r]);
   rc = launch_featprep_phase1(fp, st);
   std::vector<int> h_neq(std::max(n_rooms, 1), 0);
   int bad_room = 0;
@@ -899,6 +902,11 @@ static int upload_raw_impl(LrgEngine* e, int n_rooms, const int64_t* raw_offsets
     fp.eq_off = d_eq_off; fp.feat = e->d_feat; fp.curv = d_curv; fp.order = e->d_order; fp.equalized_idx = e->d_equalized_idx;
     fp.unequalized_idx = e->d_unequalized_idx;
     fp.extent = d_extent; fp.cmax = d_cmax; fp.has_nan = d_has_nan;
+    for (int r = 0; r < n_rooms; ++r) {
+      long long pe = 2;
+      while (pe < h_neq[r]) pe <<= 1;
+      fp.max_order_sort = std::max<long long>(fp.max_order_sort, std::min<long long>(pe, sort_off[r + 1] - sort_off[r]));
+    }
     rc = launch_featprep_phase2(fp, st);
     if (rc == LRG_OK) rc = pack_rooms(e, e->d_feat);
     cudaEventRecord(pev1, st);

@@ -12,6 +12,9 @@
 #include <limits.h>
 
 #include "lrg_featprep.cuh"
+#include <algorithm>
+
+#include "lrg_sort.cuh"
 #include "lrg_step_body.cuh"
 
 namespace lrg {
@@ -19,39 +22,8 @@ namespace lrg {
 constexpr int kFpThreads = 1024;
 constexpr unsigned long long kIdxMask = 0xFFFFFull;     // low 20 bits of a sort key: a room-local index
 
-// In-place ascending bitonic sort of P (power of two) 64-bit keys in global memory by one CTA.
-__device__ void bitonic_sort_u64(unsigned long long* keys, int P) {
-  const int tid = threadIdx.x, half = P >> 1;
-  for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < half; t += kFpThreads) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const unsigned long long a = keys[i], b = keys[i | j];
-        const bool up = (i & k) == 0;
-        if ((a > b) == up) { keys[i] = b; keys[i | j] = a; }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-// Same for (key, value) pairs ordered lexicographically.
-__device__ void bitonic_sort_pairs(unsigned long long* keys, int* vals, int P) {
-  const int tid = threadIdx.x, half = P >> 1;
-  for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < half; t += kFpThreads) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const unsigned long long a = keys[i], b = keys[i | j];
-        const int va = vals[i], vb = vals[i | j];
-        const bool up = (i & k) == 0;
-        const bool gt = a > b || (a == b && va > vb);
-        if (gt == up) { keys[i] = b; keys[i | j] = a; vals[i] = vb; vals[i | j] = va; }
-      }
-      __syncthreads();
-    }
-  }
-}
+// (the per-room sorts: lrg_sort.cuh -- bitonic networks whose short-distance passes run on chunks staged in shared memory)
+constexpr int kSortChunk = 4096, kSortChunkPairs = 2048;
 
 // -------------------------------------------------------------------------------------------- phase 1: equalisation
 __global__ void __launch_bounds__(kFpThreads) fp_keys_kernel(const __grid_constant__ FeatPrepArgs a) {
@@ -88,8 +60,7 @@ __global__ void __launch_bounds__(kFpThreads) fp_keys_kernel(const __grid_consta
     }
     keys[i] = key;
   }
-  __syncthreads();
-  bitonic_sort_u64(keys, P);                      // by voxel, then by insertion index
+  // (sorted by voxel, then by insertion index, by launch_room_sort behind this kernel)
 }
 
 __global__ void __launch_bounds__(kFpThreads) fp_unique_kernel(const __grid_constant__ FeatPrepArgs a) {
@@ -137,9 +108,15 @@ __global__ void __launch_bounds__(kFpThreads) fp_unique_kernel(const __grid_cons
   const int n_eq = running;
   if (tid == 0) a.n_eq[room] = n_eq;
   for (int i = n_eq + tid; i < P; i += kFpThreads) keys2[i] = ~0ull;
-  __syncthreads();
-  bitonic_sort_u64(keys2, P);                     // voxels in first-seen order (:127-129)
-  for (int j = tid; j < n_eq; j += kFpThreads) a.eq_of_uniq[base + (int)(keys2[j] & kIdxMask)] = j;
+  // (keys2 is sorted -- voxels in first-seen order, :127-129 -- by launch_room_sort; fp_unique_post_kernel follows)
+}
+
+__global__ void fp_unique_post_kernel(const __grid_constant__ FeatPrepArgs a) {
+  const int room = blockIdx.y;
+  const long long base = a.raw_off[room];
+  const int n_eq = a.n_eq[room];
+  const unsigned long long* keys2 = a.keys2 + a.sort_off[room];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_eq; j += gridDim.x * blockDim.x) a.eq_of_uniq[base + (int)(keys2[j] & kIdxMask)] = j;
 }
 
 // per voxel: n, sum p, sum of the float32 outer products in float64 (:151-155)
@@ -333,10 +310,17 @@ __global__ void __launch_bounds__(kFpThreads) fp_order_kernel(const __grid_const
     okeys[j] = j < n_eq ? dmax_bits(a.curv[ebase + j]) : ~0ull;
     oidx[j] = j < n_eq ? j : INT_MAX;
   }
-  __syncthreads();
-  bitonic_sort_pairs(okeys, oidx, Pe);
-  for (int j = tid; j < n_eq; j += kFpThreads) a.order[ebase + j] = oidx[j];
-  for (int i = tid; i < (int)(a.raw_off[room + 1] - rbase); i += kFpThreads)
+  // (the pairs are sorted by launch_room_sort; fp_order_post_kernel follows)
+}
+
+__global__ void fp_order_post_kernel(const __grid_constant__ FeatPrepArgs a) {
+  const int room = blockIdx.y;
+  const long long rbase = a.raw_off[room], ebase = a.eq_off[room];
+  const int n_eq = (int)(a.eq_off[room + 1] - ebase);
+  const int* oidx = reinterpret_cast<const int*>(a.keys2 + a.sort_off[room]);
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (int j = t0; j < n_eq; j += nt) a.order[ebase + j] = oidx[j];
+  for (int i = t0; i < (int)(a.raw_off[room + 1] - rbase); i += nt)
     a.unequalized_idx[rbase + i] = a.eq_of_uniq[rbase + a.raw_rank[rbase + i]];          // :130
 }
 
@@ -360,9 +344,16 @@ int launch_labels_raw(int n_rooms, const long long* raw_off, const long long* eq
 
 int launch_featprep_phase1(const FeatPrepArgs& a, cudaStream_t stream) {
   if (a.n_rooms <= 0) return LRG_OK;
+  // (grid-stride kernels: enough CTAs per room to fill the machine when the upload holds few, large rooms)
+  const int per_room = std::max(8, std::min(148, (4 * 148 + a.n_rooms - 1) / std::max(a.n_rooms, 1)));
   fp_keys_kernel<<<a.n_rooms, kFpThreads, 0, stream>>>(a);
+  RoomSort s1{a.keys, nullptr, 0, a.sort_off, nullptr};
+  launch_room_sort<false>(s1, a.n_rooms, a.max_sort, stream);
   fp_unique_kernel<<<a.n_rooms, kFpThreads, 0, stream>>>(a);
-  fp_voxel_sums_kernel<<<dim3(16, a.n_rooms), 256, 0, stream>>>(a);
+  RoomSort s2{a.keys2, nullptr, 0, a.sort_off, nullptr};
+  launch_room_sort<false>(s2, a.n_rooms, a.max_sort, stream);
+  fp_unique_post_kernel<<<dim3(per_room, a.n_rooms), 256, 0, stream>>>(a);
+  fp_voxel_sums_kernel<<<dim3(2 * per_room, a.n_rooms), 256, 0, stream>>>(a);
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;
 }
@@ -370,8 +361,12 @@ int launch_featprep_phase1(const FeatPrepArgs& a, cudaStream_t stream) {
 int launch_featprep_phase2(const FeatPrepArgs& a, cudaStream_t stream) {
   if (a.n_rooms <= 0) return LRG_OK;
   fp_extent_kernel<<<a.n_rooms, kFpThreads, 0, stream>>>(a);
-  fp_features_kernel<<<dim3(8, a.n_rooms), kFpThreads, 0, stream>>>(a);
+  const int per_room = std::max(8, std::min(148, (4 * 148 + a.n_rooms - 1) / std::max(a.n_rooms, 1)));
+  fp_features_kernel<<<dim3(per_room, a.n_rooms), kFpThreads, 0, stream>>>(a);
   fp_order_kernel<<<a.n_rooms, kFpThreads, 0, stream>>>(a);
+  RoomSort s3{a.keys, reinterpret_cast<int*>(a.keys2), 2, a.sort_off, a.eq_off};
+  launch_room_sort<true>(s3, a.n_rooms, a.max_order_sort, stream);
+  fp_order_post_kernel<<<dim3(per_room, a.n_rooms), 256, 0, stream>>>(a);
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;
 }

@@ -12,6 +12,8 @@ struct FeatPrepArgs {
   const long long* raw_off;       // (R+1) raw point offsets
   const float* raw;               // (sum Nr, C)
   const long long* sort_off;      // (R+1) offsets of the per-room sort buffers (power-of-two sizes >= Nr)
+  long long max_sort;             // host: the largest sort buffer (phase 1 sorts whole buffers)
+  long long max_order_sort;       // host: the largest seed-order sort of phase 2 = max over rooms of min(buffer, pow2ceil(max(2, Neq)))
   unsigned long long* keys;       // (sum P) voxel sort keys; later the seed-order keys
   unsigned long long* keys2;      // (sum P) first-seen sort keys; later the seed-order indices
   int4* raw_vmin;                 // (R) voxel origin of every room
