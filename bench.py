@@ -355,7 +355,9 @@ class Rig:
                 pr = eng.profile()
                 dev_ms.append(prep_ms + pr['grow_ms'] + pr['fill_ms'] + (1e3 * t_ag if self.dist is not None else 0.0))
                 grow_ms.append(pr['grow_ms']); prep_ms_l.append(prep_ms); fill_ms.append(pr['fill_ms'])
-                launches += pr['kernel_launches'] + 6      # + 4 feature-preparation kernels, pack, flag reset
+                # grow (+ lock-step kernels) + fill (2) + flag reset + raw labels, and what the upload launched (feature preparation
+                # with its sort passes, pack, spatial index) -- counted by the library
+                launches += pr['kernel_launches'] + 2 + eng.prepare_launches()
         self.barrier()
         wall = time.perf_counter() - wall0
         return dict(total_raw=total_raw, offsets=offsets, lengths=lengths, dev_ms=dev_ms, grow_ms=grow_ms, prep_ms=prep_ms_l, fill_ms=fill_ms,

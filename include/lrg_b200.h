@@ -194,6 +194,8 @@ int lrg_rooms_upload_raw_device(LrgEngine* e, int n_rooms, const int64_t* raw_of
 /* Device time (ms, CUDA events on the engine stream) of the last lrg_rooms_upload_raw / _device call: host-to-device copy (host
  * variant), feature preparation and packing, including the one host round trip that sizes the equalised rooms. */
 int lrg_last_prepare_ms(LrgEngine* e, float* ms);
+/* Kernels launched by the last upload (feature preparation with its sort passes, packing, spatial index). */
+int lrg_last_prepare_launches(LrgEngine* e, int* n);
 /* After an upload: (n_rooms+1) prefix sums of the equalised room sizes. */
 int lrg_rooms_equalized_offsets(LrgEngine* e, int64_t* eq_offsets);
 /* After lrg_rooms_upload_raw: the prepared features (sum Neq, F), the seed order, equalized_idx (sum Neq: raw index of every

@@ -77,6 +77,7 @@ _SIGNATURES = {
     'lrg_rooms_upload_raw': (_I, [_P, _I, _P, _P, _I, C.c_float]),
     'lrg_rooms_upload_raw_device': (_I, [_P, _I, _P, _P, _I, C.c_float]),
     'lrg_last_prepare_ms': (_I, [_P, C.POINTER(C.c_float)]),
+    'lrg_last_prepare_launches': (_I, [_P, C.POINTER(_I)]),
     'lrg_rooms_equalized_offsets': (_I, [_P, _P]),
     'lrg_rooms_features_download': (_I, [_P, _P, _P, _P, _P]),
     'lrg_labels_download_raw': (_I, [_P, _P, _I]),

@@ -134,12 +134,13 @@ __global__ void __launch_bounds__(256) lrg_spatial_blocks_kernel(const long long
 
 int launch_spatial_index(int n_rooms, const long long* d_room_off, const long long* d_pw_off, const unsigned* d_pw, const long long* d_sp_off,
                          const long long* d_key_off, unsigned long long* d_keys, long long max_keys, int* d_sp_perm, unsigned* d_sp_vox,
-                         uint2* d_sp_box, cudaStream_t stream) {
+                         uint2* d_sp_box, cudaStream_t stream, int* n_launches) {
   if (n_rooms <= 0) return LRG_OK;
   const int per_room = std::max(4, std::min(148, (4 * 148 + n_rooms - 1) / n_rooms));
   lrg_spatial_keys_kernel<<<dim3(per_room, n_rooms), 256, 0, stream>>>(d_room_off, d_pw_off, d_pw, d_key_off, d_keys);
   RoomSort rs{d_keys, nullptr, 0, d_key_off, nullptr};
-  launch_room_sort<false>(rs, n_rooms, max_keys, stream);
+  const int ns = launch_room_sort<false>(rs, n_rooms, max_keys, stream);
+  if (n_launches) *n_launches += 2 + ns;
   lrg_spatial_blocks_kernel<<<dim3(per_room, n_rooms), 256, 0, stream>>>(d_room_off, d_pw_off, d_pw, d_sp_off, d_key_off, d_keys, d_sp_perm, d_sp_vox, d_sp_box);
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;

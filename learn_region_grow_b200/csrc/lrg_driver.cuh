@@ -171,7 +171,7 @@ constexpr int kSpMinN = 2048;          // ... and smaller rooms are not worth th
 // Morton order + block boxes of every room; d_keys: (sum of P_r) sort scratch, P_r = power of two >= N_r at d_key_off[r]
 int launch_spatial_index(int n_rooms, const long long* d_room_off, const long long* d_pw_off, const unsigned* d_pw, const long long* d_sp_off,
                          const long long* d_key_off, unsigned long long* d_keys, long long max_keys, int* d_sp_perm, unsigned* d_sp_vox,
-                         uint2* d_sp_box, cudaStream_t stream);
+                         uint2* d_sp_box, cudaStream_t stream, int* n_launches = nullptr);
 // feature rows -> padded 16-float rows + state words; *d_err is set to a room index + 1 if a room spans > 1022 voxels
 int launch_pack(const float* d_points, int F, int n_rooms, const long long* d_room_off, const long long* d_pw_off, float resolution,
                 float* d_pts16, unsigned* d_pw, int4* d_room_vmin, int* d_err, cudaStream_t stream);

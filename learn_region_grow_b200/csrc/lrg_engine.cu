@@ -156,6 +156,7 @@ struct LrgEngine {
   float grow_ms = 0, fill_ms = 0, forward_ms = 0, prep_ms = 0;
   float kernel_ms[4] = {0, 0, 0, 0};
   long long iterations = 0, launches = 0;
+  int prep_launches = 0;               // kernels of the last upload (feature preparation, pack, spatial index)
 };
 
 namespace lrg {
@@ -719,6 +720,7 @@ static int pack_rooms(LrgEngine* e, const float* d_dense, bool validate = false)
   if (e->total_pts <= 0) return LRG_OK;
   LRG_CUDA(cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(int), e->stream));
   LRG_TRY(launch_pack(d_dense, e->F, e->n_rooms, e->d_room_off, e->d_pw_off, e->resolution, e->d_pts, e->d_pw, e->d_room_vmin, e->d_counters, e->stream));
+  e->prep_launches += 1;
   int bad_room = 0;
   LRG_CUDA(cudaMemcpyAsync(&bad_room, e->d_counters, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   LRG_CUDA(cudaStreamSynchronize(e->stream));
@@ -750,7 +752,7 @@ static int pack_rooms(LrgEngine* e, const float* d_dense, bool validate = false)
       ce = cudaMemcpyAsync(e->d_sp_off, h_sp_off.data(), sizeof(long long) * (R + 1), cudaMemcpyHostToDevice, e->stream);
       if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_key_off, h_key_off.data(), sizeof(long long) * (R + 1), cudaMemcpyHostToDevice, e->stream);
       if (ce == cudaSuccess)
-        rc = launch_spatial_index(R, e->d_room_off, e->d_pw_off, e->d_pw, e->d_sp_off, d_key_off, d_keys, max_keys, e->d_sp_perm, e->d_sp_vox, e->d_sp_box, e->stream);
+        rc = launch_spatial_index(R, e->d_room_off, e->d_pw_off, e->d_pw, e->d_sp_off, d_key_off, d_keys, max_keys, e->d_sp_perm, e->d_sp_vox, e->d_sp_box, e->stream, &e->prep_launches);
       if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);       // (the host vectors and the scratch go away)
     }
     pool_free(e, d_key_off);
@@ -788,6 +790,7 @@ int lrg_rooms_upload(LrgEngine* e, int n_rooms, const int64_t* room_offsets, con
   LRG_REQUIRE(total == 0 || (points != nullptr && seed_order != nullptr), "NULL points/seed_order");
   LRG_CUDA(cudaSetDevice(e->device));
   LRG_TRY(alloc_rooms(e, n_rooms, room_offsets, resolution));
+  e->prep_launches = 0;
   if (total > 0) {
     const size_t T = (size_t)total;
     float* d_raw = nullptr;     // staging for the dense (T, F) rows; freed after the pack kernel
@@ -813,6 +816,12 @@ int lrg_rooms_upload_raw(LrgEngine* e, int n_rooms, const int64_t* raw_offsets, 
 
 int lrg_rooms_upload_raw_device(LrgEngine* e, int n_rooms, const int64_t* raw_offsets, const float* d_raw_points, int n_cols, float resolution) {
   return upload_raw_impl(e, n_rooms, raw_offsets, d_raw_points, n_cols, resolution, true);
+}
+
+int lrg_last_prepare_launches(LrgEngine* e, int* n) {
+  LRG_REQUIRE(e != nullptr && n != nullptr, "NULL argument");
+  *n = e->prep_launches;
+  return LRG_OK;
 }
 
 int lrg_last_prepare_ms(LrgEngine* e, float* ms) {
@@ -874,7 +883,8 @@ static int upload_raw_impl(LrgEngine* e, int n_rooms, const int64_t* raw_offsets
   fp.raw_off = d_raw_off; fp.raw = device_src ? raw_points : d_raw; fp.sort_off = d_sort_off; fp.keys = d_keys; fp.keys2 = d_keys2; fp.raw_vmin = d_vmin;
   fp.n_eq = d_neq; fp.err = d_err; fp.uniq_vox = d_uvox; fp.uniq_start = d_ustart; fp.eq_of_uniq = d_equ; fp.sums = d_sums; fp.raw_rank = d_rank;
   for (int r = 0; r < n_rooms; ++r) fp.max_sort = std::max<long long>(fp.max_sort, sort_off[r + 1] - sort_off[r]);
-  rc = launch_featprep_phase1(fp, st);
+  e->prep_launches = 0;
+  rc = launch_featprep_phase1(fp, st, &e->prep_launches);
   std::vector<int> h_neq(std::max(n_rooms, 1), 0);
   int bad_room = 0;
   if (rc == LRG_OK) {
@@ -907,7 +917,7 @@ static int upload_raw_impl(LrgEngine* e, int n_rooms, const int64_t* raw_offsets
       while (pe < h_neq[r]) pe <<= 1;
       fp.max_order_sort = std::max<long long>(fp.max_order_sort, std::min<long long>(pe, sort_off[r + 1] - sort_off[r]));
     }
-    rc = launch_featprep_phase2(fp, st);
+    rc = launch_featprep_phase2(fp, st, &e->prep_launches);
     if (rc == LRG_OK) rc = pack_rooms(e, e->d_feat);
     cudaEventRecord(pev1, st);
     cudaError_t ce = cudaStreamSynchronize(st);

@@ -342,31 +342,35 @@ int launch_labels_raw(int n_rooms, const long long* raw_off, const long long* eq
   return LRG_OK;
 }
 
-int launch_featprep_phase1(const FeatPrepArgs& a, cudaStream_t stream) {
+int launch_featprep_phase1(const FeatPrepArgs& a, cudaStream_t stream, int* n_launches) {
   if (a.n_rooms <= 0) return LRG_OK;
+  int nl = 5;
   // (grid-stride kernels: enough CTAs per room to fill the machine when the upload holds few, large rooms)
   const int per_room = std::max(8, std::min(148, (4 * 148 + a.n_rooms - 1) / std::max(a.n_rooms, 1)));
   fp_keys_kernel<<<a.n_rooms, kFpThreads, 0, stream>>>(a);
   RoomSort s1{a.keys, nullptr, 0, a.sort_off, nullptr};
-  launch_room_sort<false>(s1, a.n_rooms, a.max_sort, stream);
+  nl += launch_room_sort<false>(s1, a.n_rooms, a.max_sort, stream);
   fp_unique_kernel<<<a.n_rooms, kFpThreads, 0, stream>>>(a);
   RoomSort s2{a.keys2, nullptr, 0, a.sort_off, nullptr};
-  launch_room_sort<false>(s2, a.n_rooms, a.max_sort, stream);
+  nl += launch_room_sort<false>(s2, a.n_rooms, a.max_sort, stream);
   fp_unique_post_kernel<<<dim3(per_room, a.n_rooms), 256, 0, stream>>>(a);
   fp_voxel_sums_kernel<<<dim3(2 * per_room, a.n_rooms), 256, 0, stream>>>(a);
+  if (n_launches) *n_launches += nl - 1;               // (keys, unique, unique_post, voxel_sums + the sorts)
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;
 }
 
-int launch_featprep_phase2(const FeatPrepArgs& a, cudaStream_t stream) {
+int launch_featprep_phase2(const FeatPrepArgs& a, cudaStream_t stream, int* n_launches) {
   if (a.n_rooms <= 0) return LRG_OK;
+  int nl = 4;                                          // extent, features, order, order_post
   fp_extent_kernel<<<a.n_rooms, kFpThreads, 0, stream>>>(a);
   const int per_room = std::max(8, std::min(148, (4 * 148 + a.n_rooms - 1) / std::max(a.n_rooms, 1)));
   fp_features_kernel<<<dim3(per_room, a.n_rooms), kFpThreads, 0, stream>>>(a);
   fp_order_kernel<<<a.n_rooms, kFpThreads, 0, stream>>>(a);
   RoomSort s3{a.keys, reinterpret_cast<int*>(a.keys2), 2, a.sort_off, a.eq_off};
-  launch_room_sort<true>(s3, a.n_rooms, a.max_order_sort, stream);
+  nl += launch_room_sort<true>(s3, a.n_rooms, a.max_order_sort, stream);
   fp_order_post_kernel<<<dim3(per_room, a.n_rooms), 256, 0, stream>>>(a);
+  if (n_launches) *n_launches += nl;
   LRG_CUDA(cudaGetLastError());
   return LRG_OK;
 }

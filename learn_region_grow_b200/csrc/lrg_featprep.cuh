@@ -37,8 +37,9 @@ struct FeatPrepArgs {
   int* has_nan;                   // (R) a curvature of the room is NaN
 };
 
-int launch_featprep_phase1(const FeatPrepArgs& a, cudaStream_t stream);
-int launch_featprep_phase2(const FeatPrepArgs& a, cudaStream_t stream);
+// n_launches (optional) is incremented by the kernels launched
+int launch_featprep_phase1(const FeatPrepArgs& a, cudaStream_t stream, int* n_launches = nullptr);
+int launch_featprep_phase2(const FeatPrepArgs& a, cudaStream_t stream, int* n_launches = nullptr);
 int launch_labels_raw(int n_rooms, const long long* raw_off, const long long* eq_off, const int* unequalized_idx, const int* label,
                       int* out, cudaStream_t stream);
 

@@ -203,6 +203,12 @@ class Engine:
         _lib.check(self.lib.lrg_last_prepare_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def prepare_launches(self):
+        """Kernels the last upload launched (feature preparation incl. its sort passes, packing, spatial index)."""
+        n = C.c_int(0)
+        _lib.check(self.lib.lrg_last_prepare_launches(self._h, C.byref(n)))
+        return n.value
+
     def raw_labels(self, filled=True):
         """cluster_label[unequalized_idx] per room (test_region_grow.py:366)."""
         tr = int(self._raw_offsets[-1])
