@@ -1958,6 +1958,13 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
 
     // sampling (:237-240, :249-252) with the Philox stream of oracle/lrg_driver.py PhiloxRng
     const bool fullI = n_in >= da.Ni, fullJ = n_nb >= da.Nj;
+    // (sets of up to kKeyCap points keep their sampling keys in shared memory -- behind the histograms of the radix select, in the
+    //  scratch of the median planes, which are dead by now -- instead of in global memory: the select reads every key five times)
+    constexpr int kKeyCap = 4096;
+    static_assert(sizeof(sh.planes) >= 32768 + 2 * kKeyCap * sizeof(unsigned) && sizeof(sh.hist) <= 32768, "sampling keys behind the histograms");
+    unsigned* const s_keys = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(sh.planes) + 32768);
+    if (n_in <= kKeyCap) keyI = s_keys;
+    if (n_nb <= kKeyCap) keyJ = s_keys + kKeyCap;
     if (fullI) for (int j = tid; j < n_in; j += NT) keyI[j] = philox_draw(da.seed, room_rng, step_rng, rng_lane + kStreamInlierKey, j);
     if (fullJ) for (int j = tid; j < n_nb; j += NT) keyJ[j] = philox_draw(da.seed, room_rng, step_rng, rng_lane + kStreamNeighborKey, j);
     if (tid == 0) { sh.rank[0] = da.Ni - 1; sh.rank[1] = da.Nj - 1; }
