@@ -124,8 +124,10 @@ typedef struct LrgGrowParams {
 enum {
   LRG_FLAG_KERNEL_TIMING = 1,  /* time the forward kernels separately with CUDA events (no graph; slower) */
   LRG_FLAG_NO_GRAPH = 2,       /* lock-step loop with direct kernel launches instead of a CUDA graph */
-  LRG_FLAG_PRIORITY = 8,       /* persistent kernel: reserve 24 CTAs for the two slots with the most unvisited points (off by default:
-                                  measured 1-3% slower than the plain FIFO; the loaded step latency is not queueing) */
+  LRG_FLAG_PRIORITY = 8,       /* persistent kernel: reserve CTAs for the rooms the run ends with -- with speculative lanes 16 CTAs for
+                                  the rooms the window calls critical (spec_crit), with one lane 24 CTAs for the two slots with the
+                                  most unvisited points.  Off by default: it shortens a run only when a GPU holds few enough rooms to
+                                  be chain-bound yet enough of them to queue (34 rooms: 7 % faster) and costs throughput otherwise */
   LRG_FLAG_LOCKSTEP = 4,       /* lock-step loop (one {step, branch, gproj, head} kernel quartet per iteration, CUDA graph)
                                   instead of the persistent grow kernel; implied by the two flags above and by FMA mode */
   /* A/B switches of the persistent kernel (the defaults are the measured best, profiles/README.md; results do not depend on

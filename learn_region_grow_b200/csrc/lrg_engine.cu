@@ -1049,7 +1049,7 @@ static int segment_resident_impl(LrgEngine* e, const LrgGrowParams* params, LrgR
     e->d_pw_lanes = nullptr; e->d_groups = nullptr; e->d_lane_steps = nullptr; e->d_parI = nullptr; e->d_spec_sync = nullptr; e->d_clog = nullptr;
     if (spec) {
       pool_free(e, e->d_spec_est); e->d_spec_est = nullptr;
-      LRG_TRY(pool_alloc(e, &e->d_spec_est, (size_t)n_groups));
+      LRG_TRY(pool_alloc(e, &e->d_spec_est, (size_t)2 * n_groups));       // [0,n): work estimates, [n,2n): the room is critical
       LRG_TRY(pool_alloc(e, &e->d_spec_sync, (size_t)n_groups));
       LRG_TRY(pool_alloc(e, &e->d_clog, (size_t)n_groups * std::max(e->slots_maxN, 1)));
     }
@@ -1082,7 +1082,7 @@ static int segment_resident_impl(LrgEngine* e, const LrgGrowParams* params, LrgR
     LRG_CUDA(cudaMemsetAsync(e->d_lane_steps, 0, sizeof(int) * (size_t)std::max(n_rooms, 1) * lanes, st));
     if (spec) {
       LRG_CUDA(cudaMemsetAsync(e->d_spec_sync, 0, sizeof(SpecSync) * (size_t)n_groups, st));
-      LRG_CUDA(cudaMemsetAsync(e->d_spec_est, 0, sizeof(int) * (size_t)n_groups, st));
+      LRG_CUDA(cudaMemsetAsync(e->d_spec_est, 0, sizeof(int) * (size_t)2 * n_groups, st));
     }
     LRG_CUDA(cudaStreamSynchronize(st));      // (ginit is a host temporary)
   }
@@ -1214,7 +1214,12 @@ static int segment_resident_impl(LrgEngine* e, const LrgGrowParams* params, LrgR
       ga.remaining = e->d_remaining;
       // reserved CTAs for the slots with the most work left (LRG_FLAG_PRIORITY; LRG_HI="slots,ctas" overrides for experiments)
       ga.hi_slots = 0; ga.hi_ctas = 0;
-      if (lanes == 1 && !beam) {
+      if (spec && (params->flags & LRG_FLAG_PRIORITY)) {
+        // speculative lanes: 16 reserved CTAs serve the CRITICAL rooms (DriverArgs::spec_crit).  Off by default: it pays only when a
+        // GPU holds few enough rooms to be chain-bound but enough to queue (34 rooms: 204 -> 190 ms) and costs throughput elsewhere
+        // (68 rooms 210 -> 217 ms, 272 rooms 632 -> 711 ms; profiles/r2an_*)
+        ga.hi_slots = 1; ga.hi_ctas = 16; ga.hi_crit = 1;
+      } else if (lanes == 1 && !beam) {
         const int hs = (params->flags & LRG_FLAG_PRIORITY) ? 2 : 0, hc = (params->flags & LRG_FLAG_PRIORITY) ? 24 : 0;
         const int n_ctas = e->sm_count > 0 ? e->sm_count : 148;
         if (hs > 0 && hc > 0 && hc < n_ctas) { ga.hi_slots = std::min(hs, 8); ga.hi_ctas = hc; }

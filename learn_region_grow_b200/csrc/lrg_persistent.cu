@@ -313,7 +313,10 @@ __global__ void __launch_bounds__(kGrowThreads, 1) lrg_grow_kernel(const __grid_
           // scheduling (optional): rank this slot by the unvisited points of its room; the bar for the high-priority queue
           // (the hi_slots-th largest count over all slots) is refreshed by every 64th step of a slot
           sy->prio = 1;
-          if (ga.hi_ctas > 0) {
+          if (ga.hi_ctas > 0 && ga.hi_crit) {
+            const int L2 = ga.da.lanes > 1 ? ga.da.lanes : 1;
+            if (*reinterpret_cast<volatile int*>(ga.da.spec_est + ga.da.n_slots / L2 + slot / L2) != 0) sy->prio = 0;
+          } else if (ga.hi_ctas > 0) {
             const int mine = (int)(ga.da.room_off[sh.S.room + 1] - ga.da.room_off[sh.S.room]) - sh.S.visited;
             *reinterpret_cast<volatile int*>(ga.remaining + slot) = mine;
             volatile int* bar = ga.remaining + ga.da.n_slots;

@@ -38,6 +38,7 @@ struct GrowArgs {
                                 // count a slot needs to be served from the high-priority queue (refreshed every 64 steps of a slot)
   int hi_slots;                 // how many slots are served from the high-priority queue
   int hi_ctas;                  // CTAs reserved for the high-priority queue (blockIdx < hi_ctas pop ring 0 only, the rest ring 1 only)
+  int hi_crit;                  // 1: the reserved CTAs serve the rooms flagged critical by the speculative window instead of the largest rooms
   int tune;                     // bit 0: split branch tiles over CTAs when the backlog is short; bit 1: publish head tiles with the projection blocks
   // pooled-projection servers (n_servers = 16 or 0): the first n_servers CTAs keep one 32-column slice of a head's pooled
   // weights W0[:1024] in shared memory for the whole run and answer one request per (slot, grow step)

@@ -1270,6 +1270,7 @@ __device__ void step_body(const DriverArgs& da, const int slot, StepShared& sh) 
             total_est += (da.pending_pts != nullptr ? da.pending_pts[nr] : da.total_pts - da.room_off[nr]) / 5;
           }
           const bool critical = da.spec_crit <= 0 || (long long)mine * da.spec_crit >= total_est;
+          if (tid == 0) *reinterpret_cast<volatile int*>(da.spec_est + ng + gi) = (critical && ahead < da.spec_top) ? 1 : 0;
           // (the queue counters move while they are read: ONE thread looks, the verdict must be the same for the whole CTA)
           int idle_ok = 0;
           if (tid == 0 && da.q_ctr != nullptr) {

@@ -15,19 +15,23 @@ for cfg in configs:
     rows = [bench._room(kind, g) for g in range(total)]
     cases = [('all rooms', rows)]
     if cfg == 4:     # what one of 8 ranks gets (LPT shard 0): the strong-scaling case is bound by the rank's longest chain
-        shards = parallel.shard_rooms(np.array([len(r) for r in rows], np.int64), 8)
-        cases.append(('rank 0 of 8', [rows[int(g)] for g in shards[0]]))
+        for nr in (8, 4, 16):
+            shards = parallel.shard_rooms(np.array([len(r) for r in rows], np.int64), nr)
+            cases.append(('rank 0 of %d' % nr, [rows[int(g)] for g in shards[0]]))
+        cases = cases[1:]
+    if cfg == 2:
+        cases = [('room 26 alone', [rows[26]])]
     for cname, rr in cases:
         raw_off, raw = bench.concat_rooms([r[:, :6] for r in rr])
         e.upload_raw_concatenated(raw_off, raw, res)
         ref = None
-        for label, kw in (('default', dict()), ('rooms in index order', dict(flags=_lib.FLAG_ROOMS_IN_ORDER)), ('top 4 crit off (first rule)', dict(spec_top=4, spec_crit=-1)),
-                          ('crit 25', dict(spec_crit=25)), ('8 lanes', dict(spec_lanes=8)), ('1 lane', dict(spec_lanes=1))):
+        for label, kw in (('default', dict()), ('reserved CTAs for critical rooms', dict(flags=_lib.FLAG_PRIORITY)), ('rooms in index order', dict(flags=_lib.FLAG_ROOMS_IN_ORDER)),
+                          ('top 4 crit off (first rule)', dict(spec_top=4, spec_crit=-1)), ('8 lanes', dict(spec_lanes=8)), ('1 lane', dict(spec_lanes=1))):
             ms = []
             for rep in range(2):
-                st = e.segment_resident(resolution=res, seed=0, spec_lanes=kw.get('spec_lanes', 0), spec_top=kw.get('spec_top', 0), flags=kw.get('flags', 0), spec_crit=kw.get('spec_crit', 0), spec_min_idle=kw.get('spec_min_idle', 0))
+                st = e.segment_resident(resolution=res, seed=0, spec_lanes=kw.get('spec_lanes', 0), spec_top=kw.get('spec_top', 0), flags=kw.get('flags', 0), spec_crit=kw.get('spec_crit', 0), spec_min_idle=kw.get('spec_min_idle', 0), max_steps_per_region=kw.get('msr', 0))
                 ms.append(e.profile()['grow_ms'])
             lab = np.concatenate(e.labels(True))
             ref = lab if ref is None else ref
-            print('config %d %-12s %-30s grow %8.1f ms | steps %d longest %d | labels %s' % (cfg, cname, label, min(ms), int(st['grow_steps'].sum()),
+            print('config %d %-13s %-32s grow %8.1f ms | steps %d longest %d | labels %s' % (cfg, cname, label, min(ms), int(st['grow_steps'].sum()),
                   int(st['grow_steps'].max()), 'same' if np.array_equal(lab, ref) else 'DIFFERENT'), flush=True)
